@@ -1,0 +1,47 @@
+# rehuel_b200 -- builds the sm_100a library that replaces librehuel.so's implicit-RK path
+# (reference Makefile:2-9,49-56 builds librehuel.so from *.cpp with clang++/Armadillo; here the
+# same shared-library target is produced by nvcc, with no Armadillo/LAPACK dependency).
+#
+#   make            -> rehuel_b200/librehuel_b200.so   (the product)
+#   make oracle     -> oracle/libirk_port.so (+ oracle/_ref/librehuel_ref.so when /root/reference exists)
+#   make sass       -> profiles/ SASS + ptxas listings of the hot kernel
+NVCC      ?= /usr/local/cuda/bin/nvcc
+# The image exports CXX=/opt/gcc/bin/g++ whose libstdc++ link is static (see oracle/Makefile);
+# use the distro compiler as nvcc's host compiler so the .so links libstdc++.so.6 dynamically.
+HOSTCXX   := /usr/bin/g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-Wextra \
+             --expt-relaxed-constexpr -Xptxas -v
+SRC       := rehuel_b200/csrc
+LIB       := rehuel_b200/librehuel_b200.so
+OBJS      := build/capi.o build/tableau.o
+
+.PHONY: all oracle clean sass
+all: $(LIB)
+
+build:
+	mkdir -p build
+
+build/capi.o: $(SRC)/capi.cu $(SRC)/irk_thread.cuh $(SRC)/functors.cuh $(SRC)/tableau.hpp include/rehuel_b200.h | build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/capi.ptxas.log || (cat build/capi.ptxas.log; false)
+
+build/tableau.o: $(SRC)/tableau.cpp $(SRC)/tableau.hpp $(SRC)/tableau_eig.inc | build
+	$(HOSTCXX) -O2 -std=c++17 -fPIC -Wall -Wextra -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(OBJS) -cudart shared
+
+$(SRC)/tableau_eig.inc: tools/gen_tableaux.py
+	python tools/gen_tableaux.py > $@ 2>/dev/null
+
+oracle:
+	$(MAKE) -C oracle all
+
+sass: $(LIB)
+	mkdir -p profiles
+	/usr/local/cuda/bin/cuobjdump -sass $(LIB) > profiles/librehuel_b200.sass
+	cp build/capi.ptxas.log profiles/ptxas_v.log
+
+clean:
+	rm -rf build $(LIB)
+	$(MAKE) -C oracle clean

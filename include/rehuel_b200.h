@@ -1,0 +1,220 @@
+/* rehuel_b200 -- C ABI of the B200-native batched ensemble integrator.
+ *
+ * Drop-in boundary for ONE path of Pakketeretet2/rehuel: the adaptive implicit Runge-Kutta
+ * solver  irk::odeint -> irk_guts -> newton_solve_stages -> error estimator -> step controller
+ * (reference irk.hpp:884-898, 509-869, 398-493).  The reference has no FFI layer of its own
+ * (C_interface_test/main.c is an empty file), so every entry point below cites the C++ interface
+ * it stands in for.  Plain pointers and sizes only; no C++, CUDA or torch types.
+ *
+ * Arrays are structure-of-arrays over the M ensemble members: component k of member i of an
+ * [n][M] array lives at ptr[k*M + i].  All arithmetic is IEEE FP64.
+ *
+ * Thread safety: every function may be called concurrently from several host threads as long as
+ * the output objects are distinct.  The library never prints unless options.out_interval > 0.
+ */
+#ifndef REHUEL_B200_H
+#define REHUEL_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library error codes (return values).  Numerical status is per member, see below. ---- */
+#define REHUEL_OK            0
+#define REHUEL_EINVAL       (-1) /* bad argument, unknown problem/method, unsupported combination */
+#define REHUEL_ECUDA        (-2) /* CUDA runtime error, text in rehuel_last_error() */
+#define REHUEL_ENCCL        (-3) /* reserved: collective error (the library itself uses none) */
+#define REHUEL_ENOMEM       (-4) /* host or device allocation failed */
+
+/* ---- per-member integration status: odeint_status_codes, reference enums.hpp:103-127 ---- */
+#define REHUEL_SUCCESS                    0
+#define REHUEL_DT_TOO_SMALL               1
+#define REHUEL_INTERNAL_SOLVE_FEW_ITERS   2
+#define REHUEL_GENERAL_ERROR              4
+#define REHUEL_DT_TOO_LARGE               8
+#define REHUEL_INTERNAL_SOLVE_FAILURE     16
+#define REHUEL_ERROR_LARGER_THAN_RELTOL   32
+#define REHUEL_ERROR_LARGER_THAN_ABSTOL   64
+#define REHUEL_ERROR_MAX_STEPS_EXCEEDED   128
+
+/* ---- method ids: irk::rk_methods, reference enums.hpp:38-58 (same integers) ---- */
+#define REHUEL_IMPLICIT_EULER   200
+#define REHUEL_RADAU_IIA_32     210
+#define REHUEL_RADAU_IIA_53     211
+#define REHUEL_RADAU_IIA_95     212
+#define REHUEL_RADAU_IIA_137    213
+#define REHUEL_LOBATTO_IIIA_43  220
+#define REHUEL_LOBATTO_IIIC_43  230
+#define REHUEL_LOBATTO_IIIC_64  231
+#define REHUEL_LOBATTO_IIIC_85  232
+
+/* ---- built-in device functors (the functor.hpp:35-73 concept compiled for the GPU).
+ *      Names follow examples/example_equations.cpp:475-494. ---- */
+#define REHUEL_PROBLEM_ROBERTSON      1 /* n=3, params (k1,k2,k3); test_equations.hpp:150-176 with the constants as parameters */
+#define REHUEL_PROBLEM_VAN_DER_POL    2 /* n=2, params (mu);       test_equations.hpp:91-115 */
+#define REHUEL_PROBLEM_BRUSSELATOR_1D 3 /* n=2*Ng, params (alpha,A,B); 1-D method-of-lines Brusselator */
+#define REHUEL_PROBLEM_EXPONENTIAL    5 /* n=1, params (lambda);   test_equations.hpp:37-59 */
+#define REHUEL_PROBLEM_STIFF_EQ       6 /* n=2, no params;         test_equations.hpp:207-250 */
+#define REHUEL_PROBLEM_BRUSSELATOR    7 /* n=2, params (a,b);      test_equations.hpp:120-145 */
+
+/* Solver options.  Replaces irk::solver_options (irk.hpp:95-124) : common_solver_options
+ * (options.hpp:40-85), the newton::options it points to (newton.hpp:57-78; only tol, dx_delta,
+ * maxit, refresh_jac are read by the irk path) and output_options (options.hpp:93-133). */
+typedef struct rehuel_options {
+	double rel_tol;                 /* options.hpp:50   default 1e-4 */
+	double abs_tol;                 /* options.hpp:51   default 10*rel_tol */
+	double max_dt;                  /* options.hpp:52   0 = no cap */
+	long long max_steps;            /* options.hpp:53   <0 = unlimited; compared against ACCEPTED steps (irk.hpp:612) */
+	int adaptive_step_size;         /* irk.hpp:103      default 1 */
+	int out_interval;               /* options.hpp:55   >0: keep a per-attempt trace "step t dt err iters" (irk.hpp:805-810) */
+	double newton_tol;              /* newton.hpp:58    tol      -> Rtol, default 1e-4 */
+	double newton_dx_delta;         /* newton.hpp:58    dx_delta -> xtol, default 1e-4 */
+	int newton_maxit;               /* newton.hpp:58    default 5000 */
+	int newton_refresh_jac;         /* newton.hpp:59    default 10 */
+	int output_mode;                /* options.hpp:96-103 bit 0: store samples (STORE_IN_VECTORS); default 1 */
+	unsigned long long output_interval; /* options.hpp:104 every k-th ACCEPTED step is a sample; default 1 */
+} rehuel_options;
+
+/* Fills in the reference's constructor defaults (options.hpp:49-58, irk.hpp:103-107,
+ * newton.hpp:58-60, options.hpp:103-104). */
+void rehuel_default_options(rehuel_options *opts);
+
+/* irk::name_to_method / irk::method_to_name (irk.cpp:709-718).  Unknown name -> 0;
+ * unknown id -> "". */
+int rehuel_name_to_method(const char *name);
+const char *rehuel_method_to_name(int method);
+
+/* Problem registry ("robertson", "van-der-pol", "brusselator-1d", "exponential",
+ * "stiff-equation", "brusselator").  Unknown -> 0. */
+int rehuel_name_to_problem(const char *name);
+/* n = number of equations, p = number of parameters.  n_hint selects n for size-generic
+ * problems (brusselator-1d: n = 2*Ng), ignored otherwise.  Returns REHUEL_EINVAL if unknown. */
+int rehuel_problem_dims(int problem, int n_hint, int *n, int *p);
+
+/* irk::get_coefficients (irk.cpp:215-689) + the derived weights of irk.hpp:599-601.
+ * A row-major s*s; all output arrays must hold 7 (49 for A) doubles.  Returns s, 0 if the
+ * method is unknown to this library. */
+int rehuel_get_coefficients(int method, double *A, double *b, double *c, double *b2, double *gamma,
+                            int *order, int *order2, double *d_weights, double *d2_weights);
+
+/* Ensemble sums of the per-member counters (rk_output::counters, irk.hpp:142-154) plus
+ * newton_iters (sum of newton::status::iters over successful solves) and steps (accepted). */
+typedef struct rehuel_stats {
+	unsigned long long attempt, reject_newton, reject_err, newton_success, newton_incr_diverge,
+	    newton_iter_error_too_large, newton_maxit_exceed, fun_evals, jac_evals;
+	unsigned long long newton_iters, steps, n_failed; /* n_failed = members with status != 0 */
+	unsigned long long max_attempt;                   /* max over members */
+} rehuel_stats;
+
+/* Result of an ensemble solve; replaces irk::rk_output (irk.hpp:140-163) : basic_output
+ * (output.hpp:30-35), one entry per member.  OWNERSHIP: the library allocates every array
+ * (page-locked host memory); release with rehuel_result_free().  Inputs are only borrowed for
+ * the duration of the call. */
+typedef struct rehuel_result {
+	size_t M;
+	int n;
+	double *t_final;        /* [M]    time reached (== t1 on success) */
+	double *y;              /* [n][M] state at t_final */
+	double *err_last;       /* [M]    scaled error norm of the last accepted step (rk_output::err.back()) */
+	int *status;            /* [M]    REHUEL_SUCCESS or a status bit */
+	unsigned *attempt, *reject_newton, *reject_err, *newton_success, *newton_maxit_exceed,
+	    *fun_evals, *jac_evals, *newton_iters, *steps; /* [M] each */
+	/* samples (only when output_mode bit 0 is set and n_samples_cap > 0) */
+	size_t n_samples_cap;   /* rows allocated per member */
+	unsigned *n_samples;    /* [M] samples produced (may exceed the cap; rows beyond it are dropped) */
+	double *t_samples;      /* [cap][M]    sample 0 is (t0, y0), irk.hpp:581-585 */
+	double *y_samples;      /* [cap][n][M] */
+	double *err_samples;    /* [cap][M] */
+	double elapsed_ms;      /* host wall time of the call (rk_output::elapsed_time is in ms, my_timer.hpp:142-149) */
+	double kernel_ms;       /* device time of the integration kernel(s), max over GPUs */
+	double accept_frac;     /* sum(steps)/sum(attempt)  (irk.hpp:864) */
+	rehuel_stats sum;
+	void *impl;             /* private */
+} rehuel_result;
+
+/* Batched irk::odeint (irk.hpp:884-898): every member is its own adaptive integration.
+ *   y0      [n][M], or [n] when y0_broadcast != 0
+ *   params  [p][M]
+ *   n_hint  see rehuel_problem_dims
+ *   n_samples_cap  rows of sample storage per member (0: final state only)
+ *   n_gpus  devices 0..n_gpus-1 of this process each take a contiguous share of the members
+ * Blocking.  Returns REHUEL_OK or a negative library error; numerical failures are reported per
+ * member in out->status[]. */
+int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt0, size_t M,
+                        int n_hint, const double *y0, int y0_broadcast, const double *params,
+                        const rehuel_options *opts, size_t n_samples_cap, int n_gpus,
+                        rehuel_result *out);
+void rehuel_result_free(rehuel_result *out);
+
+/* Single system = the reference call itself: returns the whole trajectory like
+ * rk_output::t_vals / y_vals / err (irk.hpp:581-585, 825-832).  *n_out = samples written into
+ * t_vals[cap], y_vals[cap][n] (row-major, one state per row), err_vals[cap]; if the trajectory
+ * is longer than cap the function still returns REHUEL_OK, *n_out holds the full length and only
+ * the first cap rows are valid.  counters[9] in the order of rk_output::counters;
+ * *accept_frac as irk.hpp:864; *status per-member status. */
+int rehuel_irk_single(int problem, int method, double t0, double t1, double dt0, int n_hint,
+                      const double *y0, const double *params, const rehuel_options *opts,
+                      size_t cap, size_t *n_out, double *t_vals, double *y_vals, double *err_vals,
+                      unsigned long long *counters, double *accept_frac, int *status);
+
+/* Device-resident variant used when inputs already live in HBM (bench "value", pipelines that
+ * generate parameters on the GPU).  Every pointer is a DEVICE pointer on the current device;
+ * optional outputs may be NULL.  Enqueues on `cuda_stream` (a cudaStream_t, NULL = default
+ * stream) and returns without synchronising.  `queue` is an 8-byte scratch word. */
+typedef struct rehuel_device_io {
+	const double *y0;      /* [n][M] or [n] */
+	int y0_broadcast;
+	const double *params;  /* [p][M] */
+	double *y;             /* [n][M] */
+	double *t_final;       /* [M] */
+	double *err_last;      /* [M] or NULL */
+	int *status;           /* [M] */
+	unsigned *counters;    /* [REHUEL_NCOUNTERS][M] or NULL; rows in REHUEL_CNT_* order */
+	size_t n_samples_cap;
+	unsigned *n_samples;   /* [M] or NULL */
+	double *t_samples, *y_samples, *err_samples; /* as in rehuel_result, or NULL */
+	unsigned long long *queue; /* [1] work-queue cursor, zeroed by the call */
+	double *trace;         /* [trace_cap][5] (step,t,dt,err,iters) of member trace_member, or NULL */
+	size_t trace_cap;
+	size_t trace_member;
+	unsigned *trace_len;   /* [1] */
+} rehuel_device_io;
+
+#define REHUEL_CNT_ATTEMPT             0
+#define REHUEL_CNT_REJECT_NEWTON       1
+#define REHUEL_CNT_REJECT_ERR          2
+#define REHUEL_CNT_NEWTON_SUCCESS      3
+#define REHUEL_CNT_NEWTON_MAXIT_EXCEED 4
+#define REHUEL_CNT_FUN_EVALS           5
+#define REHUEL_CNT_JAC_EVALS           6
+#define REHUEL_CNT_NEWTON_ITERS        7
+#define REHUEL_CNT_STEPS               8
+#define REHUEL_NCOUNTERS               9
+
+int rehuel_irk_ensemble_device(int problem, int method, double t0, double t1, double dt0, size_t M,
+                               int n_hint, const rehuel_options *opts, const rehuel_device_io *io,
+                               void *cuda_stream);
+
+/* Batched irk::merge_rk_output (irk.cpp:750-783): concatenates two legs of a restarted ensemble
+ * into `a` (counters added -- fun_evals/jac_evals are NOT, exactly like the reference --, status
+ * OR-ed, accept_frac weighted by the number of stored samples).  `b` is left untouched. */
+int rehuel_result_merge(rehuel_result *a, const rehuel_result *b);
+
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+unsigned long long rehuel_kernel_launches(void);
+/* Theoretical occupancy / register use of the kernel a (problem, method) pair dispatches to:
+ * fills regs per thread, local (spill) bytes per thread, static smem bytes, resident CTAs/SM,
+ * block size.  For profiles/ and DESIGN.md. */
+int rehuel_kernel_info(int problem, int method, int n_hint, int *regs, int *local_bytes,
+                       int *smem_bytes, int *ctas_per_sm, int *block);
+
+/* Last error text of the calling thread (the reference reports through free-text log_out). */
+const char *rehuel_last_error(void);
+const char *rehuel_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REHUEL_B200_H */

@@ -1,0 +1,632 @@
+// Host layer + C ABI (include/rehuel_b200.h) of the batched ensemble integrator.
+//
+// Maps the reference's public surface for the implicit-RK path onto kernel launches:
+//   irk::odeint (irk.hpp:884-898)            -> rehuel_irk_ensemble / rehuel_irk_single
+//   irk::get_coefficients (irk.cpp:215-689)  -> rehuel_get_coefficients
+//   irk::merge_rk_output (irk.cpp:750-783)   -> rehuel_result_merge
+//   default option constructors              -> rehuel_default_options
+// There is NO CPU fallback: every solve runs the sm_100a kernels or fails with REHUEL_ECUDA.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rehuel_b200.h"
+#include "functors.cuh"
+#include "irk_thread.cuh"
+#include "tableau.hpp"
+
+namespace rehuel {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+	return code;
+}
+#define CUDA_TRY(expr)                                                                            \
+	do {                                                                                          \
+		cudaError_t e_ = (expr);                                                                  \
+		if (e_ != cudaSuccess)                                                                    \
+			return fail(e_ == cudaErrorMemoryAllocation ? REHUEL_ENOMEM : REHUEL_ECUDA,           \
+			            "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+static std::atomic<unsigned long long> g_launches{0};
+
+// ------------------------------------------------------------------ problem registry
+struct ProblemInfo {
+	int id;
+	const char *name;
+	int n, p; // n == 0: size-generic (n = n_hint)
+};
+static const ProblemInfo kProblems[] = {
+    {REHUEL_PROBLEM_ROBERTSON, "robertson", 3, 3},
+    {REHUEL_PROBLEM_VAN_DER_POL, "van-der-pol", 2, 1},
+    {REHUEL_PROBLEM_BRUSSELATOR_1D, "brusselator-1d", 0, 3},
+    {REHUEL_PROBLEM_EXPONENTIAL, "exponential", 1, 1},
+    {REHUEL_PROBLEM_STIFF_EQ, "stiff-equation", 2, 0},
+    {REHUEL_PROBLEM_BRUSSELATOR, "brusselator", 2, 2},
+};
+static const ProblemInfo *find_problem(int id)
+{
+	for (const ProblemInfo &p : kProblems)
+		if (p.id == id) return &p;
+	return nullptr;
+}
+
+// ------------------------------------------------------------------ kernel dispatch
+struct KernelInfo {
+	int regs, local_bytes, smem_bytes, ctas_per_sm, block;
+};
+
+// Launch (or, when `info` is given, only describe) the thread-per-system kernel.
+template <class F, int S, int NR, int NC, int EST>
+static int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	constexpr int BLOCK = 128, MIN_BLOCKS = 2;
+	auto kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS>;
+	int dev = 0, sms = 0, per_sm = 0;
+	CUDA_TRY(cudaGetDevice(&dev));
+	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0));
+	if (per_sm < 1) return fail(REHUEL_ECUDA, "kernel does not fit on an SM");
+	if (info) {
+		cudaFuncAttributes fa;
+		CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+		info->regs = fa.numRegs;
+		info->local_bytes = (int)fa.localSizeBytes;
+		info->smem_bytes = (int)fa.sharedSizeBytes;
+		info->ctas_per_sm = per_sm;
+		info->block = BLOCK;
+		return REHUEL_OK;
+	}
+	if (ka.M == 0) return REHUEL_OK;
+	// persistent grid: one wave of resident CTAs, lanes pull members from io.queue
+	unsigned long long want = (ka.M + BLOCK - 1) / BLOCK;
+	unsigned long long cap = (unsigned long long)sms * per_sm;
+	unsigned grid = (unsigned)(want < cap ? want : cap);
+	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
+	CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	if (ka.io.trace_len) CUDA_TRY(cudaMemsetAsync(ka.io.trace_len, 0, sizeof(unsigned), stream));
+	kern<<<grid, BLOCK, 0, stream>>>(ka, dtb);
+	CUDA_TRY(cudaGetLastError());
+	g_launches.fetch_add(1);
+	return REHUEL_OK;
+}
+
+template <class F>
+static int dispatch_method(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	switch (tb.method) {
+	case REHUEL_RADAU_IIA_32: return launch_thread<F, 2, 0, 1, EST_OWN_LU>(ka, tb, stream, info);
+	case REHUEL_RADAU_IIA_53: return launch_thread<F, 3, 1, 1, EST_REUSE>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_43: return launch_thread<F, 3, 1, 1, EST_IDENTITY>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_64: return launch_thread<F, 4, 0, 2, EST_IDENTITY>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_85: return launch_thread<F, 5, 1, 2, EST_OWN_LU>(ka, tb, stream, info);
+	}
+	return fail(REHUEL_EINVAL, "method %d (%s) has no GPU kernel", tb.method, tb.name);
+}
+
+static int dispatch(int problem, int n, const KernelArgs &ka, const Tableau &tb, cudaStream_t stream,
+                    KernelInfo *info)
+{
+	(void)n;
+	switch (problem) {
+	case REHUEL_PROBLEM_ROBERTSON: return dispatch_method<RobertsonF>(ka, tb, stream, info);
+	case REHUEL_PROBLEM_VAN_DER_POL: return dispatch_method<VanDerPolF>(ka, tb, stream, info);
+	case REHUEL_PROBLEM_EXPONENTIAL: return dispatch_method<ExponentialF>(ka, tb, stream, info);
+	case REHUEL_PROBLEM_STIFF_EQ: return dispatch_method<StiffEqF>(ka, tb, stream, info);
+	case REHUEL_PROBLEM_BRUSSELATOR: return dispatch_method<BrusselatorF>(ka, tb, stream, info);
+	}
+	return fail(REHUEL_EINVAL, "problem %d has no GPU kernel", problem);
+}
+
+// Shared argument checking; fills the tableau and the scalar part of KernelArgs.
+static int prepare(int problem, int method, double t0, double t1, double dt0, size_t M, int n_hint,
+                   const rehuel_options *o, Tableau &tb, KernelArgs &ka, int &n, int &p)
+{
+	if (!o) return fail(REHUEL_EINVAL, "options must not be NULL (the reference asserts newton_opts, irk.hpp:548)");
+	if (rehuel_problem_dims(problem, n_hint, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
+	if (!get_coefficients(method, tb)) return fail(REHUEL_EINVAL, "Method %d not supported!", method); // irk.cpp:234-236
+	if (!(dt0 > 0.0)) return fail(REHUEL_EINVAL, "Cannot use time step size <= 0!"); // irk.hpp:549
+	if (o->newton_maxit < 1) return fail(REHUEL_EINVAL, "newton_maxit must be >= 1");
+	if (o->newton_refresh_jac <= 0) return fail(REHUEL_EINVAL, "newton_refresh_jac must be > 0 (the reference divides by it, irk.hpp:485)");
+	if (o->output_interval == 0) return fail(REHUEL_EINVAL, "output_interval must be > 0 (irk.hpp:825 takes step %% output_interval)");
+	std::memset(&ka, 0, sizeof ka);
+	ka.t0 = t0;
+	ka.t1 = t1;
+	ka.dt0 = dt0;
+	ka.rtol = o->rel_tol;
+	ka.atol = o->abs_tol;
+	ka.max_dt = o->max_dt;
+	ka.max_steps = o->max_steps;
+	// irk.hpp:890-895: adaptivity is switched off for tableaux without an embedded pair
+	ka.adaptive = (o->adaptive_step_size != 0 && tb.has_b2) ? 1 : 0;
+	ka.xtol2 = o->newton_dx_delta * o->newton_dx_delta;
+	ka.Rtol2 = o->newton_tol * o->newton_tol;
+	ka.maxit0 = o->newton_maxit;
+	ka.refresh_jac = o->newton_refresh_jac;
+	ka.store_samples = (o->output_mode & 1) ? 1 : 0;
+	ka.output_interval = o->output_interval;
+	ka.M = M;
+	return REHUEL_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer path
+struct ResultImpl {
+	std::vector<void *> pinned; // every cudaMallocHost'ed block owned by the result
+};
+
+template <class T>
+static int pinned_alloc(ResultImpl *impl, T **ptr, size_t count)
+{
+	*ptr = nullptr;
+	if (count == 0) return REHUEL_OK;
+	void *q = nullptr;
+	cudaError_t e = cudaMallocHost(&q, count * sizeof(T));
+	if (e != cudaSuccess) return fail(REHUEL_ENOMEM, "cudaMallocHost(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+	impl->pinned.push_back(q);
+	*ptr = static_cast<T *>(q);
+	return REHUEL_OK;
+}
+
+struct DeviceShard {
+	int dev = 0;
+	size_t off = 0, m = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::vector<void *> dptr;
+	rehuel_device_io io{};
+	~DeviceShard()
+	{
+		cudaSetDevice(dev);
+		for (void *q : dptr) cudaFree(q);
+		if (ev0) cudaEventDestroy(ev0);
+		if (ev1) cudaEventDestroy(ev1);
+		if (stream) cudaStreamDestroy(stream);
+	}
+	template <class T>
+	int alloc(T **ptr, size_t count)
+	{
+		*ptr = nullptr;
+		if (!count) return REHUEL_OK;
+		void *q = nullptr;
+		cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+		if (e != cudaSuccess) return fail(REHUEL_ENOMEM, "cudaMalloc(%zu bytes) on device %d: %s", count * sizeof(T), dev, cudaGetErrorString(e));
+		dptr.push_back(q);
+		*ptr = static_cast<T *>(q);
+		return REHUEL_OK;
+	}
+};
+
+static void free_result(rehuel_result *r)
+{
+	if (!r) return;
+	ResultImpl *impl = static_cast<ResultImpl *>(r->impl);
+	if (impl) {
+		for (void *q : impl->pinned) cudaFreeHost(q);
+		delete impl;
+	}
+	std::memset(r, 0, sizeof *r);
+}
+
+} // namespace rehuel
+
+using namespace rehuel;
+
+// =================================================================== C ABI
+extern "C" {
+
+const char *rehuel_last_error(void) { return g_err; }
+const char *rehuel_version(void) { return "rehuel_b200 0.1 (sm_100a)"; }
+unsigned long long rehuel_kernel_launches(void) { return g_launches.load(); }
+
+void rehuel_default_options(rehuel_options *o)
+{
+	if (!o) return;
+	o->rel_tol = 1e-4;                 // options.hpp:50
+	o->abs_tol = 10 * o->rel_tol;      // options.hpp:51
+	o->max_dt = 0.0;                   // options.hpp:52
+	o->max_steps = -1;                 // options.hpp:53
+	o->adaptive_step_size = 1;         // irk.hpp:103
+	o->out_interval = 0;               // options.hpp:55
+	o->newton_tol = 1e-4;              // newton.hpp:58
+	o->newton_dx_delta = 1e-4;         // newton.hpp:58
+	o->newton_maxit = 5000;            // newton.hpp:58
+	o->newton_refresh_jac = 10;        // newton.hpp:59
+	o->output_mode = 1;                // options.hpp:103 STORE_IN_VECTORS
+	o->output_interval = 1;            // options.hpp:104
+}
+
+int rehuel_name_to_method(const char *name) { return name_to_method(name); }
+const char *rehuel_method_to_name(int method) { return method_to_name(method); }
+
+int rehuel_name_to_problem(const char *name)
+{
+	if (!name) return 0;
+	for (const ProblemInfo &p : kProblems)
+		if (!std::strcmp(p.name, name)) return p.id;
+	return 0;
+}
+
+int rehuel_problem_dims(int problem, int n_hint, int *n, int *p)
+{
+	const ProblemInfo *pi = find_problem(problem);
+	if (!pi || !n || !p) return REHUEL_EINVAL;
+	*n = pi->n ? pi->n : n_hint;
+	*p = pi->p;
+	if (*n <= 0) return REHUEL_EINVAL;
+	return REHUEL_OK;
+}
+
+int rehuel_get_coefficients(int method, double *A, double *b, double *c, double *b2, double *gamma,
+                            int *order, int *order2, double *d_weights, double *d2_weights)
+{
+	Tableau tb;
+	if (!get_coefficients(method, tb)) return 0;
+	for (int i = 0; i < tb.s; ++i) {
+		for (int j = 0; j < tb.s; ++j)
+			if (A) A[i * tb.s + j] = tb.A[i][j];
+		if (b) b[i] = tb.b[i];
+		if (c) c[i] = tb.c[i];
+		if (b2) b2[i] = tb.b2[i];
+		if (d_weights) d_weights[i] = tb.d[i];
+		if (d2_weights) d2_weights[i] = tb.d2[i];
+	}
+	if (gamma) *gamma = tb.gamma;
+	if (order) *order = tb.order;
+	if (order2) *order2 = tb.order2;
+	return tb.s;
+}
+
+int rehuel_project_b(int method, double theta, double *out)
+{
+	Tableau tb;
+	if (!get_coefficients(method, tb) || !project_b(tb, theta, out)) return 0;
+	return tb.s;
+}
+
+// Eigen-structure used by the kernels (for tests): T, Ti row-major s*s; lambda as
+// (gamma_hat, alpha_0, beta_0, alpha_1, beta_1, ...).  Returns s.
+int rehuel_get_eigen(int method, double *T, double *Ti, double *lambda, int *n_real, int *n_cplx, int *est_mode)
+{
+	Tableau tb;
+	if (!get_coefficients(method, tb)) return 0;
+	for (int i = 0; i < tb.s; ++i)
+		for (int j = 0; j < tb.s; ++j) {
+			T[i * tb.s + j] = tb.T[i][j];
+			Ti[i * tb.s + j] = tb.Ti[i][j];
+		}
+	lambda[0] = tb.gamma_hat;
+	for (int k = 0; k < tb.n_cplx; ++k) {
+		lambda[1 + 2 * k] = tb.alpha[k];
+		lambda[2 + 2 * k] = tb.beta[k];
+	}
+	*n_real = tb.n_real;
+	*n_cplx = tb.n_cplx;
+	*est_mode = tb.est_mode;
+	return tb.s;
+}
+
+int rehuel_kernel_info(int problem, int method, int n_hint, int *regs, int *local_bytes, int *smem_bytes,
+                       int *ctas_per_sm, int *block)
+{
+	Tableau tb;
+	KernelArgs ka;
+	rehuel_options o;
+	rehuel_default_options(&o);
+	int n = 0, p = 0;
+	int rc = prepare(problem, method, 0.0, 1.0, 1e-6, 0, n_hint, &o, tb, ka, n, p);
+	if (rc) return rc;
+	KernelInfo ki{};
+	rc = dispatch(problem, n, ka, tb, nullptr, &ki);
+	if (rc) return rc;
+	if (regs) *regs = ki.regs;
+	if (local_bytes) *local_bytes = ki.local_bytes;
+	if (smem_bytes) *smem_bytes = ki.smem_bytes;
+	if (ctas_per_sm) *ctas_per_sm = ki.ctas_per_sm;
+	if (block) *block = ki.block;
+	return REHUEL_OK;
+}
+
+int rehuel_irk_ensemble_device(int problem, int method, double t0, double t1, double dt0, size_t M,
+                               int n_hint, const rehuel_options *opts, const rehuel_device_io *io,
+                               void *cuda_stream)
+{
+	Tableau tb;
+	KernelArgs ka;
+	int n = 0, p = 0;
+	int rc = prepare(problem, method, t0, t1, dt0, M, n_hint, opts, tb, ka, n, p);
+	if (rc) return rc;
+	if (!io || !io->y0 || (p && !io->params) || !io->y || !io->t_final || !io->status || !io->queue)
+		return fail(REHUEL_EINVAL, "rehuel_device_io: y0, params, y, t_final, status and queue are required");
+	ka.io = *io;
+	if (!ka.io.t_samples || !ka.io.y_samples || ka.io.n_samples_cap == 0) {
+		ka.io.n_samples_cap = 0; // samples are counted but not stored
+	}
+	if (!ka.io.trace || !ka.io.trace_len) {
+		ka.io.trace = nullptr;
+		ka.io.trace_len = nullptr;
+	}
+	return dispatch(problem, n, ka, tb, static_cast<cudaStream_t>(cuda_stream), nullptr);
+}
+
+int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt0, size_t M, int n_hint,
+                        const double *y0, int y0_broadcast, const double *params,
+                        const rehuel_options *opts, size_t n_samples_cap, int n_gpus, rehuel_result *out)
+{
+	auto tic = std::chrono::steady_clock::now();
+	if (!out) return fail(REHUEL_EINVAL, "out must not be NULL");
+	std::memset(out, 0, sizeof *out);
+	Tableau tb;
+	KernelArgs ka;
+	int n = 0, p = 0;
+	int rc = prepare(problem, method, t0, t1, dt0, M, n_hint, opts, tb, ka, n, p);
+	if (rc) return rc;
+	if (!y0 || (p && !params)) return fail(REHUEL_EINVAL, "y0/params must not be NULL");
+	int ndev = 0;
+	CUDA_TRY(cudaGetDeviceCount(&ndev));
+	if (n_gpus < 1) n_gpus = 1;
+	if (n_gpus > ndev) return fail(REHUEL_EINVAL, "n_gpus=%d but only %d CUDA devices are visible", n_gpus, ndev);
+	if (!ka.store_samples) n_samples_cap = 0;
+	int cur_dev = 0;
+	CUDA_TRY(cudaGetDevice(&cur_dev));
+	const int dev0 = (n_gpus == 1) ? cur_dev : 0;
+
+	// ---- result storage (page-locked so that the D2H copies are asynchronous)
+	ResultImpl *impl = new (std::nothrow) ResultImpl();
+	if (!impl) return fail(REHUEL_ENOMEM, "out of host memory");
+	out->impl = impl;
+	out->M = M;
+	out->n = n;
+	out->n_samples_cap = n_samples_cap;
+	unsigned *counters = nullptr; // [NCOUNTERS][M], sliced into the named pointers
+	rc = pinned_alloc(impl, &out->t_final, M);
+	if (!rc) rc = pinned_alloc(impl, &out->y, (size_t)n * M);
+	if (!rc) rc = pinned_alloc(impl, &out->err_last, M);
+	if (!rc) rc = pinned_alloc(impl, &out->status, M);
+	if (!rc) rc = pinned_alloc(impl, &counters, (size_t)REHUEL_NCOUNTERS * M);
+	if (!rc) rc = pinned_alloc(impl, &out->n_samples, M);
+	if (!rc && n_samples_cap) {
+		rc = pinned_alloc(impl, &out->t_samples, n_samples_cap * M);
+		if (!rc) rc = pinned_alloc(impl, &out->y_samples, n_samples_cap * n * M);
+		if (!rc) rc = pinned_alloc(impl, &out->err_samples, n_samples_cap * M);
+	}
+	if (rc) {
+		free_result(out);
+		return rc;
+	}
+	out->attempt = counters + (size_t)REHUEL_CNT_ATTEMPT * M;
+	out->reject_newton = counters + (size_t)REHUEL_CNT_REJECT_NEWTON * M;
+	out->reject_err = counters + (size_t)REHUEL_CNT_REJECT_ERR * M;
+	out->newton_success = counters + (size_t)REHUEL_CNT_NEWTON_SUCCESS * M;
+	out->newton_maxit_exceed = counters + (size_t)REHUEL_CNT_NEWTON_MAXIT_EXCEED * M;
+	out->fun_evals = counters + (size_t)REHUEL_CNT_FUN_EVALS * M;
+	out->jac_evals = counters + (size_t)REHUEL_CNT_JAC_EVALS * M;
+	out->newton_iters = counters + (size_t)REHUEL_CNT_NEWTON_ITERS * M;
+	out->steps = counters + (size_t)REHUEL_CNT_STEPS * M;
+
+	// ---- one shard per GPU: contiguous member ranges [M*g/G, M*(g+1)/G)
+	std::vector<DeviceShard> shards(n_gpus);
+	auto body = [&]() -> int {
+		for (int g = 0; g < n_gpus; ++g) {
+			DeviceShard &sh = shards[g];
+			sh.dev = dev0 + g;
+			sh.off = M * (size_t)g / (size_t)n_gpus;
+			sh.m = M * (size_t)(g + 1) / (size_t)n_gpus - sh.off;
+			CUDA_TRY(cudaSetDevice(sh.dev));
+			CUDA_TRY(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
+			CUDA_TRY(cudaEventCreate(&sh.ev0));
+			CUDA_TRY(cudaEventCreate(&sh.ev1));
+			const size_t m = sh.m;
+			double *d_y0 = nullptr, *d_par = nullptr;
+			int r = sh.alloc(&d_y0, y0_broadcast ? (size_t)n : (size_t)n * m);
+			if (!r) r = sh.alloc(&d_par, (size_t)p * m);
+			if (!r) r = sh.alloc(&sh.io.y, (size_t)n * m);
+			if (!r) r = sh.alloc(&sh.io.t_final, m);
+			if (!r) r = sh.alloc(&sh.io.err_last, m);
+			if (!r) r = sh.alloc(&sh.io.status, m);
+			if (!r) r = sh.alloc(&sh.io.counters, (size_t)REHUEL_NCOUNTERS * m);
+			if (!r) r = sh.alloc(&sh.io.n_samples, m);
+			if (!r) r = sh.alloc(&sh.io.queue, 1);
+			if (!r && n_samples_cap) {
+				r = sh.alloc(&sh.io.t_samples, n_samples_cap * m);
+				if (!r) r = sh.alloc(&sh.io.y_samples, n_samples_cap * n * m);
+				if (!r) r = sh.alloc(&sh.io.err_samples, n_samples_cap * m);
+			}
+			if (r) return r;
+			sh.io.y0 = d_y0;
+			sh.io.params = d_par;
+			sh.io.y0_broadcast = y0_broadcast;
+			sh.io.n_samples_cap = n_samples_cap;
+			if (m == 0) continue;
+			// H2D: SoA rows are strided by M on the host and by m on the device
+			if (y0_broadcast) {
+				CUDA_TRY(cudaMemcpyAsync(d_y0, y0, sizeof(double) * n, cudaMemcpyHostToDevice, sh.stream));
+			} else {
+				CUDA_TRY(cudaMemcpy2DAsync(d_y0, sizeof(double) * m, y0 + sh.off, sizeof(double) * M,
+				                           sizeof(double) * m, n, cudaMemcpyHostToDevice, sh.stream));
+			}
+			if (p)
+				CUDA_TRY(cudaMemcpy2DAsync(d_par, sizeof(double) * m, params + sh.off, sizeof(double) * M,
+				                           sizeof(double) * m, p, cudaMemcpyHostToDevice, sh.stream));
+			KernelArgs k = ka;
+			k.M = m;
+			k.io = sh.io;
+			CUDA_TRY(cudaEventRecord(sh.ev0, sh.stream));
+			int rr = dispatch(problem, n, k, tb, sh.stream, nullptr);
+			if (rr) return rr;
+			CUDA_TRY(cudaEventRecord(sh.ev1, sh.stream));
+			// D2H
+			CUDA_TRY(cudaMemcpy2DAsync(out->y + sh.off, sizeof(double) * M, sh.io.y, sizeof(double) * m,
+			                           sizeof(double) * m, n, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(out->t_final + sh.off, sh.io.t_final, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(out->err_last + sh.off, sh.io.err_last, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(out->status + sh.off, sh.io.status, sizeof(int) * m, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpy2DAsync(counters + sh.off, sizeof(unsigned) * M, sh.io.counters, sizeof(unsigned) * m,
+			                           sizeof(unsigned) * m, REHUEL_NCOUNTERS, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(out->n_samples + sh.off, sh.io.n_samples, sizeof(unsigned) * m, cudaMemcpyDeviceToHost, sh.stream));
+			if (n_samples_cap) {
+				CUDA_TRY(cudaMemcpy2DAsync(out->t_samples + sh.off, sizeof(double) * M, sh.io.t_samples, sizeof(double) * m,
+				                           sizeof(double) * m, n_samples_cap, cudaMemcpyDeviceToHost, sh.stream));
+				CUDA_TRY(cudaMemcpy2DAsync(out->err_samples + sh.off, sizeof(double) * M, sh.io.err_samples, sizeof(double) * m,
+				                           sizeof(double) * m, n_samples_cap, cudaMemcpyDeviceToHost, sh.stream));
+				CUDA_TRY(cudaMemcpy2DAsync(out->y_samples + sh.off, sizeof(double) * M, sh.io.y_samples, sizeof(double) * m,
+				                           sizeof(double) * m, n_samples_cap * n, cudaMemcpyDeviceToHost, sh.stream));
+			}
+		}
+		double kms = 0.0;
+		for (int g = 0; g < n_gpus; ++g) {
+			DeviceShard &sh = shards[g];
+			if (sh.m == 0) continue;
+			CUDA_TRY(cudaSetDevice(sh.dev));
+			CUDA_TRY(cudaStreamSynchronize(sh.stream));
+			float ms = 0.f;
+			CUDA_TRY(cudaEventElapsedTime(&ms, sh.ev0, sh.ev1));
+			if (ms > kms) kms = ms;
+		}
+		out->kernel_ms = kms;
+		return REHUEL_OK;
+	};
+	rc = body();
+	shards.clear(); // frees device memory on the right devices
+	cudaSetDevice(cur_dev);
+	if (rc) {
+		free_result(out);
+		return rc;
+	}
+
+	// ---- ensemble statistics (the "stats reduction epilogue"; merge_rk_output counters in spirit)
+	rehuel_stats &s = out->sum;
+	for (size_t i = 0; i < M; ++i) {
+		s.attempt += out->attempt[i];
+		s.reject_newton += out->reject_newton[i];
+		s.reject_err += out->reject_err[i];
+		s.newton_success += out->newton_success[i];
+		s.newton_maxit_exceed += out->newton_maxit_exceed[i];
+		s.fun_evals += out->fun_evals[i];
+		s.jac_evals += out->jac_evals[i];
+		s.newton_iters += out->newton_iters[i];
+		s.steps += out->steps[i];
+		s.n_failed += out->status[i] != 0;
+		if (out->attempt[i] > s.max_attempt) s.max_attempt = out->attempt[i];
+	}
+	out->accept_frac = s.attempt ? (double)s.steps / (double)s.attempt : 0.0; // irk.hpp:864
+	out->elapsed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();
+	return REHUEL_OK;
+}
+
+void rehuel_result_free(rehuel_result *out) { free_result(out); }
+
+int rehuel_irk_single(int problem, int method, double t0, double t1, double dt0, int n_hint,
+                      const double *y0, const double *params, const rehuel_options *opts, size_t cap,
+                      size_t *n_out, double *t_vals, double *y_vals, double *err_vals,
+                      unsigned long long *counters, double *accept_frac, int *status)
+{
+	rehuel_result r;
+	int rc = rehuel_irk_ensemble(problem, method, t0, t1, dt0, 1, n_hint, y0, 1, params, opts, cap, 1, &r);
+	if (rc) return rc;
+	const size_t produced = r.n_samples ? r.n_samples[0] : 0;
+	const size_t valid = produced < r.n_samples_cap ? produced : r.n_samples_cap;
+	if (n_out) *n_out = produced;
+	for (size_t k = 0; k < valid; ++k) {
+		if (t_vals) t_vals[k] = r.t_samples[k];
+		if (err_vals) err_vals[k] = r.err_samples[k];
+		if (y_vals)
+			for (int c = 0; c < r.n; ++c) y_vals[k * r.n + c] = r.y_samples[k * r.n + c];
+	}
+	if (counters) { // order of rk_output::counters, irk.hpp:149-153
+		counters[0] = r.attempt[0];
+		counters[1] = r.reject_newton[0];
+		counters[2] = r.reject_err[0];
+		counters[3] = r.newton_success[0];
+		counters[4] = 0; // newton_incr_diverge: never produced by the irk path
+		counters[5] = 0; // newton_iter_error_too_large: idem
+		counters[6] = r.newton_maxit_exceed[0];
+		counters[7] = r.fun_evals[0];
+		counters[8] = r.jac_evals[0];
+	}
+	if (accept_frac) *accept_frac = r.attempt[0] ? (double)r.steps[0] / (double)r.attempt[0] : 0.0;
+	if (status) *status = r.status[0];
+	rehuel_result_free(&r);
+	return REHUEL_OK;
+}
+
+int rehuel_result_merge(rehuel_result *a, const rehuel_result *b)
+{
+	if (!a || !b || a->M != b->M || a->n != b->n) return fail(REHUEL_EINVAL, "merge: results must describe the same ensemble");
+	const size_t M = a->M;
+	const int n = a->n;
+	ResultImpl *impl = static_cast<ResultImpl *>(a->impl);
+	if (!impl) return fail(REHUEL_EINVAL, "merge: `a` was not produced by this library");
+	// concatenate the sample rows: [cap_a + cap_b][...][M]
+	const size_t cap = a->n_samples_cap + b->n_samples_cap;
+	double *ts = nullptr, *ys = nullptr, *es = nullptr;
+	if (cap) {
+		int rc = pinned_alloc(impl, &ts, cap * M);
+		if (!rc) rc = pinned_alloc(impl, &ys, cap * n * M);
+		if (!rc) rc = pinned_alloc(impl, &es, cap * M);
+		if (rc) return rc;
+	}
+	double w1 = 0.0, w2 = 0.0; // irk.cpp:767-771: weights are the numbers of stored samples
+	for (size_t i = 0; i < M; ++i) {
+		const size_t na = a->n_samples[i] < a->n_samples_cap ? a->n_samples[i] : a->n_samples_cap;
+		const size_t nb = b->n_samples[i] < b->n_samples_cap ? b->n_samples[i] : b->n_samples_cap;
+		for (size_t k = 0; k < na; ++k) {
+			ts[k * M + i] = a->t_samples[k * M + i];
+			es[k * M + i] = a->err_samples[k * M + i];
+			for (int c = 0; c < n; ++c) ys[(k * n + c) * M + i] = a->y_samples[(k * n + c) * M + i];
+		}
+		for (size_t k = 0; k < nb; ++k) {
+			ts[(na + k) * M + i] = b->t_samples[k * M + i];
+			es[(na + k) * M + i] = b->err_samples[k * M + i];
+			for (int c = 0; c < n; ++c) ys[((na + k) * n + c) * M + i] = b->y_samples[(k * n + c) * M + i];
+		}
+		w1 += (double)a->n_samples[i];
+		w2 += (double)b->n_samples[i];
+		a->n_samples[i] = (unsigned)(na + nb);
+		a->status[i] |= b->status[i];
+		a->attempt[i] += b->attempt[i];
+		a->reject_newton[i] += b->reject_newton[i];
+		a->reject_err[i] += b->reject_err[i];
+		a->newton_success[i] += b->newton_success[i];
+		a->newton_maxit_exceed[i] += b->newton_maxit_exceed[i];
+		a->newton_iters[i] += b->newton_iters[i];
+		a->steps[i] += b->steps[i];
+		// fun_evals / jac_evals are NOT merged by the reference (irk.cpp:773-780): keep leg 1's
+		a->t_final[i] = b->t_final[i];
+		a->err_last[i] = b->err_last[i];
+		for (int c = 0; c < n; ++c) a->y[c * M + i] = b->y[c * M + i];
+	}
+	a->t_samples = ts;
+	a->y_samples = ys;
+	a->err_samples = es;
+	a->n_samples_cap = cap;
+	a->elapsed_ms += b->elapsed_ms;
+	a->kernel_ms += b->kernel_ms;
+	a->accept_frac = (w1 + w2) > 0 ? (w1 * a->accept_frac + w2 * b->accept_frac) / (w1 + w2) : 0.0;
+	a->sum.attempt += b->sum.attempt;
+	a->sum.reject_newton += b->sum.reject_newton;
+	a->sum.reject_err += b->sum.reject_err;
+	a->sum.newton_success += b->sum.newton_success;
+	a->sum.newton_maxit_exceed += b->sum.newton_maxit_exceed;
+	a->sum.newton_iters += b->sum.newton_iters;
+	a->sum.steps += b->sum.steps;
+	a->sum.n_failed = 0;
+	for (size_t i = 0; i < M; ++i) a->sum.n_failed += a->status[i] != 0;
+	if (b->sum.max_attempt > a->sum.max_attempt) a->sum.max_attempt = b->sum.max_attempt;
+	return REHUEL_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,115 @@
+// Device functors: the reference's functor concept (functor.hpp:35-73: fun(t,y), jac(t,y) with
+// J(i,j) = d f_i / d y_j) as templated __device__ callables.  Parameters the reference keeps as
+// data members (vdpol::mu, bruss::a/b, exponential::l) or hard-codes (rober: 0.04/1e4/3e7,
+// test_equations.hpp:155-157) are per-member parameter vectors p[P] here.
+//
+// Expression shapes follow test_equations.hpp so that the CPU oracle and the device agree to
+// rounding; --fmad contraction is allowed.
+#pragma once
+
+namespace rehuel {
+
+// Robertson chemical kinetics; test_equations.hpp:150-176.  p = (k1, k2, k3).
+struct RobertsonF {
+	static constexpr int N = 3;
+	static constexpr int P = 3;
+	static constexpr bool kAutonomous = true;
+	static constexpr int kFunFlops = 11, kJacFlops = 8; // SURVEY.md 8(d) accounting
+	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&p)[P], double (&f)[N])
+	{
+		f[0] = -p[0] * y[0] + p[1] * y[1] * y[2];
+		f[1] = p[0] * y[0] - p[1] * y[1] * y[2] - p[2] * y[1] * y[1];
+		f[2] = p[2] * y[1] * y[1];
+	}
+	__device__ __forceinline__ static void jac(double, const double (&y)[N], const double (&p)[P], double (&J)[N][N])
+	{
+		J[0][0] = -p[0];
+		J[0][1] = p[1] * y[2];
+		J[0][2] = p[1] * y[1];
+		J[1][0] = p[0];
+		J[1][1] = -p[1] * y[2] - (2.0 * p[2]) * y[1];
+		J[1][2] = -p[1] * y[1];
+		J[2][0] = 0.0;
+		J[2][1] = (2.0 * p[2]) * y[1];
+		J[2][2] = 0.0;
+	}
+};
+
+// Van der Pol in the reference's form (mu is the SMALL parameter); test_equations.hpp:91-115.
+struct VanDerPolF {
+	static constexpr int N = 2;
+	static constexpr int P = 1;
+	static constexpr bool kAutonomous = true;
+	static constexpr int kFunFlops = 6, kJacFlops = 7;
+	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&p)[P], double (&f)[N])
+	{
+		f[0] = y[1];
+		f[1] = ((1 - y[0] * y[0]) * y[1] - y[0]) / p[0];
+	}
+	__device__ __forceinline__ static void jac(double, const double (&y)[N], const double (&p)[P], double (&J)[N][N])
+	{
+		J[0][0] = 0.0;
+		J[0][1] = 1.0;
+		J[1][0] = -(2.0 * y[0] * y[1] + 1.0) / p[0];
+		J[1][1] = (1.0 - y[0] * y[0]) / p[0];
+	}
+};
+
+// y' = l*y; test_equations.hpp:37-59.  p = (l).
+struct ExponentialF {
+	static constexpr int N = 1;
+	static constexpr int P = 1;
+	static constexpr bool kAutonomous = true;
+	static constexpr int kFunFlops = 1, kJacFlops = 0;
+	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&p)[P], double (&f)[N])
+	{
+		f[0] = p[0] * y[0];
+	}
+	__device__ __forceinline__ static void jac(double, const double (&)[N], const double (&p)[P], double (&J)[N][N])
+	{
+		J[0][0] = p[0];
+	}
+};
+
+// y'' + 1001 y' + 1000 y = 0 as a 2x2 linear system; test_equations.hpp:207-250.  No parameters
+// (P is 1 only so that arrays have a size; the value is ignored).
+struct StiffEqF {
+	static constexpr int N = 2;
+	static constexpr int P = 0;
+	static constexpr bool kAutonomous = true;
+	static constexpr int kFunFlops = 3, kJacFlops = 0;
+	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&)[1], double (&f)[N])
+	{
+		f[0] = y[1];
+		f[1] = -1000.0 * y[0] + -1001.0 * y[1];
+	}
+	__device__ __forceinline__ static void jac(double, const double (&)[N], const double (&)[1], double (&J)[N][N])
+	{
+		J[0][0] = 0.0;
+		J[0][1] = 1.0;
+		J[1][0] = -1000.0;
+		J[1][1] = -1001.0;
+	}
+};
+
+// Two-variable Brusselator; test_equations.hpp:120-145.  p = (a, b).
+struct BrusselatorF {
+	static constexpr int N = 2;
+	static constexpr int P = 2;
+	static constexpr bool kAutonomous = true;
+	static constexpr int kFunFlops = 9, kJacFlops = 8;
+	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&p)[P], double (&f)[N])
+	{
+		f[0] = p[0] + y[0] * y[0] * y[1] - p[1] * y[0] - y[0];
+		f[1] = p[1] * y[0] - y[0] * y[0] * y[1];
+	}
+	__device__ __forceinline__ static void jac(double, const double (&y)[N], const double (&p)[P], double (&J)[N][N])
+	{
+		J[0][0] = 2 * y[0] * y[1] - p[1] - 1;
+		J[0][1] = y[0] * y[0];
+		J[1][0] = p[1] - 2 * y[0] * y[1];
+		J[1][1] = -y[0] * y[0];
+	}
+};
+
+} // namespace rehuel

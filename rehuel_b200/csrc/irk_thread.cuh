@@ -1,0 +1,588 @@
+// Thread-per-system ensemble integrator for small systems (n <= 4): one CUDA thread runs one
+// member's whole adaptive integration, lanes refill from a global work queue when their member
+// finishes (persistent warps, warp-aggregated atomics).
+//
+// One loop trip of a lane = one ATTEMPT of the reference time loop irk.hpp:604-860:
+//   newton_solve_stages<F,false,true>  irk.hpp:398-493   -> newton_solve()
+//   construct_R                         irk.hpp:366-386   -> residual()
+//   solution update                     irk.hpp:691-707
+//   embedded error estimate (8.19/8.20) irk.hpp:713-731
+//   error norm                          irk.hpp:733-758
+//   accept / reject                     irk.hpp:761-766, 813-846
+//   step-size controller                irk.hpp:770-801, 850-855
+//   Newton-failure policy               irk.hpp:634-665
+//
+// The one structural difference from the reference: the (s*n)x(s*n) system
+//   (I - dt*kron(A,J)) dY = -R                                   (irk.hpp:426-432, 461-462)
+// is not factorised densely.  With inv(A) = T Lambda T^-1 (tableau_eig.inc) it decouples into
+//   (mu_r I - J) W_r = -mu_r Z_r,            mu_r = gamma_hat/dt           (one real  n x n LU)
+//   (mu_c I - J) w_c = -mu_c z_c,            mu_c = (alpha+i*beta)/dt      (one complex n x n LU per pair)
+// with Z = (T^-1 (x) I) R and dY = (T (x) I) W.  Same linear system, same Newton iterates up to
+// rounding; 27 instead of 81 doubles of factor storage for n = s = 3, so everything lives in
+// registers.  All LUs are row-partial-pivoted like LAPACK's (predicated swaps, static indexing).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/rehuel_b200.h"
+#include "tableau.hpp"
+
+namespace rehuel {
+
+struct KernelArgs {
+	double t0, t1, dt0;
+	double rtol, atol, max_dt;
+	long long max_steps;
+	int adaptive;
+	double xtol2, Rtol2; // dx_delta^2, tol^2 (irk.hpp:441-442)
+	int maxit0, refresh_jac;
+	int store_samples;
+	unsigned long long output_interval;
+	unsigned long long M;
+	rehuel_device_io io;
+};
+
+constexpr double kMachinePrecision = 1e-17; // enums.hpp:129
+constexpr int kNewtonSuccess = 0, kNewtonMaxit = 3; // newton.hpp:45-51
+
+// ------------------------------------------------------------------ small dense LU, registers
+template <int N>
+struct LuReal {
+	double a[N][N]; // unit-lower L below the diagonal, U above, RECIPROCAL pivots on the diagonal
+	int piv[N];
+};
+
+template <int N>
+__device__ __forceinline__ void lu_factor(LuReal<N> &m)
+{
+#pragma unroll
+	for (int k = 0; k < N; ++k) {
+		int p = k;
+		double best = fabs(m.a[k][k]);
+#pragma unroll
+		for (int i = k + 1; i < N; ++i) {
+			double v = fabs(m.a[i][k]);
+			if (v > best) {
+				best = v;
+				p = i;
+			}
+		}
+		m.piv[k] = p;
+#pragma unroll
+		for (int i = k + 1; i < N; ++i) {
+			const bool sw = (p == i);
+#pragma unroll
+			for (int j = 0; j < N; ++j) {
+				const double u = m.a[k][j], w = m.a[i][j];
+				m.a[k][j] = sw ? w : u;
+				m.a[i][j] = sw ? u : w;
+			}
+		}
+		const double rp = 1.0 / m.a[k][k];
+		m.a[k][k] = rp;
+#pragma unroll
+		for (int i = k + 1; i < N; ++i) {
+			m.a[i][k] *= rp;
+#pragma unroll
+			for (int j = k + 1; j < N; ++j) m.a[i][j] = fma(-m.a[i][k], m.a[k][j], m.a[i][j]);
+		}
+	}
+}
+
+template <int N>
+__device__ __forceinline__ void lu_solve(const LuReal<N> &m, double (&x)[N])
+{
+#pragma unroll
+	for (int k = 0; k < N; ++k)
+#pragma unroll
+		for (int i = k + 1; i < N; ++i) {
+			const bool sw = (m.piv[k] == i);
+			const double u = x[k], w = x[i];
+			x[k] = sw ? w : u;
+			x[i] = sw ? u : w;
+		}
+#pragma unroll
+	for (int i = 1; i < N; ++i)
+#pragma unroll
+		for (int k = 0; k < i; ++k) x[i] = fma(-m.a[i][k], x[k], x[i]);
+#pragma unroll
+	for (int i = N - 1; i >= 0; --i) {
+#pragma unroll
+		for (int k = i + 1; k < N; ++k) x[i] = fma(-m.a[i][k], x[k], x[i]);
+		x[i] *= m.a[i][i];
+	}
+}
+
+template <int N>
+struct LuCplx {
+	double re[N][N], im[N][N];
+	int piv[N];
+};
+
+template <int N>
+__device__ __forceinline__ void lu_factor(LuCplx<N> &m)
+{
+#pragma unroll
+	for (int k = 0; k < N; ++k) {
+		int p = k;
+		double best = fabs(m.re[k][k]) + fabs(m.im[k][k]); // izamax's |re|+|im|
+#pragma unroll
+		for (int i = k + 1; i < N; ++i) {
+			double v = fabs(m.re[i][k]) + fabs(m.im[i][k]);
+			if (v > best) {
+				best = v;
+				p = i;
+			}
+		}
+		m.piv[k] = p;
+#pragma unroll
+		for (int i = k + 1; i < N; ++i) {
+			const bool sw = (p == i);
+#pragma unroll
+			for (int j = 0; j < N; ++j) {
+				double u = m.re[k][j], w = m.re[i][j];
+				m.re[k][j] = sw ? w : u;
+				m.re[i][j] = sw ? u : w;
+				u = m.im[k][j];
+				w = m.im[i][j];
+				m.im[k][j] = sw ? w : u;
+				m.im[i][j] = sw ? u : w;
+			}
+		}
+		// reciprocal pivot 1/(a+ib) = (a-ib)/(a^2+b^2)
+		const double pr = m.re[k][k], pi = m.im[k][k];
+		const double rden = 1.0 / fma(pr, pr, pi * pi);
+		const double rr = pr * rden, ri = -pi * rden;
+		m.re[k][k] = rr;
+		m.im[k][k] = ri;
+#pragma unroll
+		for (int i = k + 1; i < N; ++i) {
+			const double lr = fma(m.re[i][k], rr, -m.im[i][k] * ri);
+			const double li = fma(m.re[i][k], ri, m.im[i][k] * rr);
+			m.re[i][k] = lr;
+			m.im[i][k] = li;
+#pragma unroll
+			for (int j = k + 1; j < N; ++j) {
+				m.re[i][j] = fma(-lr, m.re[k][j], fma(li, m.im[k][j], m.re[i][j]));
+				m.im[i][j] = fma(-lr, m.im[k][j], fma(-li, m.re[k][j], m.im[i][j]));
+			}
+		}
+	}
+}
+
+template <int N>
+__device__ __forceinline__ void lu_solve(const LuCplx<N> &m, double (&xr)[N], double (&xi)[N])
+{
+#pragma unroll
+	for (int k = 0; k < N; ++k)
+#pragma unroll
+		for (int i = k + 1; i < N; ++i) {
+			const bool sw = (m.piv[k] == i);
+			double u = xr[k], w = xr[i];
+			xr[k] = sw ? w : u;
+			xr[i] = sw ? u : w;
+			u = xi[k];
+			w = xi[i];
+			xi[k] = sw ? w : u;
+			xi[i] = sw ? u : w;
+		}
+#pragma unroll
+	for (int i = 1; i < N; ++i)
+#pragma unroll
+		for (int k = 0; k < i; ++k) {
+			xr[i] = fma(-m.re[i][k], xr[k], fma(m.im[i][k], xi[k], xr[i]));
+			xi[i] = fma(-m.re[i][k], xi[k], fma(-m.im[i][k], xr[k], xi[i]));
+		}
+#pragma unroll
+	for (int i = N - 1; i >= 0; --i) {
+#pragma unroll
+		for (int k = i + 1; k < N; ++k) {
+			xr[i] = fma(-m.re[i][k], xr[k], fma(m.im[i][k], xi[k], xr[i]));
+			xi[i] = fma(-m.re[i][k], xi[k], fma(-m.im[i][k], xr[k], xi[i]));
+		}
+		const double tr = xr[i], ti = xi[i];
+		xr[i] = fma(tr, m.re[i][i], -ti * m.im[i][i]);
+		xi[i] = fma(tr, m.im[i][i], ti * m.re[i][i]);
+	}
+}
+
+// ------------------------------------------------------------------ controller power
+// err^(1/(1+min_order)) (irk.hpp:774-782).  The exponent is a tableau constant; the common
+// values get exact-root forms (each correctly rounded step, <= 1 ulp from pow()).
+__device__ __forceinline__ double ctrl_pow(double x, int min_order, double expo)
+{
+	if (min_order == 3) return sqrt(sqrt(x));
+	if (min_order == 2) return cbrt(x);
+	if (min_order == 5) return sqrt(cbrt(x));
+	return pow(x, expo);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <class F, int S, int NR, int NC, int EST, int BLOCK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
+ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant__ DevTableau<S, NC> tb)
+{
+	static_assert(S == NR + 2 * NC, "stage count must match the eigen-structure");
+	static_assert(NR <= 1, "at most one real eigenvalue");
+	constexpr int N = F::N;
+	constexpr int PA = F::P > 0 ? F::P : 1;
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned long long M = a.M;
+	const rehuel_device_io &io = a.io;
+
+	// ---- lane-persistent member state
+	bool have = false, exhausted = false;
+	unsigned long long mem = 0;
+	double y[N], p[PA];
+	double t = 0.0, dt = 0.0;
+	double dts0 = 0.0, dts1 = 0.0, errs0 = 0.9, errs1 = 0.9, err = 0.0;
+	bool alt = true;
+	int maxit = a.maxit0;
+	long long step = 0, last_relax = 0;
+	int status = REHUEL_SUCCESS;
+	unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0,
+	         c_iters = 0, n_stored = 0;
+
+	for (;;) {
+		// ---------------- refill idle lanes from the global queue (warp-aggregated)
+		const unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
+		if (need) {
+			const int leader = __ffs(need) - 1;
+			unsigned long long base = 0;
+			if ((int)lane == leader) base = atomicAdd(io.queue, (unsigned long long)__popc(need));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (!have && !exhausted) {
+				mem = base + __popc(need & ((1u << lane) - 1u));
+				if (mem < M) {
+#pragma unroll
+					for (int k = 0; k < N; ++k) y[k] = io.y0_broadcast ? io.y0[k] : io.y0[k * M + mem];
+#pragma unroll
+					for (int k = 0; k < F::P; ++k) p[k] = io.params[k * M + mem];
+					if (F::P == 0) p[0] = 0.0;
+					t = a.t0;
+					dt = a.dt0;
+					if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
+					dts0 = dts1 = dt;                 // irk.hpp:572
+					errs0 = errs1 = 0.9;              // irk.hpp:573
+					err = 0.0;
+					alt = true;                       // irk.hpp:587
+					maxit = a.maxit0;
+					step = 0;
+					last_relax = 0;
+					status = REHUEL_SUCCESS;
+					c_attempt = c_rej_newton = c_rej_err = c_newton_ok = c_fun = c_jac = c_iters = 0;
+					n_stored = 0;
+					have = true;
+					if (a.store_samples && io.n_samples_cap) { // sample 0 = (t0, y0), irk.hpp:581-585
+						io.t_samples[mem] = t;
+						if (io.err_samples) io.err_samples[mem] = 0.0;
+#pragma unroll
+						for (int k = 0; k < N; ++k) io.y_samples[k * M + mem] = y[k];
+					}
+					n_stored = a.store_samples ? 1u : 0u;
+				} else {
+					exhausted = true;
+				}
+			}
+		}
+		if (__all_sync(0xffffffffu, !have)) break;
+		if (!have) continue;
+
+		bool finished = false;
+		if (!(t < a.t1)) { // irk.hpp:604 (also covers t0 >= t1: zero attempts)
+			finished = true;
+		} else {
+			// ================= one attempt =================
+			if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:607-609
+			++c_attempt;
+			if (a.max_steps >= 0 && step > a.max_steps) { // irk.hpp:612-616
+				status = REHUEL_ERROR_MAX_STEPS_EXCEEDED;
+				finished = true;
+			} else {
+				// -------- simplified Newton on the stage increments, irk.hpp:398-493
+				double Y[S][N], R[S][N];
+				LuReal<N> lur;  // (mu_r I - J)        (dummy when NR == 0 and EST != EST_OWN_LU)
+				LuCplx<N> luc[NC > 0 ? NC : 1];
+				LuReal<N> lue;  // E/gam = (1/gam) I - J, only for EST_OWN_LU
+				const double rdt = 1.0 / dt;
+				// EST_REUSE: mu_r = 1/(gamma*dt) instead of gamma_hat/dt (equal to 1e-15) so that
+				// the same factors also serve E = I - gamma*dt*J of the error estimate.
+				const double mur = (EST == EST_REUSE) ? 1.0 / (tb.gamma * dt) : tb.gamma_hat * rdt;
+				{
+					double J[N][N];
+					F::jac(t, y, p, J); // irk.hpp:425
+					++c_jac;
+					if (NR) {
+#pragma unroll
+						for (int i = 0; i < N; ++i)
+#pragma unroll
+							for (int j = 0; j < N; ++j) lur.a[i][j] = (i == j ? mur : 0.0) - J[i][j];
+						lu_factor(lur);
+					}
+#pragma unroll
+					for (int c = 0; c < NC; ++c) {
+						const double mr = tb.alpha[c] * rdt, mi = tb.beta[c] * rdt;
+#pragma unroll
+						for (int i = 0; i < N; ++i)
+#pragma unroll
+							for (int j = 0; j < N; ++j) {
+								luc[c].re[i][j] = (i == j ? mr : 0.0) - J[i][j];
+								luc[c].im[i][j] = (i == j ? mi : 0.0);
+							}
+						lu_factor(luc[c]);
+					}
+					if (EST == EST_OWN_LU) {
+						const double mue = 1.0 / (tb.gamma * dt);
+#pragma unroll
+						for (int i = 0; i < N; ++i)
+#pragma unroll
+							for (int j = 0; j < N; ++j) lue.a[i][j] = (i == j ? mue : 0.0) - J[i][j];
+						lu_factor(lue);
+					}
+				}
+
+				// residual R = Y - dt*(A (x) I) F(y + Y), irk.hpp:366-386
+				auto residual = [&]() -> double {
+					double Fv[S][N];
+#pragma unroll
+					for (int i = 0; i < S; ++i) {
+						double yi[N];
+#pragma unroll
+						for (int k = 0; k < N; ++k) yi[k] = y[k] + Y[i][k];
+						F::fun(fma(tb.c[i], dt, t), yi, p, Fv[i]);
+					}
+					c_fun += S;
+					double r2 = 0.0;
+#pragma unroll
+					for (int i = 0; i < S; ++i)
+#pragma unroll
+						for (int k = 0; k < N; ++k) {
+							double acc = 0.0;
+#pragma unroll
+							for (int j = 0; j < S; ++j) acc = fma(tb.A[i][j], Fv[j][k], acc);
+							R[i][k] = fma(-dt, acc, Y[i][k]);
+							r2 = fma(R[i][k], R[i][k], r2);
+						}
+					return r2;
+				};
+
+#pragma unroll
+				for (int i = 0; i < S; ++i)
+#pragma unroll
+					for (int k = 0; k < N; ++k) Y[i][k] = 0.0; // irk.hpp:415
+				double Rnorm2 = residual();                   // irk.hpp:443-446
+				int nstat = kNewtonMaxit;
+				int it = 1;
+				for (; it < maxit; ++it) { // irk.hpp:458
+					// dY = -(I - dt A(x)J)^-1 R through the decoupled blocks
+					double Z[S][N];
+#pragma unroll
+					for (int i = 0; i < S; ++i)
+#pragma unroll
+						for (int k = 0; k < N; ++k) {
+							double acc = 0.0;
+#pragma unroll
+							for (int j = 0; j < S; ++j) acc = fma(tb.Ti[i][j], R[j][k], acc);
+							Z[i][k] = acc;
+						}
+					if (NR) {
+						lu_solve(lur, Z[0]);
+#pragma unroll
+						for (int k = 0; k < N; ++k) Z[0][k] *= -mur;
+					}
+#pragma unroll
+					for (int c = 0; c < NC; ++c) {
+						const double mr = tb.alpha[c] * rdt, mi = tb.beta[c] * rdt;
+						lu_solve(luc[c], Z[NR + 2 * c], Z[NR + 2 * c + 1]);
+#pragma unroll
+						for (int k = 0; k < N; ++k) { // w = -(mr + i mi) * w
+							const double wr = Z[NR + 2 * c][k], wi = Z[NR + 2 * c + 1][k];
+							Z[NR + 2 * c][k] = fma(-mr, wr, mi * wi);
+							Z[NR + 2 * c + 1][k] = fma(-mr, wi, -mi * wr);
+						}
+					}
+					double xnorm2 = 0.0;
+#pragma unroll
+					for (int i = 0; i < S; ++i)
+#pragma unroll
+						for (int k = 0; k < N; ++k) {
+							double acc = 0.0;
+#pragma unroll
+							for (int j = 0; j < S; ++j) acc = fma(tb.T[i][j], Z[j][k], acc);
+							xnorm2 = fma(acc, acc, xnorm2); // irk.hpp:466
+							Y[i][k] += acc;                 // irk.hpp:468 (step == 1)
+						}
+					Rnorm2 = residual();                    // irk.hpp:469-472
+					if (Rnorm2 < a.Rtol2) { nstat = kNewtonSuccess; break; } // irk.hpp:473-476
+					if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; } // irk.hpp:477-480
+					if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac; // irk.hpp:485-487 (no-op refactor)
+					if (!(Rnorm2 <= 1.79769313486231570e308)) {
+						// NaN/Inf residual can never pass either test again (Y stays non-finite):
+						// the reference spins to maxit; account the remaining evaluations and stop.
+						const int rest = maxit - 1 - it;
+						if (rest > 0) {
+							c_fun += (unsigned)rest * S;
+							if (a.refresh_jac > 0) c_jac += (unsigned)((maxit - 1) / a.refresh_jac - it / a.refresh_jac);
+						}
+						it = maxit;
+						break;
+					}
+				}
+
+				if (nstat != kNewtonSuccess) { // irk.hpp:634-665
+					if (!a.adaptive) {
+						status = REHUEL_GENERAL_ERROR;
+						finished = true;
+					} else {
+						dt *= 0.7;
+						if (step - last_relax > 15) {
+							maxit += a.maxit0;
+							last_relax = step;
+						}
+						++c_rej_newton;
+					}
+					if (io.trace && mem == io.trace_member) {
+						unsigned r = atomicAdd(io.trace_len, 1u);
+						if (r < io.trace_cap) {
+							double *row = io.trace + 5 * (size_t)r;
+							row[0] = (double)step; row[1] = t; row[2] = dt; row[3] = -1.0; row[4] = (double)it;
+						}
+					}
+				} else {
+					++c_newton_ok;
+					c_iters += (unsigned)it;
+					// -------- new solution + embedded error, irk.hpp:691-731
+					const double gam = tb.gamma * dt;
+					double dy[N], dalt[N], fy[N], e[N], yn[N];
+#pragma unroll
+					for (int k = 0; k < N; ++k) {
+						double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+						for (int i = 0; i < S; ++i) {
+							s1 = fma(Y[i][k], tb.d[i], s1);
+							s2 = fma(Y[i][k], tb.d2[i], s2);
+						}
+						dy[k] = s1;
+						dalt[k] = s2;
+					}
+					if (EST != EST_IDENTITY) {
+						F::fun(t, y, p, fy); // irk.hpp:702 (multiplied by gam == 0 when EST_IDENTITY)
+					}
+					++c_fun;
+#pragma unroll
+					for (int k = 0; k < N; ++k) {
+						yn[k] = y[k] + dy[k];
+						const double dyalt = (EST != EST_IDENTITY) ? fma(gam, fy[k], dalt[k]) : dalt[k];
+						e[k] = dyalt - dy[k]; // delta_delta, irk.hpp:707
+					}
+					// err_est = dt * E^-1 * (.), E = I - gam*J = gam*((1/gam) I - J), so
+					// dt*E^-1 = (dt/gam) ((1/gam) I - J)^-1 = (1/gamma) (mu I - J)^-1
+					auto apply_Einv_dt = [&](double (&v)[N]) {
+						if (EST == EST_REUSE) {
+							lu_solve(lur, v);
+						} else if (EST == EST_OWN_LU) {
+							lu_solve(lue, v);
+						}
+						const double sc = (EST == EST_IDENTITY) ? dt : 1.0 / tb.gamma;
+#pragma unroll
+						for (int k = 0; k < N; ++k) v[k] *= sc;
+					};
+					apply_Einv_dt(e); // 8.19, irk.hpp:718
+					if (alt) {        // 8.20, irk.hpp:722-731
+						double y2[N], f2[N];
+#pragma unroll
+						for (int k = 0; k < N; ++k) y2[k] = y[k] + e[k];
+						if (EST != EST_IDENTITY) F::fun(t, y2, p, f2);
+						++c_fun;
+#pragma unroll
+						for (int k = 0; k < N; ++k) {
+							const double v = (EST != EST_IDENTITY) ? fma(gam, f2[k], dalt[k]) : dalt[k];
+							e[k] = v - dy[k];
+						}
+						apply_Einv_dt(e);
+					}
+					// scaled RMS norm, irk.hpp:733-754
+					double tot = 0.0;
+#pragma unroll
+					for (int k = 0; k < N; ++k) {
+						const double sc = fma(a.rtol, fmax(fabs(y[k]), fabs(yn[k])), a.atol);
+						const double q = e[k] / sc;
+						tot = fma(q, q, tot);
+					}
+					err = sqrt(tot / (double)N);
+					if (err < kMachinePrecision) err = kMachinePrecision;
+					errs1 = errs0; // irk.hpp:756-758 (errs[2] is never read)
+					errs0 = err;
+					const bool rejected = a.adaptive && (err > 1.0); // irk.hpp:761
+					if (rejected) {
+						alt = true;
+						++c_rej_err;
+					}
+					// -------- step-size proposal, irk.hpp:770-801
+					const double fac = 0.9 * (maxit + 1.0) / (double)(maxit + it);
+					const double s27 = ctrl_pow(1.0 / err, tb.min_order, tb.expo);
+					const double dt_rat = dts0 / dts1;
+					double err_frac = errs1 / errs0;
+					if (errs1 == 0.0 || errs0 == 0.0) err_frac = 1.0;
+					const double s28 = s27 * dt_rat * ctrl_pow(err_frac, tb.min_order, tb.expo);
+					const double msc = (s28 < s27) ? s28 : s27;
+					double new_dt = fac * dt * (msc < 8.0 ? msc : 8.0);
+					if (a.max_dt > 0.0) new_dt = new_dt < a.max_dt ? new_dt : a.max_dt;
+
+					if (io.trace && mem == io.trace_member) { // irk.hpp:805-810
+						unsigned r = atomicAdd(io.trace_len, 1u);
+						if (r < io.trace_cap) {
+							double *row = io.trace + 5 * (size_t)r;
+							row[0] = (double)step; row[1] = t; row[2] = dt; row[3] = err; row[4] = (double)it;
+						}
+					}
+					if (!rejected) { // irk.hpp:813-846
+#pragma unroll
+						for (int k = 0; k < N; ++k) y[k] = yn[k];
+						t += dt;
+						++step;
+						if (a.store_samples && (unsigned long long)step % a.output_interval == 0ull) {
+							if (n_stored < io.n_samples_cap) {
+								const size_t row = n_stored;
+								io.t_samples[row * M + mem] = t;
+								if (io.err_samples) io.err_samples[row * M + mem] = err;
+#pragma unroll
+								for (int k = 0; k < N; ++k) io.y_samples[(row * N + k) * M + mem] = y[k];
+							}
+							++n_stored;
+						}
+						alt = false;
+						if (!(t < a.t1)) finished = true;
+					}
+					if (a.adaptive) dt = new_dt; // irk.hpp:850-852
+					dts1 = dts0;                 // irk.hpp:853-855 (dts[2] is never read)
+					dts0 = dt;
+				}
+			}
+		}
+
+		if (finished) {
+#pragma unroll
+			for (int k = 0; k < N; ++k) io.y[k * M + mem] = y[k];
+			io.t_final[mem] = t;
+			if (io.err_last) io.err_last[mem] = err;
+			io.status[mem] = status;
+			if (io.counters) {
+				io.counters[REHUEL_CNT_ATTEMPT * M + mem] = c_attempt;
+				io.counters[REHUEL_CNT_REJECT_NEWTON * M + mem] = c_rej_newton;
+				io.counters[REHUEL_CNT_REJECT_ERR * M + mem] = c_rej_err;
+				io.counters[REHUEL_CNT_NEWTON_SUCCESS * M + mem] = c_newton_ok;
+				io.counters[REHUEL_CNT_NEWTON_MAXIT_EXCEED * M + mem] = c_rej_newton;
+				io.counters[REHUEL_CNT_FUN_EVALS * M + mem] = c_fun;
+				io.counters[REHUEL_CNT_JAC_EVALS * M + mem] = c_jac;
+				io.counters[REHUEL_CNT_NEWTON_ITERS * M + mem] = c_iters;
+				io.counters[REHUEL_CNT_STEPS * M + mem] = (unsigned)step;
+			}
+			if (io.n_samples) io.n_samples[mem] = n_stored;
+			have = false;
+		}
+	}
+}
+
+} // namespace rehuel

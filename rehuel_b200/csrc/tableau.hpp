@@ -1,0 +1,87 @@
+// Butcher tableaux of the implicit methods + everything the kernels derive from them.
+// Replaces irk::solver_coeffs (reference irk.hpp:68-89) and irk::get_coefficients
+// (irk.cpp:215-689); the derived weights d = A^-T b, d2 = A^-T b2 are irk.hpp:599-601.
+#pragma once
+
+namespace rehuel {
+
+constexpr int MAX_S = 7;
+
+// How the kernels obtain E^-1 for the embedded error estimate, E = I - gamma*dt*J (irk.hpp:717):
+enum EstMode {
+	EST_IDENTITY = 0, // gamma == 0 (LOBATTO_IIIC_43/64 leave it at 0, irk.cpp:231) => E = I
+	EST_REUSE = 1,    // gamma == 1/gamma_hat: E is a multiple of the real Newton block, reuse its LU
+	EST_OWN_LU = 2    // anything else: factorise E separately
+};
+
+// Host-side description of a method.
+struct Tableau {
+	const char *name = "";
+	int method = 0;
+	int s = 0;
+	double A[MAX_S][MAX_S] = {};
+	double b[MAX_S] = {}, c[MAX_S] = {}, b2[MAX_S] = {};
+	bool has_b2 = false;
+	double gamma = 0.0;
+	int order = 0, order2 = 0;
+	double d[MAX_S] = {}, d2[MAX_S] = {}; // A^-T b, A^-T b2
+	// inv(A) = T Lambda Ti with Lambda = diag(gamma_hat, [[alpha,-beta],[beta,alpha]], ...)
+	int n_real = 0, n_cplx = 0;
+	double gamma_hat = 0.0, alpha[3] = {}, beta[3] = {};
+	double T[MAX_S][MAX_S] = {}, Ti[MAX_S][MAX_S] = {};
+	int est_mode = EST_IDENTITY;
+	// dense output: b_j(theta) = sum_k b_interp[j][k] theta^(s-k)  (irk.cpp:111-210, 731-747)
+	bool has_interp = false;
+	double b_interp[MAX_S][MAX_S] = {};
+};
+
+// Returns false if the method id is unknown / unsupported by the GPU path.
+bool get_coefficients(int method, Tableau &tb);
+
+int name_to_method(const char *name);   // irk.cpp:715-718 (0 if unknown)
+const char *method_to_name(int method); // irk.cpp:709-712 ("" if unknown)
+
+// irk::project_b (irk.cpp:731-747): { b_1(theta), ..., b_s(theta) }.
+bool project_b(const Tableau &tb, double theta, double *out);
+
+// Device-side constant block, passed by value as a __grid_constant__ kernel parameter so that
+// every coefficient is a constant-bank operand of the FP64 instructions.
+template <int S, int NC>
+struct DevTableau {
+	double A[S][S];
+	double c[S];
+	double d[S], d2[S];
+	double T[S][S], Ti[S][S];
+	double gamma;     // tableau gamma (error estimator)
+	double gamma_hat; // real eigenvalue of inv(A) (0 if none)
+	double alpha[NC > 0 ? NC : 1], beta[NC > 0 ? NC : 1];
+	double expo;      // 1/(1+min(order,order2))  (irk.hpp:588, 774)
+	int min_order;
+};
+
+template <int S, int NC>
+inline DevTableau<S, NC> make_dev_tableau(const Tableau &tb)
+{
+	DevTableau<S, NC> dt{};
+	for (int i = 0; i < S; ++i) {
+		for (int j = 0; j < S; ++j) {
+			dt.A[i][j] = tb.A[i][j];
+			dt.T[i][j] = tb.T[i][j];
+			dt.Ti[i][j] = tb.Ti[i][j];
+		}
+		dt.c[i] = tb.c[i];
+		dt.d[i] = tb.d[i];
+		dt.d2[i] = tb.d2[i];
+	}
+	dt.gamma = tb.gamma;
+	dt.gamma_hat = tb.gamma_hat;
+	for (int k = 0; k < NC; ++k) {
+		dt.alpha[k] = tb.alpha[k];
+		dt.beta[k] = tb.beta[k];
+	}
+	dt.min_order = tb.order < tb.order2 ? tb.order : tb.order2;
+	dt.expo = 1.0 / (1.0 + dt.min_order);
+	return dt;
+}
+
+} // namespace rehuel

@@ -1,0 +1,70 @@
+"""Device-resident entry: torch tensors in HBM -> rehuel_irk_ensemble_device on torch's current stream.
+
+torch is plumbing only (device memory + stream handle); the integration itself is the library's
+CUDA kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import capi
+
+
+class DeviceEnsemble:
+    """Pre-allocated device buffers for one ensemble shape, reusable across solves."""
+
+    def __init__(self, problem: int, method: int, M: int, y0: torch.Tensor, params: torch.Tensor,
+                 n_samples_cap: int = 0, n_hint: int = 0, trace_cap: int = 0, trace_member: int = 0):
+        assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
+        dev = y0.device
+        n, p = capi.problem_dims(problem, n_hint or y0.shape[0])
+        assert y0.shape[0] == n
+        if p:
+            assert params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
+            assert tuple(params.shape) == (p, M)
+        self.problem, self.method, self.M, self.n, self.p, self.n_hint = problem, method, M, n, p, n_hint or n
+        self.y0, self.params = y0, params
+        self.y = torch.empty((n, M), dtype=torch.float64, device=dev)
+        self.t_final = torch.empty(M, dtype=torch.float64, device=dev)
+        self.err_last = torch.empty(M, dtype=torch.float64, device=dev)
+        self.status = torch.empty(M, dtype=torch.int32, device=dev)
+        self.counters = torch.empty((capi.NCOUNTERS, M), dtype=torch.int32, device=dev)
+        self.n_samples = torch.empty(M, dtype=torch.int32, device=dev)
+        self.queue = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.cap = n_samples_cap
+        if n_samples_cap:
+            self.t_samples = torch.empty((n_samples_cap, M), dtype=torch.float64, device=dev)
+            self.y_samples = torch.empty((n_samples_cap, n, M), dtype=torch.float64, device=dev)
+            self.err_samples = torch.empty((n_samples_cap, M), dtype=torch.float64, device=dev)
+        self.trace_cap = trace_cap
+        if trace_cap:
+            self.trace = torch.zeros((trace_cap, 5), dtype=torch.float64, device=dev)
+            self.trace_len = torch.zeros(1, dtype=torch.int32, device=dev)
+        io = capi.DeviceIO()
+        io.y0 = y0.data_ptr()
+        io.y0_broadcast = int(y0.dim() == 1)
+        io.params = params.data_ptr() if p else None
+        io.y, io.t_final, io.err_last = self.y.data_ptr(), self.t_final.data_ptr(), self.err_last.data_ptr()
+        io.status, io.counters, io.n_samples = self.status.data_ptr(), self.counters.data_ptr(), self.n_samples.data_ptr()
+        io.queue = self.queue.data_ptr()
+        io.n_samples_cap = n_samples_cap
+        if n_samples_cap:
+            io.t_samples, io.y_samples, io.err_samples = (self.t_samples.data_ptr(), self.y_samples.data_ptr(),
+                                                          self.err_samples.data_ptr())
+        if trace_cap:
+            io.trace, io.trace_cap, io.trace_member = self.trace.data_ptr(), trace_cap, trace_member
+            io.trace_len = self.trace_len.data_ptr()
+        self.io = io
+
+    def solve(self, t0: float, t1: float, dt0: float, opts: capi.Options) -> None:
+        """Enqueue one ensemble solve on torch's current CUDA stream (asynchronous)."""
+        stream = torch.cuda.current_stream(self.y.device).cuda_stream
+        with torch.cuda.device(self.y.device):
+            capi.check(capi.lib.rehuel_irk_ensemble_device(
+                self.problem, self.method, t0, t1, dt0, self.M, self.n_hint, C.byref(opts), C.byref(self.io),
+                C.c_void_p(stream)))
+
+    def counter(self, name: str) -> torch.Tensor:
+        return self.counters[capi.COUNTER_ROWS.index(name)]
