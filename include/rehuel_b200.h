@@ -210,6 +210,11 @@ unsigned long long rehuel_kernel_launches(void);
 int rehuel_kernel_info(int problem, int method, int n_hint, int *regs, int *local_bytes,
                        int *smem_bytes, int *ctas_per_sm, int *block);
 
+/* Measures the achievable FP64 FMA rate of the current device (register-resident DFMA chains,
+ * best of 5) in TFLOP/s: the roofline denominator for the compute-bound integration kernels.
+ * MEASURED_PEAKS.json carries no FP64 figure. */
+int rehuel_fp64_peak(double *tflops, double *ms);
+
 /* Last error text of the calling thread (the reference reports through free-text log_out). */
 const char *rehuel_last_error(void);
 const char *rehuel_version(void);

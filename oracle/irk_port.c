@@ -779,3 +779,44 @@ int ref_newton_solve_stages(int problem_id, int method, int variant, int n_hint,
 	ws_free(&w);
 	return st;
 }
+
+/* Fixed-step oracle: loop of newton_solve_stages<F,false,true> + y += YYs*d_weights
+ * (test/irk.cpp:271-286; see ref_driver.cpp ref_fixed_step). */
+int ref_fixed_step(int problem_id, int method, int n_hint, const double *params, const double *y_in,
+                   double t0, double dt, long long nsteps, int maxit, int refresh_jac, double xtol,
+                   double Rtol, double *y_out, unsigned long long *newton_iters)
+{
+	int n = 0, P = 0;
+	tableau tb;
+	workspace w;
+	if (ref_problem_dims(problem_id, n_hint, &n, &P)) return -1;
+	if (!get_tableau(method, &tb)) return -1;
+	if (!ws_alloc(&w, n, tb.s)) { ws_free(&w); return -4; }
+	problem pr = { problem_id, n, {0, 0, 0, 0} };
+	for (int k = 0; k < P; ++k) pr.p[k] = params[k];
+	double d[MAX_S], y[n];
+	inv_transpose_times(&tb, tb.b, d);
+	for (int k = 0; k < n; ++k) y[k] = y_in[k];
+	int failed = 0;
+	double t = t0;
+	*newton_iters = 0;
+	for (long long st = 0; st < nsteps; ++st) {
+		counters c;
+		int iters = 0;
+		double res = 0.0;
+		memset(&c, 0, sizeof c);
+		int status = newton_solve_stages(&pr, &tb, &w, y, t, dt, maxit, refresh_jac, xtol, Rtol, 0, 1,
+		                                 &iters, &res, &c);
+		if (status != NEWTON_SUCCESS) ++failed;
+		*newton_iters += (unsigned long long)iters;
+		for (int k = 0; k < n; ++k) {
+			double acc = 0.0;
+			for (int i = 0; i < tb.s; ++i) acc += w.Y[i*n + k] * d[i];
+			y[k] = y[k] + acc;
+		}
+		t += dt;
+	}
+	for (int k = 0; k < n; ++k) y_out[k] = y[k];
+	ws_free(&w);
+	return failed;
+}

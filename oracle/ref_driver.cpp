@@ -347,6 +347,58 @@ int ref_newton_solve_stages(int problem, int method, int variant, int n_hint, co
 	return status;
 }
 
+// Sanctioned fixed-step oracle: the reference's own fixed-step irk_guts path throws
+// (delta_alt is never assigned, irk.hpp:698-702), so fixed-step parity is defined as a loop over
+// irk::newton_solve_stages<F,false,true> + y += reshape(Y,n,s)*d_weights, exactly what
+// test/irk.cpp:271-286 does for one step.  Returns the number of failed Newton solves.
+int ref_fixed_step(int problem, int method, int n_hint, const double *params, const double *y_in,
+                   double t0, double dt, long long nsteps, int maxit, int refresh_jac, double xtol,
+                   double Rtol, double *y_out, unsigned long long *newton_iters)
+{
+	int n = 0, P = 0;
+	if (ref_problem_dims(problem, n_hint, &n, &P)) return -1;
+	irk::solver_coeffs sc = irk::get_coefficients(method);
+	std::size_t Ns = sc.b.size(), NN = Ns * n;
+	mat_type Ai = arma::inv(sc.A);
+	vec_type d_weights = (Ai.t())*sc.b;
+	vec_type y(n);
+	for (int k = 0; k < n; ++k) y(k) = y_in[k];
+	int failed = 0;
+	*newton_iters = 0;
+	double t = t0;
+	try {
+		for (long long st = 0; st < nsteps; ++st) {
+			arma::mat J(n, n);
+			vec_type Y(NN);
+			newton::status stats;
+			std::size_t fc = 0, jc = 0;
+			int status = -1;
+#define CALL(F) status = irk::newton_solve_stages<decltype(F), false, true>(F, y, t, dt, sc, maxit, \
+	refresh_jac, xtol, Rtol, Y, J, stats, fc, jc)
+			switch (problem) {
+			case REF_ROBERTSON: { rober_p f(params[0], params[1], params[2]); CALL(f); break; }
+			case REF_VDPOL: { test_equations::vdpol f(params[0]); CALL(f); break; }
+			case REF_BRUSS1D: { bruss1d f(n/2, params[0], params[1], params[2]); CALL(f); break; }
+			case REF_ROBER_HARDCODED: { test_equations::rober f; CALL(f); break; }
+			case REF_EXPONENTIAL: { test_equations::exponential f(params[0]); CALL(f); break; }
+			case REF_STIFF_EQ: { test_equations::stiff_eq f; CALL(f); break; }
+			case REF_BRUSS2: { test_equations::bruss f(params[0], params[1]); CALL(f); break; }
+			}
+#undef CALL
+			if (status != newton::SUCCESS) ++failed;
+			*newton_iters += stats.iters;
+			arma::mat YYs = arma::reshape(Y, n, Ns);
+			y = y + YYs*d_weights;
+			t += dt;
+		}
+	} catch (std::exception &e) {
+		g_err = e.what();
+		return -2;
+	}
+	for (int k = 0; k < n; ++k) y_out[k] = y(k);
+	return failed;
+}
+
 // irk::merge_rk_output (irk.cpp:750-783) on two synthetic legs: returns merged counters and
 // accept_frac so that the product's batched merge can be compared (test/irk.cpp:185-216).
 int ref_merge_counts(const double *t1v, std::size_t n1, double af1, const unsigned long long *c1,

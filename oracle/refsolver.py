@@ -173,3 +173,20 @@ class RefSolver:
         s = self.get_coefficients(method)["s"]
         return dict(status=st, Y=Y[:s * n].copy(), y1=y1, iters=iters.value, res=res.value,
                     fun_evals=fe.value, jac_evals=je.value)
+
+    # ------------------------------------------------------------------ fixed-step oracle
+    def fixed_step(self, problem, method, params, y, t0, dt, nsteps, maxit=100, refresh_jac=25, xtol=1e-14,
+                   Rtol=1e-14, n_hint=0):
+        """Loop of newton_solve_stages<F,false,true> + y += YYs*d_weights (test/irk.cpp:271-286)."""
+        pid = PROBLEM_IDS[problem] if isinstance(problem, str) else problem
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        params = np.ascontiguousarray(params if params is not None else [0.0], dtype=np.float64)
+        out = np.zeros_like(y)
+        its = C.c_ulonglong()
+        failed = self.lib.ref_fixed_step(
+            C.c_int(pid), C.c_int(method), C.c_int(n_hint or y.shape[0]), _p(params), _p(y), C.c_double(t0),
+            C.c_double(dt), C.c_longlong(nsteps), C.c_int(maxit), C.c_int(refresh_jac), C.c_double(xtol),
+            C.c_double(Rtol), _p(out), C.byref(its))
+        if failed < 0:
+            raise RuntimeError(f"ref_fixed_step rc={failed}")
+        return dict(y=out, failed=failed, newton_iters=its.value)

@@ -114,7 +114,7 @@ EXPORTS = (
     "rehuel_default_options", "rehuel_name_to_method", "rehuel_method_to_name", "rehuel_name_to_problem",
     "rehuel_problem_dims", "rehuel_get_coefficients", "rehuel_irk_ensemble", "rehuel_result_free",
     "rehuel_irk_single", "rehuel_irk_ensemble_device", "rehuel_result_merge", "rehuel_kernel_launches",
-    "rehuel_kernel_info", "rehuel_last_error", "rehuel_version",
+    "rehuel_kernel_info", "rehuel_last_error", "rehuel_version", "rehuel_fp64_peak",
 )
 
 
@@ -197,6 +197,13 @@ def kernel_info(problem: int, method: int, n_hint: int = 0) -> dict:
     v = [C.c_int() for _ in range(5)]
     check(lib.rehuel_kernel_info(C.c_int(problem), C.c_int(method), C.c_int(n_hint), *[C.byref(x) for x in v]))
     return dict(zip(("regs", "local_bytes", "smem_bytes", "ctas_per_sm", "block"), [x.value for x in v]))
+
+
+def fp64_peak_tflops() -> float:
+    """Measured FP64 FMA peak of the current device (TFLOP/s)."""
+    t, ms = C.c_double(), C.c_double()
+    check(lib.rehuel_fp64_peak(C.byref(t), C.byref(ms)))
+    return t.value
 
 
 def kernel_launches() -> int:

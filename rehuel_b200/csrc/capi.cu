@@ -44,6 +44,25 @@ static int fail(int code, const char *fmt, ...)
 
 static std::atomic<unsigned long long> g_launches{0};
 
+// ------------------------------------------------------------------ FP64 FMA peak probe
+// Register-resident DFMA chains: 8 independent accumulators per thread, no memory traffic.
+// Gives the achievable FP64 FMA rate of THIS device at its current clocks = the roofline
+// denominator for the (compute-bound) integration kernels.
+__global__ void __launch_bounds__(256) fp64_fma_peak_kernel(double *sink, int iters, double a, double b)
+{
+	double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+	       x7 = x0 + 7;
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int u = 0; u < 8; ++u) {
+			x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+			x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+		}
+	}
+	const double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+	if (r == 123.456) sink[0] = r; // never true; keeps the chains alive
+}
+
 // ------------------------------------------------------------------ problem registry
 struct ProblemInfo {
 	int id;
@@ -231,6 +250,39 @@ extern "C" {
 const char *rehuel_last_error(void) { return g_err; }
 const char *rehuel_version(void) { return "rehuel_b200 0.1 (sm_100a)"; }
 unsigned long long rehuel_kernel_launches(void) { return g_launches.load(); }
+
+int rehuel_fp64_peak(double *tflops, double *ms_out)
+{
+	if (!tflops) return fail(REHUEL_EINVAL, "tflops must not be NULL");
+	int dev = 0, sms = 0;
+	CUDA_TRY(cudaGetDevice(&dev));
+	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	double *sink = nullptr;
+	CUDA_TRY(cudaMalloc(&sink, sizeof(double)));
+	cudaEvent_t e0, e1;
+	CUDA_TRY(cudaEventCreate(&e0));
+	CUDA_TRY(cudaEventCreate(&e1));
+	const int iters = 4096, block = 256, grid = sms * 8;
+	fp64_fma_peak_kernel<<<grid, block>>>(sink, iters / 8, 1.0000001, 1e-9); // warm-up
+	float best = 1e30f;
+	for (int rep = 0; rep < 5; ++rep) {
+		CUDA_TRY(cudaEventRecord(e0));
+		fp64_fma_peak_kernel<<<grid, block>>>(sink, iters, 1.0000001, 1e-9);
+		CUDA_TRY(cudaEventRecord(e1));
+		CUDA_TRY(cudaEventSynchronize(e1));
+		float ms = 0.f;
+		CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+		if (ms < best) best = ms;
+	}
+	CUDA_TRY(cudaGetLastError());
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(sink);
+	const double flops = 2.0 * 64.0 * (double)iters * (double)block * (double)grid;
+	*tflops = flops / (best * 1e-3) / 1e12;
+	if (ms_out) *ms_out = best;
+	return REHUEL_OK;
+}
 
 void rehuel_default_options(rehuel_options *o)
 {

@@ -299,6 +299,12 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 			if (a.max_steps >= 0 && step > a.max_steps) { // irk.hpp:612-616
 				status = REHUEL_ERROR_MAX_STEPS_EXCEEDED;
 				finished = true;
+			} else if (!(dt > 0.0)) {
+				// DELIBERATE DEVIATION: dt == 0 (underflow after endless Newton back-offs) or NaN
+				// (a NaN error estimate is "accepted" by irk.hpp:761) makes the reference loop
+				// forever; a GPU lane must terminate.  Flag the member instead.
+				status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
+				finished = true;
 			} else {
 				// -------- simplified Newton on the stage increments, irk.hpp:398-493
 				double Y[S][N], R[S][N];

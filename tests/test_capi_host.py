@@ -1,0 +1,143 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/rehuel_b200.h declares,
+its host-side pieces (defaults, tableaux, name maps, eigen-structure, dense-output weights) agree
+with the oracle, and -- no GPU here -- every compute entry point fails LOUDLY (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, cases_of, unhex
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from rehuel_b200 import capi as m
+    return m
+
+
+def test_library_exports_every_declared_symbol(capi):
+    header = open(os.path.join(ROOT, "include", "rehuel_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rehuel_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(capi.lib, name), f"{name} declared in the header but not exported"
+    assert set(capi.EXPORTS) <= declared
+
+
+def test_struct_layouts_match_header(capi):
+    # sizes a C compiler gives the header's structs (x86-64 SysV)
+    assert C.sizeof(capi.Options) == 8 * 3 + 8 + 4 + 4 + 8 + 8 + 4 + 4 + 4 + 4 + 8
+    assert C.sizeof(capi.Stats) == 13 * 8
+
+
+def test_default_options_are_the_reference_defaults(capi):
+    o = capi.default_options()
+    # options.hpp:49-58, irk.hpp:103-107, newton.hpp:58-60, options.hpp:103-104
+    assert (o.rel_tol, o.abs_tol, o.max_dt, o.max_steps) == (1e-4, 1e-3, 0.0, -1)
+    assert (o.adaptive_step_size, o.out_interval) == (1, 0)
+    assert (o.newton_tol, o.newton_dx_delta, o.newton_maxit, o.newton_refresh_jac) == (1e-4, 1e-4, 5000, 10)
+    assert (o.output_mode, o.output_interval) == (1, 1)
+
+
+def test_method_and_problem_names(capi, port):
+    for name in ("IMPLICIT_EULER", "RADAU_IIA_32", "RADAU_IIA_53", "RADAU_IIA_95", "RADAU_IIA_137", "LOBATTO_IIIA_43",
+                 "LOBATTO_IIIC_43", "LOBATTO_IIIC_64", "LOBATTO_IIIC_85", "GAUSS_LEGENDRE_147", "bogus"):
+        assert capi.name_to_method(name) == port.name_to_method(name)
+    for m in (200, 210, 211, 212, 213, 230, 231, 232, 243, 999):
+        assert capi.method_to_name(m) == port.method_to_name(m)
+    assert capi.name_to_problem("robertson") == capi.ROBERTSON
+    assert capi.name_to_problem("van-der-pol") == capi.VAN_DER_POL
+    assert capi.name_to_problem("brusselator-1d") == capi.BRUSSELATOR_1D
+    assert capi.name_to_problem("nope") == 0
+    assert capi.problem_dims(capi.ROBERTSON) == (3, 3)
+    assert capi.problem_dims(capi.VAN_DER_POL) == (2, 1)
+    assert capi.problem_dims(capi.BRUSSELATOR_1D, 64) == (64, 3)
+
+
+def test_tableaux_match_reference_golden(capi, golden):
+    for c in cases_of(golden, "tableau"):
+        t = capi.get_coefficients(c["method"])
+        assert t is not None, c["name"]
+        assert (t["s"], t["order"], t["order2"]) == (c["s"], c["order"], c["order2"])
+        for k in ("A", "b", "c", "b2"):
+            assert np.array_equal(np.asarray(t[k]).ravel(), unhex(c[k])), (c["name"], k)
+        assert t["gamma"] == float.fromhex(c["gamma"])
+        # d = A^-T b goes through a different elimination order: equal to rounding
+        np.testing.assert_allclose(t["d"], unhex(c["d"]), rtol=0, atol=4e-15)
+        np.testing.assert_allclose(t["d2"], unhex(c["d2"]), rtol=0, atol=4e-14)
+    assert capi.get_coefficients(12345) is None
+
+
+def test_eigen_structure_reconstructs_inverse_of_A(capi):
+    """inv(A) = T Lambda Ti with the block structure the kernels assume."""
+    for m in (210, 211, 230, 231, 232):
+        t = capi.get_coefficients(m)
+        e = capi.get_eigen(m)
+        s = t["s"]
+        assert e["n_real"] + 2 * e["n_cplx"] == s
+        L = np.zeros((s, s))
+        j = 0
+        if e["n_real"]:
+            L[0, 0] = e["lam"][0]
+            j = 1
+        for k in range(e["n_cplx"]):
+            a, b = e["lam"][1 + 2 * k], e["lam"][2 + 2 * k]
+            assert b > 0
+            L[j:j + 2, j:j + 2] = [[a, -b], [b, a]]
+            j += 2
+        Ai = np.linalg.inv(t["A"])
+        np.testing.assert_allclose(e["T"] @ L @ e["Ti"], Ai, rtol=0, atol=2e-13 * np.abs(Ai).max())
+        np.testing.assert_allclose(e["T"] @ e["Ti"], np.eye(s), atol=1e-14)
+    # estimator mode: LOBATTO_IIIC_43/64 keep gamma = 0 (irk.cpp:231) -> identity; RADAU_IIA_53's gamma is
+    # 1/gamma_hat -> reuse; LOBATTO_IIIC_85's printed gamma is NOT (4e-6 off) -> own LU
+    assert [capi.get_eigen(m)["est_mode"] for m in (230, 231, 211, 232, 210)] == [0, 0, 1, 2, 2]
+    e = capi.get_eigen(211)
+    assert abs(capi.get_coefficients(211)["gamma"] * e["lam"][0] - 1.0) < 1e-14
+
+
+def test_project_b_matches_reference_and_identities(capi, golden):
+    """test/test_interpolate.cpp:5-44: b(1) = b, b(c_i) = A(i,:)."""
+    for c in cases_of(golden, "project_b"):
+        got = capi.project_b(c["method"], float.fromhex(c["theta"]))
+        np.testing.assert_allclose(got, unhex(c["b"]), rtol=0, atol=5e-14)
+    for m in (210, 211):
+        t = capi.get_coefficients(m)
+        np.testing.assert_allclose(capi.project_b(m, 1.0), t["b"], atol=1e-14)
+        for i in range(t["s"]):
+            np.testing.assert_allclose(capi.project_b(m, t["c"][i]), t["A"][i], atol=1e-14)
+    assert capi.project_b(230, 0.5) is None  # no b_interp for LOBATTO_IIIC_43 (irk.cpp:261-272)
+
+
+def test_no_gpu_means_loud_failure_not_a_fallback(capi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rehuel_b200 import ensembles
+    with pytest.raises(capi.RehuelError) as ei:
+        capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, ensembles.robertson_params(8),
+                          capi.make_options(1e-6, 1e-6))
+    assert ei.value.code == -2 and "cuda" in str(ei.value).lower()
+    assert capi.kernel_launches() == 0
+
+
+def test_argument_validation(capi):
+    from rehuel_b200 import ensembles
+    P = ensembles.robertson_params(4)
+    o = capi.make_options(1e-6, 1e-6)
+    for kwargs, frag in ((dict(method=999), "not supported"), (dict(dt0=0.0), "step size"), (dict(problem=77), "problem")):
+        args = dict(problem=capi.ROBERTSON, method=211, dt0=1e-6)
+        args.update(kwargs)
+        res = capi.Result()
+        rc = capi.lib.rehuel_irk_ensemble(args["problem"], args["method"], 0.0, 1.0, args["dt0"], 4, 3,
+                                          ensembles.ROBERTSON_Y0.ctypes.data_as(C.POINTER(C.c_double)), 1,
+                                          P.ctypes.data_as(C.POINTER(C.c_double)), C.byref(o), 0, 1, C.byref(res))
+        assert rc == -1 and frag in capi.last_error()
+    bad = capi.make_options(1e-6, 1e-6, newton_refresh_jac=0)  # the reference would divide by zero (irk.hpp:485)
+    res = capi.Result()
+    rc = capi.lib.rehuel_irk_ensemble(capi.ROBERTSON, 211, 0.0, 1.0, 1e-6, 4, 3,
+                                      ensembles.ROBERTSON_Y0.ctypes.data_as(C.POINTER(C.c_double)), 1,
+                                      P.ctypes.data_as(C.POINTER(C.c_double)), C.byref(bad), 0, 1, C.byref(res))
+    assert rc == -1

@@ -1,0 +1,278 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against
+  (a) golden vectors produced by the unmodified reference (tests/golden/oracle_cases.json),
+  (b) the CPU oracle run live on the same seeded inputs,
+  (c) size-independent properties at BASELINE.json's full size (2^20 members).
+
+Tolerance (north_star): per member  max_i |y_gpu - y_ref| / (atol + rtol*|y_ref|) <= 10  at equal
+rtol/atol; <= 1e-12 relative in fixed-step mode.  Step counts are compared next to the reference's.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import cases_of, scaled_err, unhex
+from oracle.refsolver import make_options as ref_options
+
+pytestmark = pytest.mark.gpu
+
+PARITY_BOUND = 10.0  # north_star: max relative error <= 10 x rtol-scaled tolerance
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from rehuel_b200 import capi as m
+    return m
+
+
+PROBLEM_ID = {"robertson": 1, "van-der-pol": 2, "exponential": 5, "stiff-equation": 6, "brusselator": 7}
+
+
+def _gpu_single(capi, c, **kw):
+    par = np.array(c["params"], dtype=np.float64)[:, None] if c["params"] is not None else None
+    o = c["options"]
+    opts = capi.make_options(rel_tol=o.get("rel_tol", 1e-4), abs_tol=o.get("abs_tol"))
+    return capi.irk_ensemble(PROBLEM_ID[c["problem"]], c["method"], c["t0"], c["t1"], c["dt0"], np.array(c["y0"]), par,
+                             opts, **kw)
+
+
+def test_golden_single_systems(capi, golden):
+    """Every single-system golden case that has a thread-per-system kernel."""
+    rows = []
+    for c in cases_of(golden, "single"):
+        if c["problem"] not in PROBLEM_ID:
+            continue
+        g = _gpu_single(capi, c)
+        o = c["options"]
+        rtol = o.get("rel_tol", 1e-4)
+        atol = o.get("abs_tol", 10 * rtol)
+        se = float(scaled_err(g.y, unhex(c["y"])[:, None], rtol, atol)[0])
+        ref = c["counters"]
+        rows.append((c["name"], se, int(g.counters["attempt"][0]), ref["attempt"], int(g.counters["reject_err"][0]),
+                     ref["reject_err"], int(g.counters["reject_newton"][0]), ref["reject_newton"],
+                     int(g.counters["fun_evals"][0]), ref["fun_evals"], int(g.counters["jac_evals"][0]), ref["jac_evals"]))
+        assert int(g.status[0]) == c["status"], c["name"]
+        assert g.t_final[0] == unhex(c["t_final"])[0], c["name"]
+        assert se <= PARITY_BOUND, (c["name"], se)
+        # accepted/rejected step counts next to the reference's: equal up to rare accept/reject flips
+        assert abs(int(g.counters["attempt"][0]) - ref["attempt"]) <= max(3, 0.02 * ref["attempt"]), rows[-1]
+        assert abs(int(g.counters["fun_evals"][0]) - ref["fun_evals"]) <= max(30, 0.05 * ref["fun_evals"]), rows[-1]
+    print("\nname | scaled_err | attempts gpu/ref | rejE gpu/ref | rejN gpu/ref | fun gpu/ref | jac gpu/ref")
+    for r in rows:
+        print("%-28s %.3e  %d/%d  %d/%d  %d/%d  %d/%d  %d/%d" % r)
+    assert len(rows) >= 14
+
+
+def test_golden_ensembles(capi, golden):
+    for c in cases_of(golden, "ensemble"):
+        M = c["M"]
+        P = unhex(c["params"]).reshape(-1, M)
+        o = c["options"]
+        g = capi.irk_ensemble(PROBLEM_ID[c["problem"]], c["method"], c["t0"], c["t1"], c["dt0"], np.array(c["y0"]), P,
+                              capi.make_options(o["rel_tol"], o["abs_tol"]))
+        yref = unhex(c["y"]).reshape(-1, M)
+        se = scaled_err(g.y, yref, o["rel_tol"], o["abs_tol"])
+        same = np.mean(g.counters["attempt"] == np.array(c["attempt"]))
+        print(f"\n{c['name']}: max scaled err {se.max():.3e}; members with identical attempt count {same:.3f}; "
+              f"attempts gpu {g.counters['attempt'].sum()} ref {sum(c['attempt'])}; fun gpu {g.counters['fun_evals'].sum()} ref {sum(c['fun_evals'])}")
+        assert np.all(g.status == np.array(c["status"]))
+        assert se.max() <= PARITY_BOUND, c["name"]
+        assert same >= 0.75
+
+
+def test_live_oracle_4096_member_robertson_sweep(capi, port):
+    """Config 2 inputs (members 4096..8191 of the sweep), CUDA vs the CPU oracle, same seeded inputs."""
+    from rehuel_b200 import ensembles
+    M = 4096
+    P = ensembles.robertson_params(M, start=4096)
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, capi.make_options(1e-6, 1e-6))
+    r = port.solve("robertson", 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, ref_options(1e-6, 1e-6))
+    se = scaled_err(g.y, r.y, 1e-6, 1e-6)
+    same = np.mean(g.counters["attempt"] == r.counters["attempt"])
+    print(f"\n4096-member sweep: max scaled err {se.max():.3e} (bound {PARITY_BOUND}); identical attempt counts {same:.4f}; "
+          f"accepted gpu/ref {g.counters['steps'].sum()}/{(r.counters['attempt'] - r.counters['reject_err'] - r.counters['reject_newton']).sum()}; "
+          f"rejected(err) gpu/ref {g.counters['reject_err'].sum()}/{r.counters['reject_err'].sum()}; "
+          f"fun gpu/ref {g.counters['fun_evals'].sum()}/{r.counters['fun_evals'].sum()}; jac gpu/ref {g.counters['jac_evals'].sum()}/{r.counters['jac_evals'].sum()}")
+    assert np.all(g.status == 0) and np.all(g.t_final == 40.0)
+    assert se.max() <= PARITY_BOUND
+    assert same >= 0.98
+    assert abs(int(g.counters["fun_evals"].sum()) - int(r.counters["fun_evals"].sum())) <= 0.005 * r.counters["fun_evals"].sum()
+
+
+def test_live_oracle_long_span_and_other_methods(capi, port):
+    from rehuel_b200 import ensembles
+    o, ro = capi.make_options(1e-6, 1e-6), ref_options(1e-6, 1e-6)
+    P = ensembles.robertson_params(64, start=20000)
+    for method, t1 in ((211, 1e11), (230, 40.0), (232, 40.0), (210, 1.0), (231, 40.0)):
+        g = capi.irk_ensemble(capi.ROBERTSON, method, 0.0, t1, 1e-6, ensembles.ROBERTSON_Y0, P, o)
+        r = port.solve("robertson", method, 0.0, t1, 1e-6, ensembles.ROBERTSON_Y0, P, ro)
+        se = scaled_err(g.y, r.y, 1e-6, 1e-6)
+        print(f"\nmethod {method} t1={t1:g}: max scaled err {se.max():.3e}; attempts gpu/ref {g.counters['attempt'].sum()}/{r.counters['attempt'].sum()}")
+        assert np.all(g.status == 0) and se.max() <= PARITY_BOUND
+        assert abs(int(g.counters["attempt"].sum()) - int(r.counters["attempt"].sum())) <= 0.02 * r.counters["attempt"].sum()
+
+
+def test_van_der_pol_sweep_with_newton_failures(capi, port):
+    """Config 3 shape: mu_ref = 1 .. 1e-6 (the stiff end runs into 4999-iteration Newton failures)."""
+    from rehuel_b200 import ensembles
+    M = 64
+    P = ensembles.vdpol_params(M)
+    g = capi.irk_ensemble(capi.VAN_DER_POL, 230, 0.0, 2.0, 1e-6, ensembles.VDPOL_Y0, P, capi.make_options(1e-6, 1e-6))
+    r = port.solve("van-der-pol", 230, 0.0, 2.0, 1e-6, ensembles.VDPOL_Y0, P, ref_options(1e-6, 1e-6))
+    se = scaled_err(g.y, r.y, 1e-6, 1e-6)
+    print(f"\nvdpol sweep: max scaled err {se.max():.3e}; newton rejections gpu/ref {g.counters['reject_newton'].sum()}/{r.counters['reject_newton'].sum()}; "
+          f"fun gpu/ref {g.counters['fun_evals'].sum()}/{r.counters['fun_evals'].sum()}")
+    assert np.all(g.status == 0) and se.max() <= PARITY_BOUND
+    assert g.counters["reject_newton"].sum() > 0  # the failure policy (irk.hpp:634-665) was exercised
+    assert abs(int(g.counters["reject_newton"].sum()) - int(r.counters["reject_newton"].sum())) <= 2
+
+
+def test_fixed_step_mode_1e12(capi, golden):
+    """Fixed-step parity <= 1e-12 against the sanctioned fixed-step oracle."""
+    for c in cases_of(golden, "fixed_step"):
+        par = np.array(c["params"], dtype=np.float64)[:, None]
+        opts = capi.make_options(1e-6, 1e-6, adaptive=False, newton_tol=c["Rtol"], newton_dx_delta=c["xtol"], newton_maxit=100,
+                                 newton_refresh_jac=25)
+        t1 = c["t0"] + c["nsteps"] * c["dt"]
+        g = capi.irk_ensemble(PROBLEM_ID[c["problem"]], c["method"], c["t0"], t1, c["dt"], np.array(c["y0"]), par, opts)
+        yref = unhex(c["y"])
+        big = np.abs(yref) > 1e-3 * np.abs(yref).max()
+        rel = np.abs(g.y[:, 0] - yref) / np.maximum(np.abs(yref), 1e-300)
+        absd = np.abs(g.y[:, 0] - yref)
+        print(f"\n{c['name']}: rel diff {rel}, steps {g.counters['steps'][0]}, newton iters gpu/ref {g.counters['newton_iters'][0]}/{c['newton_iters']}")
+        assert int(g.status[0]) == 0
+        assert np.all(rel[big] <= 1e-12)
+        assert np.all(absd[~big] <= 1e-12 * np.abs(yref).max())
+        assert c["nsteps"] <= int(g.counters["steps"][0]) <= c["nsteps"] + 1
+
+
+def test_trajectory_samples_and_trace(capi, golden):
+    """rk_output::t_vals / y_vals / err (irk.hpp:581-585, 825-832) through rehuel_irk_single."""
+    c = [c for c in cases_of(golden, "single") if c["name"] == "robertson_211_t40"][0]
+    s = capi.irk_single(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, c["y0"], c["params"], capi.make_options(1e-6, 1e-6))
+    assert s["n_total"] == c["traj_len"] == 33 and s["status"] == 0
+    tref = unhex(c["traj_t"])[:33]
+    yref = unhex(c["traj_y"]).reshape(-1, 3)[:33]
+    assert s["t"][0] == 0.0 and np.array_equal(s["y"][0], [1.0, 0.0, 0.0]) and s["err"][0] == 0.0
+    np.testing.assert_allclose(s["t"], tref, rtol=1e-9)
+    assert scaled_err(s["y"].T, yref.T, 1e-6, 1e-6).max() <= 1e-3
+    np.testing.assert_allclose(s["err"][1:], unhex(c["traj_err"])[1:33], rtol=1e-5)
+    assert s["counters"] == c["counters"]
+    assert s["accept_frac"] == float.fromhex(c["accept_frac"])
+    # output_interval = 4: every 4th accepted step is stored (irk.hpp:825)
+    o4 = capi.make_options(1e-6, 1e-6, output_interval=4)
+    s4 = capi.irk_single(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, c["y0"], c["params"], o4)
+    assert s4["n_total"] == 1 + 32 // 4
+    np.testing.assert_allclose(s4["t"][1:], s["t"][4::4], rtol=0, atol=0)
+    # cap smaller than the trajectory: full length is still reported
+    s8 = capi.irk_single(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, c["y0"], c["params"], capi.make_options(1e-6, 1e-6), cap=8)
+    assert s8["n_total"] == 33 and len(s8["t"]) == 8 and np.array_equal(s8["t"], s["t"][:8])
+
+
+def test_edge_cases(capi, port):
+    from rehuel_b200 import ensembles
+    o, ro = capi.make_options(1e-6, 1e-6), ref_options(1e-6, 1e-6)
+    # ragged member counts: 1, one warp + 1, not a multiple of the block
+    for M in (1, 33, 129, 1000):
+        P = ensembles.robertson_params(M, start=7)
+        g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 1.0, 1e-6, ensembles.ROBERTSON_Y0, P, o)
+        r = port.solve("robertson", 211, 0.0, 1.0, 1e-6, ensembles.ROBERTSON_Y0, P, ro)
+        assert g.y.shape == (3, M) and np.all(g.status == 0)
+        assert scaled_err(g.y, r.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+    # empty interval: no attempts, y0 comes back (irk.hpp:604 loop never entered)
+    P = ensembles.robertson_params(5)
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 3.0, 3.0, 1e-6, ensembles.ROBERTSON_Y0, P, o)
+    assert np.all(g.counters["attempt"] == 0) and np.array_equal(g.y, np.tile(ensembles.ROBERTSON_Y0[:, None], (1, 5)))
+    # initial dt larger than the interval is clamped (irk.hpp:514-520)
+    g = capi.irk_ensemble(capi.EXPONENTIAL, 211, 0.0, 0.5, 10.0, [1.0], np.array([[-1.0]]), o)
+    r = port.solve("exponential", 211, 0.0, 0.5, 10.0, [1.0], np.array([[-1.0]]), ro)
+    assert g.t_final[0] == 0.5 and scaled_err(g.y, r.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+    assert int(g.counters["attempt"][0]) == int(r.counters["attempt"][0])
+    # per-member initial conditions (y0 not broadcast)
+    M = 40
+    y0 = np.stack([np.linspace(0.5, 1.0, M), np.zeros(M), np.linspace(0.5, 0.0, M)])
+    P = ensembles.robertson_params(M)
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 10.0, 1e-6, y0, P, o)
+    r = port.solve("robertson", 211, 0.0, 10.0, 1e-6, y0, P, ro)
+    assert scaled_err(g.y, r.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+    # max_steps compares ACCEPTED steps (irk.hpp:612): status 128 and the same counts as the oracle
+    om, rom = capi.make_options(1e-6, 1e-6, max_steps=5), ref_options(1e-6, 1e-6, max_steps=5)
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, :4], om)
+    r = port.solve("robertson", 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, :4], rom)
+    assert np.all(g.status == capi.ERROR_MAX_STEPS_EXCEEDED) and np.all(r.status == 128)
+    assert np.array_equal(g.counters["attempt"], r.counters["attempt"].astype(np.uint32))
+    # max_dt cap (irk.hpp:799-801)
+    oc, roc = capi.make_options(1e-6, 1e-6, max_dt=0.5), ref_options(1e-6, 1e-6, max_dt=0.5)
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, :4], oc)
+    r = port.solve("robertson", 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, :4], roc)
+    assert np.array_equal(g.counters["attempt"], r.counters["attempt"].astype(np.uint32))
+    assert scaled_err(g.y, r.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+    # a member the reference would spin on forever (NaN state) terminates with an error flag instead
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, np.array([1e200, 1e200, 1e200]), P[:, :2],
+                          capi.make_options(1e-6, 1e-6, newton_maxit=50))
+    assert np.all(g.status != 0)
+
+
+def test_member_results_do_not_depend_on_placement(capi):
+    """Determinism per member: the same member gives bit-identical results whatever its position,
+    the ensemble size or the lane that ran it (what lets shards be compared across GPU counts)."""
+    from rehuel_b200 import ensembles
+    o = capi.make_options(1e-6, 1e-6)
+    P = ensembles.robertson_params(3000)
+    full = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, o)
+    part = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, 1234:1301].copy(), o)
+    assert np.array_equal(full.y[:, 1234:1301], part.y)
+    perm = np.random.default_rng(0).permutation(3000)
+    shuf = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, perm].copy(), o)
+    assert np.array_equal(full.y[:, perm], shuf.y)
+    for k in full.counters:
+        assert np.array_equal(full.counters[k][perm], shuf.counters[k]), k
+
+
+def test_full_size_properties_1M(capi, port):
+    """BASELINE config 2 at full size (2^20 members): properties that need no oracle run, plus a
+    strided sample of members checked against the oracle."""
+    from rehuel_b200 import ensembles
+    M = 1 << 20
+    P = ensembles.robertson_params(M)
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, capi.make_options(1e-6, 1e-6))
+    assert np.all(g.status == 0) and np.all(g.t_final == 40.0)
+    assert np.abs(g.y.sum(axis=0) - 1.0).max() < 1e-13           # mass conservation (columns of J sum to 0)
+    assert np.all(g.y >= -1e-9)
+    c = g.counters
+    assert np.array_equal(c["attempt"], c["steps"] + c["reject_err"] + c["reject_newton"])
+    assert np.array_equal(c["newton_success"], c["attempt"] - c["reject_newton"])
+    # fun_evals = 3*(newton_success + iters) + 1 per success + 1 per use of formula 8.20:
+    lo = 3 * (c["newton_success"] + c["newton_iters"]) + c["newton_success"] + 1
+    assert np.all(c["fun_evals"] >= lo) and np.all(c["fun_evals"] <= lo + c["reject_err"] + c["steps"])
+    assert g.sum["attempt"] == int(c["attempt"].astype(np.int64).sum()) and g.sum["n_failed"] == 0
+    idx = np.arange(0, M, M // 512)
+    r = port.solve("robertson", 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, idx].copy(), ref_options(1e-6, 1e-6))
+    se = scaled_err(g.y[:, idx], r.y, 1e-6, 1e-6)
+    print(f"\n1M members: {g.kernel_ms:.2f} ms kernel, {g.elapsed_ms:.1f} ms call; sample of {len(idx)} vs oracle: max scaled err {se.max():.3e}")
+    assert se.max() <= PARITY_BOUND
+
+
+def test_merge_two_legs(capi):
+    """merge_rk_output semantics (irk.cpp:750-783; test/irk.cpp:218-244): integrate [0,2] then [2,4]."""
+    lam = np.array([[-0.4, -0.4]])
+    o = capi.make_options(rel_tol=1e-4)
+    a = capi.irk_ensemble(capi.EXPONENTIAL, 211, 0.0, 2.0, 1e-6, [1.0], lam, o, n_samples_cap=64, raw=True)
+    na = a.n_samples[0]
+    dt_last = a.t_samples[(na - 1) * 2] - a.t_samples[(na - 2) * 2]
+    y1 = np.array([[a.y[0], a.y[1]]])
+    b = capi.irk_ensemble(capi.EXPONENTIAL, 211, 2.0, 4.0, dt_last, y1, lam, o, n_samples_cap=64, raw=True)
+    nb = b.n_samples[0]
+    att = a.attempt[0] + b.attempt[0]
+    fe = a.fun_evals[0]
+    ta = [a.t_samples[k * 2] for k in range(na)]
+    tb = [b.t_samples[k * 2] for k in range(nb)]
+    capi.check(capi.lib.rehuel_result_merge(C.byref(a), C.byref(b)))
+    assert a.n_samples[0] == na + nb and a.attempt[0] == att
+    assert a.fun_evals[0] == fe  # the reference forgets fun/jac evals when merging (irk.cpp:773-780)
+    assert [a.t_samples[k * 2] for k in range(na + nb)] == ta + tb
+    assert a.t_final[0] == 4.0 and abs(a.y[0] - np.exp(-1.6)) < 1e-4
+    capi.lib.rehuel_result_free(C.byref(a))
+    capi.lib.rehuel_result_free(C.byref(b))
