@@ -232,7 +232,6 @@ def run_gpu_arm(args) -> None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ll, op=dist.ReduceOp.SUM)
     total_ms_max = tt.item()
-    clocks = sampler.stop() if sampler else None
 
     # ---------------- statistics from the kernel's own counters (the one collective of the path)
     att = ens.counter("attempt").double()
@@ -276,6 +275,7 @@ def run_gpu_arm(args) -> None:
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_value = world * M * args.steps / et.item()
+    clocks = sampler.stop() if sampler else None  # sampled over the device-timed AND the e2e region
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

@@ -147,6 +147,9 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
                         const rehuel_options *opts, size_t n_samples_cap, int n_gpus,
                         rehuel_result *out);
 void rehuel_result_free(rehuel_result *out);
+/* The library recycles page-locked host and device blocks across calls (cudaMallocHost/cudaMalloc
+ * cost more than a solve); this returns every block not in use to the driver. */
+void rehuel_release_cached_memory(void);
 
 /* Single system = the reference call itself: returns the whole trajectory like
  * rk_output::t_vals / y_vals / err (irk.hpp:581-585, 825-832).  *n_out = samples written into

@@ -12,7 +12,10 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -183,8 +186,121 @@ static int prepare(int problem, int method, double t0, double t1, double dt0, si
 }
 
 // ------------------------------------------------------------------ host-buffer path
+// Block cache for page-locked host memory and device memory: cudaMallocHost / cudaMalloc /
+// cudaFree cost milliseconds (and synchronise the device), far more than the solve itself, so
+// blocks are recycled across calls.  rehuel_release_cached_memory() returns them to the driver.
+class BlockCache {
+public:
+	// kind < 0: page-locked host memory; kind >= 0: device memory of that device
+	void *get(int kind, size_t bytes)
+	{
+		if (bytes == 0) bytes = 1;
+		{
+			std::lock_guard<std::mutex> g(mu_);
+			size_t best = SIZE_MAX;
+			for (size_t i = 0; i < blocks_.size(); ++i) {
+				const Block &b = blocks_[i];
+				if (b.used || b.kind != kind || b.bytes < bytes || b.bytes > 2 * bytes + (1u << 20)) continue;
+				if (best == SIZE_MAX || b.bytes < blocks_[best].bytes) best = i;
+			}
+			if (best != SIZE_MAX) {
+				blocks_[best].used = true;
+				return blocks_[best].ptr;
+			}
+		}
+		void *q = nullptr;
+		cudaError_t e;
+		if (kind < 0) {
+			e = cudaMallocHost(&q, bytes);
+		} else {
+			int cur = 0;
+			cudaGetDevice(&cur);
+			if (cur != kind) cudaSetDevice(kind);
+			e = cudaMalloc(&q, bytes);
+			if (cur != kind) cudaSetDevice(cur);
+		}
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			trim(); // give cached blocks back and retry once
+			e = (kind < 0) ? cudaMallocHost(&q, bytes) : cudaErrorMemoryAllocation;
+			if (kind >= 0) {
+				int cur = 0;
+				cudaGetDevice(&cur);
+				if (cur != kind) cudaSetDevice(kind);
+				e = cudaMalloc(&q, bytes);
+				if (cur != kind) cudaSetDevice(cur);
+			}
+			if (e != cudaSuccess) {
+				cudaGetLastError();
+				fail(REHUEL_ENOMEM, "%s(%zu bytes): %s", kind < 0 ? "cudaMallocHost" : "cudaMalloc", bytes, cudaGetErrorString(e));
+				return nullptr;
+			}
+		}
+		std::lock_guard<std::mutex> g(mu_);
+		blocks_.push_back(Block{q, bytes, kind, true});
+		return q;
+	}
+	void put(void *ptr)
+	{
+		if (!ptr) return;
+		std::lock_guard<std::mutex> g(mu_);
+		for (Block &b : blocks_)
+			if (b.ptr == ptr) {
+				b.used = false;
+				return;
+			}
+	}
+	void trim()
+	{
+		std::lock_guard<std::mutex> g(mu_);
+		std::vector<Block> keep;
+		for (Block &b : blocks_) {
+			if (b.used) {
+				keep.push_back(b);
+				continue;
+			}
+			if (b.kind < 0) {
+				cudaFreeHost(b.ptr);
+			} else {
+				int cur = 0;
+				cudaGetDevice(&cur);
+				cudaSetDevice(b.kind);
+				cudaFree(b.ptr);
+				cudaSetDevice(cur);
+			}
+		}
+		blocks_.swap(keep);
+	}
+
+private:
+	struct Block {
+		void *ptr;
+		size_t bytes;
+		int kind;
+		bool used;
+	};
+	std::mutex mu_;
+	std::vector<Block> blocks_;
+};
+static BlockCache g_cache;
+
+// Bump allocator over one cached slab (256-byte aligned sub-arrays).
+struct Slab {
+	char *base = nullptr;
+	size_t size = 0, used = 0;
+	template <class T>
+	T *take(size_t count)
+	{
+		if (count == 0) return nullptr;
+		size_t off = (used + 255) & ~size_t(255);
+		used = off + count * sizeof(T);
+		return (base && used <= size) ? reinterpret_cast<T *>(base + off) : nullptr;
+	}
+	static size_t need(size_t count, size_t elem) { return count ? ((count * elem + 255) & ~size_t(255)) + 256 : 0; }
+};
+
 struct ResultImpl {
-	std::vector<void *> pinned; // every cudaMallocHost'ed block owned by the result
+	std::vector<void *> pinned; // cached page-locked slabs owned by the result
 };
 
 template <class T>
@@ -192,40 +308,33 @@ static int pinned_alloc(ResultImpl *impl, T **ptr, size_t count)
 {
 	*ptr = nullptr;
 	if (count == 0) return REHUEL_OK;
-	void *q = nullptr;
-	cudaError_t e = cudaMallocHost(&q, count * sizeof(T));
-	if (e != cudaSuccess) return fail(REHUEL_ENOMEM, "cudaMallocHost(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+	void *q = g_cache.get(-1, count * sizeof(T));
+	if (!q) return REHUEL_ENOMEM;
 	impl->pinned.push_back(q);
 	*ptr = static_cast<T *>(q);
 	return REHUEL_OK;
 }
 
+// One unit of device work: a contiguous member range on one device with its own stream, so that
+// the H2D copy, the kernel and the D2H copies of different chunks overlap.
 struct DeviceShard {
 	int dev = 0;
 	size_t off = 0, m = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	std::vector<void *> dptr;
+	void *slab = nullptr;
 	rehuel_device_io io{};
+	unsigned long long *d_stats = nullptr;
+	DeviceShard() = default;
+	DeviceShard(const DeviceShard &) = delete;
+	DeviceShard &operator=(const DeviceShard &) = delete;
 	~DeviceShard()
 	{
-		cudaSetDevice(dev);
-		for (void *q : dptr) cudaFree(q);
+		g_cache.put(slab);
+		if (ev0 || ev1 || stream) cudaSetDevice(dev);
 		if (ev0) cudaEventDestroy(ev0);
 		if (ev1) cudaEventDestroy(ev1);
 		if (stream) cudaStreamDestroy(stream);
-	}
-	template <class T>
-	int alloc(T **ptr, size_t count)
-	{
-		*ptr = nullptr;
-		if (!count) return REHUEL_OK;
-		void *q = nullptr;
-		cudaError_t e = cudaMalloc(&q, count * sizeof(T));
-		if (e != cudaSuccess) return fail(REHUEL_ENOMEM, "cudaMalloc(%zu bytes) on device %d: %s", count * sizeof(T), dev, cudaGetErrorString(e));
-		dptr.push_back(q);
-		*ptr = static_cast<T *>(q);
-		return REHUEL_OK;
 	}
 };
 
@@ -234,10 +343,43 @@ static void free_result(rehuel_result *r)
 	if (!r) return;
 	ResultImpl *impl = static_cast<ResultImpl *>(r->impl);
 	if (impl) {
-		for (void *q : impl->pinned) cudaFreeHost(q);
+		for (void *q : impl->pinned) g_cache.put(q);
 		delete impl;
 	}
 	std::memset(r, 0, sizeof *r);
+}
+
+// ------------------------------------------------------------------ stats reduction epilogue
+// Ensemble sums of the per-member counters (the role merge_rk_output's counter adds play in the
+// reference, irk.cpp:773-780): one pass over counters[9][m] + status[m] -> 13 words.
+constexpr int kStatWords = 13;
+__global__ void __launch_bounds__(256) ensemble_stats_kernel(const unsigned *__restrict__ counters,
+                                                            const int *__restrict__ status, size_t m,
+                                                            unsigned long long *__restrict__ out)
+{
+	unsigned long long acc[REHUEL_NCOUNTERS] = {};
+	unsigned long long failed = 0, maxatt = 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+		for (int c = 0; c < REHUEL_NCOUNTERS; ++c) acc[c] += counters[c * m + i];
+		failed += status[i] != 0;
+		const unsigned long long a = counters[REHUEL_CNT_ATTEMPT * m + i];
+		maxatt = a > maxatt ? a : maxatt;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+		for (int c = 0; c < REHUEL_NCOUNTERS; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], o);
+		failed += __shfl_down_sync(0xffffffffu, failed, o);
+		const unsigned long long other = __shfl_down_sync(0xffffffffu, maxatt, o);
+		maxatt = other > maxatt ? other : maxatt;
+	}
+	if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+		for (int c = 0; c < REHUEL_NCOUNTERS; ++c) atomicAdd(out + c, acc[c]);
+		atomicAdd(out + REHUEL_NCOUNTERS, failed);
+		atomicMax(out + REHUEL_NCOUNTERS + 1, maxatt);
+	}
 }
 
 } // namespace rehuel
@@ -436,28 +578,37 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 	CUDA_TRY(cudaGetDevice(&cur_dev));
 	const int dev0 = (n_gpus == 1) ? cur_dev : 0;
 
-	// ---- result storage (page-locked so that the D2H copies are asynchronous)
+	// ---- result storage: ONE cached page-locked slab (so that the D2H copies are asynchronous)
 	ResultImpl *impl = new (std::nothrow) ResultImpl();
 	if (!impl) return fail(REHUEL_ENOMEM, "out of host memory");
 	out->impl = impl;
 	out->M = M;
 	out->n = n;
 	out->n_samples_cap = n_samples_cap;
-	unsigned *counters = nullptr; // [NCOUNTERS][M], sliced into the named pointers
-	rc = pinned_alloc(impl, &out->t_final, M);
-	if (!rc) rc = pinned_alloc(impl, &out->y, (size_t)n * M);
-	if (!rc) rc = pinned_alloc(impl, &out->err_last, M);
-	if (!rc) rc = pinned_alloc(impl, &out->status, M);
-	if (!rc) rc = pinned_alloc(impl, &counters, (size_t)REHUEL_NCOUNTERS * M);
-	if (!rc) rc = pinned_alloc(impl, &out->n_samples, M);
-	if (!rc && n_samples_cap) {
-		rc = pinned_alloc(impl, &out->t_samples, n_samples_cap * M);
-		if (!rc) rc = pinned_alloc(impl, &out->y_samples, n_samples_cap * n * M);
-		if (!rc) rc = pinned_alloc(impl, &out->err_samples, n_samples_cap * M);
-	}
-	if (rc) {
+	const size_t max_shards = (size_t)n_gpus * 8;
+	size_t hbytes = Slab::need(M, 8) + Slab::need((size_t)n * M, 8) + Slab::need(M, 8) + Slab::need(M, 4) +
+	                Slab::need((size_t)REHUEL_NCOUNTERS * M, 4) + Slab::need(M, 4) +
+	                Slab::need(max_shards * kStatWords, 8) + 3 * Slab::need(n_samples_cap * M, 8) * (size_t)(n > 1 ? n : 1);
+	Slab hs;
+	hs.base = static_cast<char *>(g_cache.get(-1, hbytes));
+	hs.size = hbytes;
+	if (!hs.base) {
 		free_result(out);
-		return rc;
+		return REHUEL_ENOMEM;
+	}
+	impl->pinned.push_back(hs.base);
+	out->t_final = hs.take<double>(M);
+	out->y = hs.take<double>((size_t)n * M);
+	out->err_last = hs.take<double>(M);
+	out->status = hs.take<int>(M);
+	unsigned *counters = hs.take<unsigned>((size_t)REHUEL_NCOUNTERS * M); // [NCOUNTERS][M]
+	out->n_samples = hs.take<unsigned>(M);
+	unsigned long long *h_stats = hs.take<unsigned long long>(max_shards * kStatWords);
+	std::memset(h_stats, 0, sizeof(unsigned long long) * max_shards * kStatWords);
+	if (n_samples_cap) {
+		out->t_samples = hs.take<double>(n_samples_cap * M);
+		out->y_samples = hs.take<double>(n_samples_cap * n * M);
+		out->err_samples = hs.take<double>(n_samples_cap * M);
 	}
 	out->attempt = counters + (size_t)REHUEL_CNT_ATTEMPT * M;
 	out->reject_newton = counters + (size_t)REHUEL_CNT_REJECT_NEWTON * M;
@@ -469,40 +620,60 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 	out->newton_iters = counters + (size_t)REHUEL_CNT_NEWTON_ITERS * M;
 	out->steps = counters + (size_t)REHUEL_CNT_STEPS * M;
 
-	// ---- one shard per GPU: contiguous member ranges [M*g/G, M*(g+1)/G)
-	std::vector<DeviceShard> shards(n_gpus);
-	auto body = [&]() -> int {
-		for (int g = 0; g < n_gpus; ++g) {
-			DeviceShard &sh = shards[g];
+	// ---- work units: GPU g owns the contiguous members [M*g/G, M*(g+1)/G); each GPU's share is cut
+	// into up to 8 chunks (>= 128 Ki members each) on separate streams so that the H2D copy of
+	// chunk i+1 and the D2H copies of chunk i-1 overlap the kernel of chunk i.
+	std::deque<DeviceShard> shards; // deque: elements are never moved (DeviceShard owns CUDA handles)
+	for (int g = 0; g < n_gpus; ++g) {
+		const size_t lo = M * (size_t)g / (size_t)n_gpus, hi = M * (size_t)(g + 1) / (size_t)n_gpus;
+		size_t chunks = (hi - lo) / (128u << 10);
+		chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+		if (n_samples_cap) chunks = 1;
+		for (size_t c = 0; c < chunks; ++c) {
+			shards.emplace_back();
+			DeviceShard &sh = shards.back();
 			sh.dev = dev0 + g;
-			sh.off = M * (size_t)g / (size_t)n_gpus;
-			sh.m = M * (size_t)(g + 1) / (size_t)n_gpus - sh.off;
+			sh.off = lo + (hi - lo) * c / chunks;
+			sh.m = lo + (hi - lo) * (c + 1) / chunks - sh.off;
+		}
+	}
+	auto body = [&]() -> int {
+		for (size_t si = 0; si < shards.size(); ++si) {
+			DeviceShard &sh = shards[si];
+			const size_t m = sh.m;
+			if (m == 0) continue;
 			CUDA_TRY(cudaSetDevice(sh.dev));
 			CUDA_TRY(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
 			CUDA_TRY(cudaEventCreate(&sh.ev0));
 			CUDA_TRY(cudaEventCreate(&sh.ev1));
-			const size_t m = sh.m;
-			double *d_y0 = nullptr, *d_par = nullptr;
-			int r = sh.alloc(&d_y0, y0_broadcast ? (size_t)n : (size_t)n * m);
-			if (!r) r = sh.alloc(&d_par, (size_t)p * m);
-			if (!r) r = sh.alloc(&sh.io.y, (size_t)n * m);
-			if (!r) r = sh.alloc(&sh.io.t_final, m);
-			if (!r) r = sh.alloc(&sh.io.err_last, m);
-			if (!r) r = sh.alloc(&sh.io.status, m);
-			if (!r) r = sh.alloc(&sh.io.counters, (size_t)REHUEL_NCOUNTERS * m);
-			if (!r) r = sh.alloc(&sh.io.n_samples, m);
-			if (!r) r = sh.alloc(&sh.io.queue, 1);
-			if (!r && n_samples_cap) {
-				r = sh.alloc(&sh.io.t_samples, n_samples_cap * m);
-				if (!r) r = sh.alloc(&sh.io.y_samples, n_samples_cap * n * m);
-				if (!r) r = sh.alloc(&sh.io.err_samples, n_samples_cap * m);
+			const size_t dbytes = Slab::need(y0_broadcast ? (size_t)n : (size_t)n * m, 8) + Slab::need((size_t)p * m, 8) +
+			                      Slab::need((size_t)n * m, 8) + 2 * Slab::need(m, 8) + 2 * Slab::need(m, 4) +
+			                      Slab::need((size_t)REHUEL_NCOUNTERS * m, 4) + Slab::need(1, 8) + Slab::need(kStatWords, 8) +
+			                      3 * Slab::need(n_samples_cap * m, 8) * (size_t)(n > 1 ? n : 1);
+			Slab ds;
+			sh.slab = g_cache.get(sh.dev, dbytes);
+			if (!sh.slab) return REHUEL_ENOMEM;
+			ds.base = static_cast<char *>(sh.slab);
+			ds.size = dbytes;
+			double *d_y0 = ds.take<double>(y0_broadcast ? (size_t)n : (size_t)n * m);
+			double *d_par = ds.take<double>((size_t)p * m);
+			sh.io.y = ds.take<double>((size_t)n * m);
+			sh.io.t_final = ds.take<double>(m);
+			sh.io.err_last = ds.take<double>(m);
+			sh.io.status = ds.take<int>(m);
+			sh.io.n_samples = ds.take<unsigned>(m);
+			sh.io.counters = ds.take<unsigned>((size_t)REHUEL_NCOUNTERS * m);
+			sh.io.queue = ds.take<unsigned long long>(1);
+			sh.d_stats = ds.take<unsigned long long>(kStatWords);
+			if (n_samples_cap) {
+				sh.io.t_samples = ds.take<double>(n_samples_cap * m);
+				sh.io.y_samples = ds.take<double>(n_samples_cap * n * m);
+				sh.io.err_samples = ds.take<double>(n_samples_cap * m);
 			}
-			if (r) return r;
 			sh.io.y0 = d_y0;
 			sh.io.params = d_par;
 			sh.io.y0_broadcast = y0_broadcast;
 			sh.io.n_samples_cap = n_samples_cap;
-			if (m == 0) continue;
 			// H2D: SoA rows are strided by M on the host and by m on the device
 			if (y0_broadcast) {
 				CUDA_TRY(cudaMemcpyAsync(d_y0, y0, sizeof(double) * n, cudaMemcpyHostToDevice, sh.stream));
@@ -513,6 +684,7 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 			if (p)
 				CUDA_TRY(cudaMemcpy2DAsync(d_par, sizeof(double) * m, params + sh.off, sizeof(double) * M,
 				                           sizeof(double) * m, p, cudaMemcpyHostToDevice, sh.stream));
+			CUDA_TRY(cudaMemsetAsync(sh.d_stats, 0, sizeof(unsigned long long) * kStatWords, sh.stream));
 			KernelArgs k = ka;
 			k.M = m;
 			k.io = sh.io;
@@ -520,6 +692,9 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 			int rr = dispatch(problem, n, k, tb, sh.stream, nullptr);
 			if (rr) return rr;
 			CUDA_TRY(cudaEventRecord(sh.ev1, sh.stream));
+			ensemble_stats_kernel<<<148, 256, 0, sh.stream>>>(sh.io.counters, sh.io.status, m, sh.d_stats);
+			CUDA_TRY(cudaGetLastError());
+			g_launches.fetch_add(1);
 			// D2H
 			CUDA_TRY(cudaMemcpy2DAsync(out->y + sh.off, sizeof(double) * M, sh.io.y, sizeof(double) * m,
 			                           sizeof(double) * m, n, cudaMemcpyDeviceToHost, sh.stream));
@@ -529,6 +704,8 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 			CUDA_TRY(cudaMemcpy2DAsync(counters + sh.off, sizeof(unsigned) * M, sh.io.counters, sizeof(unsigned) * m,
 			                           sizeof(unsigned) * m, REHUEL_NCOUNTERS, cudaMemcpyDeviceToHost, sh.stream));
 			CUDA_TRY(cudaMemcpyAsync(out->n_samples + sh.off, sh.io.n_samples, sizeof(unsigned) * m, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(h_stats + si * kStatWords, sh.d_stats, sizeof(unsigned long long) * kStatWords,
+			                         cudaMemcpyDeviceToHost, sh.stream));
 			if (n_samples_cap) {
 				CUDA_TRY(cudaMemcpy2DAsync(out->t_samples + sh.off, sizeof(double) * M, sh.io.t_samples, sizeof(double) * m,
 				                           sizeof(double) * m, n_samples_cap, cudaMemcpyDeviceToHost, sh.stream));
@@ -538,46 +715,58 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 				                           sizeof(double) * m, n_samples_cap * n, cudaMemcpyDeviceToHost, sh.stream));
 			}
 		}
-		double kms = 0.0;
-		for (int g = 0; g < n_gpus; ++g) {
-			DeviceShard &sh = shards[g];
+		// wait; kernel_ms = per device, first kernel start -> last kernel end; max over devices
+		std::vector<double> kms(n_gpus, 0.0);
+		for (DeviceShard &sh : shards) {
 			if (sh.m == 0) continue;
 			CUDA_TRY(cudaSetDevice(sh.dev));
 			CUDA_TRY(cudaStreamSynchronize(sh.stream));
-			float ms = 0.f;
-			CUDA_TRY(cudaEventElapsedTime(&ms, sh.ev0, sh.ev1));
-			if (ms > kms) kms = ms;
 		}
-		out->kernel_ms = kms;
+		for (int g = 0; g < n_gpus; ++g) {
+			DeviceShard *first = nullptr;
+			for (DeviceShard &sh : shards) {
+				if (sh.dev != dev0 + g || sh.m == 0) continue;
+				if (!first) first = &sh;
+				float ms = 0.f;
+				CUDA_TRY(cudaSetDevice(sh.dev));
+				CUDA_TRY(cudaEventElapsedTime(&ms, first->ev0, sh.ev1));
+				if (ms > kms[g]) kms[g] = ms;
+			}
+			if (kms[g] > out->kernel_ms) out->kernel_ms = kms[g];
+		}
 		return REHUEL_OK;
 	};
 	rc = body();
-	shards.clear(); // frees device memory on the right devices
+	const size_t n_shards = shards.size();
+	shards.clear(); // returns the device slabs to the cache
 	cudaSetDevice(cur_dev);
 	if (rc) {
 		free_result(out);
 		return rc;
 	}
 
-	// ---- ensemble statistics (the "stats reduction epilogue"; merge_rk_output counters in spirit)
+	// ---- ensemble statistics: sums of the device-side reductions
 	rehuel_stats &s = out->sum;
-	for (size_t i = 0; i < M; ++i) {
-		s.attempt += out->attempt[i];
-		s.reject_newton += out->reject_newton[i];
-		s.reject_err += out->reject_err[i];
-		s.newton_success += out->newton_success[i];
-		s.newton_maxit_exceed += out->newton_maxit_exceed[i];
-		s.fun_evals += out->fun_evals[i];
-		s.jac_evals += out->jac_evals[i];
-		s.newton_iters += out->newton_iters[i];
-		s.steps += out->steps[i];
-		s.n_failed += out->status[i] != 0;
-		if (out->attempt[i] > s.max_attempt) s.max_attempt = out->attempt[i];
+	for (size_t si = 0; si < n_shards; ++si) {
+		const unsigned long long *w = h_stats + si * kStatWords;
+		s.attempt += w[REHUEL_CNT_ATTEMPT];
+		s.reject_newton += w[REHUEL_CNT_REJECT_NEWTON];
+		s.reject_err += w[REHUEL_CNT_REJECT_ERR];
+		s.newton_success += w[REHUEL_CNT_NEWTON_SUCCESS];
+		s.newton_maxit_exceed += w[REHUEL_CNT_NEWTON_MAXIT_EXCEED];
+		s.fun_evals += w[REHUEL_CNT_FUN_EVALS];
+		s.jac_evals += w[REHUEL_CNT_JAC_EVALS];
+		s.newton_iters += w[REHUEL_CNT_NEWTON_ITERS];
+		s.steps += w[REHUEL_CNT_STEPS];
+		s.n_failed += w[REHUEL_NCOUNTERS];
+		if (w[REHUEL_NCOUNTERS + 1] > s.max_attempt) s.max_attempt = w[REHUEL_NCOUNTERS + 1];
 	}
 	out->accept_frac = s.attempt ? (double)s.steps / (double)s.attempt : 0.0; // irk.hpp:864
 	out->elapsed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();
 	return REHUEL_OK;
 }
+
+void rehuel_release_cached_memory(void) { g_cache.trim(); }
 
 void rehuel_result_free(rehuel_result *out) { free_result(out); }
 

@@ -299,10 +299,11 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 			if (a.max_steps >= 0 && step > a.max_steps) { // irk.hpp:612-616
 				status = REHUEL_ERROR_MAX_STEPS_EXCEEDED;
 				finished = true;
-			} else if (!(dt > 0.0)) {
-				// DELIBERATE DEVIATION: dt == 0 (underflow after endless Newton back-offs) or NaN
-				// (a NaN error estimate is "accepted" by irk.hpp:761) makes the reference loop
-				// forever; a GPU lane must terminate.  Flag the member instead.
+			} else if (!(dt >= 2.2250738585072014e-308)) {
+				// DELIBERATE DEVIATION: a subnormal dt (endless Newton back-offs: 0.7*denorm_min
+				// rounds back to denorm_min, so dt never even reaches 0) or a NaN dt (a NaN error
+				// estimate is "accepted" by irk.hpp:761) makes the reference loop forever; a GPU
+				// lane must terminate.  Flag the member instead.
 				status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
 				finished = true;
 			} else {
@@ -546,8 +547,13 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					if (!rejected) { // irk.hpp:813-846
 #pragma unroll
 						for (int k = 0; k < N; ++k) y[k] = yn[k];
+						const double t_old = t;
 						t += dt;
 						++step;
+						if (t == t_old) { // dt below ulp(t): the reference would accept steps forever
+							status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
+							finished = true;
+						}
 						if (a.store_samples && (unsigned long long)step % a.output_interval == 0ull) {
 							if (n_stored < io.n_samples_cap) {
 								const size_t row = n_stored;
