@@ -287,26 +287,37 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 			}
 		}
 		if (__all_sync(0xffffffffu, !have)) break;
-		if (!have) continue;
 
-		bool finished = false;
-		if (!(t < a.t1)) { // irk.hpp:604 (also covers t0 >= t1: zero attempts)
-			finished = true;
-		} else {
-			// ================= one attempt =================
-			if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:607-609
-			++c_attempt;
-			if (a.max_steps >= 0 && step > a.max_steps) { // irk.hpp:612-616
-				status = REHUEL_ERROR_MAX_STEPS_EXCEEDED;
-				finished = true;
-			} else if (!(dt >= 2.2250738585072014e-308)) {
-				// DELIBERATE DEVIATION: a subnormal dt (endless Newton back-offs: 0.7*denorm_min
-				// rounds back to denorm_min, so dt never even reaches 0) or a NaN dt (a NaN error
-				// estimate is "accepted" by irk.hpp:761) makes the reference loop forever; a GPU
-				// lane must terminate.  Flag the member instead.
-				status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
+		// ---------------- classify this trip: finish the member, or run one attempt
+		bool finished = false, run = false;
+		if (have) {
+			if (!(t < a.t1)) { // irk.hpp:604 (also covers t0 >= t1: zero attempts)
 				finished = true;
 			} else {
+				if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:607-609
+				++c_attempt;
+				if (a.max_steps >= 0 && step > a.max_steps) { // irk.hpp:612-616
+					status = REHUEL_ERROR_MAX_STEPS_EXCEEDED;
+					finished = true;
+				} else if (!(dt >= 2.2250738585072014e-308)) {
+					// DELIBERATE DEVIATION: a subnormal dt (endless Newton back-offs: 0.7*denorm_min
+					// rounds back to denorm_min, so dt never even reaches 0) or a NaN dt (a NaN error
+					// estimate is "accepted" by irk.hpp:761) makes the reference loop forever; a GPU
+					// lane must terminate.  Flag the member instead.
+					status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
+					finished = true;
+				} else {
+					run = true;
+				}
+			}
+		}
+		// Lanes that run an attempt this trip.  The mask is taken while all 32 lanes are converged
+		// and is used to RE-converge them after the data-dependent Newton loop: without it the
+		// compiler lets every group of lanes that leaves the loop at a different iteration run
+		// the whole error-estimate/controller tail on its own (ncu: 2.4x executions at 13/32 lanes).
+		const unsigned amask = __ballot_sync(0xffffffffu, run);
+		if (run) {
+			{
 				// -------- simplified Newton on the stage increments, irk.hpp:398-493
 				double Y[S][N], R[S][N];
 				LuReal<N> lur;  // (mu_r I - J)        (dummy when NR == 0 and EST != EST_OWN_LU)
@@ -436,6 +447,8 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						break;
 					}
 				}
+
+				__syncwarp(amask);
 
 				if (nstat != kNewtonSuccess) { // irk.hpp:634-665
 					if (!a.adaptive) {
