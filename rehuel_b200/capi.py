@@ -13,7 +13,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librehuel_b200.so")
+# REHUEL_B200_LIB: development override used by tools/time_variants.py to time alternative builds
+LIB_PATH = os.environ.get("REHUEL_B200_LIB") or os.path.join(_HERE, "librehuel_b200.so")
 
 NCOUNTERS = 9
 COUNTER_ROWS = ("attempt", "reject_newton", "reject_err", "newton_success", "newton_maxit_exceed",

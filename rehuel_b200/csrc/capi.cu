@@ -96,7 +96,13 @@ struct KernelInfo {
 template <class F, int S, int NR, int NC, int EST>
 static int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
 {
-	constexpr int BLOCK = 128, MIN_BLOCKS = 2;
+#ifndef REHUEL_BLOCK
+#define REHUEL_BLOCK 128
+#endif
+#ifndef REHUEL_MINB
+#define REHUEL_MINB 3
+#endif
+	constexpr int BLOCK = REHUEL_BLOCK, MIN_BLOCKS = REHUEL_MINB;
 	auto kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS>;
 	int dev = 0, sms = 0, per_sm = 0;
 	CUDA_TRY(cudaGetDevice(&dev));
