@@ -100,7 +100,7 @@ static int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t s
 #define REHUEL_BLOCK 128
 #endif
 #ifndef REHUEL_MINB
-#define REHUEL_MINB 3
+#define REHUEL_MINB 4
 #endif
 	constexpr int BLOCK = REHUEL_BLOCK, MIN_BLOCKS = REHUEL_MINB;
 	auto kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS>;
@@ -559,6 +559,7 @@ int rehuel_irk_ensemble_device(int problem, int method, double t0, double t1, do
 		ka.io.trace = nullptr;
 		ka.io.trace_len = nullptr;
 	}
+	if (ka.io.n_samples_cap == 0 && !ka.io.n_samples) ka.store_samples = 0; // nobody looks at the sample count
 	return dispatch(problem, n, ka, tb, static_cast<cudaStream_t>(cuda_stream), nullptr);
 }
 
@@ -694,6 +695,7 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 			KernelArgs k = ka;
 			k.M = m;
 			k.io = sh.io;
+			if (n_samples_cap == 0) k.store_samples = 0; // final state only: skip the per-step sample bookkeeping
 			CUDA_TRY(cudaEventRecord(sh.ev0, sh.stream));
 			int rr = dispatch(problem, n, k, tb, sh.stream, nullptr);
 			if (rr) return rr;

@@ -220,7 +220,11 @@ __device__ __forceinline__ double ctrl_pow(double x, int min_order, double expo)
 
 // ------------------------------------------------------------------ the kernel
 template <class F, int S, int NR, int NC, int EST, int BLOCK, int MIN_BLOCKS>
+#ifdef REHUEL_MAXNREG
+__global__ void __maxnreg__(REHUEL_MAXNREG)
+#else
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
+#endif
 ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant__ DevTableau<S, NC> tb)
 {
 	static_assert(S == NR + 2 * NC, "stage count must match the eigen-structure");
@@ -527,7 +531,11 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 #pragma unroll
 					for (int k = 0; k < N; ++k) {
 						const double sc = fma(a.rtol, fmax(fabs(y[k]), fabs(yn[k])), a.atol);
-						const double q = e[k] / sc;
+						// e[k] == 0 (e.g. the first Robertson attempts) would send the whole warp through
+						// the division's slow path for one lane; 0/sc is 0 anyway.
+						const bool zero = (e[k] == 0.0);
+						double q = (zero ? 1.0 : e[k]) / sc;
+						q = zero ? 0.0 : q;
 						tot = fma(q, q, tot);
 					}
 					err = sqrt(tot / (double)N);
@@ -567,7 +575,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
 							finished = true;
 						}
-						if (a.store_samples && (unsigned long long)step % a.output_interval == 0ull) {
+						if (a.store_samples && (a.output_interval == 1ull || (unsigned long long)step % a.output_interval == 0ull)) {
 							if (n_stored < io.n_samples_cap) {
 								const size_t row = n_stored;
 								io.t_samples[row * M + mem] = t;

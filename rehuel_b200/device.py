@@ -47,7 +47,8 @@ class DeviceEnsemble:
         io.y0_broadcast = int(y0.dim() == 1)
         io.params = params.data_ptr() if p else None
         io.y, io.t_final, io.err_last = self.y.data_ptr(), self.t_final.data_ptr(), self.err_last.data_ptr()
-        io.status, io.counters, io.n_samples = self.status.data_ptr(), self.counters.data_ptr(), self.n_samples.data_ptr()
+        io.status, io.counters = self.status.data_ptr(), self.counters.data_ptr()
+        io.n_samples = self.n_samples.data_ptr() if n_samples_cap else None  # None: skip sample bookkeeping
         io.queue = self.queue.data_ptr()
         io.n_samples_cap = n_samples_cap
         if n_samples_cap:
