@@ -16,13 +16,13 @@ SRC       := rehuel_b200/csrc
 LIB       := rehuel_b200/librehuel_b200.so
 OBJS      := build/capi.o build/tableau.o
 
-.PHONY: all oracle clean sass
+.PHONY: all oracle clean sass examples
 all: $(LIB)
 
 build:
 	mkdir -p build
 
-build/capi.o: $(SRC)/capi.cu $(SRC)/irk_thread.cuh $(SRC)/functors.cuh $(SRC)/tableau.hpp include/rehuel_b200.h | build
+build/capi.o: $(SRC)/capi.cu $(SRC)/irk_thread.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh $(SRC)/tableau.hpp include/rehuel_b200.h | build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/capi.ptxas.log || (cat build/capi.ptxas.log; false)
 
 build/tableau.o: $(SRC)/tableau.cpp $(SRC)/tableau.hpp $(SRC)/tableau_eig.inc | build
@@ -33,6 +33,16 @@ $(LIB): $(OBJS)
 
 $(SRC)/tableau_eig.inc: tools/gen_tableaux.py
 	python tools/gen_tableaux.py > $@ 2>/dev/null
+
+# Programs on the three faces of the boundary: C ABI, C++ API (built-in problem), C++ user functor.
+examples: build/c_interface_test build/cpp_api build/user_functor
+build/c_interface_test: examples/c_interface_test.c include/rehuel_b200.h $(LIB)
+	/usr/bin/gcc -std=c11 -O2 -Wall -Iinclude $< -o $@ -Lrehuel_b200 -lrehuel_b200 -lm -Wl,-rpath,'$$ORIGIN/../rehuel_b200'
+build/cpp_api: examples/cpp_api.cpp include/rehuel_b200/irk.hpp $(LIB)
+	$(HOSTCXX) -std=c++11 -O2 -Wall -Iinclude $< -o $@ -Lrehuel_b200 -lrehuel_b200 -Wl,-rpath,'$$ORIGIN/../rehuel_b200'
+build/user_functor: examples/user_functor.cu include/rehuel_b200/irk.cuh $(SRC)/launch.cuh $(SRC)/irk_thread.cuh $(LIB)
+	$(NVCC) -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) --expt-relaxed-constexpr -Iinclude $< -o $@ \
+	    -Lrehuel_b200 -lrehuel_b200 -cudart shared -Xlinker -rpath,'$$ORIGIN/../rehuel_b200'
 
 oracle:
 	$(MAKE) -C oracle all

@@ -23,13 +23,14 @@
 #include "../../include/rehuel_b200.h"
 #include "functors.cuh"
 #include "irk_thread.cuh"
+#include "launch.cuh"
 #include "tableau.hpp"
 
 namespace rehuel {
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
-static int fail(int code, const char *fmt, ...)
+int set_error(int code, const char *fmt, ...)
 {
 	va_list ap;
 	va_start(ap, fmt);
@@ -37,15 +38,11 @@ static int fail(int code, const char *fmt, ...)
 	va_end(ap);
 	return code;
 }
-#define CUDA_TRY(expr)                                                                            \
-	do {                                                                                          \
-		cudaError_t e_ = (expr);                                                                  \
-		if (e_ != cudaSuccess)                                                                    \
-			return fail(e_ == cudaErrorMemoryAllocation ? REHUEL_ENOMEM : REHUEL_ECUDA,           \
-			            "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-	} while (0)
+#define fail set_error
+#define CUDA_TRY REHUEL_CUDA_TRY
 
 static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1); }
 
 // ------------------------------------------------------------------ FP64 FMA peak probe
 // Register-resident DFMA chains: 8 independent accumulators per thread, no memory traffic.
@@ -87,85 +84,25 @@ static const ProblemInfo *find_problem(int id)
 	return nullptr;
 }
 
-// ------------------------------------------------------------------ kernel dispatch
-struct KernelInfo {
-	int regs, local_bytes, smem_bytes, ctas_per_sm, block;
-};
-
-// Launch (or, when `info` is given, only describe) the thread-per-system kernel.
-template <class F, int S, int NR, int NC, int EST>
-static int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+// ------------------------------------------------------------------ kernel dispatch (templates: launch.cuh)
+static LaunchFn find_launcher(int problem)
 {
-#ifndef REHUEL_BLOCK
-#define REHUEL_BLOCK 128
-#endif
-#ifndef REHUEL_MINB
-#define REHUEL_MINB 4
-#endif
-	constexpr int BLOCK = REHUEL_BLOCK, MIN_BLOCKS = REHUEL_MINB;
-	auto kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS>;
-	int dev = 0, sms = 0, per_sm = 0;
-	CUDA_TRY(cudaGetDevice(&dev));
-	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0));
-	if (per_sm < 1) return fail(REHUEL_ECUDA, "kernel does not fit on an SM");
-	if (info) {
-		cudaFuncAttributes fa;
-		CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
-		info->regs = fa.numRegs;
-		info->local_bytes = (int)fa.localSizeBytes;
-		info->smem_bytes = (int)fa.sharedSizeBytes;
-		info->ctas_per_sm = per_sm;
-		info->block = BLOCK;
-		return REHUEL_OK;
-	}
-	if (ka.M == 0) return REHUEL_OK;
-	// persistent grid: one wave of resident CTAs, lanes pull members from io.queue
-	unsigned long long want = (ka.M + BLOCK - 1) / BLOCK;
-	unsigned long long cap = (unsigned long long)sms * per_sm;
-	unsigned grid = (unsigned)(want < cap ? want : cap);
-	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
-	CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
-	if (ka.io.trace_len) CUDA_TRY(cudaMemsetAsync(ka.io.trace_len, 0, sizeof(unsigned), stream));
-	kern<<<grid, BLOCK, 0, stream>>>(ka, dtb);
-	CUDA_TRY(cudaGetLastError());
-	g_launches.fetch_add(1);
-	return REHUEL_OK;
-}
-
-template <class F>
-static int dispatch_method(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
-{
-	switch (tb.method) {
-	case REHUEL_RADAU_IIA_32: return launch_thread<F, 2, 0, 1, EST_OWN_LU>(ka, tb, stream, info);
-	case REHUEL_RADAU_IIA_53: return launch_thread<F, 3, 1, 1, EST_REUSE>(ka, tb, stream, info);
-	case REHUEL_LOBATTO_IIIC_43: return launch_thread<F, 3, 1, 1, EST_IDENTITY>(ka, tb, stream, info);
-	case REHUEL_LOBATTO_IIIC_64: return launch_thread<F, 4, 0, 2, EST_IDENTITY>(ka, tb, stream, info);
-	case REHUEL_LOBATTO_IIIC_85: return launch_thread<F, 5, 1, 2, EST_OWN_LU>(ka, tb, stream, info);
-	}
-	return fail(REHUEL_EINVAL, "method %d (%s) has no GPU kernel", tb.method, tb.name);
-}
-
-static int dispatch(int problem, int n, const KernelArgs &ka, const Tableau &tb, cudaStream_t stream,
-                    KernelInfo *info)
-{
-	(void)n;
 	switch (problem) {
-	case REHUEL_PROBLEM_ROBERTSON: return dispatch_method<RobertsonF>(ka, tb, stream, info);
-	case REHUEL_PROBLEM_VAN_DER_POL: return dispatch_method<VanDerPolF>(ka, tb, stream, info);
-	case REHUEL_PROBLEM_EXPONENTIAL: return dispatch_method<ExponentialF>(ka, tb, stream, info);
-	case REHUEL_PROBLEM_STIFF_EQ: return dispatch_method<StiffEqF>(ka, tb, stream, info);
-	case REHUEL_PROBLEM_BRUSSELATOR: return dispatch_method<BrusselatorF>(ka, tb, stream, info);
+	case REHUEL_PROBLEM_ROBERTSON: return &dispatch_method<RobertsonF>;
+	case REHUEL_PROBLEM_VAN_DER_POL: return &dispatch_method<VanDerPolF>;
+	case REHUEL_PROBLEM_EXPONENTIAL: return &dispatch_method<ExponentialF>;
+	case REHUEL_PROBLEM_STIFF_EQ: return &dispatch_method<StiffEqF>;
+	case REHUEL_PROBLEM_BRUSSELATOR: return &dispatch_method<BrusselatorF>;
 	}
-	return fail(REHUEL_EINVAL, "problem %d has no GPU kernel", problem);
+	set_error(REHUEL_EINVAL, "problem %d has no GPU kernel", problem);
+	return nullptr;
 }
 
 // Shared argument checking; fills the tableau and the scalar part of KernelArgs.
-static int prepare(int problem, int method, double t0, double t1, double dt0, size_t M, int n_hint,
-                   const rehuel_options *o, Tableau &tb, KernelArgs &ka, int &n, int &p)
+static int prepare(int method, double t0, double t1, double dt0, size_t M, const rehuel_options *o, Tableau &tb,
+                   KernelArgs &ka)
 {
 	if (!o) return fail(REHUEL_EINVAL, "options must not be NULL (the reference asserts newton_opts, irk.hpp:548)");
-	if (rehuel_problem_dims(problem, n_hint, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
 	if (!get_coefficients(method, tb)) return fail(REHUEL_EINVAL, "Method %d not supported!", method); // irk.cpp:234-236
 	if (!(dt0 > 0.0)) return fail(REHUEL_EINVAL, "Cannot use time step size <= 0!"); // irk.hpp:549
 	if (o->newton_maxit < 1) return fail(REHUEL_EINVAL, "newton_maxit must be >= 1");
@@ -388,6 +325,238 @@ __global__ void __launch_bounds__(256) ensemble_stats_kernel(const unsigned *__r
 	}
 }
 
+int ensemble_device(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
+                    const rehuel_options *opts, const rehuel_device_io *io, cudaStream_t stream)
+{
+	(void)n;
+	Tableau tb;
+	KernelArgs ka;
+	int rc = prepare(method, t0, t1, dt0, M, opts, tb, ka);
+	if (rc) return rc;
+	if (!io || !io->y0 || (p && !io->params) || !io->y || !io->t_final || !io->status || !io->queue)
+		return fail(REHUEL_EINVAL, "rehuel_device_io: y0, params, y, t_final, status and queue are required");
+	ka.io = *io;
+	if (!ka.io.t_samples || !ka.io.y_samples || ka.io.n_samples_cap == 0) {
+		ka.io.n_samples_cap = 0; // samples are counted but not stored
+	}
+	if (!ka.io.trace || !ka.io.trace_len) {
+		ka.io.trace = nullptr;
+		ka.io.trace_len = nullptr;
+	}
+	if (ka.io.n_samples_cap == 0 && !ka.io.n_samples) ka.store_samples = 0; // nobody looks at the sample count
+	return launch(ka, tb, stream, nullptr);
+}
+
+int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
+                  const double *y0, int y0_broadcast, const double *params, const rehuel_options *opts,
+                  size_t n_samples_cap, int n_gpus, rehuel_result *out)
+{
+	auto tic = std::chrono::steady_clock::now();
+	if (!out) return fail(REHUEL_EINVAL, "out must not be NULL");
+	std::memset(out, 0, sizeof *out);
+	Tableau tb;
+	KernelArgs ka;
+	int rc = prepare(method, t0, t1, dt0, M, opts, tb, ka);
+	if (rc) return rc;
+	if (!y0 || (p && !params)) return fail(REHUEL_EINVAL, "y0/params must not be NULL");
+	int ndev = 0;
+	CUDA_TRY(cudaGetDeviceCount(&ndev));
+	if (n_gpus < 1) n_gpus = 1;
+	if (n_gpus > ndev) return fail(REHUEL_EINVAL, "n_gpus=%d but only %d CUDA devices are visible", n_gpus, ndev);
+	if (!ka.store_samples) n_samples_cap = 0;
+	int cur_dev = 0;
+	CUDA_TRY(cudaGetDevice(&cur_dev));
+	const int dev0 = (n_gpus == 1) ? cur_dev : 0;
+
+	// ---- result storage: ONE cached page-locked slab (so that the D2H copies are asynchronous)
+	ResultImpl *impl = new (std::nothrow) ResultImpl();
+	if (!impl) return fail(REHUEL_ENOMEM, "out of host memory");
+	out->impl = impl;
+	out->M = M;
+	out->n = n;
+	out->n_samples_cap = n_samples_cap;
+	const size_t max_shards = (size_t)n_gpus * 8;
+	size_t hbytes = Slab::need(M, 8) + Slab::need((size_t)n * M, 8) + Slab::need(M, 8) + Slab::need(M, 4) +
+	                Slab::need((size_t)REHUEL_NCOUNTERS * M, 4) + Slab::need(M, 4) +
+	                Slab::need(max_shards * kStatWords, 8) + 3 * Slab::need(n_samples_cap * M, 8) * (size_t)(n > 1 ? n : 1);
+	Slab hs;
+	hs.base = static_cast<char *>(g_cache.get(-1, hbytes));
+	hs.size = hbytes;
+	if (!hs.base) {
+		free_result(out);
+		return REHUEL_ENOMEM;
+	}
+	impl->pinned.push_back(hs.base);
+	out->t_final = hs.take<double>(M);
+	out->y = hs.take<double>((size_t)n * M);
+	out->err_last = hs.take<double>(M);
+	out->status = hs.take<int>(M);
+	unsigned *counters = hs.take<unsigned>((size_t)REHUEL_NCOUNTERS * M); // [NCOUNTERS][M]
+	out->n_samples = hs.take<unsigned>(M);
+	unsigned long long *h_stats = hs.take<unsigned long long>(max_shards * kStatWords);
+	std::memset(h_stats, 0, sizeof(unsigned long long) * max_shards * kStatWords);
+	if (n_samples_cap) {
+		out->t_samples = hs.take<double>(n_samples_cap * M);
+		out->y_samples = hs.take<double>(n_samples_cap * n * M);
+		out->err_samples = hs.take<double>(n_samples_cap * M);
+	}
+	out->attempt = counters + (size_t)REHUEL_CNT_ATTEMPT * M;
+	out->reject_newton = counters + (size_t)REHUEL_CNT_REJECT_NEWTON * M;
+	out->reject_err = counters + (size_t)REHUEL_CNT_REJECT_ERR * M;
+	out->newton_success = counters + (size_t)REHUEL_CNT_NEWTON_SUCCESS * M;
+	out->newton_maxit_exceed = counters + (size_t)REHUEL_CNT_NEWTON_MAXIT_EXCEED * M;
+	out->fun_evals = counters + (size_t)REHUEL_CNT_FUN_EVALS * M;
+	out->jac_evals = counters + (size_t)REHUEL_CNT_JAC_EVALS * M;
+	out->newton_iters = counters + (size_t)REHUEL_CNT_NEWTON_ITERS * M;
+	out->steps = counters + (size_t)REHUEL_CNT_STEPS * M;
+
+	// ---- work units: GPU g owns the contiguous members [M*g/G, M*(g+1)/G); each GPU's share is cut
+	// into up to 8 chunks (>= 128 Ki members each) on separate streams so that the H2D copy of
+	// chunk i+1 and the D2H copies of chunk i-1 overlap the kernel of chunk i.
+	std::deque<DeviceShard> shards; // deque: elements are never moved (DeviceShard owns CUDA handles)
+	for (int g = 0; g < n_gpus; ++g) {
+		const size_t lo = M * (size_t)g / (size_t)n_gpus, hi = M * (size_t)(g + 1) / (size_t)n_gpus;
+		size_t chunks = (hi - lo) / (128u << 10);
+		chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+		if (n_samples_cap) chunks = 1;
+		for (size_t c = 0; c < chunks; ++c) {
+			shards.emplace_back();
+			DeviceShard &sh = shards.back();
+			sh.dev = dev0 + g;
+			sh.off = lo + (hi - lo) * c / chunks;
+			sh.m = lo + (hi - lo) * (c + 1) / chunks - sh.off;
+		}
+	}
+	auto body = [&]() -> int {
+		for (size_t si = 0; si < shards.size(); ++si) {
+			DeviceShard &sh = shards[si];
+			const size_t m = sh.m;
+			if (m == 0) continue;
+			CUDA_TRY(cudaSetDevice(sh.dev));
+			CUDA_TRY(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
+			CUDA_TRY(cudaEventCreate(&sh.ev0));
+			CUDA_TRY(cudaEventCreate(&sh.ev1));
+			const size_t dbytes = Slab::need(y0_broadcast ? (size_t)n : (size_t)n * m, 8) + Slab::need((size_t)p * m, 8) +
+			                      Slab::need((size_t)n * m, 8) + 2 * Slab::need(m, 8) + 2 * Slab::need(m, 4) +
+			                      Slab::need((size_t)REHUEL_NCOUNTERS * m, 4) + Slab::need(1, 8) + Slab::need(kStatWords, 8) +
+			                      3 * Slab::need(n_samples_cap * m, 8) * (size_t)(n > 1 ? n : 1);
+			Slab ds;
+			sh.slab = g_cache.get(sh.dev, dbytes);
+			if (!sh.slab) return REHUEL_ENOMEM;
+			ds.base = static_cast<char *>(sh.slab);
+			ds.size = dbytes;
+			double *d_y0 = ds.take<double>(y0_broadcast ? (size_t)n : (size_t)n * m);
+			double *d_par = ds.take<double>((size_t)p * m);
+			sh.io.y = ds.take<double>((size_t)n * m);
+			sh.io.t_final = ds.take<double>(m);
+			sh.io.err_last = ds.take<double>(m);
+			sh.io.status = ds.take<int>(m);
+			sh.io.n_samples = ds.take<unsigned>(m);
+			sh.io.counters = ds.take<unsigned>((size_t)REHUEL_NCOUNTERS * m);
+			sh.io.queue = ds.take<unsigned long long>(1);
+			sh.d_stats = ds.take<unsigned long long>(kStatWords);
+			if (n_samples_cap) {
+				sh.io.t_samples = ds.take<double>(n_samples_cap * m);
+				sh.io.y_samples = ds.take<double>(n_samples_cap * n * m);
+				sh.io.err_samples = ds.take<double>(n_samples_cap * m);
+			}
+			sh.io.y0 = d_y0;
+			sh.io.params = d_par;
+			sh.io.y0_broadcast = y0_broadcast;
+			sh.io.n_samples_cap = n_samples_cap;
+			// H2D: SoA rows are strided by M on the host and by m on the device
+			if (y0_broadcast) {
+				CUDA_TRY(cudaMemcpyAsync(d_y0, y0, sizeof(double) * n, cudaMemcpyHostToDevice, sh.stream));
+			} else {
+				CUDA_TRY(cudaMemcpy2DAsync(d_y0, sizeof(double) * m, y0 + sh.off, sizeof(double) * M,
+				                           sizeof(double) * m, n, cudaMemcpyHostToDevice, sh.stream));
+			}
+			if (p)
+				CUDA_TRY(cudaMemcpy2DAsync(d_par, sizeof(double) * m, params + sh.off, sizeof(double) * M,
+				                           sizeof(double) * m, p, cudaMemcpyHostToDevice, sh.stream));
+			CUDA_TRY(cudaMemsetAsync(sh.d_stats, 0, sizeof(unsigned long long) * kStatWords, sh.stream));
+			KernelArgs k = ka;
+			k.M = m;
+			k.io = sh.io;
+			if (n_samples_cap == 0) k.store_samples = 0; // final state only: skip the per-step sample bookkeeping
+			CUDA_TRY(cudaEventRecord(sh.ev0, sh.stream));
+			int rr = launch(k, tb, sh.stream, nullptr);
+			if (rr) return rr;
+			CUDA_TRY(cudaEventRecord(sh.ev1, sh.stream));
+			ensemble_stats_kernel<<<148, 256, 0, sh.stream>>>(sh.io.counters, sh.io.status, m, sh.d_stats);
+			CUDA_TRY(cudaGetLastError());
+			g_launches.fetch_add(1);
+			// D2H
+			CUDA_TRY(cudaMemcpy2DAsync(out->y + sh.off, sizeof(double) * M, sh.io.y, sizeof(double) * m,
+			                           sizeof(double) * m, n, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(out->t_final + sh.off, sh.io.t_final, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(out->err_last + sh.off, sh.io.err_last, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(out->status + sh.off, sh.io.status, sizeof(int) * m, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpy2DAsync(counters + sh.off, sizeof(unsigned) * M, sh.io.counters, sizeof(unsigned) * m,
+			                           sizeof(unsigned) * m, REHUEL_NCOUNTERS, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(out->n_samples + sh.off, sh.io.n_samples, sizeof(unsigned) * m, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpyAsync(h_stats + si * kStatWords, sh.d_stats, sizeof(unsigned long long) * kStatWords,
+			                         cudaMemcpyDeviceToHost, sh.stream));
+			if (n_samples_cap) {
+				CUDA_TRY(cudaMemcpy2DAsync(out->t_samples + sh.off, sizeof(double) * M, sh.io.t_samples, sizeof(double) * m,
+				                           sizeof(double) * m, n_samples_cap, cudaMemcpyDeviceToHost, sh.stream));
+				CUDA_TRY(cudaMemcpy2DAsync(out->err_samples + sh.off, sizeof(double) * M, sh.io.err_samples, sizeof(double) * m,
+				                           sizeof(double) * m, n_samples_cap, cudaMemcpyDeviceToHost, sh.stream));
+				CUDA_TRY(cudaMemcpy2DAsync(out->y_samples + sh.off, sizeof(double) * M, sh.io.y_samples, sizeof(double) * m,
+				                           sizeof(double) * m, n_samples_cap * n, cudaMemcpyDeviceToHost, sh.stream));
+			}
+		}
+		// wait; kernel_ms = per device, first kernel start -> last kernel end; max over devices
+		std::vector<double> kms(n_gpus, 0.0);
+		for (DeviceShard &sh : shards) {
+			if (sh.m == 0) continue;
+			CUDA_TRY(cudaSetDevice(sh.dev));
+			CUDA_TRY(cudaStreamSynchronize(sh.stream));
+		}
+		for (int g = 0; g < n_gpus; ++g) {
+			DeviceShard *first = nullptr;
+			for (DeviceShard &sh : shards) {
+				if (sh.dev != dev0 + g || sh.m == 0) continue;
+				if (!first) first = &sh;
+				float ms = 0.f;
+				CUDA_TRY(cudaSetDevice(sh.dev));
+				CUDA_TRY(cudaEventElapsedTime(&ms, first->ev0, sh.ev1));
+				if (ms > kms[g]) kms[g] = ms;
+			}
+			if (kms[g] > out->kernel_ms) out->kernel_ms = kms[g];
+		}
+		return REHUEL_OK;
+	};
+	rc = body();
+	const size_t n_shards = shards.size();
+	shards.clear(); // returns the device slabs to the cache
+	cudaSetDevice(cur_dev);
+	if (rc) {
+		free_result(out);
+		return rc;
+	}
+
+	// ---- ensemble statistics: sums of the device-side reductions
+	rehuel_stats &s = out->sum;
+	for (size_t si = 0; si < n_shards; ++si) {
+		const unsigned long long *w = h_stats + si * kStatWords;
+		s.attempt += w[REHUEL_CNT_ATTEMPT];
+		s.reject_newton += w[REHUEL_CNT_REJECT_NEWTON];
+		s.reject_err += w[REHUEL_CNT_REJECT_ERR];
+		s.newton_success += w[REHUEL_CNT_NEWTON_SUCCESS];
+		s.newton_maxit_exceed += w[REHUEL_CNT_NEWTON_MAXIT_EXCEED];
+		s.fun_evals += w[REHUEL_CNT_FUN_EVALS];
+		s.jac_evals += w[REHUEL_CNT_JAC_EVALS];
+		s.newton_iters += w[REHUEL_CNT_NEWTON_ITERS];
+		s.steps += w[REHUEL_CNT_STEPS];
+		s.n_failed += w[REHUEL_NCOUNTERS];
+		if (w[REHUEL_NCOUNTERS + 1] > s.max_attempt) s.max_attempt = w[REHUEL_NCOUNTERS + 1];
+	}
+	out->accept_frac = s.attempt ? (double)s.steps / (double)s.attempt : 0.0; // irk.hpp:864
+	out->elapsed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();
+	return REHUEL_OK;
+}
+
 } // namespace rehuel
 
 using namespace rehuel;
@@ -527,10 +696,13 @@ int rehuel_kernel_info(int problem, int method, int n_hint, int *regs, int *loca
 	rehuel_options o;
 	rehuel_default_options(&o);
 	int n = 0, p = 0;
-	int rc = prepare(problem, method, 0.0, 1.0, 1e-6, 0, n_hint, &o, tb, ka, n, p);
+	if (rehuel_problem_dims(problem, n_hint, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
+	LaunchFn launch = find_launcher(problem);
+	if (!launch) return REHUEL_EINVAL;
+	int rc = prepare(method, 0.0, 1.0, 1e-6, 0, &o, tb, ka);
 	if (rc) return rc;
 	KernelInfo ki{};
-	rc = dispatch(problem, n, ka, tb, nullptr, &ki);
+	rc = launch(ka, tb, nullptr, &ki);
 	if (rc) return rc;
 	if (regs) *regs = ki.regs;
 	if (local_bytes) *local_bytes = ki.local_bytes;
@@ -544,234 +716,22 @@ int rehuel_irk_ensemble_device(int problem, int method, double t0, double t1, do
                                int n_hint, const rehuel_options *opts, const rehuel_device_io *io,
                                void *cuda_stream)
 {
-	Tableau tb;
-	KernelArgs ka;
 	int n = 0, p = 0;
-	int rc = prepare(problem, method, t0, t1, dt0, M, n_hint, opts, tb, ka, n, p);
-	if (rc) return rc;
-	if (!io || !io->y0 || (p && !io->params) || !io->y || !io->t_final || !io->status || !io->queue)
-		return fail(REHUEL_EINVAL, "rehuel_device_io: y0, params, y, t_final, status and queue are required");
-	ka.io = *io;
-	if (!ka.io.t_samples || !ka.io.y_samples || ka.io.n_samples_cap == 0) {
-		ka.io.n_samples_cap = 0; // samples are counted but not stored
-	}
-	if (!ka.io.trace || !ka.io.trace_len) {
-		ka.io.trace = nullptr;
-		ka.io.trace_len = nullptr;
-	}
-	if (ka.io.n_samples_cap == 0 && !ka.io.n_samples) ka.store_samples = 0; // nobody looks at the sample count
-	return dispatch(problem, n, ka, tb, static_cast<cudaStream_t>(cuda_stream), nullptr);
+	if (rehuel_problem_dims(problem, n_hint, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
+	LaunchFn launch = find_launcher(problem);
+	if (!launch) return REHUEL_EINVAL;
+	return ensemble_device(launch, n, p, method, t0, t1, dt0, M, opts, io, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt0, size_t M, int n_hint,
                         const double *y0, int y0_broadcast, const double *params,
                         const rehuel_options *opts, size_t n_samples_cap, int n_gpus, rehuel_result *out)
 {
-	auto tic = std::chrono::steady_clock::now();
-	if (!out) return fail(REHUEL_EINVAL, "out must not be NULL");
-	std::memset(out, 0, sizeof *out);
-	Tableau tb;
-	KernelArgs ka;
 	int n = 0, p = 0;
-	int rc = prepare(problem, method, t0, t1, dt0, M, n_hint, opts, tb, ka, n, p);
-	if (rc) return rc;
-	if (!y0 || (p && !params)) return fail(REHUEL_EINVAL, "y0/params must not be NULL");
-	int ndev = 0;
-	CUDA_TRY(cudaGetDeviceCount(&ndev));
-	if (n_gpus < 1) n_gpus = 1;
-	if (n_gpus > ndev) return fail(REHUEL_EINVAL, "n_gpus=%d but only %d CUDA devices are visible", n_gpus, ndev);
-	if (!ka.store_samples) n_samples_cap = 0;
-	int cur_dev = 0;
-	CUDA_TRY(cudaGetDevice(&cur_dev));
-	const int dev0 = (n_gpus == 1) ? cur_dev : 0;
-
-	// ---- result storage: ONE cached page-locked slab (so that the D2H copies are asynchronous)
-	ResultImpl *impl = new (std::nothrow) ResultImpl();
-	if (!impl) return fail(REHUEL_ENOMEM, "out of host memory");
-	out->impl = impl;
-	out->M = M;
-	out->n = n;
-	out->n_samples_cap = n_samples_cap;
-	const size_t max_shards = (size_t)n_gpus * 8;
-	size_t hbytes = Slab::need(M, 8) + Slab::need((size_t)n * M, 8) + Slab::need(M, 8) + Slab::need(M, 4) +
-	                Slab::need((size_t)REHUEL_NCOUNTERS * M, 4) + Slab::need(M, 4) +
-	                Slab::need(max_shards * kStatWords, 8) + 3 * Slab::need(n_samples_cap * M, 8) * (size_t)(n > 1 ? n : 1);
-	Slab hs;
-	hs.base = static_cast<char *>(g_cache.get(-1, hbytes));
-	hs.size = hbytes;
-	if (!hs.base) {
-		free_result(out);
-		return REHUEL_ENOMEM;
-	}
-	impl->pinned.push_back(hs.base);
-	out->t_final = hs.take<double>(M);
-	out->y = hs.take<double>((size_t)n * M);
-	out->err_last = hs.take<double>(M);
-	out->status = hs.take<int>(M);
-	unsigned *counters = hs.take<unsigned>((size_t)REHUEL_NCOUNTERS * M); // [NCOUNTERS][M]
-	out->n_samples = hs.take<unsigned>(M);
-	unsigned long long *h_stats = hs.take<unsigned long long>(max_shards * kStatWords);
-	std::memset(h_stats, 0, sizeof(unsigned long long) * max_shards * kStatWords);
-	if (n_samples_cap) {
-		out->t_samples = hs.take<double>(n_samples_cap * M);
-		out->y_samples = hs.take<double>(n_samples_cap * n * M);
-		out->err_samples = hs.take<double>(n_samples_cap * M);
-	}
-	out->attempt = counters + (size_t)REHUEL_CNT_ATTEMPT * M;
-	out->reject_newton = counters + (size_t)REHUEL_CNT_REJECT_NEWTON * M;
-	out->reject_err = counters + (size_t)REHUEL_CNT_REJECT_ERR * M;
-	out->newton_success = counters + (size_t)REHUEL_CNT_NEWTON_SUCCESS * M;
-	out->newton_maxit_exceed = counters + (size_t)REHUEL_CNT_NEWTON_MAXIT_EXCEED * M;
-	out->fun_evals = counters + (size_t)REHUEL_CNT_FUN_EVALS * M;
-	out->jac_evals = counters + (size_t)REHUEL_CNT_JAC_EVALS * M;
-	out->newton_iters = counters + (size_t)REHUEL_CNT_NEWTON_ITERS * M;
-	out->steps = counters + (size_t)REHUEL_CNT_STEPS * M;
-
-	// ---- work units: GPU g owns the contiguous members [M*g/G, M*(g+1)/G); each GPU's share is cut
-	// into up to 8 chunks (>= 128 Ki members each) on separate streams so that the H2D copy of
-	// chunk i+1 and the D2H copies of chunk i-1 overlap the kernel of chunk i.
-	std::deque<DeviceShard> shards; // deque: elements are never moved (DeviceShard owns CUDA handles)
-	for (int g = 0; g < n_gpus; ++g) {
-		const size_t lo = M * (size_t)g / (size_t)n_gpus, hi = M * (size_t)(g + 1) / (size_t)n_gpus;
-		size_t chunks = (hi - lo) / (128u << 10);
-		chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
-		if (n_samples_cap) chunks = 1;
-		for (size_t c = 0; c < chunks; ++c) {
-			shards.emplace_back();
-			DeviceShard &sh = shards.back();
-			sh.dev = dev0 + g;
-			sh.off = lo + (hi - lo) * c / chunks;
-			sh.m = lo + (hi - lo) * (c + 1) / chunks - sh.off;
-		}
-	}
-	auto body = [&]() -> int {
-		for (size_t si = 0; si < shards.size(); ++si) {
-			DeviceShard &sh = shards[si];
-			const size_t m = sh.m;
-			if (m == 0) continue;
-			CUDA_TRY(cudaSetDevice(sh.dev));
-			CUDA_TRY(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
-			CUDA_TRY(cudaEventCreate(&sh.ev0));
-			CUDA_TRY(cudaEventCreate(&sh.ev1));
-			const size_t dbytes = Slab::need(y0_broadcast ? (size_t)n : (size_t)n * m, 8) + Slab::need((size_t)p * m, 8) +
-			                      Slab::need((size_t)n * m, 8) + 2 * Slab::need(m, 8) + 2 * Slab::need(m, 4) +
-			                      Slab::need((size_t)REHUEL_NCOUNTERS * m, 4) + Slab::need(1, 8) + Slab::need(kStatWords, 8) +
-			                      3 * Slab::need(n_samples_cap * m, 8) * (size_t)(n > 1 ? n : 1);
-			Slab ds;
-			sh.slab = g_cache.get(sh.dev, dbytes);
-			if (!sh.slab) return REHUEL_ENOMEM;
-			ds.base = static_cast<char *>(sh.slab);
-			ds.size = dbytes;
-			double *d_y0 = ds.take<double>(y0_broadcast ? (size_t)n : (size_t)n * m);
-			double *d_par = ds.take<double>((size_t)p * m);
-			sh.io.y = ds.take<double>((size_t)n * m);
-			sh.io.t_final = ds.take<double>(m);
-			sh.io.err_last = ds.take<double>(m);
-			sh.io.status = ds.take<int>(m);
-			sh.io.n_samples = ds.take<unsigned>(m);
-			sh.io.counters = ds.take<unsigned>((size_t)REHUEL_NCOUNTERS * m);
-			sh.io.queue = ds.take<unsigned long long>(1);
-			sh.d_stats = ds.take<unsigned long long>(kStatWords);
-			if (n_samples_cap) {
-				sh.io.t_samples = ds.take<double>(n_samples_cap * m);
-				sh.io.y_samples = ds.take<double>(n_samples_cap * n * m);
-				sh.io.err_samples = ds.take<double>(n_samples_cap * m);
-			}
-			sh.io.y0 = d_y0;
-			sh.io.params = d_par;
-			sh.io.y0_broadcast = y0_broadcast;
-			sh.io.n_samples_cap = n_samples_cap;
-			// H2D: SoA rows are strided by M on the host and by m on the device
-			if (y0_broadcast) {
-				CUDA_TRY(cudaMemcpyAsync(d_y0, y0, sizeof(double) * n, cudaMemcpyHostToDevice, sh.stream));
-			} else {
-				CUDA_TRY(cudaMemcpy2DAsync(d_y0, sizeof(double) * m, y0 + sh.off, sizeof(double) * M,
-				                           sizeof(double) * m, n, cudaMemcpyHostToDevice, sh.stream));
-			}
-			if (p)
-				CUDA_TRY(cudaMemcpy2DAsync(d_par, sizeof(double) * m, params + sh.off, sizeof(double) * M,
-				                           sizeof(double) * m, p, cudaMemcpyHostToDevice, sh.stream));
-			CUDA_TRY(cudaMemsetAsync(sh.d_stats, 0, sizeof(unsigned long long) * kStatWords, sh.stream));
-			KernelArgs k = ka;
-			k.M = m;
-			k.io = sh.io;
-			if (n_samples_cap == 0) k.store_samples = 0; // final state only: skip the per-step sample bookkeeping
-			CUDA_TRY(cudaEventRecord(sh.ev0, sh.stream));
-			int rr = dispatch(problem, n, k, tb, sh.stream, nullptr);
-			if (rr) return rr;
-			CUDA_TRY(cudaEventRecord(sh.ev1, sh.stream));
-			ensemble_stats_kernel<<<148, 256, 0, sh.stream>>>(sh.io.counters, sh.io.status, m, sh.d_stats);
-			CUDA_TRY(cudaGetLastError());
-			g_launches.fetch_add(1);
-			// D2H
-			CUDA_TRY(cudaMemcpy2DAsync(out->y + sh.off, sizeof(double) * M, sh.io.y, sizeof(double) * m,
-			                           sizeof(double) * m, n, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(out->t_final + sh.off, sh.io.t_final, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(out->err_last + sh.off, sh.io.err_last, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(out->status + sh.off, sh.io.status, sizeof(int) * m, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpy2DAsync(counters + sh.off, sizeof(unsigned) * M, sh.io.counters, sizeof(unsigned) * m,
-			                           sizeof(unsigned) * m, REHUEL_NCOUNTERS, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(out->n_samples + sh.off, sh.io.n_samples, sizeof(unsigned) * m, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(h_stats + si * kStatWords, sh.d_stats, sizeof(unsigned long long) * kStatWords,
-			                         cudaMemcpyDeviceToHost, sh.stream));
-			if (n_samples_cap) {
-				CUDA_TRY(cudaMemcpy2DAsync(out->t_samples + sh.off, sizeof(double) * M, sh.io.t_samples, sizeof(double) * m,
-				                           sizeof(double) * m, n_samples_cap, cudaMemcpyDeviceToHost, sh.stream));
-				CUDA_TRY(cudaMemcpy2DAsync(out->err_samples + sh.off, sizeof(double) * M, sh.io.err_samples, sizeof(double) * m,
-				                           sizeof(double) * m, n_samples_cap, cudaMemcpyDeviceToHost, sh.stream));
-				CUDA_TRY(cudaMemcpy2DAsync(out->y_samples + sh.off, sizeof(double) * M, sh.io.y_samples, sizeof(double) * m,
-				                           sizeof(double) * m, n_samples_cap * n, cudaMemcpyDeviceToHost, sh.stream));
-			}
-		}
-		// wait; kernel_ms = per device, first kernel start -> last kernel end; max over devices
-		std::vector<double> kms(n_gpus, 0.0);
-		for (DeviceShard &sh : shards) {
-			if (sh.m == 0) continue;
-			CUDA_TRY(cudaSetDevice(sh.dev));
-			CUDA_TRY(cudaStreamSynchronize(sh.stream));
-		}
-		for (int g = 0; g < n_gpus; ++g) {
-			DeviceShard *first = nullptr;
-			for (DeviceShard &sh : shards) {
-				if (sh.dev != dev0 + g || sh.m == 0) continue;
-				if (!first) first = &sh;
-				float ms = 0.f;
-				CUDA_TRY(cudaSetDevice(sh.dev));
-				CUDA_TRY(cudaEventElapsedTime(&ms, first->ev0, sh.ev1));
-				if (ms > kms[g]) kms[g] = ms;
-			}
-			if (kms[g] > out->kernel_ms) out->kernel_ms = kms[g];
-		}
-		return REHUEL_OK;
-	};
-	rc = body();
-	const size_t n_shards = shards.size();
-	shards.clear(); // returns the device slabs to the cache
-	cudaSetDevice(cur_dev);
-	if (rc) {
-		free_result(out);
-		return rc;
-	}
-
-	// ---- ensemble statistics: sums of the device-side reductions
-	rehuel_stats &s = out->sum;
-	for (size_t si = 0; si < n_shards; ++si) {
-		const unsigned long long *w = h_stats + si * kStatWords;
-		s.attempt += w[REHUEL_CNT_ATTEMPT];
-		s.reject_newton += w[REHUEL_CNT_REJECT_NEWTON];
-		s.reject_err += w[REHUEL_CNT_REJECT_ERR];
-		s.newton_success += w[REHUEL_CNT_NEWTON_SUCCESS];
-		s.newton_maxit_exceed += w[REHUEL_CNT_NEWTON_MAXIT_EXCEED];
-		s.fun_evals += w[REHUEL_CNT_FUN_EVALS];
-		s.jac_evals += w[REHUEL_CNT_JAC_EVALS];
-		s.newton_iters += w[REHUEL_CNT_NEWTON_ITERS];
-		s.steps += w[REHUEL_CNT_STEPS];
-		s.n_failed += w[REHUEL_NCOUNTERS];
-		if (w[REHUEL_NCOUNTERS + 1] > s.max_attempt) s.max_attempt = w[REHUEL_NCOUNTERS + 1];
-	}
-	out->accept_frac = s.attempt ? (double)s.steps / (double)s.attempt : 0.0; // irk.hpp:864
-	out->elapsed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();
-	return REHUEL_OK;
+	if (rehuel_problem_dims(problem, n_hint, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
+	LaunchFn launch = find_launcher(problem);
+	if (!launch) return REHUEL_EINVAL;
+	return ensemble_host(launch, n, p, method, t0, t1, dt0, M, y0, y0_broadcast, params, opts, n_samples_cap, n_gpus, out);
 }
 
 void rehuel_release_cached_memory(void) { g_cache.trim(); }

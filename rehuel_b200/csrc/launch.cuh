@@ -1,0 +1,106 @@
+// Kernel launch templates + the host-side entry points that a C++ user functor needs.
+//
+// The library instantiates these for its built-in functors (capi.cu).  A user-written functor
+// (the reference's functor.hpp:35-73 concept as a __device__ callable, see functors.cuh for the
+// shape) is compiled by nvcc in the USER's translation unit through include/rehuel_b200/irk.cuh,
+// which instantiates dispatch_method<F> there and hands its address to ensemble_host() exported
+// by librehuel_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+#include "../../include/rehuel_b200.h"
+#include "irk_thread.cuh"
+#include "tableau.hpp"
+
+namespace rehuel {
+
+// ---- exported by librehuel_b200.so (capi.cu)
+int set_error(int code, const char *fmt, ...); // records the thread's last error text, returns code
+void count_launch();                            // bumps rehuel_kernel_launches()
+
+struct KernelInfo {
+	int regs, local_bytes, smem_bytes, ctas_per_sm, block;
+};
+// Launches (info == nullptr) or describes (info != nullptr) the kernel for one tableau.
+using LaunchFn = int (*)(const KernelArgs &, const Tableau &, cudaStream_t, KernelInfo *);
+
+// Batched irk::odeint with HOST buffers for an arbitrary functor (n equations, p parameters);
+// same semantics as rehuel_irk_ensemble (include/rehuel_b200.h).
+int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
+                  const double *y0, int y0_broadcast, const double *params, const rehuel_options *opts,
+                  size_t n_samples_cap, int n_gpus, rehuel_result *out);
+// Device-resident variant; same semantics as rehuel_irk_ensemble_device.
+int ensemble_device(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
+                    const rehuel_options *opts, const rehuel_device_io *io, cudaStream_t stream);
+
+#define REHUEL_CUDA_TRY(expr)                                                                              \
+	do {                                                                                                   \
+		cudaError_t e_ = (expr);                                                                           \
+		if (e_ != cudaSuccess)                                                                             \
+			return ::rehuel::set_error(e_ == cudaErrorMemoryAllocation ? REHUEL_ENOMEM : REHUEL_ECUDA,     \
+			                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+#ifndef REHUEL_BLOCK
+#define REHUEL_BLOCK 128
+#endif
+#ifndef REHUEL_MINB
+#define REHUEL_MINB 4
+#endif
+
+// Launch (or, when `info` is given, only describe) the thread-per-system kernel.
+template <class F, int S, int NR, int NC, int EST>
+int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	// 128 registers/thread (4 CTAs of 128 per SM) is the measured optimum for stage systems up to
+	// 3x3 (a few spills, 16 warps/SM); larger stage systems keep 255 registers.
+	constexpr int BLOCK = REHUEL_BLOCK, MIN_BLOCKS = (S * F::N <= 9) ? REHUEL_MINB : 2;
+	auto kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS>;
+	int dev = 0, sms = 0, per_sm = 0;
+	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
+	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	REHUEL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0));
+	if (per_sm < 1) return set_error(REHUEL_ECUDA, "kernel does not fit on an SM");
+	if (info) {
+		cudaFuncAttributes fa;
+		REHUEL_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+		info->regs = fa.numRegs;
+		info->local_bytes = (int)fa.localSizeBytes;
+		info->smem_bytes = (int)fa.sharedSizeBytes;
+		info->ctas_per_sm = per_sm;
+		info->block = BLOCK;
+		return REHUEL_OK;
+	}
+	if (ka.M == 0) return REHUEL_OK;
+	// persistent grid: one wave of resident CTAs, lanes pull members from io.queue
+	unsigned long long want = (ka.M + BLOCK - 1) / BLOCK;
+	unsigned long long cap = (unsigned long long)sms * per_sm;
+	unsigned grid = (unsigned)(want < cap ? want : cap);
+	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
+	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	if (ka.io.trace_len) REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.trace_len, 0, sizeof(unsigned), stream));
+	kern<<<grid, BLOCK, 0, stream>>>(ka, dtb);
+	REHUEL_CUDA_TRY(cudaGetLastError());
+	count_launch();
+	return REHUEL_OK;
+}
+
+// Method id -> kernel instantiation (stage count and eigen-structure are compile-time).
+template <class F>
+int dispatch_method(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	static_assert(F::N >= 1 && F::N <= 4, "thread-per-system kernels cover n <= 4 (larger systems: CTA-per-system path)");
+	switch (tb.method) {
+	case REHUEL_RADAU_IIA_32: return launch_thread<F, 2, 0, 1, EST_OWN_LU>(ka, tb, stream, info);
+	case REHUEL_RADAU_IIA_53: return launch_thread<F, 3, 1, 1, EST_REUSE>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_43: return launch_thread<F, 3, 1, 1, EST_IDENTITY>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_64: return launch_thread<F, 4, 0, 2, EST_IDENTITY>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_85: return launch_thread<F, 5, 1, 2, EST_OWN_LU>(ka, tb, stream, info);
+	}
+	return set_error(REHUEL_EINVAL, "method %d (%s) has no GPU kernel", tb.method, tb.name);
+}
+
+} // namespace rehuel

@@ -141,3 +141,17 @@ def test_argument_validation(capi):
                                       ensembles.ROBERTSON_Y0.ctypes.data_as(C.POINTER(C.c_double)), 1,
                                       P.ctypes.data_as(C.POINTER(C.c_double)), C.byref(bad), 0, 1, C.byref(res))
     assert rc == -1
+
+
+def test_c_program_fails_loudly_without_gpu():
+    """examples/c_interface_test.c (plain C against the C ABI): on a box without a GPU it must exit
+    non-zero with the CUDA error text, not produce numbers from somewhere else."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = os.path.join(ROOT, "build", "c_interface_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", ROOT, "build/c_interface_test"], stdout=subprocess.DEVNULL)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "failed" in r.stderr

@@ -276,3 +276,19 @@ def test_merge_two_legs(capi):
     assert a.t_final[0] == 4.0 and abs(a.y[0] - np.exp(-1.6)) < 1e-4
     capi.lib.rehuel_result_free(C.byref(a))
     capi.lib.rehuel_result_free(C.byref(b))
+
+
+def test_boundary_programs_c_abi_cpp_api_user_functor(capi):
+    """The three faces of the drop-in boundary as real programs (examples/): plain C against the C
+    ABI (the reference's empty C_interface_test/main.c), the C++ option/odeint mirror, and a
+    USER-defined functor (`dimer`, test_equations.hpp:180-203) compiled into the kernel template."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    for exe in ("c_interface_test", "cpp_api", "user_functor"):
+        path = os.path.join(ROOT, "build", exe)
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", ROOT, "examples"])
+        r = subprocess.run([path], capture_output=True, text=True, timeout=120)
+        print("\n" + r.stdout.strip())
+        assert r.returncode == 0, (exe, r.stdout, r.stderr)
