@@ -140,7 +140,7 @@ class ClockSampler:
         self.fh = open(self.path, "w")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
