@@ -183,6 +183,9 @@ typedef struct rehuel_device_io {
 	size_t trace_cap;
 	size_t trace_member;
 	unsigned *trace_len;   /* [1] */
+	const unsigned *order; /* [M] or NULL: queue position q -> member index order[q].  Lets the caller hand out
+	                          expensive members first (longest-processing-time-first) when cost correlates with a
+	                          parameter; results do not depend on it. */
 } rehuel_device_io;
 
 #define REHUEL_CNT_ATTEMPT             0

@@ -45,6 +45,11 @@ struct KernelArgs {
 
 constexpr double kMachinePrecision = 1e-17; // enums.hpp:129
 constexpr int kNewtonSuccess = 0, kNewtonMaxit = 3; // newton.hpp:45-51
+#ifndef REHUEL_FAST_ITERS
+#define REHUEL_FAST_ITERS 64
+#endif
+constexpr int kFastIters = REHUEL_FAST_ITERS; // Newton iterations a lane may take before it is parked for a slow trip
+constexpr int kParkLanes = 16; // parked lanes per warp that trigger a slow trip
 
 // ------------------------------------------------------------------ small dense LU, registers
 template <int N>
@@ -237,6 +242,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 
 	// ---- lane-persistent member state
 	bool have = false, exhausted = false;
+	bool parked = false; // this lane's attempt ran past kFastIters Newton iterations: redo it in a slow trip
 	unsigned long long mem = 0;
 	double y[N], p[PA];
 	double t = 0.0, dt = 0.0;
@@ -259,6 +265,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 			if (!have && !exhausted) {
 				mem = base + __popc(need & ((1u << lane) - 1u));
 				if (mem < M) {
+					if (io.order) mem = io.order[mem]; // caller-chosen hand-out order (e.g. costly members first)
 #pragma unroll
 					for (int k = 0; k < N; ++k) y[k] = io.y0_broadcast ? io.y0[k] : io.y0[k * M + mem];
 #pragma unroll
@@ -277,6 +284,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					status = REHUEL_SUCCESS;
 					c_attempt = c_rej_newton = c_rej_err = c_newton_ok = c_fun = c_jac = c_iters = 0;
 					n_stored = 0;
+					parked = false;
 					have = true;
 					if (a.store_samples && io.n_samples_cap) { // sample 0 = (t0, y0), irk.hpp:581-585
 						io.t_samples[mem] = t;
@@ -292,9 +300,24 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 		}
 		if (__all_sync(0xffffffffu, !have)) break;
 
+		// ---------------- slow-lane handling.  A failing simplified Newton iteration spins to maxit
+		// (4999 iterations by default; the reference has no divergence test, irk.hpp:458-488) while
+		// a normal one needs 1-3, so one such lane would idle the other 31 for thousands of
+		// iterations.  A lane whose attempt is still unconverged after kFastIters iterations
+		// abandons it and PARKS (keeps its member, sits out); once kParkLanes lanes of the warp are
+		// parked -- or nothing else is left -- the warp runs a "slow trip" in which only the parked
+		// lanes redo their attempt with the full iteration budget, side by side.  The redo starts
+		// from Y = 0 with the same (t, y, dt) as the reference does, so results and counters are
+		// unchanged; only the schedule differs.
+		const unsigned pmask = __ballot_sync(0xffffffffu, have && parked);
+		const unsigned cmask = __ballot_sync(0xffffffffu, have && !parked);
+		const bool slow_trip = pmask != 0u && (__popc(pmask) >= kParkLanes || cmask == 0u);
+
 		// ---------------- classify this trip: finish the member, or run one attempt
 		bool finished = false, run = false;
-		if (have) {
+		if (slow_trip) {
+			run = have && parked; // attempt already counted and clamped when it was first tried
+		} else if (have && !parked) {
 			if (!(t < a.t1)) { // irk.hpp:604 (also covers t0 >= t1: zero attempts)
 				finished = true;
 			} else {
@@ -396,7 +419,8 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				double Rnorm2 = residual();                   // irk.hpp:443-446
 				int nstat = kNewtonMaxit;
 				int it = 1;
-				for (; it < maxit; ++it) { // irk.hpp:458
+				const int cap = (slow_trip || maxit <= kFastIters) ? maxit : kFastIters + 1;
+				for (; it < cap; ++it) { // irk.hpp:458 (cap == maxit unless this is a fast trip)
 					// dY = -(I - dt A(x)J)^-1 R through the decoupled blocks
 					double Z[S][N];
 #pragma unroll
@@ -454,7 +478,16 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 
 				__syncwarp(amask);
 
-				if (nstat != kNewtonSuccess) { // irk.hpp:634-665
+				if (nstat != kNewtonSuccess && it < maxit) {
+					// fast-trip budget exhausted: forget this try (counters back to the attempt's
+					// start) and wait for a slow trip
+					// (this try evaluated S residual stages before and in each of its cap-1 iterations,
+					// one Jacobian, and one no-op refresh per refresh_jac iterations)
+					c_fun -= (unsigned)(S * cap);
+					c_jac -= 1u + (a.refresh_jac > 0 ? (unsigned)((cap - 1) / a.refresh_jac) : 0u);
+					parked = true;
+				} else if (nstat != kNewtonSuccess) { // irk.hpp:634-665
+					parked = false;
 					if (!a.adaptive) {
 						status = REHUEL_GENERAL_ERROR;
 						finished = true;
@@ -474,6 +507,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						}
 					}
 				} else {
+					parked = false;
 					++c_newton_ok;
 					c_iters += (unsigned)it;
 					// -------- new solution + embedded error, irk.hpp:691-731

@@ -16,7 +16,8 @@ class DeviceEnsemble:
     """Pre-allocated device buffers for one ensemble shape, reusable across solves."""
 
     def __init__(self, problem: int, method: int, M: int, y0: torch.Tensor, params: torch.Tensor,
-                 n_samples_cap: int = 0, n_hint: int = 0, trace_cap: int = 0, trace_member: int = 0):
+                 n_samples_cap: int = 0, n_hint: int = 0, trace_cap: int = 0, trace_member: int = 0,
+                 order: torch.Tensor | None = None):
         assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
         dev = y0.device
         n, p = capi.problem_dims(problem, n_hint or y0.shape[0])
@@ -57,6 +58,10 @@ class DeviceEnsemble:
         if trace_cap:
             io.trace, io.trace_cap, io.trace_member = self.trace.data_ptr(), trace_cap, trace_member
             io.trace_len = self.trace_len.data_ptr()
+        if order is not None:
+            assert order.is_cuda and order.dtype == torch.int32 and order.numel() == M
+            self.order = order.contiguous()
+            io.order = self.order.data_ptr()
         self.io = io
 
     def solve(self, t0: float, t1: float, dt0: float, opts: capi.Options) -> None:

@@ -292,3 +292,36 @@ def test_boundary_programs_c_abi_cpp_api_user_functor(capi):
         r = subprocess.run([path], capture_output=True, text=True, timeout=120)
         print("\n" + r.stdout.strip())
         assert r.returncode == 0, (exe, r.stdout, r.stderr)
+
+
+def test_handout_order_and_slow_lane_parking_do_not_change_results(capi, port):
+    """Config-3 shape (Van der Pol, mu_ref 1..1e-6, LOBATTO_IIIC_43): members that spin to maxit are
+    parked and redone in slow trips, and the caller may choose the hand-out order; neither may change
+    a single bit of any member's result or counters -- and both must match the oracle's counts."""
+    import torch
+    from rehuel_b200 import ensembles
+    from rehuel_b200.device import DeviceEnsemble
+    M = 512
+    P = ensembles.vdpol_params(M)
+    o = capi.make_options(1e-6, 1e-6)
+    Pd = torch.from_numpy(P).cuda()
+    y0 = torch.from_numpy(ensembles.VDPOL_Y0.copy()).cuda()
+    outs = []
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    for order in (None, torch.arange(M - 1, -1, -1, dtype=torch.int32, device="cuda"),
+                  torch.randperm(M, device="cuda", generator=g).to(torch.int32)):
+        de = DeviceEnsemble(capi.VAN_DER_POL, 230, M, y0, Pd, order=order)
+        de.solve(0.0, 2.0, 1e-6, o)
+        torch.cuda.synchronize()
+        outs.append((de.y.cpu().numpy().copy(), de.counters.cpu().numpy().copy(), de.status.cpu().numpy().copy()))
+    for y, c, s in outs[1:]:
+        assert np.array_equal(y, outs[0][0]) and np.array_equal(c, outs[0][1]) and np.array_equal(s, outs[0][2])
+    idx = np.arange(0, M, 8)
+    r = port.solve("van-der-pol", 230, 0.0, 2.0, 1e-6, ensembles.VDPOL_Y0, P[:, idx].copy(), ref_options(1e-6, 1e-6))
+    y, c, s = outs[0]
+    fun = c[capi.COUNTER_ROWS.index("fun_evals")][idx]
+    rejn = c[capi.COUNTER_ROWS.index("reject_newton")][idx]
+    print(f"\nvdpol 512: newton rejections gpu/ref {rejn.sum()}/{r.counters['reject_newton'].sum()}, fun gpu/ref {fun.sum()}/{r.counters['fun_evals'].sum()}")
+    assert np.array_equal(rejn, r.counters["reject_newton"].astype(np.int32))
+    assert abs(int(fun.sum()) - int(r.counters["fun_evals"].sum())) <= 0.01 * r.counters["fun_evals"].sum()
+    assert scaled_err(y[:, idx], r.y, 1e-6, 1e-6).max() <= PARITY_BOUND

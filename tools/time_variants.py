@@ -20,6 +20,13 @@ for span, t1, M in (("short", 40.0, 1 << 20), ("long", 1e11, 1 << 18)):
         e0.record(); de.solve(0.0, t1, 1e-6, o); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     out.append("%%s %%.3f ms" %% (span, best))
+M = 1 << 16
+P = torch.from_numpy(ensembles.vdpol_params(M)).cuda(); y0 = torch.from_numpy(ensembles.VDPOL_Y0.copy()).cuda()
+de = DeviceEnsemble(capi.VAN_DER_POL, 230, M, y0, P)
+de.solve(0.0, 2.0, 1e-6, o); torch.cuda.synchronize()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record(); de.solve(0.0, 2.0, 1e-6, o); e1.record(); torch.cuda.synchronize()
+out.append("vdpol-64k %%.1f ms (rejN %%d, fun %%.3g)" %% (e0.elapsed_time(e1), int(de.counter("reject_newton").sum()), float(de.counter("fun_evals").double().sum())))
 info = capi.kernel_info(capi.ROBERTSON, 211)
 print(os.environ.get("REHUEL_B200_LIB", "default"), info, " | ".join(out), flush=True)
 ''' % ROOT
