@@ -85,8 +85,14 @@ static const ProblemInfo *find_problem(int id)
 }
 
 // ------------------------------------------------------------------ kernel dispatch (templates: launch.cuh)
-static LaunchFn find_launcher(int problem)
+static LaunchFn find_launcher(int problem, int n)
 {
+	if (problem == REHUEL_PROBLEM_BRUSSELATOR_1D) {
+		if (n == 64) return &dispatch_method_cta<Brusselator1dF<32>>;
+		if (n == 8) return &dispatch_method_cta<Brusselator1dF<4>>;
+		set_error(REHUEL_EINVAL, "brusselator-1d is built for n = 64 (Ng = 32) and n = 8 (Ng = 4), got n = %d", n);
+		return nullptr;
+	}
 	switch (problem) {
 	case REHUEL_PROBLEM_ROBERTSON: return &dispatch_method<RobertsonF>;
 	case REHUEL_PROBLEM_VAN_DER_POL: return &dispatch_method<VanDerPolF>;
@@ -697,7 +703,7 @@ int rehuel_kernel_info(int problem, int method, int n_hint, int *regs, int *loca
 	rehuel_default_options(&o);
 	int n = 0, p = 0;
 	if (rehuel_problem_dims(problem, n_hint, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
-	LaunchFn launch = find_launcher(problem);
+	LaunchFn launch = find_launcher(problem, n);
 	if (!launch) return REHUEL_EINVAL;
 	int rc = prepare(method, 0.0, 1.0, 1e-6, 0, &o, tb, ka);
 	if (rc) return rc;
@@ -718,7 +724,7 @@ int rehuel_irk_ensemble_device(int problem, int method, double t0, double t1, do
 {
 	int n = 0, p = 0;
 	if (rehuel_problem_dims(problem, n_hint, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
-	LaunchFn launch = find_launcher(problem);
+	LaunchFn launch = find_launcher(problem, n);
 	if (!launch) return REHUEL_EINVAL;
 	return ensemble_device(launch, n, p, method, t0, t1, dt0, M, opts, io, static_cast<cudaStream_t>(cuda_stream));
 }
@@ -729,7 +735,7 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 {
 	int n = 0, p = 0;
 	if (rehuel_problem_dims(problem, n_hint, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
-	LaunchFn launch = find_launcher(problem);
+	LaunchFn launch = find_launcher(problem, n);
 	if (!launch) return REHUEL_EINVAL;
 	return ensemble_host(launch, n, p, method, t0, t1, dt0, M, y0, y0_broadcast, params, opts, n_samples_cap, n_gpus, out);
 }

@@ -112,4 +112,48 @@ struct BrusselatorF {
 	}
 };
 
+// 1-D Brusselator, method of lines on NG interior grid points, interleaved (u_i, v_i), boundary
+// values u = 1, v = 3 (the reference only has a "TODO: Discretization of a
+// PDE", test_equations.hpp:546).  p = (alpha, A, B).  Componentwise functor for the CTA-per-system
+// path (irk_cta.cuh); expression shapes are those of the oracle twin (oracle/ref_driver.cpp).
+template <int NG>
+struct Brusselator1dF {
+	static constexpr int N = 2 * NG;
+	static constexpr int P = 3;
+	static constexpr int kBand = 2; // interleaved (u_i,v_i): couplings reach i +- 2
+	__device__ __forceinline__ static double fun(int i, double, const double *y, const double *p)
+	{
+		const int g = i >> 1;
+		const double alpha = p[0], A = p[1], B = p[2];
+		const double d = alpha * (NG + 1.0) * (NG + 1.0);
+		const double u = y[2 * g], v = y[2 * g + 1];
+		if ((i & 1) == 0) {
+			const double ul = (g == 0) ? 1.0 : y[2 * (g - 1)];
+			const double ur = (g == NG - 1) ? 1.0 : y[2 * (g + 1)];
+			return A + u * u * v - (B + 1.0) * u + d * (ul - 2.0 * u + ur);
+		}
+		const double vl = (g == 0) ? 3.0 : y[2 * (g - 1) + 1];
+		const double vr = (g == NG - 1) ? 3.0 : y[2 * (g + 1) + 1];
+		return B * u - u * u * v + d * (vl - 2.0 * v + vr);
+	}
+	__device__ __forceinline__ static void jac_row(int i, double, const double *y, const double *p, double *row)
+	{
+		const int g = i >> 1;
+		const double alpha = p[0], B = p[2];
+		const double d = alpha * (NG + 1.0) * (NG + 1.0);
+		const double u = y[2 * g], v = y[2 * g + 1];
+		if ((i & 1) == 0) {
+			row[2 * g] = 2.0 * u * v - (B + 1.0) - 2.0 * d;
+			row[2 * g + 1] = u * u;
+			if (g > 0) row[2 * (g - 1)] = d;
+			if (g < NG - 1) row[2 * (g + 1)] = d;
+		} else {
+			row[2 * g] = B - 2.0 * u * v;
+			row[2 * g + 1] = -u * u - 2.0 * d;
+			if (g > 0) row[2 * (g - 1) + 1] = d;
+			if (g < NG - 1) row[2 * (g + 1) + 1] = d;
+		}
+	}
+};
+
 } // namespace rehuel

@@ -1,0 +1,644 @@
+// CTA-per-system ensemble integrator for larger systems (4 < n <= 64): one thread block runs one
+// member's adaptive integration, persistent blocks pull members from the global work queue.
+//
+// Same algorithm, statement for statement, as the thread-per-system kernel (irk_thread.cuh) and
+// hence as the reference loop irk.hpp:604-860 / newton_solve_stages irk.hpp:398-493; what changes
+// is where the data lives and who does the work:
+//   * state vectors (y, Y, R, Z, F) and the Jacobian live in shared memory;
+//   * the decoupled Newton matrices  mu_r I - J  (real) and  mu_c I - J  (complex, one per
+//     conjugate eigenvalue pair of inv(A)) are factorised IN shared memory by the whole block in
+//     ONE fused right-looking loop (row partial pivoting like dgetrf/zgetrf): warp m picks the
+//     pivot, swaps and scales for matrix m, then all threads apply the rank-1 updates of all
+//     matrices -- two block barriers per elimination step for the whole set;
+//   * the triangular solves of matrix m are done by warp m alone, warp-synchronously: each lane
+//     keeps rows lane, lane+32 of the right-hand side in registers and the pivot entry is
+//     broadcast with a shuffle, so a Newton iteration costs no block barrier inside the solves;
+//   * scalar control (dt, controller history, counters) is kept redundantly by every thread; all
+//     threads see identical reduction results (fixed summation order), so control flow is uniform.
+// For the 64-equation Brusselator with LOBATTO_IIIC_85 this replaces the reference's dense
+// 320x320 LU (21.8 Mflop per attempt) by one real and two complex 64x64 LUs (1.6 Mflop).
+//
+// Functor concept for this path (componentwise, so that the block can share the work):
+//   static constexpr int N, P;
+//   __device__ static double fun(int i, double t, const double *y, const double *p);          // f_i(t,y)
+//   __device__ static void   jac_row(int i, double t, const double *y, const double *p, double *row); // row i, pre-zeroed
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/rehuel_b200.h"
+#include "irk_thread.cuh"
+#include "tableau.hpp"
+
+namespace rehuel {
+
+// Optional functor trait: half bandwidth of the Jacobian (J(i,j) == 0 for |i-j| > kBand).  The LU
+// and the triangular solves then skip the entries that are structurally zero -- with row partial
+// pivoting U fills in up to 2*kBand above the diagonal, L stays within kBand below it (dgbtrf's
+// pattern).  Skipped operations act on exact zeros, so results are those of the dense path.
+template <class F, typename = void>
+struct jac_band { static constexpr int value = F::N - 1; };
+template <class F>
+struct jac_band<F, decltype((void)F::kBand)> { static constexpr int value = F::kBand < F::N - 1 ? F::kBand : F::N - 1; };
+
+template <class F, int S, int NC>
+struct CtaSmem {
+	static constexpr int N = F::N;
+	static constexpr int LD = N + 1; // odd leading dimension: column walks are bank-conflict free
+	static constexpr int PA = ((F::P > 0 ? F::P : 1) + 1) & ~1;
+	// offsets in doubles
+	static constexpr int o_y = 0;
+	static constexpr int o_yn = o_y + N;
+	static constexpr int o_p = o_yn + N;
+	static constexpr int o_Y = o_p + PA;
+	static constexpr int o_R = o_Y + S * N;
+	static constexpr int o_Z = o_R + S * N;
+	static constexpr int o_F = o_Z + S * N;
+	static constexpr int o_e = o_F + S * N;
+	static constexpr int o_dy = o_e + N;
+	static constexpr int o_dalt = o_dy + N;
+	static constexpr int o_fy = o_dalt + N;
+	static constexpr int o_red = o_fy + N;           // 64 doubles of reduction scratch
+	static constexpr int o_rdr = o_red + 64;         // reciprocal pivots, real matrix
+	static constexpr int o_rdc = o_rdr + N;          // reciprocal pivots, complex matrices (re, im)
+	static constexpr int o_J = o_rdc + 2 * N * (NC > 0 ? NC : 1);
+	static constexpr int o_LUr = o_J + N * N;
+	static constexpr int o_LUc = o_LUr + N * LD;
+	static constexpr int o_int = o_LUc + 2 * N * LD * NC; // int region: perm arrays
+	static constexpr int n_int = N * (1 + NC) + 8;
+	static constexpr size_t bytes = (size_t)o_int * 8 + (size_t)n_int * 4;
+};
+
+// Sum over the block, identical on every thread (fixed order: butterfly inside a warp, then the
+// warp partials in ascending order).  Two block barriers.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0.0;
+#pragma unroll
+	for (int w = 0; w < THREADS / 32; ++w) s += red[w];
+	__syncthreads();
+	return s;
+}
+
+// Fused LU of NRm real (0 or 1) and NCm complex N x N matrices in shared memory; matrix m is
+// piloted by warp m.  perm[m][k] = row exchanged with row k at step k (ipiv); reciprocal pivots go
+// to rdr / rdc so that the solves multiply.
+template <int N, int LD, int NRm, int NCm, int THREADS, int KB>
+__device__ __forceinline__ void lu_factor_set(double *Ar, double *Ac, double *rdr, double *rdc, int *permr, int *permc)
+{
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	constexpr int NM = NRm + NCm;
+	static_assert(NM <= THREADS / 32, "one pilot warp per matrix");
+	for (int k = 0; k < N; ++k) {
+		if (warp < NM) {
+			const bool is_real = warp < NRm;
+			const int c = warp - NRm;
+			double *are = is_real ? Ar : Ac + (size_t)c * 2 * N * LD;
+			double *aim = are + N * LD; // only for complex
+			// ---- pivot search: first row of maximal magnitude in column k (izamax: |re|+|im|)
+			double best = -1.0;
+			int bi = k;
+			const int rmax = (k + KB + 1 < N) ? k + KB + 1 : N;         // rows that can be non-zero in column k
+			const int cmax = (k + 2 * KB + 1 < N) ? k + 2 * KB + 1 : N; // columns that can be non-zero in those rows
+			for (int r = k + lane; r < rmax; r += 32) {
+				const double v = is_real ? fabs(are[r * LD + k]) : fabs(are[r * LD + k]) + fabs(aim[r * LD + k]);
+				if (v > best) {
+					best = v;
+					bi = r;
+				}
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				const double ob = __shfl_down_sync(0xffffffffu, best, o);
+				const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+				if (ob > best || (ob == best && oi < bi)) {
+					best = ob;
+					bi = oi;
+				}
+			}
+			const int p = __shfl_sync(0xffffffffu, bi, 0);
+			if (lane == 0) (is_real ? permr : permc + c * N)[k] = p; // interchange list, as ipiv of dgetrf
+			if (p != k) {
+				// like dgbtrf, only the not yet eliminated part of the rows is exchanged; the
+				// solves apply the interchanges step by step, so the multipliers stay put
+				for (int j = k + lane; j < cmax; j += 32) {
+					double u = are[k * LD + j];
+					are[k * LD + j] = are[p * LD + j];
+					are[p * LD + j] = u;
+					if (!is_real) {
+						u = aim[k * LD + j];
+						aim[k * LD + j] = aim[p * LD + j];
+						aim[p * LD + j] = u;
+					}
+				}
+			}
+			__syncwarp();
+			// ---- reciprocal pivot, multipliers
+			if (is_real) {
+				const double rp = 1.0 / are[k * LD + k];
+				if (lane == 0) rdr[k] = rp;
+				for (int r = k + 1 + lane; r < rmax; r += 32) are[r * LD + k] *= rp;
+			} else {
+				const double pr = are[k * LD + k], pi = aim[k * LD + k];
+				const double rden = 1.0 / fma(pr, pr, pi * pi);
+				const double rr = pr * rden, ri = -pi * rden;
+				if (lane == 0) {
+					rdc[(c * 2 + 0) * N + k] = rr;
+					rdc[(c * 2 + 1) * N + k] = ri;
+				}
+				for (int r = k + 1 + lane; r < rmax; r += 32) {
+					const double xr = are[r * LD + k], xi = aim[r * LD + k];
+					are[r * LD + k] = fma(xr, rr, -xi * ri);
+					aim[r * LD + k] = fma(xr, ri, xi * rr);
+				}
+			}
+		}
+		__syncthreads();
+		// ---- rank-1 update of every trailing block: 16x16 thread tiles, strided
+		const int m = N - k - 1;
+		if (m > 0) {
+			constexpr int TX = 16, TY = THREADS / 16;
+			const int tx = tid % TX, ty = tid / TX;
+			const int rmax = (k + KB + 1 < N) ? k + KB + 1 : N;
+			const int cmax = (k + 2 * KB + 1 < N) ? k + 2 * KB + 1 : N;
+			for (int i = k + 1 + ty; i < rmax; i += TY) {
+				if (NRm) {
+					const double l = Ar[i * LD + k];
+					for (int j = k + 1 + tx; j < cmax; j += TX) Ar[i * LD + j] = fma(-l, Ar[k * LD + j], Ar[i * LD + j]);
+				}
+#pragma unroll
+				for (int c = 0; c < NCm; ++c) {
+					double *are = Ac + (size_t)c * 2 * N * LD;
+					double *aim = are + N * LD;
+					const double lr = are[i * LD + k], li = aim[i * LD + k];
+					for (int j = k + 1 + tx; j < cmax; j += TX) {
+						const double ur = are[k * LD + j], ui = aim[k * LD + j];
+						are[i * LD + j] = fma(-lr, ur, fma(li, ui, are[i * LD + j]));
+						aim[i * LD + j] = fma(-lr, ui, fma(-li, ur, aim[i * LD + j]));
+					}
+				}
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// Warp-synchronous solve with the packed real LU: x <- U^-1 L^-1 P x.  x in shared memory.
+template <int N, int LD, int KB>
+__device__ __forceinline__ void lu_solve_real_warp(const double *A, const double *rd, const int *perm, double *x)
+{
+	constexpr int Q = (N + 31) / 32;
+	const int lane = threadIdx.x & 31;
+	double v[Q];
+#pragma unroll
+	for (int q = 0; q < Q; ++q) {
+		const int i = lane + 32 * q;
+		v[q] = (i < N) ? x[i] : 0.0;
+	}
+#pragma unroll
+	for (int kq = 0; kq < Q; ++kq) // forward, unit lower (kq static: v[] stays in registers)
+		for (int kk = 0; kk < 32 && kq * 32 + kk < N; ++kk) {
+			const int k = kq * 32 + kk;
+			const int p = perm[k]; // warp-uniform
+			double xk = __shfl_sync(0xffffffffu, v[kq], kk);
+			if (p != k) { // exchange entries k and p (p > k)
+				const double xp = __shfl_sync(0xffffffffu, (Q > 1 && p >= 32) ? v[Q - 1] : v[0], p & 31);
+#pragma unroll
+				for (int q = 0; q < Q; ++q) {
+					const int i = lane + 32 * q;
+					if (i == k) v[q] = xp;
+					if (i == p) v[q] = xk;
+				}
+				xk = xp;
+			}
+#pragma unroll
+			for (int q = 0; q < Q; ++q) {
+				const int i = lane + 32 * q;
+				if (i > k && i < N && i <= k + KB) v[q] = fma(-A[i * LD + k], xk, v[q]);
+			}
+		}
+#pragma unroll
+	for (int kq = Q - 1; kq >= 0; --kq) // backward
+		for (int kk = 31; kk >= 0; --kk) {
+			const int k = kq * 32 + kk;
+			if (k >= N) continue;
+			const double xk = __shfl_sync(0xffffffffu, v[kq], kk) * rd[k];
+#pragma unroll
+			for (int q = 0; q < Q; ++q) {
+				const int i = lane + 32 * q;
+				if (i == k) v[q] = xk;
+				if (i < k && i + 2 * KB >= k) v[q] = fma(-A[i * LD + k], xk, v[q]);
+			}
+		}
+	__syncwarp();
+#pragma unroll
+	for (int q = 0; q < Q; ++q) {
+		const int i = lane + 32 * q;
+		if (i < N) x[i] = v[q];
+	}
+	__syncwarp();
+}
+
+template <int N, int LD, int KB>
+__device__ __forceinline__ void lu_solve_cplx_warp(const double *Are, const double *rdre, const double *rdim,
+                                                   const int *perm, double *xr, double *xi)
+{
+	constexpr int Q = (N + 31) / 32;
+	const int lane = threadIdx.x & 31;
+	const double *Aim = Are + N * LD;
+	double vr[Q], vi[Q];
+#pragma unroll
+	for (int q = 0; q < Q; ++q) {
+		const int i = lane + 32 * q;
+		vr[q] = (i < N) ? xr[i] : 0.0;
+		vi[q] = (i < N) ? xi[i] : 0.0;
+	}
+#pragma unroll
+	for (int kq = 0; kq < Q; ++kq)
+		for (int kk = 0; kk < 32 && kq * 32 + kk < N; ++kk) {
+			const int k = kq * 32 + kk;
+			const int p = perm[k];
+			double kr = __shfl_sync(0xffffffffu, vr[kq], kk);
+			double ki = __shfl_sync(0xffffffffu, vi[kq], kk);
+			if (p != k) {
+				const double pr = __shfl_sync(0xffffffffu, (Q > 1 && p >= 32) ? vr[Q - 1] : vr[0], p & 31);
+				const double pi = __shfl_sync(0xffffffffu, (Q > 1 && p >= 32) ? vi[Q - 1] : vi[0], p & 31);
+#pragma unroll
+				for (int q = 0; q < Q; ++q) {
+					const int i = lane + 32 * q;
+					if (i == k) { vr[q] = pr; vi[q] = pi; }
+					if (i == p) { vr[q] = kr; vi[q] = ki; }
+				}
+				kr = pr;
+				ki = pi;
+			}
+#pragma unroll
+			for (int q = 0; q < Q; ++q) {
+				const int i = lane + 32 * q;
+				if (i > k && i < N && i <= k + KB) {
+					const double lr = Are[i * LD + k], li = Aim[i * LD + k];
+					vr[q] = fma(-lr, kr, fma(li, ki, vr[q]));
+					vi[q] = fma(-lr, ki, fma(-li, kr, vi[q]));
+				}
+			}
+		}
+#pragma unroll
+	for (int kq = Q - 1; kq >= 0; --kq)
+		for (int kk = 31; kk >= 0; --kk) {
+			const int k = kq * 32 + kk;
+			if (k >= N) continue;
+			const double tr = __shfl_sync(0xffffffffu, vr[kq], kk);
+			const double ti = __shfl_sync(0xffffffffu, vi[kq], kk);
+			const double kr = fma(tr, rdre[k], -ti * rdim[k]);
+			const double ki = fma(tr, rdim[k], ti * rdre[k]);
+#pragma unroll
+			for (int q = 0; q < Q; ++q) {
+				const int i = lane + 32 * q;
+				if (i == k) {
+					vr[q] = kr;
+					vi[q] = ki;
+				}
+				if (i < k && i + 2 * KB >= k) {
+					const double ur = Are[i * LD + k], ui = Aim[i * LD + k];
+					vr[q] = fma(-ur, kr, fma(ui, ki, vr[q]));
+					vi[q] = fma(-ur, ki, fma(-ui, kr, vi[q]));
+				}
+			}
+		}
+	__syncwarp();
+#pragma unroll
+	for (int q = 0; q < Q; ++q) {
+		const int i = lane + 32 * q;
+		if (i < N) {
+			xr[i] = vr[q];
+			xi[i] = vi[q];
+		}
+	}
+	__syncwarp();
+}
+
+template <class F, int S, int NR, int NC, int EST, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ DevTableau<S, NC> tb)
+{
+	static_assert(S == NR + 2 * NC && NR <= 1, "eigen-structure");
+	using L = CtaSmem<F, S, NC>;
+	constexpr int N = F::N, LD = L::LD, KB = jac_band<F>::value;
+	static_assert(N <= 64, "the warp-synchronous solves keep at most two rows per lane");
+	extern __shared__ double sm[];
+	double *y = sm + L::o_y, *yn = sm + L::o_yn, *par = sm + L::o_p, *Y = sm + L::o_Y, *R = sm + L::o_R,
+	       *Z = sm + L::o_Z, *Fv = sm + L::o_F, *ev = sm + L::o_e, *dyv = sm + L::o_dy, *dalt = sm + L::o_dalt,
+	       *fy = sm + L::o_fy, *red = sm + L::o_red, *rdr = sm + L::o_rdr, *rdc = sm + L::o_rdc, *J = sm + L::o_J,
+	       *LUr = sm + L::o_LUr, *LUc = sm + L::o_LUc;
+	int *permr = reinterpret_cast<int *>(sm + L::o_int);
+	int *permc = permr + N;
+	int *s_ctl = permc + N * NC; // [0..1]: member index (64 bit)
+	const int tid = threadIdx.x, warp = tid >> 5;
+	const unsigned long long M = a.M;
+	const rehuel_device_io &io = a.io;
+
+	for (;;) {
+		// ---------------- next member
+		if (tid == 0) {
+			unsigned long long q = atomicAdd(io.queue, 1ull);
+			if (q < M && io.order) q = io.order[q];
+			*reinterpret_cast<unsigned long long *>(s_ctl) = q;
+		}
+		__syncthreads();
+		const unsigned long long mem = *reinterpret_cast<unsigned long long *>(s_ctl);
+		if (mem >= M) break;
+		for (int k = tid; k < N; k += THREADS) y[k] = io.y0_broadcast ? io.y0[k] : io.y0[k * M + mem];
+		for (int k = tid; k < F::P; k += THREADS) par[k] = io.params[k * M + mem];
+		__syncthreads();
+
+		// ---------------- per-member scalar state (identical in every thread)
+		double t = a.t0, dt = a.dt0;
+		if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
+		double dts0 = dt, dts1 = dt, errs0 = 0.9, errs1 = 0.9, err = 0.0;
+		bool alt = true;
+		int maxit = a.maxit0;
+		long long step = 0, last_relax = 0;
+		int status = REHUEL_SUCCESS;
+		unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0, c_iters = 0,
+		         n_stored = 0;
+		if (a.store_samples) {
+			if (io.n_samples_cap) {
+				if (tid == 0) {
+					io.t_samples[mem] = t;
+					if (io.err_samples) io.err_samples[mem] = 0.0;
+				}
+				for (int k = tid; k < N; k += THREADS) io.y_samples[k * M + mem] = y[k];
+			}
+			n_stored = 1;
+		}
+
+		// residual R = Y - dt*(A (x) I) F(y+Y), returns |R|^2   (irk.hpp:366-386)
+		auto residual = [&]() -> double {
+			for (int e = tid; e < S * N; e += THREADS) Z[e] = y[e % N] + Y[e]; // stage states (Z is free here)
+			__syncthreads();
+			for (int e = tid; e < S * N; e += THREADS) {
+				const int s = e / N, i = e % N;
+				Fv[e] = F::fun(i, fma(tb.c[s], dt, t), Z + s * N, par);
+			}
+			__syncthreads();
+			c_fun += S;
+			double r2 = 0.0;
+			for (int e = tid; e < S * N; e += THREADS) {
+				const int s = e / N, i = e % N;
+				double acc = 0.0;
+#pragma unroll
+				for (int j = 0; j < S; ++j) acc = fma(tb.A[s][j], Fv[j * N + i], acc);
+				const double r = fma(-dt, acc, Y[e]);
+				R[e] = r;
+				r2 = fma(r, r, r2);
+			}
+			return block_sum<THREADS>(r2, red);
+		};
+
+		while (t < a.t1) { // irk.hpp:604
+			if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:607-609
+			++c_attempt;
+			if (a.max_steps >= 0 && step > a.max_steps) { // irk.hpp:612-616
+				status = REHUEL_ERROR_MAX_STEPS_EXCEEDED;
+				break;
+			}
+			if (!(dt >= 2.2250738585072014e-308)) { // see irk_thread.cuh: the reference would never return
+				status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
+				break;
+			}
+			// -------- Jacobian and the decoupled Newton matrices (irk.hpp:422-436)
+			const double rdt = 1.0 / dt;
+			const double mur = (EST == EST_REUSE) ? 1.0 / (tb.gamma * dt) : tb.gamma_hat * rdt;
+			for (int e = tid; e < N * N; e += THREADS) J[e] = 0.0;
+			__syncthreads();
+			for (int i = tid; i < N; i += THREADS) F::jac_row(i, t, y, par, J + i * N);
+			++c_jac;
+			__syncthreads();
+			for (int e = tid; e < N * N; e += THREADS) {
+				const int i = e / N, j = e % N;
+				const double jv = J[e];
+				if (NR) LUr[i * LD + j] = (i == j ? mur : 0.0) - jv;
+#pragma unroll
+				for (int c = 0; c < NC; ++c) {
+					LUc[(size_t)c * 2 * N * LD + i * LD + j] = (i == j ? tb.alpha[c] * rdt : 0.0) - jv;
+					LUc[(size_t)c * 2 * N * LD + N * LD + i * LD + j] = (i == j ? tb.beta[c] * rdt : 0.0);
+				}
+			}
+			__syncthreads();
+			lu_factor_set<N, LD, NR, NC, THREADS, KB>(LUr, LUc, rdr, rdc, permr, permc);
+
+			// -------- simplified Newton (irk.hpp:398-493)
+			for (int e = tid; e < S * N; e += THREADS) Y[e] = 0.0; // irk.hpp:415
+			__syncthreads();
+			double Rnorm2 = residual();
+			int nstat = kNewtonMaxit;
+			int it = 1;
+			for (; it < maxit; ++it) { // irk.hpp:458
+				for (int e = tid; e < S * N; e += THREADS) { // Z = (Ti (x) I) R
+					const int s = e / N, i = e % N;
+					double acc = 0.0;
+#pragma unroll
+					for (int j = 0; j < S; ++j) acc = fma(tb.Ti[s][j], R[j * N + i], acc);
+					Z[e] = acc;
+				}
+				__syncthreads();
+				if (NR && warp == 0) {
+					lu_solve_real_warp<N, LD, KB>(LUr, rdr, permr, Z);
+					for (int i = tid & 31; i < N; i += 32) Z[i] *= -mur;
+				}
+				if (warp >= NR && warp < NR + NC) {
+					const int c = warp - NR;
+					double *zr = Z + (NR + 2 * c) * N, *zi = zr + N;
+					lu_solve_cplx_warp<N, LD, KB>(LUc + (size_t)c * 2 * N * LD, rdc + (c * 2) * N, rdc + (c * 2 + 1) * N,
+					                          permc + c * N, zr, zi);
+					const double mr = tb.alpha[c] * rdt, mi = tb.beta[c] * rdt;
+					for (int i = tid & 31; i < N; i += 32) { // w = -(mr + i mi) w
+						const double wr = zr[i], wi = zi[i];
+						zr[i] = fma(-mr, wr, mi * wi);
+						zi[i] = fma(-mr, wi, -mi * wr);
+					}
+				}
+				__syncthreads();
+				double x2 = 0.0;
+				for (int e = tid; e < S * N; e += THREADS) { // dY = (T (x) I) W ; Y += dY
+					const int s = e / N, i = e % N;
+					double acc = 0.0;
+#pragma unroll
+					for (int j = 0; j < S; ++j) acc = fma(tb.T[s][j], Z[j * N + i], acc);
+					x2 = fma(acc, acc, x2);
+					Y[e] += acc;
+				}
+				const double xnorm2 = block_sum<THREADS>(x2, red); // irk.hpp:466 (also orders Z reads before reuse)
+				Rnorm2 = residual();
+				if (Rnorm2 < a.Rtol2) { nstat = kNewtonSuccess; break; }
+				if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; }
+				if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac;
+				if (!(Rnorm2 <= 1.79769313486231570e308)) { // NaN/Inf: see irk_thread.cuh
+					const int rest = maxit - 1 - it;
+					if (rest > 0) {
+						c_fun += (unsigned)rest * S;
+						if (a.refresh_jac > 0) c_jac += (unsigned)((maxit - 1) / a.refresh_jac - it / a.refresh_jac);
+					}
+					it = maxit;
+					break;
+				}
+			}
+
+			if (nstat != kNewtonSuccess) { // irk.hpp:634-665
+				if (!a.adaptive) {
+					status = REHUEL_GENERAL_ERROR;
+					break;
+				}
+				dt *= 0.7;
+				if (step - last_relax > 15) {
+					maxit += a.maxit0;
+					last_relax = step;
+				}
+				++c_rej_newton;
+				continue;
+			}
+			++c_newton_ok;
+			c_iters += (unsigned)it;
+
+			// -------- new solution + embedded error (irk.hpp:691-731)
+			const double gam = tb.gamma * dt;
+			for (int i = tid; i < N; i += THREADS) {
+				double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+				for (int s = 0; s < S; ++s) {
+					s1 = fma(Y[s * N + i], tb.d[s], s1);
+					s2 = fma(Y[s * N + i], tb.d2[s], s2);
+				}
+				dyv[i] = s1;
+				dalt[i] = s2;
+				yn[i] = y[i] + s1;
+				if (EST != EST_IDENTITY) fy[i] = F::fun(i, t, y, par); // irk.hpp:702
+			}
+			++c_fun;
+			__syncthreads();
+			if (EST == EST_OWN_LU) { // E/gam = (1/gam) I - J gets its own factors (in the real slot)
+				const double mue = 1.0 / gam;
+				for (int e = tid; e < N * N; e += THREADS) {
+					const int i = e / N, j = e % N;
+					LUr[i * LD + j] = (i == j ? mue : 0.0) - J[e];
+				}
+				__syncthreads();
+				lu_factor_set<N, LD, 1, 0, THREADS, KB>(LUr, nullptr, rdr, nullptr, permr, nullptr);
+			}
+			for (int i = tid; i < N; i += THREADS) {
+				const double dyalt = (EST != EST_IDENTITY) ? fma(gam, fy[i], dalt[i]) : dalt[i];
+				ev[i] = dyalt - dyv[i];
+			}
+			__syncthreads();
+			const double esc = (EST == EST_IDENTITY) ? dt : 1.0 / tb.gamma; // dt*E^-1 = (1/gamma)(mu I - J)^-1
+			auto apply_Einv_dt = [&]() {
+				if (EST != EST_IDENTITY) {
+					if (warp == 0) lu_solve_real_warp<N, LD, KB>(LUr, rdr, permr, ev);
+					__syncthreads();
+				}
+				for (int i = tid; i < N; i += THREADS) ev[i] *= esc;
+				__syncthreads();
+			};
+			apply_Einv_dt(); // 8.19
+			if (alt) {       // 8.20, irk.hpp:722-731
+				if (EST != EST_IDENTITY) {
+					for (int i = tid; i < N; i += THREADS) Z[i] = y[i] + ev[i];
+					__syncthreads();
+					for (int i = tid; i < N; i += THREADS) fy[i] = F::fun(i, t, Z, par);
+					__syncthreads();
+				}
+				++c_fun;
+				for (int i = tid; i < N; i += THREADS) {
+					const double v = (EST != EST_IDENTITY) ? fma(gam, fy[i], dalt[i]) : dalt[i];
+					ev[i] = v - dyv[i];
+				}
+				__syncthreads();
+				apply_Einv_dt();
+			}
+			double tot = 0.0;
+			for (int i = tid; i < N; i += THREADS) { // irk.hpp:733-746
+				const double sc = fma(a.rtol, fmax(fabs(y[i]), fabs(yn[i])), a.atol);
+				const double q = ev[i] / sc;
+				tot = fma(q, q, tot);
+			}
+			tot = block_sum<THREADS>(tot, red);
+			err = sqrt(tot / (double)N);
+			if (err < kMachinePrecision) err = kMachinePrecision;
+			errs1 = errs0;
+			errs0 = err;
+			const bool rejected = a.adaptive && (err > 1.0); // irk.hpp:761
+			if (rejected) {
+				alt = true;
+				++c_rej_err;
+			}
+			// -------- step-size proposal (irk.hpp:770-801)
+			const double fac = 0.9 * (maxit + 1.0) / (double)(maxit + it);
+			const double s27 = ctrl_pow(1.0 / err, tb.min_order, tb.expo);
+			const double dt_rat = dts0 / dts1;
+			double err_frac = errs1 / errs0;
+			if (errs1 == 0.0 || errs0 == 0.0) err_frac = 1.0;
+			const double s28 = s27 * dt_rat * ctrl_pow(err_frac, tb.min_order, tb.expo);
+			const double msc = (s28 < s27) ? s28 : s27;
+			double new_dt = fac * dt * (msc < 8.0 ? msc : 8.0);
+			if (a.max_dt > 0.0) new_dt = new_dt < a.max_dt ? new_dt : a.max_dt;
+			bool stuck = false;
+			if (!rejected) { // irk.hpp:813-846
+				for (int i = tid; i < N; i += THREADS) y[i] = yn[i];
+				const double t_old = t;
+				t += dt;
+				++step;
+				if (t == t_old) stuck = true;
+				if (a.store_samples && (a.output_interval == 1ull || (unsigned long long)step % a.output_interval == 0ull)) {
+					if (n_stored < io.n_samples_cap) {
+						const size_t row = n_stored;
+						if (tid == 0) {
+							io.t_samples[row * M + mem] = t;
+							if (io.err_samples) io.err_samples[row * M + mem] = err;
+						}
+						for (int i = tid; i < N; i += THREADS) io.y_samples[(row * N + i) * M + mem] = yn[i];
+					}
+					++n_stored;
+				}
+				alt = false;
+				__syncthreads();
+			}
+			if (a.adaptive) dt = new_dt; // irk.hpp:850-852
+			dts1 = dts0;
+			dts0 = dt;
+			if (stuck) {
+				status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
+				break;
+			}
+		}
+
+		// ---------------- results
+		__syncthreads();
+		for (int k = tid; k < N; k += THREADS) io.y[k * M + mem] = y[k];
+		if (tid == 0) {
+			io.t_final[mem] = t;
+			if (io.err_last) io.err_last[mem] = err;
+			io.status[mem] = status;
+			if (io.counters) {
+				io.counters[REHUEL_CNT_ATTEMPT * M + mem] = c_attempt;
+				io.counters[REHUEL_CNT_REJECT_NEWTON * M + mem] = c_rej_newton;
+				io.counters[REHUEL_CNT_REJECT_ERR * M + mem] = c_rej_err;
+				io.counters[REHUEL_CNT_NEWTON_SUCCESS * M + mem] = c_newton_ok;
+				io.counters[REHUEL_CNT_NEWTON_MAXIT_EXCEED * M + mem] = c_rej_newton;
+				io.counters[REHUEL_CNT_FUN_EVALS * M + mem] = c_fun;
+				io.counters[REHUEL_CNT_JAC_EVALS * M + mem] = c_jac;
+				io.counters[REHUEL_CNT_NEWTON_ITERS * M + mem] = c_iters;
+				io.counters[REHUEL_CNT_STEPS * M + mem] = (unsigned)step;
+			}
+			if (io.n_samples) io.n_samples[mem] = n_stored;
+		}
+		__syncthreads();
+	}
+}
+
+} // namespace rehuel

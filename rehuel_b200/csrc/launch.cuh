@@ -12,6 +12,7 @@
 #include <cstddef>
 
 #include "../../include/rehuel_b200.h"
+#include "irk_cta.cuh"
 #include "irk_thread.cuh"
 #include "tableau.hpp"
 
@@ -101,6 +102,52 @@ int dispatch_method(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream
 	case REHUEL_LOBATTO_IIIC_85: return launch_thread<F, 5, 1, 2, EST_OWN_LU>(ka, tb, stream, info);
 	}
 	return set_error(REHUEL_EINVAL, "method %d (%s) has no GPU kernel", tb.method, tb.name);
+}
+
+// ---- CTA-per-system path (4 < n <= 64), irk_cta.cuh
+template <class F, int S, int NR, int NC, int EST>
+int launch_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	constexpr int THREADS = (F::N <= 16) ? 128 : 256;
+	auto kern = ensemble_irk_cta<F, S, NR, NC, EST, THREADS>;
+	const size_t smem = CtaSmem<F, S, NC>::bytes;
+	int dev = 0, sms = 0, per_sm = 0;
+	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
+	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	REHUEL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	REHUEL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+	if (per_sm < 1) return set_error(REHUEL_ECUDA, "CTA-per-system kernel needs %zu bytes of shared memory", smem);
+	if (info) {
+		cudaFuncAttributes fa;
+		REHUEL_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+		info->regs = fa.numRegs;
+		info->local_bytes = (int)fa.localSizeBytes;
+		info->smem_bytes = (int)smem;
+		info->ctas_per_sm = per_sm;
+		info->block = THREADS;
+		return REHUEL_OK;
+	}
+	if (ka.M == 0) return REHUEL_OK;
+	unsigned long long cap = (unsigned long long)sms * per_sm;
+	unsigned grid = (unsigned)(ka.M < cap ? ka.M : cap);
+	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
+	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	kern<<<grid, THREADS, smem, stream>>>(ka, dtb);
+	REHUEL_CUDA_TRY(cudaGetLastError());
+	count_launch();
+	return REHUEL_OK;
+}
+
+template <class F>
+int dispatch_method_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	static_assert(F::N > 4 && F::N <= 64, "CTA-per-system kernels cover 4 < n <= 64");
+	switch (tb.method) {
+	case REHUEL_RADAU_IIA_53: return launch_cta<F, 3, 1, 1, EST_REUSE>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_43: return launch_cta<F, 3, 1, 1, EST_IDENTITY>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_85: return launch_cta<F, 5, 1, 2, EST_OWN_LU>(ka, tb, stream, info);
+	}
+	return set_error(REHUEL_EINVAL, "method %d (%s) has no CTA-per-system kernel", tb.method, tb.name);
 }
 
 } // namespace rehuel

@@ -27,7 +27,7 @@ def capi():
     return m
 
 
-PROBLEM_ID = {"robertson": 1, "van-der-pol": 2, "exponential": 5, "stiff-equation": 6, "brusselator": 7}
+PROBLEM_ID = {"robertson": 1, "van-der-pol": 2, "brusselator-1d": 3, "exponential": 5, "stiff-equation": 6, "brusselator": 7}
 
 
 def _gpu_single(capi, c, **kw):
@@ -62,7 +62,7 @@ def test_golden_single_systems(capi, golden):
     print("\nname | scaled_err | attempts gpu/ref | rejE gpu/ref | rejN gpu/ref | fun gpu/ref | jac gpu/ref")
     for r in rows:
         print("%-28s %.3e  %d/%d  %d/%d  %d/%d  %d/%d  %d/%d" % r)
-    assert len(rows) >= 14
+    assert len(rows) >= 16
 
 
 def test_golden_ensembles(capi, golden):
@@ -325,3 +325,22 @@ def test_handout_order_and_slow_lane_parking_do_not_change_results(capi, port):
     assert np.array_equal(rejn, r.counters["reject_newton"].astype(np.int32))
     assert abs(int(fun.sum()) - int(r.counters["fun_evals"].sum())) <= 0.01 * r.counters["fun_evals"].sum()
     assert scaled_err(y[:, idx], r.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+
+
+def test_brusselator_mol_64_equations_cta_per_system(capi, port):
+    """Config-4 shape: 1-D Brusselator method of lines, Ng = 32 (n = 64), CTA-per-system kernel with
+    the decoupled LUs in shared memory, against the CPU oracle (dense 192x192 / 320x320 LU)."""
+    from rehuel_b200 import ensembles
+    M = 6
+    P = ensembles.bruss1d_params(M)
+    y0 = ensembles.bruss1d_y0(32)
+    o, ro = capi.make_options(1e-6, 1e-6), ref_options(1e-6, 1e-6)
+    for method, t1 in ((capi.RADAU_IIA_53, 10.0), (capi.LOBATTO_IIIC_43, 1.0), (capi.LOBATTO_IIIC_85, 0.25)):
+        g = capi.irk_ensemble(capi.BRUSSELATOR_1D, method, 0.0, t1, 1e-6, y0, P, o)
+        r = port.solve("brusselator-1d", method, 0.0, t1, 1e-6, y0, P, ro)
+        se = scaled_err(g.y, r.y, 1e-6, 1e-6)
+        print(f"\nbruss1d n=64 method {method} t1={t1}: max scaled err {se.max():.3e}; attempts gpu/ref {g.counters['attempt'].sum()}/{r.counters['attempt'].sum()}; "
+              f"rejE gpu/ref {g.counters['reject_err'].sum()}/{r.counters['reject_err'].sum()}; fun gpu/ref {g.counters['fun_evals'].sum()}/{r.counters['fun_evals'].sum()}; kernel {g.kernel_ms:.1f} ms")
+        assert np.all(g.status == 0) and np.all(g.t_final == t1)
+        assert se.max() <= PARITY_BOUND
+        assert abs(int(g.counters["attempt"].sum()) - int(r.counters["attempt"].sum())) <= max(3, 0.02 * r.counters["attempt"].sum())
