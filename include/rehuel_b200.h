@@ -183,6 +183,8 @@ typedef struct rehuel_device_io {
 	size_t trace_cap;
 	size_t trace_member;
 	unsigned *trace_len;   /* [1] */
+	const double *rtol, *atol, *newton_tol; /* [M] each or NULL: per-member rel_tol / abs_tol / newton tol overriding
+	                          the options (mixed-tolerance ensembles); all three or none */
 	const unsigned *order; /* [M] or NULL: queue position q -> member index order[q].  Lets the caller hand out
 	                          expensive members first (longest-processing-time-first) when cost correlates with a
 	                          parameter; results do not depend on it. */

@@ -75,7 +75,8 @@ class DeviceIO(C.Structure):
         ("t_samples", C.c_void_p), ("y_samples", C.c_void_p), ("err_samples", C.c_void_p),
         ("queue", C.c_void_p),
         ("trace", C.c_void_p), ("trace_cap", C.c_size_t), ("trace_member", C.c_size_t),
-        ("trace_len", C.c_void_p), ("order", C.c_void_p),
+        ("trace_len", C.c_void_p), ("rtol", C.c_void_p), ("atol", C.c_void_p), ("newton_tol", C.c_void_p),
+        ("order", C.c_void_p),
     ]
 
 

@@ -350,6 +350,8 @@ int ensemble_device(LaunchFn launch, int n, int p, int method, double t0, double
 		ka.io.trace_len = nullptr;
 	}
 	if (ka.io.n_samples_cap == 0 && !ka.io.n_samples) ka.store_samples = 0; // nobody looks at the sample count
+	if ((ka.io.rtol || ka.io.atol || ka.io.newton_tol) && !(ka.io.rtol && ka.io.atol && ka.io.newton_tol))
+		return fail(REHUEL_EINVAL, "per-member tolerances: rtol, atol and newton_tol must all be given");
 	return launch(ka, tb, stream, nullptr);
 }
 

@@ -224,7 +224,7 @@ __device__ __forceinline__ double ctrl_pow(double x, int min_order, double expo)
 }
 
 // ------------------------------------------------------------------ the kernel
-template <class F, int S, int NR, int NC, int EST, int BLOCK, int MIN_BLOCKS>
+template <class F, int S, int NR, int NC, int EST, int BLOCK, int MIN_BLOCKS, bool TOLV = false>
 #ifdef REHUEL_MAXNREG
 __global__ void __maxnreg__(REHUEL_MAXNREG)
 #else
@@ -253,6 +253,8 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	int status = REHUEL_SUCCESS;
 	unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0,
 	         c_iters = 0, n_stored = 0;
+	// per-member tolerances (TOLV kernels only; otherwise the uniform values of the options)
+	double m_rtol = a.rtol, m_atol = a.atol, m_Rtol2 = a.Rtol2;
 
 	for (;;) {
 		// ---------------- refill idle lanes from the global queue (warp-aggregated)
@@ -271,6 +273,12 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 #pragma unroll
 					for (int k = 0; k < F::P; ++k) p[k] = io.params[k * M + mem];
 					if (F::P == 0) p[0] = 0.0;
+					if (TOLV) {
+						m_rtol = io.rtol[mem];
+						m_atol = io.atol[mem];
+						const double nt = io.newton_tol[mem];
+						m_Rtol2 = nt * nt;
+					}
 					t = a.t0;
 					dt = a.dt0;
 					if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
@@ -460,7 +468,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							Y[i][k] += acc;                 // irk.hpp:468 (step == 1)
 						}
 					Rnorm2 = residual();                    // irk.hpp:469-472
-					if (Rnorm2 < a.Rtol2) { nstat = kNewtonSuccess; break; } // irk.hpp:473-476
+					if (Rnorm2 < (TOLV ? m_Rtol2 : a.Rtol2)) { nstat = kNewtonSuccess; break; } // irk.hpp:473-476
 					if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; } // irk.hpp:477-480
 					if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac; // irk.hpp:485-487 (no-op refactor)
 					if (!(Rnorm2 <= 1.79769313486231570e308)) {
@@ -564,7 +572,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					double tot = 0.0;
 #pragma unroll
 					for (int k = 0; k < N; ++k) {
-						const double sc = fma(a.rtol, fmax(fabs(y[k]), fabs(yn[k])), a.atol);
+						const double sc = fma(TOLV ? m_rtol : a.rtol, fmax(fabs(y[k]), fabs(yn[k])), TOLV ? m_atol : a.atol);
 						// e[k] == 0 (e.g. the first Robertson attempts) would send the whole warp through
 						// the division's slow path for one lane; 0/sc is 0 anyway.
 						const bool zero = (e[k] == 0.0);

@@ -59,7 +59,14 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 	// 128 registers/thread (4 CTAs of 128 per SM) is the measured optimum for stage systems up to
 	// 3x3 (a few spills, 16 warps/SM); larger stage systems keep 255 registers.
 	constexpr int BLOCK = REHUEL_BLOCK, MIN_BLOCKS = (S * F::N <= 9) ? REHUEL_MINB : 2;
-	auto kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS>;
+	void (*kern)(const KernelArgs, const DevTableau<S, NC>) = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS, false>;
+	if (ka.io.rtol) { // per-member tolerances: separate instantiation so the uniform kernels stay lean
+		if constexpr (S == 3) {
+			kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS, true>;
+		} else {
+			return set_error(REHUEL_EINVAL, "per-member tolerances are built for the 3-stage methods only");
+		}
+	}
 	int dev = 0, sms = 0, per_sm = 0;
 	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
 	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -128,6 +135,7 @@ int launch_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ker
 		return REHUEL_OK;
 	}
 	if (ka.M == 0) return REHUEL_OK;
+	if (ka.io.rtol) return set_error(REHUEL_EINVAL, "per-member tolerances are not built for the CTA-per-system kernels");
 	unsigned long long cap = (unsigned long long)sms * per_sm;
 	unsigned grid = (unsigned)(ka.M < cap ? ka.M : cap);
 	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);

@@ -17,7 +17,8 @@ class DeviceEnsemble:
 
     def __init__(self, problem: int, method: int, M: int, y0: torch.Tensor, params: torch.Tensor,
                  n_samples_cap: int = 0, n_hint: int = 0, trace_cap: int = 0, trace_member: int = 0,
-                 order: torch.Tensor | None = None):
+                 order: torch.Tensor | None = None, rtol: torch.Tensor | None = None,
+                 atol: torch.Tensor | None = None, newton_tol: torch.Tensor | None = None):
         assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
         dev = y0.device
         n, p = capi.problem_dims(problem, n_hint or y0.shape[0])
@@ -62,6 +63,11 @@ class DeviceEnsemble:
             assert order.is_cuda and order.dtype == torch.int32 and order.numel() == M
             self.order = order.contiguous()
             io.order = self.order.data_ptr()
+        if rtol is not None:
+            for v in (rtol, atol, newton_tol):
+                assert v is not None and v.is_cuda and v.dtype == torch.float64 and v.numel() == M and v.is_contiguous()
+            self.tols = (rtol, atol, newton_tol)
+            io.rtol, io.atol, io.newton_tol = rtol.data_ptr(), atol.data_ptr(), newton_tol.data_ptr()
         self.io = io
 
     def solve(self, t0: float, t1: float, dt0: float, opts: capi.Options) -> None:

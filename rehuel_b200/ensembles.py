@@ -72,3 +72,10 @@ def flops_per_attempt_dense_model(n: int, s: int, f_fun: int, f_jac: int):
     extra_820 = f_fun + 4 * n + 2 * n * n
     per_newton = 2 * N * N + 4 * N + c_r
     return fixed, extra_820, per_newton
+
+
+def mixed_tolerances(M: int, start: int = 0, seed: int = SEED) -> np.ndarray:
+    """Config 5: rtol_i = atol_i = 10^(-3 - 6 v_i), v_i hashed from the member index (one draw per
+    member, stream seed ^ 0x701)."""
+    v = splitmix64_uniform(start, M, seed ^ 0x701)
+    return 10.0 ** (-3.0 - 6.0 * v)

@@ -344,3 +344,45 @@ def test_brusselator_mol_64_equations_cta_per_system(capi, port):
         assert np.all(g.status == 0) and np.all(g.t_final == t1)
         assert se.max() <= PARITY_BOUND
         assert abs(int(g.counters["attempt"].sum()) - int(r.counters["attempt"].sum())) <= max(3, 0.02 * r.counters["attempt"].sum())
+
+
+def test_mixed_stiffness_mixed_tolerance_ensemble(capi, port):
+    """Config-5 shape: even members Robertson (config-2 sweep), odd members Van der Pol (config-3
+    sweep), per-member rtol = atol = 10^(-3-6v), newton tol = 0.1 rtol.  The two problem classes
+    run as two concurrently launched kernels (one work queue each); every member is checked
+    against an oracle run with ITS tolerances."""
+    import torch
+    from rehuel_b200 import ensembles
+    from rehuel_b200.device import DeviceEnsemble
+    M = 96
+    tol = ensembles.mixed_tolerances(M)
+    halves = {}
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for which, (prob, method, t1, y0h, P) in enumerate((
+            (capi.ROBERTSON, 211, 40.0, ensembles.ROBERTSON_Y0, ensembles.robertson_params(M // 2)),
+            (capi.VAN_DER_POL, 230, 2.0, ensembles.VDPOL_Y0, ensembles.vdpol_params(M // 2)))):
+        tl = torch.from_numpy(tol[which::2].copy()).cuda()
+        de = DeviceEnsemble(prob, method, M // 2, torch.from_numpy(y0h.copy()).cuda(), torch.from_numpy(P).cuda(),
+                            rtol=tl, atol=tl.clone(), newton_tol=(0.1 * tl).contiguous())
+        with torch.cuda.stream(streams[which]):
+            de.solve(0.0, t1, 1e-6, capi.make_options(1e-6, 1e-6))
+        halves[which] = (de, P, t1, method)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for which, name in ((0, "robertson"), (1, "van-der-pol")):
+        de, P, t1, method = halves[which]
+        y = de.y.cpu().numpy()
+        att = de.counter("attempt").cpu().numpy()
+        assert int((de.status != 0).sum()) == 0
+        same = 0
+        for i in range(M // 2):
+            ti = float(tol[which::2][i])
+            r = port.solve(name, method, 0.0, t1, 1e-6, [1.0, 0.0, 0.0] if which == 0 else [2.0, 0.0], P[:, i:i + 1].copy(),
+                           ref_options(ti, ti, newton_tol=0.1 * ti))
+            se = float(scaled_err(y[:, i:i + 1], r.y, ti, ti)[0])
+            worst = max(worst, se)
+            same += int(att[i] == r.counters["attempt"][0])
+            assert se <= PARITY_BOUND, (name, i, ti, se)
+        print(f"\n{name}: {M // 2} members with rtol in [{tol[which::2].min():.1e}, {tol[which::2].max():.1e}]: identical attempt counts {same}/{M // 2}")
+        assert same >= 0.9 * (M // 2)
+    print(f"mixed ensemble: worst scaled error {worst:.3e}")
