@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -270,7 +271,7 @@ struct DeviceShard {
 	int dev = 0;
 	size_t off = 0, m = 0;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 	void *slab = nullptr;
 	rehuel_device_io io{};
 	unsigned long long *d_stats = nullptr;
@@ -283,6 +284,7 @@ struct DeviceShard {
 		if (ev0 || ev1 || stream) cudaSetDevice(dev);
 		if (ev0) cudaEventDestroy(ev0);
 		if (ev1) cudaEventDestroy(ev1);
+		if (ev2) cudaEventDestroy(ev2);
 		if (stream) cudaStreamDestroy(stream);
 	}
 };
@@ -419,13 +421,17 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 	out->steps = counters + (size_t)REHUEL_CNT_STEPS * M;
 
 	// ---- work units: GPU g owns the contiguous members [M*g/G, M*(g+1)/G); each GPU's share is cut
-	// into up to 8 chunks (>= 128 Ki members each) on separate streams so that the H2D copy of
+	// into up to 6 chunks (>= 128 Ki members each) on separate streams so that the H2D copy of
 	// chunk i+1 and the D2H copies of chunk i-1 overlap the kernel of chunk i.
 	std::deque<DeviceShard> shards; // deque: elements are never moved (DeviceShard owns CUDA handles)
 	for (int g = 0; g < n_gpus; ++g) {
 		const size_t lo = M * (size_t)g / (size_t)n_gpus, hi = M * (size_t)(g + 1) / (size_t)n_gpus;
 		size_t chunks = (hi - lo) / (128u << 10);
-		chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+		chunks = chunks < 1 ? 1 : (chunks > 6 ? 6 : chunks); // measured best at 2^20 members: 6 (e2e 4.08 ms vs 5.5 unchunked)
+		if (const char *e = std::getenv("REHUEL_CHUNKS")) { // tuning aid
+			const long v = std::atol(e);
+			if (v >= 1 && v <= 8) chunks = (size_t)v;
+		}
 		if (n_samples_cap) chunks = 1;
 		for (size_t c = 0; c < chunks; ++c) {
 			shards.emplace_back();
@@ -444,6 +450,7 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			CUDA_TRY(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
 			CUDA_TRY(cudaEventCreate(&sh.ev0));
 			CUDA_TRY(cudaEventCreate(&sh.ev1));
+			CUDA_TRY(cudaEventCreate(&sh.ev2));
 			const size_t dbytes = Slab::need(y0_broadcast ? (size_t)n : (size_t)n * m, 8) + Slab::need((size_t)p * m, 8) +
 			                      Slab::need((size_t)n * m, 8) + 2 * Slab::need(m, 8) + 2 * Slab::need(m, 4) +
 			                      Slab::need((size_t)REHUEL_NCOUNTERS * m, 4) + Slab::need(1, 8) + Slab::need(kStatWords, 8) +
@@ -491,10 +498,9 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			int rr = launch(k, tb, sh.stream, nullptr);
 			if (rr) return rr;
 			CUDA_TRY(cudaEventRecord(sh.ev1, sh.stream));
-			ensemble_stats_kernel<<<148, 256, 0, sh.stream>>>(sh.io.counters, sh.io.status, m, sh.d_stats);
-			CUDA_TRY(cudaGetLastError());
-			g_launches.fetch_add(1);
-			// D2H
+			// D2H of the per-member results first: the statistics kernel below has to wait for free
+			// SM slots behind the persistent kernels of the following chunks, and must not hold the
+			// bulk copies back with it (measured: without this order no copy overlapped any kernel)
 			CUDA_TRY(cudaMemcpy2DAsync(out->y + sh.off, sizeof(double) * M, sh.io.y, sizeof(double) * m,
 			                           sizeof(double) * m, n, cudaMemcpyDeviceToHost, sh.stream));
 			CUDA_TRY(cudaMemcpyAsync(out->t_final + sh.off, sh.io.t_final, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
@@ -503,8 +509,6 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			CUDA_TRY(cudaMemcpy2DAsync(counters + sh.off, sizeof(unsigned) * M, sh.io.counters, sizeof(unsigned) * m,
 			                           sizeof(unsigned) * m, REHUEL_NCOUNTERS, cudaMemcpyDeviceToHost, sh.stream));
 			CUDA_TRY(cudaMemcpyAsync(out->n_samples + sh.off, sh.io.n_samples, sizeof(unsigned) * m, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(h_stats + si * kStatWords, sh.d_stats, sizeof(unsigned long long) * kStatWords,
-			                         cudaMemcpyDeviceToHost, sh.stream));
 			if (n_samples_cap) {
 				CUDA_TRY(cudaMemcpy2DAsync(out->t_samples + sh.off, sizeof(double) * M, sh.io.t_samples, sizeof(double) * m,
 				                           sizeof(double) * m, n_samples_cap, cudaMemcpyDeviceToHost, sh.stream));
@@ -514,6 +518,24 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 				                           sizeof(double) * m, n_samples_cap * n, cudaMemcpyDeviceToHost, sh.stream));
 			}
 		}
+		for (size_t si = 0; si < shards.size(); ++si) { // statistics epilogue, after every bulk copy is queued
+			DeviceShard &sh = shards[si];
+			if (sh.m == 0) continue;
+			CUDA_TRY(cudaSetDevice(sh.dev));
+			ensemble_stats_kernel<<<148, 256, 0, sh.stream>>>(sh.io.counters, sh.io.status, sh.m, sh.d_stats);
+			CUDA_TRY(cudaGetLastError());
+			g_launches.fetch_add(1);
+			CUDA_TRY(cudaMemcpyAsync(h_stats + si * kStatWords, sh.d_stats, sizeof(unsigned long long) * kStatWords,
+			                         cudaMemcpyDeviceToHost, sh.stream));
+		}
+		const bool timing = std::getenv("REHUEL_TIMING") != nullptr;
+		const double t_issued = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();
+		if (timing)
+			for (DeviceShard &sh : shards)
+				if (sh.m) {
+					cudaSetDevice(sh.dev);
+					cudaEventRecord(sh.ev2, sh.stream);
+				}
 		// wait; kernel_ms = per device, first kernel start -> last kernel end; max over devices
 		std::vector<double> kms(n_gpus, 0.0);
 		for (DeviceShard &sh : shards) {
@@ -532,6 +554,20 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 				if (ms > kms[g]) kms[g] = ms;
 			}
 			if (kms[g] > out->kernel_ms) out->kernel_ms = kms[g];
+		}
+		if (timing) {
+			const double t_synced = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();
+			std::fprintf(stderr, "[rehuel timing] host: all work issued at %.3f ms, synced at %.3f ms\n", t_issued, t_synced);
+			DeviceShard *first = nullptr;
+			for (DeviceShard &sh : shards) {
+				if (!sh.m) continue;
+				if (!first) first = &sh;
+				float a0 = 0, a1 = 0, a2 = 0;
+				cudaEventElapsedTime(&a0, first->ev0, sh.ev0);
+				cudaEventElapsedTime(&a1, first->ev0, sh.ev1);
+				cudaEventElapsedTime(&a2, first->ev0, sh.ev2);
+				std::fprintf(stderr, "[rehuel timing] shard off=%zu m=%zu: kernel %.3f..%.3f ms, copies done %.3f ms\n", sh.off, sh.m, a0, a1, a2);
+			}
 		}
 		return REHUEL_OK;
 	};
