@@ -51,6 +51,23 @@ constexpr int kNewtonSuccess = 0, kNewtonMaxit = 3; // newton.hpp:45-51
 constexpr int kFastIters = REHUEL_FAST_ITERS; // Newton iterations a lane may take before it is parked for a slow trip
 constexpr int kParkLanes = 16; // parked lanes per warp that trigger a slow trip
 
+// Reciprocal for LU pivots and 1/dt: MUFU.RCP64H seed (~20 bits) + two Newton steps (quadratic:
+// 20 -> 40 -> 80 bits, i.e. correctly rounded up to ~1 ulp), 5 instructions and no slow path
+// instead of the ~14-instruction IEEE division.  Only used where the result feeds the LINEAR
+// SOLVES (their rounding is not part of the parity contract: the decoupled solve already differs
+// from the reference's dense LU in the last bits); the step-size controller and the error norm
+// keep IEEE divisions.  0, Inf and NaN pivots still produce Inf/NaN and fail the Newton iteration.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	double e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	return r;
+}
+
 // ------------------------------------------------------------------ small dense LU, registers
 template <int N>
 struct LuReal {
@@ -84,7 +101,7 @@ __device__ __forceinline__ void lu_factor(LuReal<N> &m)
 				m.a[i][j] = sw ? u : w;
 			}
 		}
-		const double rp = 1.0 / m.a[k][k];
+		const double rp = fast_rcp(m.a[k][k]);
 		m.a[k][k] = rp;
 #pragma unroll
 		for (int i = k + 1; i < N; ++i) {
@@ -157,7 +174,7 @@ __device__ __forceinline__ void lu_factor(LuCplx<N> &m)
 		}
 		// reciprocal pivot 1/(a+ib) = (a-ib)/(a^2+b^2)
 		const double pr = m.re[k][k], pi = m.im[k][k];
-		const double rden = 1.0 / fma(pr, pr, pi * pi);
+		const double rden = fast_rcp(fma(pr, pr, pi * pi));
 		const double rr = pr * rden, ri = -pi * rden;
 		m.re[k][k] = rr;
 		m.im[k][k] = ri;
@@ -358,10 +375,10 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				LuReal<N> lur;  // (mu_r I - J)        (dummy when NR == 0 and EST != EST_OWN_LU)
 				LuCplx<N> luc[NC > 0 ? NC : 1];
 				LuReal<N> lue;  // E/gam = (1/gam) I - J, only for EST_OWN_LU
-				const double rdt = 1.0 / dt;
+				const double rdt = fast_rcp(dt);
 				// EST_REUSE: mu_r = 1/(gamma*dt) instead of gamma_hat/dt (equal to 1e-15) so that
 				// the same factors also serve E = I - gamma*dt*J of the error estimate.
-				const double mur = (EST == EST_REUSE) ? 1.0 / (tb.gamma * dt) : tb.gamma_hat * rdt;
+				const double mur = (EST == EST_REUSE) ? tb.rgamma * rdt : tb.gamma_hat * rdt;
 				{
 					double J[N][N];
 					F::jac(t, y, p, J); // irk.hpp:425
@@ -386,7 +403,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						lu_factor(luc[c]);
 					}
 					if (EST == EST_OWN_LU) {
-						const double mue = 1.0 / (tb.gamma * dt);
+						const double mue = tb.rgamma * rdt;
 #pragma unroll
 						for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -550,7 +567,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						} else if (EST == EST_OWN_LU) {
 							lu_solve(lue, v);
 						}
-						const double sc = (EST == EST_IDENTITY) ? dt : 1.0 / tb.gamma;
+						const double sc = (EST == EST_IDENTITY) ? dt : tb.rgamma;
 #pragma unroll
 						for (int k = 0; k < N; ++k) v[k] *= sc;
 					};

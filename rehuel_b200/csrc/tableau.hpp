@@ -53,6 +53,7 @@ struct DevTableau {
 	double d[S], d2[S];
 	double T[S][S], Ti[S][S];
 	double gamma;     // tableau gamma (error estimator)
+	double rgamma;    // 1/gamma (0 if gamma == 0)
 	double gamma_hat; // real eigenvalue of inv(A) (0 if none)
 	double alpha[NC > 0 ? NC : 1], beta[NC > 0 ? NC : 1];
 	double expo;      // 1/(1+min(order,order2))  (irk.hpp:588, 774)
@@ -74,6 +75,7 @@ inline DevTableau<S, NC> make_dev_tableau(const Tableau &tb)
 		dt.d2[i] = tb.d2[i];
 	}
 	dt.gamma = tb.gamma;
+	dt.rgamma = tb.gamma != 0.0 ? 1.0 / tb.gamma : 0.0;
 	dt.gamma_hat = tb.gamma_hat;
 	for (int k = 0; k < NC; ++k) {
 		dt.alpha[k] = tb.alpha[k];
