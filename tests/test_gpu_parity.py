@@ -386,3 +386,24 @@ def test_mixed_stiffness_mixed_tolerance_ensemble(capi, port):
         print(f"\n{name}: {M // 2} members with rtol in [{tol[which::2].min():.1e}, {tol[which::2].max():.1e}]: identical attempt counts {same}/{M // 2}")
         assert same >= 0.9 * (M // 2)
     print(f"mixed ensemble: worst scaled error {worst:.3e}")
+
+
+def test_c_abi_multi_gpu_sharding_is_bit_identical(capi):
+    """rehuel_irk_ensemble(..., n_gpus=G): contiguous member shards on G devices of one process must
+    give every member the bits the 1-GPU run gives it (members are independent,
+    the kernel is deterministic per member), and the summed statistics must agree."""
+    import torch
+    G = torch.cuda.device_count()
+    if G < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from rehuel_b200 import ensembles
+    M = 100_003  # odd on purpose
+    P = ensembles.robertson_params(M)
+    o = capi.make_options(1e-6, 1e-6)
+    one = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, o, n_gpus=1)
+    for g in sorted({2, G}):
+        many = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, o, n_gpus=g)
+        assert np.array_equal(one.y, many.y) and np.array_equal(one.status, many.status)
+        for k in one.counters:
+            assert np.array_equal(one.counters[k], many.counters[k]), k
+        assert one.sum == many.sum
