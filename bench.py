@@ -171,6 +171,32 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Pin this rank (and the pinned buffers it allocates afterwards: first touch) to the NUMA node
+    its GPU hangs off; with several ranks per box the host<->device copies of the e2e path otherwise
+    cross sockets.  Best effort: returns a note for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        bdf = f"{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa: gpu {bdf} -> node {node}, {len(allowed)} cpus"
+        return f"numa: node {node} has no allowed cpus"
+    except Exception as e:  # noqa: BLE001
+        return f"numa: not bound ({type(e).__name__})"
+
+
 def run_gpu_arm(args) -> None:
     import numpy as np
     import torch
@@ -184,6 +210,7 @@ def run_gpu_arm(args) -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa_note = bind_to_gpu_numa_node(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -260,7 +287,7 @@ def run_gpu_arm(args) -> None:
             capi.ROBERTSON, capi.RADAU_IIA_53, t0, t1, DT0, M, 3,
             capi.C.cast(y0_host.data_ptr(), capi._PD), 1, capi.C.cast(P_host.data_ptr(), capi._PD),
             capi.C.byref(opts), 0, 1, capi.C.byref(res)))
-        d2h = (3 + 1 + 1) * 8 * M + 4 * M + 4 * M * (capi.NCOUNTERS + 1)
+        d2h = (3 + 1 + 1) * 8 * M + 4 * M + 4 * M * capi.NCOUNTERS
         checksum = res.sum.attempt
         capi.lib.rehuel_result_free(capi.C.byref(res))
         return d2h, checksum
@@ -300,7 +327,7 @@ def run_gpu_arm(args) -> None:
                        "parallelism": f"member-sharded x{world} (no data-path collective)",
                        "l2": "flushed between timed steps (256 MiB fill, outside the per-step event pair)",
                        "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
-                       "wall_s_timed_region_rank0": wall},
+                       "wall_s_timed_region_rank0": wall, "host_binding_rank0": numa_note},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P_host.numel() * 8 + 24),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * et.item() / args.steps,
                     "api": "rehuel_irk_ensemble (C ABI, pinned host buffers, results copied back)"},

@@ -403,6 +403,7 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 	out->status = hs.take<int>(M);
 	unsigned *counters = hs.take<unsigned>((size_t)REHUEL_NCOUNTERS * M); // [NCOUNTERS][M]
 	out->n_samples = hs.take<unsigned>(M);
+	if (!n_samples_cap) std::memset(out->n_samples, 0, sizeof(unsigned) * M); // not copied back: no samples were kept
 	unsigned long long *h_stats = hs.take<unsigned long long>(max_shards * kStatWords);
 	std::memset(h_stats, 0, sizeof(unsigned long long) * max_shards * kStatWords);
 	if (n_samples_cap) {
@@ -508,7 +509,8 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			CUDA_TRY(cudaMemcpyAsync(out->status + sh.off, sh.io.status, sizeof(int) * m, cudaMemcpyDeviceToHost, sh.stream));
 			CUDA_TRY(cudaMemcpy2DAsync(counters + sh.off, sizeof(unsigned) * M, sh.io.counters, sizeof(unsigned) * m,
 			                           sizeof(unsigned) * m, REHUEL_NCOUNTERS, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(out->n_samples + sh.off, sh.io.n_samples, sizeof(unsigned) * m, cudaMemcpyDeviceToHost, sh.stream));
+			if (n_samples_cap)
+				CUDA_TRY(cudaMemcpyAsync(out->n_samples + sh.off, sh.io.n_samples, sizeof(unsigned) * m, cudaMemcpyDeviceToHost, sh.stream));
 			if (n_samples_cap) {
 				CUDA_TRY(cudaMemcpy2DAsync(out->t_samples + sh.off, sizeof(double) * M, sh.io.t_samples, sizeof(double) * m,
 				                           sizeof(double) * m, n_samples_cap, cudaMemcpyDeviceToHost, sh.stream));
