@@ -14,7 +14,7 @@ NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC
              --expt-relaxed-constexpr -Xptxas -v
 SRC       := rehuel_b200/csrc
 LIB       := rehuel_b200/librehuel_b200.so
-OBJS      := build/capi.o build/tableau.o
+OBJS      := build/capi.o build/order.o build/tableau.o
 
 .PHONY: all oracle clean sass examples
 all: $(LIB)
@@ -22,8 +22,11 @@ all: $(LIB)
 build:
 	mkdir -p build
 
-build/capi.o: $(SRC)/capi.cu $(SRC)/irk_thread.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh $(SRC)/tableau.hpp include/rehuel_b200.h | build
+build/capi.o: $(SRC)/capi.cu $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh $(SRC)/tableau.hpp include/rehuel_b200.h | build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/capi.ptxas.log || (cat build/capi.ptxas.log; false)
+
+build/order.o: $(SRC)/order.cu $(SRC)/launch.cuh include/rehuel_b200.h | build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/order.ptxas.log || (cat build/order.ptxas.log; false)
 
 build/tableau.o: $(SRC)/tableau.cpp $(SRC)/tableau.hpp $(SRC)/tableau_eig.inc | build
 	$(HOSTCXX) -O2 -std=c++17 -fPIC -Wall -Wextra -c $< -o $@

@@ -220,13 +220,14 @@ def run_gpu_arm(args) -> None:
 
     M = args.members
     t0, t1 = SPANS[args.span]
-    opts = capi.make_options(RTOL, ATOL)
+    handout = {"index": capi.ORDER_INDEX, "locality": capi.ORDER_LOCALITY}[args.handout]
+    opts = capi.make_options(RTOL, ATOL, handout_order=handout)
     # rank r owns members [r*M, (r+1)*M) of the sweep (weak scaling; any rank can generate its slice)
     P_host = torch.from_numpy(ensembles.robertson_params(M, start=rank * M)).pin_memory()
     y0_host = torch.from_numpy(ensembles.ROBERTSON_Y0.copy()).pin_memory()
     P_dev = P_host.to(dev)
     y0_dev = y0_host.to(dev)
-    ens = DeviceEnsemble(capi.ROBERTSON, capi.RADAU_IIA_53, M, y0_dev, P_dev)
+    ens = DeviceEnsemble(capi.ROBERTSON, capi.RADAU_IIA_53, M, y0_dev, P_dev, handout_order=handout)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -242,25 +243,28 @@ def run_gpu_arm(args) -> None:
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = capi.kernel_launches()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     barrier()
     wall0 = time.perf_counter()
-    for a, b in ev:
+    for a, m, b in ev:
         flush.fill_(1)                 # L2 flush between timed iterations (outside the event pair)
         a.record()
-        ens.solve(t0, t1, DT0, opts)   # ONE launch of the integration kernel
+        ens.reorder()                  # hand-out order from the parameters (2 kernels + radix sort); part of the step
+        m.record()
+        ens.launch(t0, t1, DT0, opts)  # ONE launch of the integration kernel
         b.record()
     barrier()
     wall = time.perf_counter() - wall0
     launches = capi.kernel_launches() - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
+    step_ms = [a.elapsed_time(b) for a, m, b in ev]
+    kernel_ms = [m.elapsed_time(b) for a, m, b in ev]   # the integration kernel alone (roofline)
     total_ms = float(sum(step_ms))
-    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    tt = torch.tensor([total_ms, float(sum(kernel_ms))], dtype=torch.float64, device=dev)
     ll = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ll, op=dist.ReduceOp.SUM)
-    total_ms_max = tt.item()
+    total_ms_max, kernel_ms_max = tt[0].item(), tt[1].item()
 
     # ---------------- statistics from the kernel's own counters (the one collective of the path)
     att = ens.counter("attempt").double()
@@ -315,7 +319,7 @@ def run_gpu_arm(args) -> None:
     if rank == 0:
         ms_per_step = total_ms_max / args.steps
         value = world * M * args.steps / (total_ms_max * 1e-3)
-        kern_s = ms_per_step * 1e-3
+        kern_s = kernel_ms_max / args.steps * 1e-3
         ach_dense = tot["flops_dense_model"] / world / kern_s / 1e12   # per GPU, per launch
         ach_exec = tot["flops_executed_model"] / world / kern_s / 1e12
         info = capi.kernel_info(capi.ROBERTSON, capi.RADAU_IIA_53)
@@ -327,6 +331,7 @@ def run_gpu_arm(args) -> None:
                        "parallelism": f"member-sharded x{world} (no data-path collective)",
                        "l2": "flushed between timed steps (256 MiB fill, outside the per-step event pair)",
                        "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
+                       "handout_order": args.handout + (" (Morton order of the rate constants, recomputed on the device inside every timed step)" if handout else ""),
                        "wall_s_timed_region_rank0": wall, "host_binding_rank0": numa_note},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P_host.numel() * 8 + 24),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * et.item() / args.steps,
@@ -335,7 +340,7 @@ def run_gpu_arm(args) -> None:
             "clocks": clocks,
             "roofline": {
                 "bound": "fp64", "achieved": ach_dense, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": ach_dense / peak_tflops, "traffic": None,
+                "frac": ach_dense / peak_tflops, "traffic": None, "kernel_ms_per_launch": kernel_ms_max / args.steps,
                 "model": "SURVEY.md 8(d) dense-algorithm flops: 873*attempts + 321*newton_iters + 41*uses_of_8.20, from the kernel's per-member counters",
                 "peak_source": "measured in this run: register-resident DFMA chains (rehuel_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": ach_dense / FP64_NOMINAL_TFLOPS,
@@ -350,7 +355,7 @@ def run_gpu_arm(args) -> None:
                       "newton_iters_per_attempt": tot["newton_iters"] / max(tot["attempt"], 1),
                       "fun_evals": tot["fun_evals"], "jac_evals": tot["jac_evals"], "failed_members": tot["n_failed"],
                       "max_attempts": tot["max_attempt"], "mass_conservation_max_abs_err_rank0": mass_err,
-                      "step_ms": step_ms},
+                      "step_ms": step_ms, "kernel_ms": kernel_ms},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -366,6 +371,8 @@ def main() -> None:
     ap.add_argument("--span", choices=tuple(SPANS), default="short")
     ap.add_argument("--members", type=int, default=M_PER_GPU, help="members per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--handout", choices=("index", "locality"), default="locality",
+                    help="order in which members are handed to the GPU lanes (results do not depend on it)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -75,7 +75,16 @@ typedef struct rehuel_options {
 	int newton_refresh_jac;         /* newton.hpp:59    default 10 */
 	int output_mode;                /* options.hpp:96-103 bit 0: store samples (STORE_IN_VECTORS); default 1 */
 	unsigned long long output_interval; /* options.hpp:104 every k-th ACCEPTED step is a sample; default 1 */
+	int handout_order;              /* NEW (scheduling of the batched overload, no reference counterpart): order in which
+	                                   the host-buffer entry points hand members to the GPU lanes.  REHUEL_ORDER_INDEX,
+	                                   REHUEL_ORDER_LOCALITY (default) or REHUEL_ORDER_LOCALITY_DESC.  Results do not
+	                                   depend on it. */
 } rehuel_options;
+
+#define REHUEL_ORDER_INDEX          0 /* member i is the i-th to be handed out */
+#define REHUEL_ORDER_LOCALITY       1 /* space-filling-curve order of the parameter vectors: members with nearby
+                                         parameters share a warp and stay in lockstep (see rehuel_locality_order) */
+#define REHUEL_ORDER_LOCALITY_DESC  2 /* the same curve walked backwards (e.g. hand out the stiff end of a sweep first) */
 
 /* Fills in the reference's constructor defaults (options.hpp:49-58, irk.hpp:103-107,
  * newton.hpp:58-60, options.hpp:103-104). */
@@ -204,6 +213,17 @@ typedef struct rehuel_device_io {
 int rehuel_irk_ensemble_device(int problem, int method, double t0, double t1, double dt0, size_t M,
                                int n_hint, const rehuel_options *opts, const rehuel_device_io *io,
                                void *cuda_stream);
+
+/* Parameter-locality hand-out order for rehuel_device_io.order (device pointers, enqueued on
+ * `cuda_stream`, no synchronisation): order[q] = index of the member handed out q-th, following a
+ * Morton curve through the first min(p,3) parameters (strictly positive parameters on a log
+ * scale).  Members with nearby parameters take nearly the same steps, so the 32 lanes of a warp
+ * stay in lockstep; results are unchanged.  `workspace` must hold
+ * rehuel_locality_order_workspace(M) bytes (0 = error, see rehuel_last_error()).
+ * rehuel_irk_ensemble does this internally per options.handout_order. */
+size_t rehuel_locality_order_workspace(size_t M);
+int rehuel_locality_order(const double *params, int p, size_t M, int descending, unsigned *order,
+                          void *workspace, size_t workspace_bytes, void *cuda_stream);
 
 /* Batched irk::merge_rk_output (irk.cpp:750-783): concatenates two legs of a restarted ensemble
  * into `a` (counters added -- fun_evals/jac_evals are NOT, exactly like the reference --, status

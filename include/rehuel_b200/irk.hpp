@@ -77,8 +77,9 @@ enum rk_methods {
 
 struct solver_options : common_solver_options {
 	solver_options() : adaptive_step_size(true), use_newton_iters_adaptive_step(true), verbose_newton(false),
-	                   extrapolate_stage(false) {}
+	                   extrapolate_stage(false), handout_order(REHUEL_ORDER_LOCALITY) {}
 	bool adaptive_step_size, use_newton_iters_adaptive_step, verbose_newton, extrapolate_stage;
+	int handout_order; // NEW: REHUEL_ORDER_* (scheduling of the batched overload only; results do not depend on it)
 };
 inline solver_options default_solver_options() { return solver_options(); }
 
@@ -102,6 +103,7 @@ inline rehuel_options to_c_options(const solver_options &so, const output_option
 	o.newton_refresh_jac = so.newton_opts->refresh_jac;
 	o.output_mode = (int)oo.output_mode;
 	o.output_interval = oo.output_interval;
+	o.handout_order = so.handout_order;
 	return o;
 }
 

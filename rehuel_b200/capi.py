@@ -37,7 +37,11 @@ class Options(C.Structure):
         ("newton_tol", C.c_double), ("newton_dx_delta", C.c_double),
         ("newton_maxit", C.c_int), ("newton_refresh_jac", C.c_int),
         ("output_mode", C.c_int), ("output_interval", C.c_ulonglong),
+        ("handout_order", C.c_int),
     ]
+
+
+ORDER_INDEX, ORDER_LOCALITY, ORDER_LOCALITY_DESC = 0, 1, 2
 
 
 class Stats(C.Structure):
@@ -104,6 +108,10 @@ def _load() -> C.CDLL:
     lib.rehuel_irk_single.argtypes = [
         C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, _PD, _PD, C.POINTER(Options),
         C.c_size_t, C.POINTER(C.c_size_t), _PD, _PD, _PD, C.POINTER(C.c_ulonglong), _PD, _PI]
+    lib.rehuel_locality_order_workspace.restype = C.c_size_t
+    lib.rehuel_locality_order_workspace.argtypes = [C.c_size_t]
+    lib.rehuel_locality_order.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.c_void_p]
     lib.rehuel_result_free.argtypes = [C.POINTER(Result)]
     lib.rehuel_result_merge.argtypes = [C.POINTER(Result), C.POINTER(Result)]
     return lib
@@ -117,6 +125,7 @@ EXPORTS = (
     "rehuel_problem_dims", "rehuel_get_coefficients", "rehuel_irk_ensemble", "rehuel_result_free",
     "rehuel_irk_single", "rehuel_irk_ensemble_device", "rehuel_result_merge", "rehuel_kernel_launches",
     "rehuel_kernel_info", "rehuel_last_error", "rehuel_version", "rehuel_fp64_peak", "rehuel_release_cached_memory",
+    "rehuel_locality_order_workspace", "rehuel_locality_order",
 )
 
 
@@ -137,7 +146,7 @@ def default_options() -> Options:
 
 def make_options(rel_tol=1e-4, abs_tol=None, max_dt=0.0, max_steps=-1, adaptive=True, out_interval=0,
                  newton_tol=None, newton_dx_delta=1e-4, newton_maxit=5000, newton_refresh_jac=10,
-                 output_mode=1, output_interval=1) -> Options:
+                 output_mode=1, output_interval=1, handout_order=ORDER_LOCALITY) -> Options:
     """Reference defaults, with newton_tol = 0.1*min(rtol, atol) unless given -- what the example
     driver and the 4-argument odeint do (examples/example_equations.cpp:220, irk.hpp:921)."""
     if abs_tol is None:
@@ -145,7 +154,7 @@ def make_options(rel_tol=1e-4, abs_tol=None, max_dt=0.0, max_steps=-1, adaptive=
     if newton_tol is None:
         newton_tol = 0.1 * min(rel_tol, abs_tol)
     return Options(rel_tol, abs_tol, max_dt, max_steps, int(adaptive), out_interval, newton_tol,
-                   newton_dx_delta, newton_maxit, newton_refresh_jac, output_mode, output_interval)
+                   newton_dx_delta, newton_maxit, newton_refresh_jac, output_mode, output_interval, handout_order)
 
 
 def name_to_method(name: str) -> int:

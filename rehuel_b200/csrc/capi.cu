@@ -115,6 +115,8 @@ static int prepare(int method, double t0, double t1, double dt0, size_t M, const
 	if (o->newton_maxit < 1) return fail(REHUEL_EINVAL, "newton_maxit must be >= 1");
 	if (o->newton_refresh_jac <= 0) return fail(REHUEL_EINVAL, "newton_refresh_jac must be > 0 (the reference divides by it, irk.hpp:485)");
 	if (o->output_interval == 0) return fail(REHUEL_EINVAL, "output_interval must be > 0 (irk.hpp:825 takes step %% output_interval)");
+	if (o->handout_order < REHUEL_ORDER_INDEX || o->handout_order > REHUEL_ORDER_LOCALITY_DESC)
+		return fail(REHUEL_EINVAL, "handout_order must be REHUEL_ORDER_INDEX, _LOCALITY or _LOCALITY_DESC");
 	std::memset(&ka, 0, sizeof ka);
 	ka.t0 = t0;
 	ka.t1 = t1;
@@ -456,11 +458,16 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			                      Slab::need((size_t)n * m, 8) + 2 * Slab::need(m, 8) + 2 * Slab::need(m, 4) +
 			                      Slab::need((size_t)REHUEL_NCOUNTERS * m, 4) + Slab::need(1, 8) + Slab::need(kStatWords, 8) +
 			                      3 * Slab::need(n_samples_cap * m, 8) * (size_t)(n > 1 ? n : 1);
+			// hand-out order (order.cu): only pays where the lanes of a warp integrate different members
+			const bool reorder = opts->handout_order != REHUEL_ORDER_INDEX && p > 0 && n <= 4 && m >= 4096;
+			const size_t order_ws = reorder ? locality_order_workspace(m) : 0;
+			if (reorder && !order_ws) return REHUEL_ECUDA;
+			const size_t dbytes_all = dbytes + (reorder ? Slab::need(m, 4) + Slab::need(order_ws, 1) : 0);
 			Slab ds;
-			sh.slab = g_cache.get(sh.dev, dbytes);
+			sh.slab = g_cache.get(sh.dev, dbytes_all);
 			if (!sh.slab) return REHUEL_ENOMEM;
 			ds.base = static_cast<char *>(sh.slab);
-			ds.size = dbytes;
+			ds.size = dbytes_all;
 			double *d_y0 = ds.take<double>(y0_broadcast ? (size_t)n : (size_t)n * m);
 			double *d_par = ds.take<double>((size_t)p * m);
 			sh.io.y = ds.take<double>((size_t)n * m);
@@ -491,6 +498,13 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 				CUDA_TRY(cudaMemcpy2DAsync(d_par, sizeof(double) * m, params + sh.off, sizeof(double) * M,
 				                           sizeof(double) * m, p, cudaMemcpyHostToDevice, sh.stream));
 			CUDA_TRY(cudaMemsetAsync(sh.d_stats, 0, sizeof(unsigned long long) * kStatWords, sh.stream));
+			if (reorder) {
+				unsigned *d_order = ds.take<unsigned>(m);
+				void *ws = ds.take<char>(order_ws);
+				int ro = locality_order(d_par, p, m, opts->handout_order == REHUEL_ORDER_LOCALITY_DESC, d_order, ws, order_ws, sh.stream);
+				if (ro) return ro;
+				sh.io.order = d_order;
+			}
 			KernelArgs k = ka;
 			k.M = m;
 			k.io = sh.io;
@@ -662,6 +676,7 @@ void rehuel_default_options(rehuel_options *o)
 	o->newton_refresh_jac = 10;        // newton.hpp:59
 	o->output_mode = 1;                // options.hpp:103 STORE_IN_VECTORS
 	o->output_interval = 1;            // options.hpp:104
+	o->handout_order = REHUEL_ORDER_LOCALITY;
 }
 
 int rehuel_name_to_method(const char *name) { return name_to_method(name); }

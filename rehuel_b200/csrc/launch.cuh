@@ -37,6 +37,11 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 int ensemble_device(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
                     const rehuel_options *opts, const rehuel_device_io *io, cudaStream_t stream);
 
+// Parameter-locality hand-out order (order.cu); same semantics as rehuel_locality_order.
+size_t locality_order_workspace(size_t M);
+int locality_order(const double *params, int p, size_t M, int descending, unsigned *order, void *workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+
 #define REHUEL_CUDA_TRY(expr)                                                                              \
 	do {                                                                                                   \
 		cudaError_t e_ = (expr);                                                                           \

@@ -40,6 +40,8 @@ const EigEntry kEig[] = {
 #include "tableau_eig.inc"
 };
 
+#include "tableau_dec.inc" // RADAU_IIA_95 / RADAU_IIA_137 as the reference prints them
+
 // x = A^-1 rhs for a small dense system, Gaussian elimination with row partial pivoting.
 bool small_solve(int s, const double A[MAX_S][MAX_S], const double *rhs, double *x)
 {
@@ -104,6 +106,23 @@ void build_interpolant(Tableau &tb)
 	tb.has_interp = true;
 }
 
+// Tableau given by decimal arrays (tableau_dec.inc): A row-major, b2 = b + coef*gamma.
+void set_decimal(Tableau &tb, int s, const double *A, const double *c, const double *b, const double *b2coef,
+                 double gamma, int order, int order2)
+{
+	tb.s = s;
+	tb.gamma = gamma;
+	tb.order = order;
+	tb.order2 = order2;
+	for (int i = 0; i < s; ++i) {
+		for (int j = 0; j < s; ++j) tb.A[i][j] = A[i * s + j];
+		tb.c[i] = c[i];
+		tb.b[i] = b[i];
+		const double cg = b2coef[i] * gamma; // the reference writes  b(i) -+ |coef|*gamma
+		tb.b2[i] = b[i] + cg;
+	}
+}
+
 void set_row(Tableau &tb, int i, std::initializer_list<double> row)
 {
 	int j = 0;
@@ -139,8 +158,28 @@ bool get_coefficients(int method, Tableau &tb)
 	tb.name = method_to_name(method);
 	const double r5 = std::sqrt(5.0), r6 = std::sqrt(6.0), r21 = std::sqrt(21.0);
 	bool interp = false;
+	tb.has_b2 = true;
 
 	switch (method) {
+	case 200: // IMPLICIT_EULER, irk.cpp:238-244: no embedded weights => odeint runs it with a fixed step (irk.hpp:890-895)
+		tb.s = 1;
+		tb.A[0][0] = 1.0;
+		tb.b[0] = 1.0;
+		tb.c[0] = 1.0;
+		tb.order = 1;
+		tb.order2 = 0;
+		tb.has_b2 = false;
+		break;
+	case 212: // RADAU_IIA_95, irk.cpp:393-437
+		set_decimal(tb, 5, radau_iia_95_A, radau_iia_95_c, radau_iia_95_b, radau_iia_95_b2_gamma_coef, radau_iia_95_gamma,
+		            radau_iia_95_order, radau_iia_95_order2);
+		interp = true;
+		break;
+	case 213: // RADAU_IIA_137, irk.cpp:439-533
+		set_decimal(tb, 7, radau_iia_137_A, radau_iia_137_c, radau_iia_137_b, radau_iia_137_b2_gamma_coef, radau_iia_137_gamma,
+		            radau_iia_137_order, radau_iia_137_order2);
+		interp = true;
+		break;
 	case 210: // RADAU_IIA_32, irk.cpp:342-360
 		tb.s = 2;
 		set_row(tb, 0, {5.0 / 12.0, -1.0 / 12.0});
@@ -208,10 +247,9 @@ bool get_coefficients(int method, Tableau &tb)
 	default:
 		return false;
 	}
-	tb.has_b2 = true;
 
 	if (!solve_transposed(tb, tb.b, tb.d)) return false;
-	if (!solve_transposed(tb, tb.b2, tb.d2)) return false;
+	if (tb.has_b2 && !solve_transposed(tb, tb.b2, tb.d2)) return false;
 
 	for (const EigEntry &e : kEig) {
 		if (std::strcmp(e.name, tb.name)) continue;

@@ -18,7 +18,10 @@ class DeviceEnsemble:
     def __init__(self, problem: int, method: int, M: int, y0: torch.Tensor, params: torch.Tensor,
                  n_samples_cap: int = 0, n_hint: int = 0, trace_cap: int = 0, trace_member: int = 0,
                  order: torch.Tensor | None = None, rtol: torch.Tensor | None = None,
-                 atol: torch.Tensor | None = None, newton_tol: torch.Tensor | None = None):
+                 atol: torch.Tensor | None = None, newton_tol: torch.Tensor | None = None,
+                 handout_order: int = capi.ORDER_INDEX):
+        """``order``: caller-supplied hand-out order (int32 [M]).  ``handout_order``: ORDER_LOCALITY(_DESC) makes
+        every ``solve`` recompute the parameter-locality order on the device first (rehuel_locality_order)."""
         assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
         dev = y0.device
         n, p = capi.problem_dims(problem, n_hint or y0.shape[0])
@@ -63,6 +66,15 @@ class DeviceEnsemble:
             assert order.is_cuda and order.dtype == torch.int32 and order.numel() == M
             self.order = order.contiguous()
             io.order = self.order.data_ptr()
+        self.handout_order = capi.ORDER_INDEX
+        if order is None and handout_order != capi.ORDER_INDEX and p:
+            self.handout_order = handout_order
+            self.order = torch.empty(M, dtype=torch.int32, device=dev)
+            ws = capi.lib.rehuel_locality_order_workspace(M)
+            if ws == 0:
+                raise capi.RehuelError(-2, capi.last_error())
+            self.order_ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+            io.order = self.order.data_ptr()
         if rtol is not None:
             for v in (rtol, atol, newton_tol):
                 assert v is not None and v.is_cuda and v.dtype == torch.float64 and v.numel() == M and v.is_contiguous()
@@ -70,13 +82,28 @@ class DeviceEnsemble:
             io.rtol, io.atol, io.newton_tol = rtol.data_ptr(), atol.data_ptr(), newton_tol.data_ptr()
         self.io = io
 
-    def solve(self, t0: float, t1: float, dt0: float, opts: capi.Options) -> None:
-        """Enqueue one ensemble solve on torch's current CUDA stream (asynchronous)."""
+    def reorder(self) -> None:
+        """Enqueue the parameter-locality hand-out order (no-op for index order / caller-given order)."""
+        if self.handout_order == capi.ORDER_INDEX:
+            return
+        stream = torch.cuda.current_stream(self.y.device).cuda_stream
+        with torch.cuda.device(self.y.device):
+            capi.check(capi.lib.rehuel_locality_order(
+                self.params.data_ptr(), self.p, self.M, int(self.handout_order == capi.ORDER_LOCALITY_DESC),
+                self.order.data_ptr(), self.order_ws.data_ptr(), self.order_ws.numel(), C.c_void_p(stream)))
+
+    def launch(self, t0: float, t1: float, dt0: float, opts: capi.Options) -> None:
+        """Enqueue the integration kernel alone on torch's current CUDA stream (asynchronous)."""
         stream = torch.cuda.current_stream(self.y.device).cuda_stream
         with torch.cuda.device(self.y.device):
             capi.check(capi.lib.rehuel_irk_ensemble_device(
                 self.problem, self.method, t0, t1, dt0, self.M, self.n_hint, C.byref(opts), C.byref(self.io),
                 C.c_void_p(stream)))
+
+    def solve(self, t0: float, t1: float, dt0: float, opts: capi.Options) -> None:
+        """One ensemble solve on torch's current CUDA stream (asynchronous): hand-out order, then the kernel."""
+        self.reorder()
+        self.launch(t0, t1, dt0, opts)
 
     def counter(self, name: str) -> torch.Tensor:
         return self.counters[capi.COUNTER_ROWS.index(name)]

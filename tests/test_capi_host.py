@@ -4,6 +4,7 @@ with the oracle, and -- no GPU here -- every compute entry point fails LOUDLY (n
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -27,9 +28,18 @@ def test_library_exports_every_declared_symbol(capi):
     assert set(capi.EXPORTS) <= declared
 
 
-def test_struct_layouts_match_header(capi):
-    # sizes a C compiler gives the header's structs (x86-64 SysV)
-    assert C.sizeof(capi.Options) == 8 * 3 + 8 + 4 + 4 + 8 + 8 + 4 + 4 + 4 + 4 + 8
+def test_struct_layouts_match_header(capi, tmp_path):
+    # the sizes and a few offsets gcc gives the header's structs must be the ctypes mirror's
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rehuel_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(rehuel_options), sizeof(rehuel_stats),'
+                   ' sizeof(rehuel_result), sizeof(rehuel_device_io), offsetof(rehuel_options, handout_order),'
+                   ' offsetof(rehuel_result, sum), offsetof(rehuel_device_io, order)); return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(capi.Options), C.sizeof(capi.Stats), C.sizeof(capi.Result), C.sizeof(capi.DeviceIO),
+                   capi.Options.handout_order.offset, capi.Result.sum.offset, capi.DeviceIO.order.offset]
     assert C.sizeof(capi.Stats) == 13 * 8
 
 

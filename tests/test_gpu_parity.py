@@ -327,6 +327,61 @@ def test_handout_order_and_slow_lane_parking_do_not_change_results(capi, port):
     assert scaled_err(y[:, idx], r.y, 1e-6, 1e-6).max() <= PARITY_BOUND
 
 
+def test_locality_handout_order_is_a_permutation_and_changes_no_result(capi):
+    """rehuel_locality_order: a permutation of the members that follows a Morton curve through the
+    parameters (checked against a numpy restatement), and solving in that order -- device path and
+    host-buffer path (options.handout_order) -- leaves every result and counter bit-identical."""
+    import torch
+    from rehuel_b200 import ensembles
+    from rehuel_b200.device import DeviceEnsemble
+    M = 20000
+    P = ensembles.robertson_params(M)
+    o = capi.make_options(1e-6, 1e-6)
+    Pd = torch.from_numpy(P).cuda()
+    y0 = torch.from_numpy(ensembles.ROBERTSON_Y0.copy()).cuda()
+    outs = {}
+    for name, mode in (("index", capi.ORDER_INDEX), ("loc", capi.ORDER_LOCALITY), ("desc", capi.ORDER_LOCALITY_DESC)):
+        de = DeviceEnsemble(capi.ROBERTSON, 211, M, y0, Pd, handout_order=mode)
+        de.solve(0.0, 40.0, 1e-6, o)
+        torch.cuda.synchronize()
+        outs[name] = (de.y.cpu().numpy().copy(), de.counters.cpu().numpy().copy(), de.status.cpu().numpy().copy())
+        if mode != capi.ORDER_INDEX:
+            order = de.order.cpu().numpy().astype(np.int64)
+            assert np.array_equal(np.sort(order), np.arange(M)), "not a permutation"
+            # numpy restatement of the key: positive parameters through their bit pattern, 7 bits per dimension
+            bits = P.view(np.int64).astype(np.float64)
+            lo, hi = bits.min(1, keepdims=True), bits.max(1, keepdims=True)
+            q = np.clip(((bits - lo) * (128.0 / (hi - lo))), 0, 127).astype(np.uint32)
+            key = np.zeros(M, dtype=np.uint32)
+            for b in range(7):
+                for d in range(3):
+                    key |= ((q[d] >> b) & 1) << (b * 3 + d)
+            if mode == capi.ORDER_LOCALITY_DESC:
+                key = (1 << 21) - 1 - key
+            assert np.all(np.diff(key[order].astype(np.int64)) >= 0), "members are not handed out along the curve"
+    for name in ("loc", "desc"):
+        for a, b in zip(outs[name], outs["index"]):
+            assert np.array_equal(a, b), name
+    for mode in (capi.ORDER_INDEX, capi.ORDER_LOCALITY):
+        h = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P,
+                              capi.make_options(1e-6, 1e-6, handout_order=mode))
+        assert np.array_equal(h.y, outs["index"][0])
+        assert np.array_equal(h.counters["attempt"], outs["index"][1][0].astype(np.uint32))
+    # one parameter (Van der Pol sweep): the curve is the sorted order
+    Pv = ensembles.vdpol_params(8192)
+    rng = np.random.default_rng(3)
+    Pv = Pv[:, rng.permutation(8192)].copy()
+    de = DeviceEnsemble(capi.VAN_DER_POL, 230, 8192, torch.from_numpy(ensembles.VDPOL_Y0.copy()).cuda(),
+                        torch.from_numpy(Pv).cuda(), handout_order=capi.ORDER_LOCALITY)
+    de.reorder()
+    torch.cuda.synchronize()
+    order = de.order.cpu().numpy().astype(np.int64)
+    assert np.array_equal(np.sort(order), np.arange(8192))
+    sorted_mu = Pv[0][order]
+    # 21-bit resolution of the log scale: sorted up to ties inside one cell
+    assert np.all(np.diff(np.log10(sorted_mu)) >= -6.0 / (1 << 21) * 1.01)
+
+
 def test_brusselator_mol_64_equations_cta_per_system(capi, port):
     """Config-4 shape: 1-D Brusselator method of lines, Ng = 32 (n = 64), CTA-per-system kernel with
     the decoupled LUs in shared memory, against the CPU oracle (dense 192x192 / 320x320 LU)."""
