@@ -16,7 +16,7 @@ SRC       := rehuel_b200/csrc
 LIB       := rehuel_b200/librehuel_b200.so
 OBJS      := build/capi.o build/order.o build/tableau.o
 
-.PHONY: all oracle clean sass examples
+.PHONY: all oracle clean sass examples tableaux
 all: $(LIB)
 
 build:
@@ -28,14 +28,16 @@ build/capi.o: $(SRC)/capi.cu $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/lau
 build/order.o: $(SRC)/order.cu $(SRC)/launch.cuh include/rehuel_b200.h | build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/order.ptxas.log || (cat build/order.ptxas.log; false)
 
-build/tableau.o: $(SRC)/tableau.cpp $(SRC)/tableau.hpp $(SRC)/tableau_eig.inc | build
+build/tableau.o: $(SRC)/tableau.cpp $(SRC)/tableau.hpp $(SRC)/tableau_eig.inc $(SRC)/tableau_dec.inc | build
 	$(HOSTCXX) -O2 -std=c++17 -fPIC -Wall -Wextra -c $< -o $@
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(OBJS) -cudart shared
 
-$(SRC)/tableau_eig.inc: tools/gen_tableaux.py
-	python tools/gen_tableaux.py > $@ 2>/dev/null
+# Regenerates the committed tableau_eig.inc / tableau_dec.inc (+ oracle/tableau_dec.inc); needs mpmath.
+# Deliberately not a file dependency: a fresh checkout must build without running the generator.
+tableaux:
+	python tools/gen_tableaux.py
 
 # Programs on the three faces of the boundary: C ABI, C++ API (built-in problem), C++ user functor.
 examples: build/c_interface_test build/cpp_api build/user_functor

@@ -132,7 +132,7 @@ typedef struct rehuel_result {
 	    *fun_evals, *jac_evals, *newton_iters, *steps; /* [M] each */
 	/* samples (only when output_mode bit 0 is set and n_samples_cap > 0) */
 	size_t n_samples_cap;   /* rows allocated per member */
-	unsigned *n_samples;    /* [M] samples produced (may exceed the cap; rows beyond it are dropped) */
+	unsigned *n_samples;    /* [M] samples produced (may exceed the cap; rows beyond it are dropped); NULL when n_samples_cap == 0 */
 	double *t_samples;      /* [cap][M]    sample 0 is (t0, y0), irk.hpp:581-585 */
 	double *y_samples;      /* [cap][n][M] */
 	double *err_samples;    /* [cap][M] */

@@ -143,7 +143,7 @@ public:
 		return v;
 	}
 	// rk_output::t_vals / y_vals / err of member i (first entry is (t0, y0): irk.hpp:581-585)
-	std::size_t n_samples(std::size_t i) const { return std::min<std::size_t>(r_.n_samples[i], r_.n_samples_cap); }
+	std::size_t n_samples(std::size_t i) const { return r_.n_samples ? std::min<std::size_t>(r_.n_samples[i], r_.n_samples_cap) : 0; }
 	double t_vals(std::size_t i, std::size_t s) const { return r_.t_samples[s * r_.M + i]; }
 	double y_vals(std::size_t i, std::size_t s, int k) const { return r_.y_samples[(s * r_.n + k) * r_.M + i]; }
 	double err(std::size_t i, std::size_t s) const { return r_.err_samples[s * r_.M + i]; }

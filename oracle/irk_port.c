@@ -60,6 +60,22 @@ typedef struct {
 
 #define SETA(i, j, v) (tb->A[(i) * tb->s + (j)] = (v))
 
+#include "tableau_dec.inc" /* RADAU_IIA_95 / RADAU_IIA_137 as the reference prints them (generated) */
+
+/* irk.cpp:393-437, 439-533: A, b, c by decimals;  b2(i) = b(i) -+ |coef| * gamma */
+static void set_decimal(tableau *tb, int s, const double *A, const double *c, const double *b,
+                        const double *b2coef, double gamma, int order, int order2)
+{
+	tb->s = s; tb->has_b2 = 1; tb->gamma = gamma; tb->order = order; tb->order2 = order2;
+	for (int i = 0; i < s; ++i) {
+		for (int j = 0; j < s; ++j) tb->A[i * s + j] = A[i * s + j];
+		tb->c[i] = c[i];
+		tb->b[i] = b[i];
+		double cg = b2coef[i] * gamma;
+		tb->b2[i] = b[i] + cg;
+	}
+}
+
 /* irk.cpp:215-689.  Only methods whose A is invertible (irk.hpp:599 inverts A) and that carry
  * an embedded pair are restated; unknown ids return 0 like verify_solver_coeffs failing. */
 static int get_tableau(int method, tableau *tb)
@@ -68,6 +84,19 @@ static int get_tableau(int method, tableau *tb)
 	memset(tb, 0, sizeof *tb);
 	tb->gamma = 0.0; /* irk.cpp:231: stays 0 unless the case sets it */
 	switch (method) {
+	case IMPLICIT_EULER: /* irk.cpp:238-244: no b2 => odeint switches adaptivity off (irk.hpp:890-895) */
+		tb->s = 1; tb->has_b2 = 0;
+		SETA(0,0, 1.0); tb->b[0] = 1.0; tb->c[0] = 1.0;
+		tb->order = 1; tb->order2 = 0;
+		return 1;
+	case RADAU_IIA_95: /* irk.cpp:393-437 */
+		set_decimal(tb, 5, radau_iia_95_A, radau_iia_95_c, radau_iia_95_b, radau_iia_95_b2_gamma_coef,
+		            radau_iia_95_gamma, radau_iia_95_order, radau_iia_95_order2);
+		return 1;
+	case RADAU_IIA_137: /* irk.cpp:439-533 */
+		set_decimal(tb, 7, radau_iia_137_A, radau_iia_137_c, radau_iia_137_b, radau_iia_137_b2_gamma_coef,
+		            radau_iia_137_gamma, radau_iia_137_order, radau_iia_137_order2);
+		return 1;
 	case RADAU_IIA_32: /* irk.cpp:342-360 */
 		tb->s = 2; tb->has_b2 = 1;
 		SETA(0,0, 5.0/12.0); SETA(0,1, -1.0/12.0);

@@ -267,27 +267,85 @@ static int pinned_alloc(ResultImpl *impl, T **ptr, size_t count)
 	return REHUEL_OK;
 }
 
+// A stream with its three timing events; recycled across calls like the memory blocks (creating and
+// destroying 6-8 streams and 18-24 events per call costs more host time than issuing the work).
+struct StreamSet {
+	int dev = -1;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+};
+class StreamPool {
+public:
+	int get(int dev, StreamSet &out) // the caller has made `dev` current
+	{
+		{
+			std::lock_guard<std::mutex> g(mu_);
+			for (size_t i = 0; i < free_.size(); ++i)
+				if (free_[i].dev == dev) {
+					out = free_[i];
+					free_.erase(free_.begin() + (long)i);
+					return REHUEL_OK;
+				}
+		}
+		out = StreamSet();
+		out.dev = dev;
+		CUDA_TRY(cudaStreamCreateWithFlags(&out.stream, cudaStreamNonBlocking));
+		CUDA_TRY(cudaEventCreate(&out.ev0));
+		CUDA_TRY(cudaEventCreate(&out.ev1));
+		CUDA_TRY(cudaEventCreate(&out.ev2));
+		return REHUEL_OK;
+	}
+	void put(const StreamSet &s) // only after the stream has been synchronised
+	{
+		if (!s.stream) return;
+		std::lock_guard<std::mutex> g(mu_);
+		free_.push_back(s);
+	}
+	void trim()
+	{
+		std::lock_guard<std::mutex> g(mu_);
+		int cur = 0;
+		cudaGetDevice(&cur);
+		for (StreamSet &s : free_) {
+			cudaSetDevice(s.dev);
+			if (s.ev0) cudaEventDestroy(s.ev0);
+			if (s.ev1) cudaEventDestroy(s.ev1);
+			if (s.ev2) cudaEventDestroy(s.ev2);
+			if (s.stream) cudaStreamDestroy(s.stream);
+		}
+		free_.clear();
+		cudaSetDevice(cur);
+	}
+
+private:
+	std::mutex mu_;
+	std::vector<StreamSet> free_;
+};
+static StreamPool g_streams;
+
 // One unit of device work: a contiguous member range on one device with its own stream, so that
 // the H2D copy, the kernel and the D2H copies of different chunks overlap.
 struct DeviceShard {
 	int dev = 0;
 	size_t off = 0, m = 0;
+	StreamSet ss;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 	void *slab = nullptr;
 	rehuel_device_io io{};
 	unsigned long long *d_stats = nullptr;
+	bool synced = false;
 	DeviceShard() = default;
 	DeviceShard(const DeviceShard &) = delete;
 	DeviceShard &operator=(const DeviceShard &) = delete;
 	~DeviceShard()
 	{
+		if (stream && !synced) { // error path: nothing may still be using the slab or the stream
+			cudaSetDevice(dev);
+			cudaStreamSynchronize(stream);
+		}
 		g_cache.put(slab);
-		if (ev0 || ev1 || stream) cudaSetDevice(dev);
-		if (ev0) cudaEventDestroy(ev0);
-		if (ev1) cudaEventDestroy(ev1);
-		if (ev2) cudaEventDestroy(ev2);
-		if (stream) cudaStreamDestroy(stream);
+		g_streams.put(ss);
 	}
 };
 
@@ -404,8 +462,7 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 	out->err_last = hs.take<double>(M);
 	out->status = hs.take<int>(M);
 	unsigned *counters = hs.take<unsigned>((size_t)REHUEL_NCOUNTERS * M); // [NCOUNTERS][M]
-	out->n_samples = hs.take<unsigned>(M);
-	if (!n_samples_cap) std::memset(out->n_samples, 0, sizeof(unsigned) * M); // not copied back: no samples were kept
+	out->n_samples = n_samples_cap ? hs.take<unsigned>(M) : nullptr; // NULL: no samples were asked for
 	unsigned long long *h_stats = hs.take<unsigned long long>(max_shards * kStatWords);
 	std::memset(h_stats, 0, sizeof(unsigned long long) * max_shards * kStatWords);
 	if (n_samples_cap) {
@@ -424,24 +481,30 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 	out->steps = counters + (size_t)REHUEL_CNT_STEPS * M;
 
 	// ---- work units: GPU g owns the contiguous members [M*g/G, M*(g+1)/G); each GPU's share is cut
-	// into up to 6 chunks (>= 128 Ki members each) on separate streams so that the H2D copy of
-	// chunk i+1 and the D2H copies of chunk i-1 overlap the kernel of chunk i.
+	// into up to 8 chunks on separate streams so that the H2D copy of chunk i+1 and the D2H copies
+	// of chunk i-1 overlap the kernel of chunk i.  Chunk sizes are tapered (1,2,3,4,4,3,2,1): the
+	// first kernel starts after a small H2D copy and only a small D2H copy is left after the last.
 	std::deque<DeviceShard> shards; // deque: elements are never moved (DeviceShard owns CUDA handles)
 	for (int g = 0; g < n_gpus; ++g) {
 		const size_t lo = M * (size_t)g / (size_t)n_gpus, hi = M * (size_t)(g + 1) / (size_t)n_gpus;
 		size_t chunks = (hi - lo) / (128u << 10);
-		chunks = chunks < 1 ? 1 : (chunks > 6 ? 6 : chunks); // measured best at 2^20 members: 6 (e2e 4.08 ms vs 5.5 unchunked)
-		if (const char *e = std::getenv("REHUEL_CHUNKS")) { // tuning aid
+		chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+		bool taper = true;
+		if (const char *e = std::getenv("REHUEL_CHUNKS")) { // tuning aids
 			const long v = std::atol(e);
 			if (v >= 1 && v <= 8) chunks = (size_t)v;
 		}
+		if (const char *e = std::getenv("REHUEL_CHUNK_TAPER")) taper = std::atol(e) != 0;
 		if (n_samples_cap) chunks = 1;
+		size_t wsum = 0, wacc = 0;
+		for (size_t c = 0; c < chunks; ++c) wsum += taper ? (c + 1 < chunks - c ? c + 1 : chunks - c) : 1;
 		for (size_t c = 0; c < chunks; ++c) {
 			shards.emplace_back();
 			DeviceShard &sh = shards.back();
 			sh.dev = dev0 + g;
-			sh.off = lo + (hi - lo) * c / chunks;
-			sh.m = lo + (hi - lo) * (c + 1) / chunks - sh.off;
+			sh.off = lo + (hi - lo) * wacc / wsum;
+			wacc += taper ? (c + 1 < chunks - c ? c + 1 : chunks - c) : 1;
+			sh.m = lo + (hi - lo) * wacc / wsum - sh.off;
 		}
 	}
 	auto body = [&]() -> int {
@@ -450,10 +513,11 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			const size_t m = sh.m;
 			if (m == 0) continue;
 			CUDA_TRY(cudaSetDevice(sh.dev));
-			CUDA_TRY(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
-			CUDA_TRY(cudaEventCreate(&sh.ev0));
-			CUDA_TRY(cudaEventCreate(&sh.ev1));
-			CUDA_TRY(cudaEventCreate(&sh.ev2));
+			if (int rs = g_streams.get(sh.dev, sh.ss)) return rs;
+			sh.stream = sh.ss.stream;
+			sh.ev0 = sh.ss.ev0;
+			sh.ev1 = sh.ss.ev1;
+			sh.ev2 = sh.ss.ev2;
 			const size_t dbytes = Slab::need(y0_broadcast ? (size_t)n : (size_t)n * m, 8) + Slab::need((size_t)p * m, 8) +
 			                      Slab::need((size_t)n * m, 8) + 2 * Slab::need(m, 8) + 2 * Slab::need(m, 4) +
 			                      Slab::need((size_t)REHUEL_NCOUNTERS * m, 4) + Slab::need(1, 8) + Slab::need(kStatWords, 8) +
@@ -558,6 +622,7 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			if (sh.m == 0) continue;
 			CUDA_TRY(cudaSetDevice(sh.dev));
 			CUDA_TRY(cudaStreamSynchronize(sh.stream));
+			sh.synced = true;
 		}
 		for (int g = 0; g < n_gpus; ++g) {
 			DeviceShard *first = nullptr;
@@ -795,7 +860,11 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 	return ensemble_host(launch, n, p, method, t0, t1, dt0, M, y0, y0_broadcast, params, opts, n_samples_cap, n_gpus, out);
 }
 
-void rehuel_release_cached_memory(void) { g_cache.trim(); }
+void rehuel_release_cached_memory(void)
+{
+	g_cache.trim();
+	g_streams.trim();
+}
 
 void rehuel_result_free(rehuel_result *out) { free_result(out); }
 
@@ -850,9 +919,16 @@ int rehuel_result_merge(rehuel_result *a, const rehuel_result *b)
 		if (rc) return rc;
 	}
 	double w1 = 0.0, w2 = 0.0; // irk.cpp:767-771: weights are the numbers of stored samples
+	unsigned *ns = a->n_samples;
+	if (cap && !ns) { // leg 1 kept no samples but leg 2 did: leg 1 now needs a count array
+		int rc = pinned_alloc(impl, &ns, M);
+		if (rc) return rc;
+		std::memset(ns, 0, sizeof(unsigned) * M);
+	}
 	for (size_t i = 0; i < M; ++i) {
-		const size_t na = a->n_samples[i] < a->n_samples_cap ? a->n_samples[i] : a->n_samples_cap;
-		const size_t nb = b->n_samples[i] < b->n_samples_cap ? b->n_samples[i] : b->n_samples_cap;
+		const size_t pa = a->n_samples ? a->n_samples[i] : 0, pb = b->n_samples ? b->n_samples[i] : 0;
+		const size_t na = pa < a->n_samples_cap ? pa : a->n_samples_cap;
+		const size_t nb = pb < b->n_samples_cap ? pb : b->n_samples_cap;
 		for (size_t k = 0; k < na; ++k) {
 			ts[k * M + i] = a->t_samples[k * M + i];
 			es[k * M + i] = a->err_samples[k * M + i];
@@ -863,9 +939,9 @@ int rehuel_result_merge(rehuel_result *a, const rehuel_result *b)
 			es[(na + k) * M + i] = b->err_samples[k * M + i];
 			for (int c = 0; c < n; ++c) ys[((na + k) * n + c) * M + i] = b->y_samples[(k * n + c) * M + i];
 		}
-		w1 += (double)a->n_samples[i];
-		w2 += (double)b->n_samples[i];
-		a->n_samples[i] = (unsigned)(na + nb);
+		w1 += (double)pa;
+		w2 += (double)pb;
+		if (ns) ns[i] = (unsigned)(na + nb);
 		a->status[i] |= b->status[i];
 		a->attempt[i] += b->attempt[i];
 		a->reject_newton[i] += b->reject_newton[i];
@@ -879,6 +955,7 @@ int rehuel_result_merge(rehuel_result *a, const rehuel_result *b)
 		a->err_last[i] = b->err_last[i];
 		for (int c = 0; c < n; ++c) a->y[c * M + i] = b->y[c * M + i];
 	}
+	a->n_samples = ns;
 	a->t_samples = ts;
 	a->y_samples = ys;
 	a->err_samples = es;

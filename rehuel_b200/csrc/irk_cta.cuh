@@ -360,7 +360,7 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 		// ---------------- per-member scalar state (identical in every thread)
 		double t = a.t0, dt = a.dt0;
 		if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
-		double dts0 = dt, dts1 = dt, errs0 = 0.9, errs1 = 0.9, err = 0.0;
+		double dts0 = dt, dts1 = dt, q_prev = tb.q_init, err = 0.0; // q_prev: see propose_dt (irk_thread.cuh)
 		bool alt = true;
 		int maxit = a.maxit0;
 		long long step = 0, last_relax = 0;
@@ -570,23 +570,13 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 			tot = block_sum<THREADS>(tot, red);
 			err = sqrt(tot / (double)N);
 			if (err < kMachinePrecision) err = kMachinePrecision;
-			errs1 = errs0;
-			errs0 = err;
 			const bool rejected = a.adaptive && (err > 1.0); // irk.hpp:761
 			if (rejected) {
 				alt = true;
 				++c_rej_err;
 			}
-			// -------- step-size proposal (irk.hpp:770-801)
-			const double fac = 0.9 * (maxit + 1.0) / (double)(maxit + it);
-			const double s27 = ctrl_pow(1.0 / err, tb.min_order, tb.expo);
-			const double dt_rat = dts0 / dts1;
-			double err_frac = errs1 / errs0;
-			if (errs1 == 0.0 || errs0 == 0.0) err_frac = 1.0;
-			const double s28 = s27 * dt_rat * ctrl_pow(err_frac, tb.min_order, tb.expo);
-			const double msc = (s28 < s27) ? s28 : s27;
-			double new_dt = fac * dt * (msc < 8.0 ? msc : 8.0);
-			if (a.max_dt > 0.0) new_dt = new_dt < a.max_dt ? new_dt : a.max_dt;
+			// -------- step-size proposal (irk.hpp:770-801; shifts the error history, irk.hpp:756-758)
+			const double new_dt = propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
 			bool stuck = false;
 			if (!rejected) { // irk.hpp:813-846
 				for (int i = tid; i < N; i += THREADS) y[i] = yn[i];

@@ -240,6 +240,28 @@ __device__ __forceinline__ double ctrl_pow(double x, int min_order, double expo)
 	return pow(x, expo);
 }
 
+// Step-size proposal, irk.hpp:770-801:
+//   fac = 0.9 (maxit+1)/(maxit+iters);  s27 = (1/err)^e;  s28 = s27 (dts0/dts1) (errs1/errs0)^e;
+//   new_dt = fac dt min(8, min(s27, s28));   e = 1/(1+min(order, order2)),  errs0 == err.
+// Evaluated with ONE root instead of two powers: with q = err^e,  s27 = 1/q  and
+// (errs1/errs0)^e = q_prev/q = q_prev * s27, so the kernels carry q_prev = errs1^e in place of errs1
+// (errs[] entries are never 0: err is floored at 1e-17 and the history starts at 0.9, irk.hpp:573,752).
+// Reciprocals go through fast_rcp (<= 1 ulp); the proposal differs from the reference expression
+// by a few ulp, like everything downstream of the decoupled Newton solve.
+__device__ __forceinline__ double propose_dt(double dt, double err, double &q_prev, double dts0, double dts1, int maxit,
+                                             int iters, int min_order, double expo, double max_dt)
+{
+	const double q = ctrl_pow(err, min_order, expo);
+	const double s27 = fast_rcp(q);
+	const double s28 = s27 * (dts0 * fast_rcp(dts1)) * (q_prev * s27);
+	q_prev = q; // irk.hpp:756-758: the history shifts on every attempt that reaches the estimator
+	const double fac = (0.9 * (maxit + 1.0)) * fast_rcp((double)(maxit + iters));
+	const double msc = (s28 < s27) ? s28 : s27;
+	double new_dt = fac * dt * (msc < 8.0 ? msc : 8.0);
+	if (max_dt > 0.0) new_dt = new_dt < max_dt ? new_dt : max_dt;
+	return new_dt;
+}
+
 // ------------------------------------------------------------------ the kernel
 template <class F, int S, int NR, int NC, int EST, int BLOCK, int MIN_BLOCKS, bool TOLV = false>
 #ifdef REHUEL_MAXNREG
@@ -263,7 +285,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	unsigned long long mem = 0;
 	double y[N], p[PA];
 	double t = 0.0, dt = 0.0;
-	double dts0 = 0.0, dts1 = 0.0, errs0 = 0.9, errs1 = 0.9, err = 0.0;
+	double dts0 = 0.0, dts1 = 0.0, q_prev = tb.q_init, err = 0.0; // q_prev = errs[1]^expo, see propose_dt
 	bool alt = true;
 	int maxit = a.maxit0;
 	long long step = 0, last_relax = 0;
@@ -300,7 +322,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					dt = a.dt0;
 					if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
 					dts0 = dts1 = dt;                 // irk.hpp:572
-					errs0 = errs1 = 0.9;              // irk.hpp:573
+					q_prev = tb.q_init;               // irk.hpp:573: errs = 0.9
 					err = 0.0;
 					alt = true;                       // irk.hpp:587
 					maxit = a.maxit0;
@@ -590,32 +612,18 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 #pragma unroll
 					for (int k = 0; k < N; ++k) {
 						const double sc = fma(TOLV ? m_rtol : a.rtol, fmax(fabs(y[k]), fabs(yn[k])), TOLV ? m_atol : a.atol);
-						// e[k] == 0 (e.g. the first Robertson attempts) would send the whole warp through
-						// the division's slow path for one lane; 0/sc is 0 anyway.
-						const bool zero = (e[k] == 0.0);
-						double q = (zero ? 1.0 : e[k]) / sc;
-						q = zero ? 0.0 : q;
+						const double q = e[k] * fast_rcp(sc);
 						tot = fma(q, q, tot);
 					}
-					err = sqrt(tot / (double)N);
+					err = sqrt(tot * (1.0 / (double)N));
 					if (err < kMachinePrecision) err = kMachinePrecision;
-					errs1 = errs0; // irk.hpp:756-758 (errs[2] is never read)
-					errs0 = err;
 					const bool rejected = a.adaptive && (err > 1.0); // irk.hpp:761
 					if (rejected) {
 						alt = true;
 						++c_rej_err;
 					}
-					// -------- step-size proposal, irk.hpp:770-801
-					const double fac = 0.9 * (maxit + 1.0) / (double)(maxit + it);
-					const double s27 = ctrl_pow(1.0 / err, tb.min_order, tb.expo);
-					const double dt_rat = dts0 / dts1;
-					double err_frac = errs1 / errs0;
-					if (errs1 == 0.0 || errs0 == 0.0) err_frac = 1.0;
-					const double s28 = s27 * dt_rat * ctrl_pow(err_frac, tb.min_order, tb.expo);
-					const double msc = (s28 < s27) ? s28 : s27;
-					double new_dt = fac * dt * (msc < 8.0 ? msc : 8.0);
-					if (a.max_dt > 0.0) new_dt = new_dt < a.max_dt ? new_dt : a.max_dt;
+					// -------- step-size proposal, irk.hpp:770-801 (shifts the error history, irk.hpp:756-758)
+					const double new_dt = propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
 
 					if (io.trace && mem == io.trace_member) { // irk.hpp:805-810
 						unsigned r = atomicAdd(io.trace_len, 1u);

@@ -72,6 +72,8 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 			return set_error(REHUEL_EINVAL, "per-member tolerances are built for the 3-stage methods only");
 		}
 	}
+	if (tb.s != S || tb.n_real != NR || tb.n_cplx != NC || tb.est_mode != EST)
+		return set_error(REHUEL_EINVAL, "internal: tableau %s does not have the structure its kernel was built for", tb.name);
 	int dev = 0, sms = 0, per_sm = 0;
 	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
 	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -107,6 +109,9 @@ int dispatch_method(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream
 {
 	static_assert(F::N >= 1 && F::N <= 4, "thread-per-system kernels cover n <= 4 (larger systems: CTA-per-system path)");
 	switch (tb.method) {
+	case REHUEL_IMPLICIT_EULER: return launch_thread<F, 1, 1, 0, EST_IDENTITY>(ka, tb, stream, info);
+	case REHUEL_RADAU_IIA_95: return launch_thread<F, 5, 1, 2, EST_REUSE>(ka, tb, stream, info);
+	case REHUEL_RADAU_IIA_137: return launch_thread<F, 7, 1, 3, EST_REUSE>(ka, tb, stream, info);
 	case REHUEL_RADAU_IIA_32: return launch_thread<F, 2, 0, 1, EST_OWN_LU>(ka, tb, stream, info);
 	case REHUEL_RADAU_IIA_53: return launch_thread<F, 3, 1, 1, EST_REUSE>(ka, tb, stream, info);
 	case REHUEL_LOBATTO_IIIC_43: return launch_thread<F, 3, 1, 1, EST_IDENTITY>(ka, tb, stream, info);

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(256) order_minmax_kernel(const double *__restr
 				}
 			}
 	}
+	// warp -> block -> one atomic per block and slot (thousands of same-address atomics would serialise)
+	__shared__ unsigned long long s_lo[8][kOrderMaxDims], s_hi[8][kOrderMaxDims];
 #pragma unroll
 	for (int d = 0; d < kOrderMaxDims; ++d) {
 #pragma unroll
@@ -70,10 +72,21 @@ __global__ void __launch_bounds__(256) order_minmax_kernel(const double *__restr
 			lo[d] = a < lo[d] ? a : lo[d];
 			hi[d] = b > hi[d] ? b : hi[d];
 		}
-		if ((threadIdx.x & 31) == 0 && d < dims) {
-			atomicMin(minmax + d, lo[d]);
-			atomicMax(minmax + kOrderMaxDims + d, hi[d]);
+		if ((threadIdx.x & 31) == 0) {
+			s_lo[threadIdx.x >> 5][d] = lo[d];
+			s_hi[threadIdx.x >> 5][d] = hi[d];
 		}
+	}
+	__syncthreads();
+	if (threadIdx.x < (unsigned)dims) {
+		const int d = threadIdx.x;
+		unsigned long long a = s_lo[0][d], b = s_hi[0][d];
+		for (int w = 1; w < 8; ++w) {
+			a = s_lo[w][d] < a ? s_lo[w][d] : a;
+			b = s_hi[w][d] > b ? s_hi[w][d] : b;
+		}
+		atomicMin(minmax + d, a);
+		atomicMax(minmax + kOrderMaxDims + d, b);
 	}
 }
 
@@ -180,7 +193,8 @@ int locality_order(const double *params, int p, size_t M, int descending, unsign
 	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 	const unsigned long long want = (M + 255) / 256;
 	const unsigned grid = (unsigned)(want < (unsigned long long)sms * 8 ? want : (unsigned long long)sms * 8);
-	order_minmax_kernel<<<grid, 256, 0, stream>>>(params, M, dims, minmax);
+	const unsigned grid_mm = (unsigned)(want < (unsigned long long)sms * 2 ? want : (unsigned long long)sms * 2);
+	order_minmax_kernel<<<grid_mm, 256, 0, stream>>>(params, M, dims, minmax);
 	REHUEL_CUDA_TRY(cudaGetLastError());
 	count_launch();
 	order_key_kernel<<<grid, 256, 0, stream>>>(params, M, dims, bits, descending, minmax, keys_in, idx_in);

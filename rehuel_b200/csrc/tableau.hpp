@@ -3,6 +3,8 @@
 // (irk.cpp:215-689); the derived weights d = A^-T b, d2 = A^-T b2 are irk.hpp:599-601.
 #pragma once
 
+#include <cmath>
+
 namespace rehuel {
 
 constexpr int MAX_S = 7;
@@ -57,6 +59,7 @@ struct DevTableau {
 	double gamma_hat; // real eigenvalue of inv(A) (0 if none)
 	double alpha[NC > 0 ? NC : 1], beta[NC > 0 ? NC : 1];
 	double expo;      // 1/(1+min(order,order2))  (irk.hpp:588, 774)
+	double q_init;    // 0.9^expo: the controller's initial error history (irk.hpp:573) as propose_dt carries it
 	int min_order;
 };
 
@@ -83,6 +86,7 @@ inline DevTableau<S, NC> make_dev_tableau(const Tableau &tb)
 	}
 	dt.min_order = tb.order < tb.order2 ? tb.order : tb.order2;
 	dt.expo = 1.0 / (1.0 + dt.min_order);
+	dt.q_init = std::pow(0.9, dt.expo);
 	return dt;
 }
 

@@ -56,9 +56,14 @@ def test_golden_single_systems(capi, golden):
         assert int(g.status[0]) == c["status"], c["name"]
         assert g.t_final[0] == unhex(c["t_final"])[0], c["name"]
         assert se <= PARITY_BOUND, (c["name"], se)
-        # accepted/rejected step counts next to the reference's: equal up to rare accept/reject flips
-        assert abs(int(g.counters["attempt"][0]) - ref["attempt"]) <= max(3, 0.02 * ref["attempt"]), rows[-1]
-        assert abs(int(g.counters["fun_evals"][0]) - ref["fun_evals"]) <= max(30, 0.05 * ref["fun_evals"]), rows[-1]
+        # accepted/rejected step counts next to the reference's: equal up to rare accept/reject flips.  The 9th/13th
+        # order Radau pairs at rtol 1e-6 are the exception: their embedded error estimate is a difference of nearly
+        # equal numbers, i.e. rounding noise, so two correct implementations that round differently (dense LU vs the
+        # decoupled solve) walk different step sequences (measured: 254 vs 272 attempts on Robertson to t = 1e11,
+        # results equal to 4e-5 of the tolerance).
+        slack = 0.10 if c["method"] in (212, 213) else 0.02
+        assert abs(int(g.counters["attempt"][0]) - ref["attempt"]) <= max(3, slack * ref["attempt"]), rows[-1]
+        assert abs(int(g.counters["fun_evals"][0]) - ref["fun_evals"]) <= max(30, (slack + 0.03) * ref["fun_evals"]), rows[-1]
     print("\nname | scaled_err | attempts gpu/ref | rejE gpu/ref | rejN gpu/ref | fun gpu/ref | jac gpu/ref")
     for r in rows:
         print("%-28s %.3e  %d/%d  %d/%d  %d/%d  %d/%d  %d/%d" % r)

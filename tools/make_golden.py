@@ -66,6 +66,14 @@ def main():
         ("stiff-equation", None, [1.0, 0.0], 232, 0.0, 10.0, 1e-2, dict(rel_tol=1e-5, abs_tol=1e-4)),
         ("brusselator", [1.0, 2.5], [1.0, 1.0], 211, 0.0, 20.0, 1e-6, o6),
         ("brusselator", [1.0, 3.5], [1.0, 1.0], 230, 0.0, 20.0, 1e-6, o6),
+        # the decimal-defined high-order Radau tableaux (irk.cpp:393-533)
+        ("robertson", [0.04, 1e4, 3e7], [1.0, 0.0, 0.0], 212, 0.0, 40.0, 1e-6, o6),
+        ("robertson", [0.04, 1e4, 3e7], [1.0, 0.0, 0.0], 213, 0.0, 40.0, 1e-6, o6),
+        ("robertson", [0.04, 1e4, 3e7], [1.0, 0.0, 0.0], 212, 0.0, 1e11, 1e-6, o6),
+        ("van-der-pol", [1e-3], [2.0, 0.0], 212, 0.0, 2.0, 1e-6, o6),
+        ("van-der-pol", [1e-2], [2.0, 0.0], 213, 0.0, 2.0, 1e-6, o6),
+        ("brusselator", [1.0, 3.0], [1.0, 1.0], 212, 0.0, 20.0, 1e-6, o6),
+        ("exponential", [-0.4], [1.0], 213, 0.0, 2.0, 1e-6, dict(rel_tol=1e-4)),
         ("brusselator-1d", [0.02, 1.0, 3.0], list(ensembles.bruss1d_y0(4)), 211, 0.0, 1.0, 1e-6, o6),
         ("brusselator-1d", [0.02, 1.0, 3.0], list(ensembles.bruss1d_y0(4)), 232, 0.0, 1.0, 1e-6, o6),
     ]
@@ -118,14 +126,26 @@ def main():
              y0=[2.0, 0.0], t0=0.0, dt=1e-3, nsteps=200, xtol=1e-14, Rtol=1e-14, y=hx(f["y"]), failed=f["failed"],
              newton_iters=f["newton_iters"]))
 
+    # implicit Euler and the high-order Radau methods through the sanctioned fixed-step loop
+    for prob, par, y0, method, dt, nsteps in (("robertson-hardcoded", None, [1.0, 0.0, 0.0], 200, 1e-4, 100),
+                                              ("van-der-pol", [1e-2], [2.0, 0.0], 200, 1e-3, 200),
+                                              ("robertson-hardcoded", None, [1.0, 0.0, 0.0], 212, 1e-3, 50),
+                                              ("van-der-pol", [1e-2], [2.0, 0.0], 213, 1e-2, 50)):
+        f = ref.fixed_step(prob, method, par, y0, 0.0, dt, nsteps, maxit=100, refresh_jac=25, xtol=1e-14, Rtol=1e-14)
+        gp = "robertson" if prob == "robertson-hardcoded" else prob
+        add(dict(kind="fixed_step", name=f"{gp}_fixed_{method}_{nsteps}x{dt:g}", problem=gp,
+                 params=[0.04, 1e4, 3e7] if par is None else par, method=method, y0=y0, t0=0.0, dt=dt, nsteps=nsteps,
+                 xtol=1e-14, Rtol=1e-14, y=hx(f["y"]), failed=f["failed"], newton_iters=f["newton_iters"]))
+
     # 5. tableaux + derived weights
-    for m in (210, 211, 230, 231, 232):
+    for m in (200, 210, 211, 212, 213, 230, 231, 232):
         c = ref.get_coefficients(m)
         add(dict(kind="tableau", name=ref.method_to_name(m), method=m, s=c["s"], A=hx(c["A"]), b=hx(c["b"]), c=hx(c["c"]),
                  b2=hx(c["b2"]), gamma=float(c["gamma"]).hex(), order=c["order"], order2=c["order2"], d=hx(c["d"]),
                  d2=hx(c["d2"])))
     # 6. dense output identities (test/test_interpolate.cpp)
-    for m, thetas in ((210, [1.0, 1.0 / 3.0, 0.5]), (211, [1.0, 0.3, 0.75]), (232, [1.0, 0.5])):
+    for m, thetas in ((210, [1.0, 1.0 / 3.0, 0.5]), (211, [1.0, 0.3, 0.75]), (232, [1.0, 0.5]), (212, [1.0, 0.25]),
+                      (213, [1.0, 0.6])):
         for th in thetas:
             add(dict(kind="project_b", method=m, theta=float(th).hex(), b=hx(ref.project_b(m, th))))
 
