@@ -229,6 +229,19 @@ __device__ __forceinline__ void lu_solve(const LuCplx<N> &m, double (&xr)[N], do
 	}
 }
 
+// Optional functor trait: `static constexpr bool kAutonomous = true` promises f(t, y) does not depend
+// on t.  Every attempt starts its Newton iteration from Y = 0 (irk.hpp:415), where all S stage
+// evaluations of the first residual are the same f(t + c_i dt, y) = f(y): the kernel then evaluates
+// it once (the evaluation counters still book the S calls the reference makes) and reuses it for
+// the gamma*dt*f(t, y) term of the error estimate (irk.hpp:702).
+#ifndef REHUEL_AUTONOMOUS_OPT
+#define REHUEL_AUTONOMOUS_OPT 2 // 0: off, 1: first residual only, 2: + error estimate
+#endif
+template <class F, typename = void>
+struct is_autonomous { static constexpr bool value = false; };
+template <class F>
+struct is_autonomous<F, decltype((void)F::kAutonomous)> { static constexpr bool value = F::kAutonomous; };
+
 // ------------------------------------------------------------------ controller power
 // err^(1/(1+min_order)) (irk.hpp:774-782).  The exponent is a tableau constant; the common
 // values get exact-root forms (each correctly rounded step, <= 1 ulp from pow()).
@@ -275,6 +288,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	static_assert(NR <= 1, "at most one real eigenvalue");
 	constexpr int N = F::N;
 	constexpr int PA = F::P > 0 ? F::P : 1;
+	constexpr int kAuto = is_autonomous<F>::value ? REHUEL_AUTONOMOUS_OPT : 0;
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned long long M = a.M;
 	const rehuel_device_io &io = a.io;
@@ -463,7 +477,24 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				for (int i = 0; i < S; ++i)
 #pragma unroll
 					for (int k = 0; k < N; ++k) Y[i][k] = 0.0; // irk.hpp:415
-				double Rnorm2 = residual();                   // irk.hpp:443-446
+				double f0[N]; // f(t, y) (autonomous functors)
+				double Rnorm2;
+				if (kAuto) { // Y = 0: R_i = -dt * sum_j A_ij f(y)
+					F::fun(t, y, p, f0);
+					c_fun += S;
+					Rnorm2 = 0.0;
+#pragma unroll
+					for (int i = 0; i < S; ++i) {
+						const double ai = -dt * tb.Asum[i];
+#pragma unroll
+						for (int k = 0; k < N; ++k) {
+							R[i][k] = ai * f0[k];
+							Rnorm2 = fma(R[i][k], R[i][k], Rnorm2);
+						}
+					}
+				} else {
+					Rnorm2 = residual(); // irk.hpp:443-446
+				}
 				int nstat = kNewtonMaxit;
 				int it = 1;
 				const int cap = (slow_trip || maxit <= kFastIters) ? maxit : kFastIters + 1;
@@ -571,8 +602,13 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						dy[k] = s1;
 						dalt[k] = s2;
 					}
-					if (EST != EST_IDENTITY) {
-						F::fun(t, y, p, fy); // irk.hpp:702 (multiplied by gam == 0 when EST_IDENTITY)
+					if (EST != EST_IDENTITY) { // irk.hpp:702 (multiplied by gam == 0 when EST_IDENTITY)
+						if (kAuto >= 2) {
+#pragma unroll
+							for (int k = 0; k < N; ++k) fy[k] = f0[k];
+						} else {
+							F::fun(t, y, p, fy);
+						}
 					}
 					++c_fun;
 #pragma unroll

@@ -17,6 +17,8 @@
 //   3. cub::DeviceRadixSort::SortPairs over the key bits actually used (plumbing, like NCCL).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/rehuel_b200.h"
@@ -174,7 +176,11 @@ int locality_order(const double *params, int p, size_t M, int descending, unsign
 	if (workspace_bytes < need)
 		return set_error(REHUEL_EINVAL, "locality order: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
 	const int dims = p < kOrderMaxDims ? p : kOrderMaxDims;
-	const int bits = kOrderKeyBits / dims;
+	int bits = kOrderKeyBits / dims;
+	if (const char *e = std::getenv("REHUEL_ORDER_BITS")) { // tuning aid: total key bits
+		const int v = std::atoi(e) / dims;
+		if (v >= 1 && v <= bits) bits = v;
+	}
 	char *w = static_cast<char *>(workspace);
 	unsigned long long *minmax = reinterpret_cast<unsigned long long *>(w);
 	w += 256;

@@ -51,6 +51,7 @@ bool project_b(const Tableau &tb, double theta, double *out);
 template <int S, int NC>
 struct DevTableau {
 	double A[S][S];
+	double Asum[S];   // row sums of A: the stage residual at Y = 0 for an autonomous f (irk_thread.cuh)
 	double c[S];
 	double d[S], d2[S];
 	double T[S][S], Ti[S][S];
@@ -73,6 +74,7 @@ inline DevTableau<S, NC> make_dev_tableau(const Tableau &tb)
 			dt.T[i][j] = tb.T[i][j];
 			dt.Ti[i][j] = tb.Ti[i][j];
 		}
+		for (int j = 0; j < S; ++j) dt.Asum[i] += tb.A[i][j];
 		dt.c[i] = tb.c[i];
 		dt.d[i] = tb.d[i];
 		dt.d2[i] = tb.d2[i];

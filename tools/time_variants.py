@@ -11,7 +11,7 @@ o = capi.make_options(1e-6, 1e-6)
 out = []
 for span, t1, M in (("short", 40.0, 1 << 20), ("long", 1e11, 1 << 18)):
     P = torch.from_numpy(ensembles.robertson_params(M)).cuda(); y0 = torch.from_numpy(ensembles.ROBERTSON_Y0.copy()).cuda()
-    de = DeviceEnsemble(capi.ROBERTSON, 211, M, y0, P)
+    de = DeviceEnsemble(capi.ROBERTSON, 211, M, y0, P, handout_order=int(os.environ.get('TV_HANDOUT', '1')))
     for _ in range(2): de.solve(0.0, t1, 1e-6, o)
     torch.cuda.synchronize()
     best = 1e9
@@ -22,7 +22,7 @@ for span, t1, M in (("short", 40.0, 1 << 20), ("long", 1e11, 1 << 18)):
     out.append("%%s %%.3f ms" %% (span, best))
 M = 1 << 16
 P = torch.from_numpy(ensembles.vdpol_params(M)).cuda(); y0 = torch.from_numpy(ensembles.VDPOL_Y0.copy()).cuda()
-de = DeviceEnsemble(capi.VAN_DER_POL, 230, M, y0, P)
+de = DeviceEnsemble(capi.VAN_DER_POL, 230, M, y0, P, handout_order=int(os.environ.get('TV_HANDOUT', '1')))
 de.solve(0.0, 2.0, 1e-6, o); torch.cuda.synchronize()
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 e0.record(); de.solve(0.0, 2.0, 1e-6, o); e1.record(); torch.cuda.synchronize()
