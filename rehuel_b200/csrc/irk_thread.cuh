@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <type_traits>
+
 #include "../../include/rehuel_b200.h"
 #include "tableau.hpp"
 
@@ -69,36 +71,67 @@ __device__ __forceinline__ double fast_rcp(double x)
 }
 
 // ------------------------------------------------------------------ small dense LU, registers
+// LAPACK-style row partial pivoting needs row interchanges; on statically indexed registers an
+// interchange is a pair of predicated selects per entry, ~45 % of the instructions of a 3x3
+// factorisation -- and for mu*I - J they are almost never needed (the shift mu = lambda/dt makes the
+// diagonal heavy).  The factorisation is therefore SPECULATIVE (REHUEL_PIVOT_MODE 2):
+//   * plain elimination first (PIVOT = false), which only CHECKS, with compares, whether partial
+//     pivoting would have exchanged rows anywhere;
+//   * if any lane of the warp says so, the warp redoes the factorisations with the pivoted routine
+//     (PIVOT = true) and remembers to start with it next time (see the kernel).
+// Where no interchange is needed the two routines perform the same operations, so the result is
+// bit-identical to always pivoting (mode 1).  The interchanges of the pivoted path are recorded
+// as 2-bit offsets p-k in one packed word and applied to right-hand sides by apply_row_swaps.
+#ifndef REHUEL_PIVOT_MODE
+#define REHUEL_PIVOT_MODE 2
+#endif
+
 template <int N>
 struct LuReal {
 	double a[N][N]; // unit-lower L below the diagonal, U above, RECIPROCAL pivots on the diagonal
-	int piv[N];
+};
+template <int N>
+struct LuCplx {
+	double re[N][N], im[N][N];
 };
 
-template <int N>
-__device__ __forceinline__ void lu_factor(LuReal<N> &m)
+// bit offset of the interchange of elimination step k of matrix `slot` (N <= 4: 3 steps x 2 bits)
+__device__ __forceinline__ constexpr int piv_shift(int slot, int k) { return (slot * 3 + k) * 2; }
+
+// PIVOT = false: returns true if partial pivoting would have exchanged rows (the factors are then
+//                not the ones LAPACK would produce and the caller falls back);
+// PIVOT = true:  records the interchanges in `pivs`, returns true if there was any.
+template <bool PIVOT, int N>
+__device__ __forceinline__ bool lu_factor(LuReal<N> &m, unsigned &pivs, int slot)
 {
+	static_assert(N <= 4, "interchanges are packed as 2-bit offsets");
+	bool flag = false;
 #pragma unroll
 	for (int k = 0; k < N; ++k) {
-		int p = k;
-		double best = fabs(m.a[k][k]);
+		if (k + 1 < N) {
+			int p = k;
+			double best = fabs(m.a[k][k]);
 #pragma unroll
-		for (int i = k + 1; i < N; ++i) {
-			double v = fabs(m.a[i][k]);
-			if (v > best) {
-				best = v;
-				p = i;
+			for (int i = k + 1; i < N; ++i) {
+				const double v = fabs(m.a[i][k]);
+				if (v > best) {
+					best = v;
+					p = i;
+				}
 			}
-		}
-		m.piv[k] = p;
+			flag |= (p != k);
+			if (PIVOT) {
+				pivs |= (unsigned)(p - k) << piv_shift(slot, k);
 #pragma unroll
-		for (int i = k + 1; i < N; ++i) {
-			const bool sw = (p == i);
+				for (int i = k + 1; i < N; ++i) {
+					const bool sw = (p == i);
 #pragma unroll
-			for (int j = 0; j < N; ++j) {
-				const double u = m.a[k][j], w = m.a[i][j];
-				m.a[k][j] = sw ? w : u;
-				m.a[i][j] = sw ? u : w;
+					for (int j = 0; j < N; ++j) {
+						const double u = m.a[k][j], w = m.a[i][j];
+						m.a[k][j] = sw ? w : u;
+						m.a[i][j] = sw ? u : w;
+					}
+				}
 			}
 		}
 		const double rp = fast_rcp(m.a[k][k]);
@@ -110,20 +143,30 @@ __device__ __forceinline__ void lu_factor(LuReal<N> &m)
 			for (int j = k + 1; j < N; ++j) m.a[i][j] = fma(-m.a[i][k], m.a[k][j], m.a[i][j]);
 		}
 	}
+	return flag;
 }
 
+// x <- P x for the interchanges recorded for matrix `slot`
 template <int N>
-__device__ __forceinline__ void lu_solve(const LuReal<N> &m, double (&x)[N])
+__device__ __forceinline__ void apply_row_swaps(unsigned pivs, int slot, double (&x)[N])
 {
 #pragma unroll
-	for (int k = 0; k < N; ++k)
+	for (int k = 0; k + 1 < N; ++k) {
+		const int d = (int)((pivs >> piv_shift(slot, k)) & 3u);
 #pragma unroll
 		for (int i = k + 1; i < N; ++i) {
-			const bool sw = (m.piv[k] == i);
+			const bool sw = (d == i - k);
 			const double u = x[k], w = x[i];
 			x[k] = sw ? w : u;
 			x[i] = sw ? u : w;
 		}
+	}
+}
+
+// x <- U^-1 L^-1 x (the interchanges, if any, have been applied to x already)
+template <int N>
+__device__ __forceinline__ void lu_solve(const LuReal<N> &m, double (&x)[N])
+{
 #pragma unroll
 	for (int i = 1; i < N; ++i)
 #pragma unroll
@@ -136,40 +179,41 @@ __device__ __forceinline__ void lu_solve(const LuReal<N> &m, double (&x)[N])
 	}
 }
 
-template <int N>
-struct LuCplx {
-	double re[N][N], im[N][N];
-	int piv[N];
-};
-
-template <int N>
-__device__ __forceinline__ void lu_factor(LuCplx<N> &m)
+template <bool PIVOT, int N>
+__device__ __forceinline__ bool lu_factor(LuCplx<N> &m, unsigned &pivs, int slot)
 {
+	static_assert(N <= 4, "interchanges are packed as 2-bit offsets");
+	bool flag = false;
 #pragma unroll
 	for (int k = 0; k < N; ++k) {
-		int p = k;
-		double best = fabs(m.re[k][k]) + fabs(m.im[k][k]); // izamax's |re|+|im|
+		if (k + 1 < N) {
+			int p = k;
+			double best = fabs(m.re[k][k]) + fabs(m.im[k][k]); // izamax's |re|+|im|
 #pragma unroll
-		for (int i = k + 1; i < N; ++i) {
-			double v = fabs(m.re[i][k]) + fabs(m.im[i][k]);
-			if (v > best) {
-				best = v;
-				p = i;
+			for (int i = k + 1; i < N; ++i) {
+				const double v = fabs(m.re[i][k]) + fabs(m.im[i][k]);
+				if (v > best) {
+					best = v;
+					p = i;
+				}
 			}
-		}
-		m.piv[k] = p;
+			flag |= (p != k);
+			if (PIVOT) {
+				pivs |= (unsigned)(p - k) << piv_shift(slot, k);
 #pragma unroll
-		for (int i = k + 1; i < N; ++i) {
-			const bool sw = (p == i);
+				for (int i = k + 1; i < N; ++i) {
+					const bool sw = (p == i);
 #pragma unroll
-			for (int j = 0; j < N; ++j) {
-				double u = m.re[k][j], w = m.re[i][j];
-				m.re[k][j] = sw ? w : u;
-				m.re[i][j] = sw ? u : w;
-				u = m.im[k][j];
-				w = m.im[i][j];
-				m.im[k][j] = sw ? w : u;
-				m.im[i][j] = sw ? u : w;
+					for (int j = 0; j < N; ++j) {
+						double u = m.re[k][j], w = m.re[i][j];
+						m.re[k][j] = sw ? w : u;
+						m.re[i][j] = sw ? u : w;
+						u = m.im[k][j];
+						w = m.im[i][j];
+						m.im[k][j] = sw ? w : u;
+						m.im[i][j] = sw ? u : w;
+					}
+				}
 			}
 		}
 		// reciprocal pivot 1/(a+ib) = (a-ib)/(a^2+b^2)
@@ -191,24 +235,12 @@ __device__ __forceinline__ void lu_factor(LuCplx<N> &m)
 			}
 		}
 	}
+	return flag;
 }
 
 template <int N>
 __device__ __forceinline__ void lu_solve(const LuCplx<N> &m, double (&xr)[N], double (&xi)[N])
 {
-#pragma unroll
-	for (int k = 0; k < N; ++k)
-#pragma unroll
-		for (int i = k + 1; i < N; ++i) {
-			const bool sw = (m.piv[k] == i);
-			double u = xr[k], w = xr[i];
-			xr[k] = sw ? w : u;
-			xr[i] = sw ? u : w;
-			u = xi[k];
-			w = xi[i];
-			xi[k] = sw ? w : u;
-			xi[i] = sw ? u : w;
-		}
 #pragma unroll
 	for (int i = 1; i < N; ++i)
 #pragma unroll
@@ -296,6 +328,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	// ---- lane-persistent member state
 	bool have = false, exhausted = false;
 	bool parked = false; // this lane's attempt ran past kFastIters Newton iterations: redo it in a slow trip
+	bool prefer_piv = false; // the warp's last factorisations needed row interchanges: skip the speculative plain attempt
 	unsigned long long mem = 0;
 	double y[N], p[PA];
 	double t = 0.0, dt = 0.0;
@@ -415,16 +448,20 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				// EST_REUSE: mu_r = 1/(gamma*dt) instead of gamma_hat/dt (equal to 1e-15) so that
 				// the same factors also serve E = I - gamma*dt*J of the error estimate.
 				const double mur = (EST == EST_REUSE) ? tb.rgamma * rdt : tb.gamma_hat * rdt;
-				{
+				// Jacobian (irk.hpp:425), the decoupled Newton matrices and their factors.  Slots of the
+				// interchange word: 0 = real block, 1.. = complex blocks, 4 = the estimator's own matrix.
+				unsigned pivs = 0u;
+				auto factor_all = [&](auto pivot_tag) -> bool {
+					constexpr bool PIV = decltype(pivot_tag)::value;
 					double J[N][N];
-					F::jac(t, y, p, J); // irk.hpp:425
-					++c_jac;
+					F::jac(t, y, p, J);
+					bool flag = false;
 					if (NR) {
 #pragma unroll
 						for (int i = 0; i < N; ++i)
 #pragma unroll
 							for (int j = 0; j < N; ++j) lur.a[i][j] = (i == j ? mur : 0.0) - J[i][j];
-						lu_factor(lur);
+						flag |= lu_factor<PIV>(lur, pivs, 0);
 					}
 #pragma unroll
 					for (int c = 0; c < NC; ++c) {
@@ -436,7 +473,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 								luc[c].re[i][j] = (i == j ? mr : 0.0) - J[i][j];
 								luc[c].im[i][j] = (i == j ? mi : 0.0);
 							}
-						lu_factor(luc[c]);
+						flag |= lu_factor<PIV>(luc[c], pivs, 1 + c);
 					}
 					if (EST == EST_OWN_LU) {
 						const double mue = tb.rgamma * rdt;
@@ -444,9 +481,16 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						for (int i = 0; i < N; ++i)
 #pragma unroll
 							for (int j = 0; j < N; ++j) lue.a[i][j] = (i == j ? mue : 0.0) - J[i][j];
-						lu_factor(lue);
+						flag |= lu_factor<PIV>(lue, pivs, 4);
 					}
-				}
+					return flag;
+				};
+				++c_jac;
+				// warp-uniform decisions (every lane of amask is here): plain elimination unless the
+				// warp's previous factorisations interchanged rows; pivoted redo if any lane needs it
+				bool piv_any = (REHUEL_PIVOT_MODE == 1) || __any_sync(amask, prefer_piv);
+				if (!piv_any) piv_any = __any_sync(amask, factor_all(std::false_type()));
+				if (piv_any) prefer_piv = __any_sync(amask, factor_all(std::true_type()));
 
 				// residual R = Y - dt*(A (x) I) F(y + Y), irk.hpp:366-386
 				auto residual = [&]() -> double {
@@ -510,6 +554,14 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							for (int j = 0; j < S; ++j) acc = fma(tb.Ti[i][j], R[j][k], acc);
 							Z[i][k] = acc;
 						}
+					if (piv_any) { // rare: the right-hand sides follow the recorded row interchanges
+						if (NR) apply_row_swaps(pivs, 0, Z[0]);
+#pragma unroll
+						for (int c = 0; c < NC; ++c) {
+							apply_row_swaps(pivs, 1 + c, Z[NR + 2 * c]);
+							apply_row_swaps(pivs, 1 + c, Z[NR + 2 * c + 1]);
+						}
+					}
 					if (NR) {
 						lu_solve(lur, Z[0]);
 #pragma unroll
@@ -620,6 +672,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					// err_est = dt * E^-1 * (.), E = I - gam*J = gam*((1/gam) I - J), so
 					// dt*E^-1 = (dt/gam) ((1/gam) I - J)^-1 = (1/gamma) (mu I - J)^-1
 					auto apply_Einv_dt = [&](double (&v)[N]) {
+						if (EST != EST_IDENTITY && piv_any) apply_row_swaps(pivs, EST == EST_REUSE ? 0 : 4, v);
 						if (EST == EST_REUSE) {
 							lu_solve(lur, v);
 						} else if (EST == EST_OWN_LU) {

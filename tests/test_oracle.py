@@ -132,3 +132,21 @@ def test_method_names(port):
     assert port.name_to_method("LOBATTO_IIIC_85") == 232
     assert port.name_to_method("no-such-method") == 0
     assert port.method_to_name(211) == "RADAU_IIA_53"
+
+
+def test_high_order_step_counts_are_noise(port):
+    """Why step counts of RADAU_IIA_95/137 are compared with a wide band (tests/test_gpu_parity.py): at rtol 1e-6 the
+    embedded estimate of a 9th/13th order pair is rounding noise, and the REFERENCE algorithm's own attempt count on
+    Robertson to t = 1e11 changes by >10 % when k1 moves by parts in 1e16 -- while RADAU_IIA_53 does not move at all."""
+    import numpy as np
+    from oracle.refsolver import make_options
+    o = make_options(rel_tol=1e-6, abs_tol=1e-6)
+    counts = {}
+    for method in (211, 212):
+        counts[method] = []
+        for eps in (0.0, -1e-16, 2e-16, 1e-15, -1e-15):
+            P = np.array([0.04 * (1 + eps), 1e4, 3e7])[:, None]
+            r = port.solve("robertson", method, 0.0, 1e11, 1e-6, np.array([1.0, 0.0, 0.0]), P, o, M=1)
+            counts[method].append(int(r.counters["attempt"][0]))
+    assert len(set(counts[211])) == 1, counts
+    assert max(counts[212]) - min(counts[212]) > 0.1 * max(counts[212]), counts
