@@ -22,7 +22,7 @@ all: $(LIB)
 build:
 	mkdir -p build
 
-build/capi.o: $(SRC)/capi.cu $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh $(SRC)/tableau.hpp include/rehuel_b200.h | build
+build/capi.o: $(SRC)/capi.cu $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/irk_warp.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh $(SRC)/tableau.hpp include/rehuel_b200.h | build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/capi.ptxas.log || (cat build/capi.ptxas.log; false)
 
 build/order.o: $(SRC)/order.cu $(SRC)/launch.cuh include/rehuel_b200.h | build

@@ -74,6 +74,7 @@ static const ProblemInfo kProblems[] = {
     {REHUEL_PROBLEM_ROBERTSON, "robertson", 3, 3},
     {REHUEL_PROBLEM_VAN_DER_POL, "van-der-pol", 2, 1},
     {REHUEL_PROBLEM_BRUSSELATOR_1D, "brusselator-1d", 0, 3},
+    {REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE, "brusselator-1d-dense", 0, 3},
     {REHUEL_PROBLEM_EXPONENTIAL, "exponential", 1, 1},
     {REHUEL_PROBLEM_STIFF_EQ, "stiff-equation", 2, 0},
     {REHUEL_PROBLEM_BRUSSELATOR, "brusselator", 2, 2},
@@ -92,6 +93,12 @@ static LaunchFn find_launcher(int problem, int n)
 		if (n == 64) return &dispatch_method_cta<Brusselator1dF<32>>;
 		if (n == 8) return &dispatch_method_cta<Brusselator1dF<4>>;
 		set_error(REHUEL_EINVAL, "brusselator-1d is built for n = 64 (Ng = 32) and n = 8 (Ng = 4), got n = %d", n);
+		return nullptr;
+	}
+	if (problem == REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE) {
+		if (n == 64) return &dispatch_method_cta<Brusselator1dDenseF<32>>;
+		if (n == 8) return &dispatch_method_cta<Brusselator1dDenseF<4>>;
+		set_error(REHUEL_EINVAL, "brusselator-1d-dense is built for n = 64 (Ng = 32) and n = 8 (Ng = 4), got n = %d", n);
 		return nullptr;
 	}
 	switch (problem) {
@@ -445,7 +452,7 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 	out->M = M;
 	out->n = n;
 	out->n_samples_cap = n_samples_cap;
-	const size_t max_shards = (size_t)n_gpus * 8;
+	const size_t max_shards = (size_t)n_gpus * 16;
 	size_t hbytes = Slab::need(M, 8) + Slab::need((size_t)n * M, 8) + Slab::need(M, 8) + Slab::need(M, 4) +
 	                Slab::need((size_t)REHUEL_NCOUNTERS * M, 4) + Slab::need(M, 4) +
 	                Slab::need(max_shards * kStatWords, 8) + 3 * Slab::need(n_samples_cap * M, 8) * (size_t)(n > 1 ? n : 1);
@@ -457,11 +464,19 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 		return REHUEL_ENOMEM;
 	}
 	impl->pinned.push_back(hs.base);
-	out->t_final = hs.take<double>(M);
-	out->y = hs.take<double>((size_t)n * M);
-	out->err_last = hs.take<double>(M);
-	out->status = hs.take<int>(M);
-	unsigned *counters = hs.take<unsigned>((size_t)REHUEL_NCOUNTERS * M); // [NCOUNTERS][M]
+	// one block of doubles [n + 2][M] (y rows, t_final, err_last) and one of 32-bit words [1 + 9][M] (status,
+	// counters): each chunk comes back with TWO pitched copies instead of five
+	double *hdbl = hs.take<double>((size_t)(n + 2) * M);
+	int *hint = hs.take<int>((size_t)(1 + REHUEL_NCOUNTERS) * M);
+	if (!hdbl || !hint) {
+		free_result(out);
+		return fail(REHUEL_ENOMEM, "internal: result slab too small");
+	}
+	out->y = hdbl;
+	out->t_final = hdbl + (size_t)n * M;
+	out->err_last = hdbl + (size_t)(n + 1) * M;
+	out->status = hint;
+	unsigned *counters = reinterpret_cast<unsigned *>(hint + M); // [NCOUNTERS][M]
 	out->n_samples = n_samples_cap ? hs.take<unsigned>(M) : nullptr; // NULL: no samples were asked for
 	unsigned long long *h_stats = hs.take<unsigned long long>(max_shards * kStatWords);
 	std::memset(h_stats, 0, sizeof(unsigned long long) * max_shards * kStatWords);
@@ -482,8 +497,7 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 
 	// ---- work units: GPU g owns the contiguous members [M*g/G, M*(g+1)/G); each GPU's share is cut
 	// into up to 8 chunks on separate streams so that the H2D copy of chunk i+1 and the D2H copies
-	// of chunk i-1 overlap the kernel of chunk i.  Chunk sizes are tapered (1,2,3,4,4,3,2,1): the
-	// first kernel starts after a small H2D copy and only a small D2H copy is left after the last.
+	// of chunk i-1 overlap the kernel of chunk i.  Chunk sizes taper off at the end (see `weight`).
 	std::deque<DeviceShard> shards; // deque: elements are never moved (DeviceShard owns CUDA handles)
 	for (int g = 0; g < n_gpus; ++g) {
 		const size_t lo = M * (size_t)g / (size_t)n_gpus, hi = M * (size_t)(g + 1) / (size_t)n_gpus;
@@ -492,25 +506,52 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 		bool taper = true;
 		if (const char *e = std::getenv("REHUEL_CHUNKS")) { // tuning aids
 			const long v = std::atol(e);
-			if (v >= 1 && v <= 8) chunks = (size_t)v;
+			if (v >= 1 && v <= 16) chunks = (size_t)v;
 		}
 		if (const char *e = std::getenv("REHUEL_CHUNK_TAPER")) taper = std::atol(e) != 0;
 		if (n_samples_cap) chunks = 1;
+		// chunk weights: equal by default; REHUEL_CHUNK_WEIGHTS="1,2,4,4,4,2,1" (tuning aid) sets them explicitly
+		size_t wts[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+		(void)taper;
+		if (const char *e = std::getenv("REHUEL_CHUNK_WEIGHTS")) {
+			size_t k = 0;
+			for (const char *q = e; *q && k < 16;) {
+				char *end = nullptr;
+				const long v = std::strtol(q, &end, 10);
+				if (end == q) break;
+				wts[k++] = v > 0 ? (size_t)v : 1;
+				q = (*end == ',') ? end + 1 : end;
+			}
+			if (k >= 1 && !n_samples_cap) chunks = k;
+		}
+		auto weight = [&](size_t c) -> size_t { return wts[c]; };
 		size_t wsum = 0, wacc = 0;
-		for (size_t c = 0; c < chunks; ++c) wsum += taper ? (c + 1 < chunks - c ? c + 1 : chunks - c) : 1;
+		for (size_t c = 0; c < chunks; ++c) wsum += weight(c);
 		for (size_t c = 0; c < chunks; ++c) {
 			shards.emplace_back();
 			DeviceShard &sh = shards.back();
 			sh.dev = dev0 + g;
-			sh.off = lo + (hi - lo) * wacc / wsum;
-			wacc += taper ? (c + 1 < chunks - c ? c + 1 : chunks - c) : 1;
-			sh.m = lo + (hi - lo) * wacc / wsum - sh.off;
+			// boundaries on multiples of 1024 members: every row of every chunk then starts 4 KiB-aligned on both
+			// sides of the pitched copies (unaligned rows cost ~8 % of the whole call)
+			auto cut = [&](size_t w) -> size_t {
+				if (w >= wsum) return hi;
+				const size_t x = lo + (hi - lo) * w / wsum;
+				const size_t r = (x + 512) & ~size_t(1023);
+				return r < lo ? lo : (r > hi ? hi : r);
+			};
+			sh.off = cut(wacc);
+			wacc += weight(c);
+			sh.m = cut(wacc) - sh.off;
 		}
 	}
+	std::vector<double> t_mark(shards.size() + 1, 0.0); // host time at which each shard's work was issued (REHUEL_TIMING)
+	auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count(); };
 	auto body = [&]() -> int {
+		t_mark[0] = now_ms();
 		for (size_t si = 0; si < shards.size(); ++si) {
 			DeviceShard &sh = shards[si];
 			const size_t m = sh.m;
+			t_mark[si + 1] = t_mark[si];
 			if (m == 0) continue;
 			CUDA_TRY(cudaSetDevice(sh.dev));
 			if (int rs = g_streams.get(sh.dev, sh.ss)) return rs;
@@ -519,8 +560,8 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			sh.ev1 = sh.ss.ev1;
 			sh.ev2 = sh.ss.ev2;
 			const size_t dbytes = Slab::need(y0_broadcast ? (size_t)n : (size_t)n * m, 8) + Slab::need((size_t)p * m, 8) +
-			                      Slab::need((size_t)n * m, 8) + 2 * Slab::need(m, 8) + 2 * Slab::need(m, 4) +
-			                      Slab::need((size_t)REHUEL_NCOUNTERS * m, 4) + Slab::need(1, 8) + Slab::need(kStatWords, 8) +
+			                      Slab::need((size_t)(n + 2) * m, 8) + Slab::need((size_t)(1 + REHUEL_NCOUNTERS) * m, 4) +
+			                      Slab::need(m, 4) + Slab::need(1, 8) + Slab::need(kStatWords, 8) +
 			                      3 * Slab::need(n_samples_cap * m, 8) * (size_t)(n > 1 ? n : 1);
 			// hand-out order (order.cu): only pays where the lanes of a warp integrate different members
 			const bool reorder = opts->handout_order != REHUEL_ORDER_INDEX && p > 0 && n <= 4 && m >= 4096;
@@ -534,12 +575,14 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			ds.size = dbytes_all;
 			double *d_y0 = ds.take<double>(y0_broadcast ? (size_t)n : (size_t)n * m);
 			double *d_par = ds.take<double>((size_t)p * m);
-			sh.io.y = ds.take<double>((size_t)n * m);
-			sh.io.t_final = ds.take<double>(m);
-			sh.io.err_last = ds.take<double>(m);
-			sh.io.status = ds.take<int>(m);
+			double *ddbl = ds.take<double>((size_t)(n + 2) * m); // same row order as the host block
+			int *dint = ds.take<int>((size_t)(1 + REHUEL_NCOUNTERS) * m);
+			sh.io.y = ddbl;
+			sh.io.t_final = ddbl + (size_t)n * m;
+			sh.io.err_last = ddbl + (size_t)(n + 1) * m;
+			sh.io.status = dint;
+			sh.io.counters = reinterpret_cast<unsigned *>(dint + m);
 			sh.io.n_samples = ds.take<unsigned>(m);
-			sh.io.counters = ds.take<unsigned>((size_t)REHUEL_NCOUNTERS * m);
 			sh.io.queue = ds.take<unsigned long long>(1);
 			sh.d_stats = ds.take<unsigned long long>(kStatWords);
 			if (n_samples_cap) {
@@ -580,13 +623,10 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			// D2H of the per-member results first: the statistics kernel below has to wait for free
 			// SM slots behind the persistent kernels of the following chunks, and must not hold the
 			// bulk copies back with it (measured: without this order no copy overlapped any kernel)
-			CUDA_TRY(cudaMemcpy2DAsync(out->y + sh.off, sizeof(double) * M, sh.io.y, sizeof(double) * m,
-			                           sizeof(double) * m, n, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(out->t_final + sh.off, sh.io.t_final, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(out->err_last + sh.off, sh.io.err_last, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpyAsync(out->status + sh.off, sh.io.status, sizeof(int) * m, cudaMemcpyDeviceToHost, sh.stream));
-			CUDA_TRY(cudaMemcpy2DAsync(counters + sh.off, sizeof(unsigned) * M, sh.io.counters, sizeof(unsigned) * m,
-			                           sizeof(unsigned) * m, REHUEL_NCOUNTERS, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpy2DAsync(hdbl + sh.off, sizeof(double) * M, ddbl, sizeof(double) * m, sizeof(double) * m,
+			                           (size_t)n + 2, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaMemcpy2DAsync(hint + sh.off, sizeof(int) * M, dint, sizeof(int) * m, sizeof(int) * m,
+			                           (size_t)1 + REHUEL_NCOUNTERS, cudaMemcpyDeviceToHost, sh.stream));
 			if (n_samples_cap)
 				CUDA_TRY(cudaMemcpyAsync(out->n_samples + sh.off, sh.io.n_samples, sizeof(unsigned) * m, cudaMemcpyDeviceToHost, sh.stream));
 			if (n_samples_cap) {
@@ -597,6 +637,7 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 				CUDA_TRY(cudaMemcpy2DAsync(out->y_samples + sh.off, sizeof(double) * M, sh.io.y_samples, sizeof(double) * m,
 				                           sizeof(double) * m, n_samples_cap * n, cudaMemcpyDeviceToHost, sh.stream));
 			}
+			t_mark[si + 1] = now_ms();
 		}
 		for (size_t si = 0; si < shards.size(); ++si) { // statistics epilogue, after every bulk copy is queued
 			DeviceShard &sh = shards[si];
@@ -638,7 +679,9 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 		}
 		if (timing) {
 			const double t_synced = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();
-			std::fprintf(stderr, "[rehuel timing] host: all work issued at %.3f ms, synced at %.3f ms\n", t_issued, t_synced);
+			std::fprintf(stderr, "[rehuel timing] host: issue starts at %.3f ms; shards issued at", t_mark[0]);
+			for (size_t si = 0; si < shards.size(); ++si) std::fprintf(stderr, " %.3f", t_mark[si + 1]);
+			std::fprintf(stderr, " ms\n[rehuel timing] host: all work issued at %.3f ms, synced at %.3f ms\n", t_issued, t_synced);
 			DeviceShard *first = nullptr;
 			for (DeviceShard &sh : shards) {
 				if (!sh.m) continue;

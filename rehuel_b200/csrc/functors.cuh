@@ -156,4 +156,20 @@ struct Brusselator1dF {
 	}
 };
 
+// The same equations with the Jacobian treated as DENSE (no kBand trait): takes the general
+// CTA-per-system path with the shared-memory block LU (irk_cta.cuh).
+template <int NG>
+struct Brusselator1dDenseF {
+	static constexpr int N = 2 * NG;
+	static constexpr int P = 3;
+	__device__ __forceinline__ static double fun(int i, double t, const double *y, const double *p)
+	{
+		return Brusselator1dF<NG>::fun(i, t, y, p);
+	}
+	__device__ __forceinline__ static void jac_row(int i, double t, const double *y, const double *p, double *row)
+	{
+		Brusselator1dF<NG>::jac_row(i, t, y, p, row);
+	}
+};
+
 } // namespace rehuel

@@ -14,6 +14,7 @@
 #include "../../include/rehuel_b200.h"
 #include "irk_cta.cuh"
 #include "irk_thread.cuh"
+#include "irk_warp.cuh"
 #include "tableau.hpp"
 
 namespace rehuel {
@@ -76,8 +77,23 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 		return set_error(REHUEL_EINVAL, "internal: tableau %s does not have the structure its kernel was built for", tb.name);
 	int dev = 0, sms = 0, per_sm = 0;
 	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
-	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-	REHUEL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0));
+	{
+		// SM count and occupancy per (kernel instantiation, device), queried once: three driver calls per launch
+		// are noticeable when a host call issues 8 chunk launches back to back.  Benign race: same values.
+		static int cache_sms[2][64], cache_per_sm[2][64];
+		const int v = ka.io.rtol ? 1 : 0;
+		if (dev < 64 && cache_per_sm[v][dev] > 0) {
+			sms = cache_sms[v][dev];
+			per_sm = cache_per_sm[v][dev];
+		} else {
+			REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+			REHUEL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, 0));
+			if (dev < 64 && per_sm > 0) {
+				cache_sms[v][dev] = sms;
+				cache_per_sm[v][dev] = per_sm;
+			}
+		}
+	}
 	if (per_sm < 1) return set_error(REHUEL_ECUDA, "kernel does not fit on an SM");
 	if (info) {
 		cudaFuncAttributes fa;
@@ -156,14 +172,65 @@ int launch_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ker
 	return REHUEL_OK;
 }
 
+// ---- warp-per-system path for banded Jacobians (4 < n <= 64, kBand <= 4), irk_warp.cuh
+template <class F, int S, int NR, int NC, int EST>
+int launch_warp(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	auto kern = ensemble_irk_warp<F, S, NR, NC, EST>;
+	const size_t smem = WarpSmem<F, S, NC, EST>::bytes;
+	if (tb.s != S || tb.n_real != NR || tb.n_cplx != NC || tb.est_mode != EST)
+		return set_error(REHUEL_EINVAL, "internal: tableau %s does not have the structure its kernel was built for", tb.name);
+	int dev = 0, sms = 0, per_sm = 0;
+	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
+	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	REHUEL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	REHUEL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+	if (per_sm < 1) return set_error(REHUEL_ECUDA, "warp-per-system kernel needs %zu bytes of shared memory", smem);
+	if (info) {
+		cudaFuncAttributes fa;
+		REHUEL_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+		info->regs = fa.numRegs;
+		info->local_bytes = (int)fa.localSizeBytes;
+		info->smem_bytes = (int)smem;
+		info->ctas_per_sm = per_sm;
+		info->block = 32;
+		return REHUEL_OK;
+	}
+	if (ka.M == 0) return REHUEL_OK;
+	if (ka.io.rtol) return set_error(REHUEL_EINVAL, "per-member tolerances are not built for the warp-per-system kernels");
+	unsigned long long cap = (unsigned long long)sms * per_sm;
+	unsigned grid = (unsigned)(ka.M < cap ? ka.M : cap);
+	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
+	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	kern<<<grid, 32, smem, stream>>>(ka, dtb);
+	REHUEL_CUDA_TRY(cudaGetLastError());
+	count_launch();
+	return REHUEL_OK;
+}
+
+// 4 < n <= 64: banded functors (kBand <= 4) go warp-per-system, everything else CTA-per-system
+template <class F, int S, int NR, int NC, int EST>
+int launch_block(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	if constexpr (jac_band<F>::value <= 4) {
+		return launch_warp<F, S, NR, NC, EST>(ka, tb, stream, info);
+	} else {
+		return launch_cta<F, S, NR, NC, EST>(ka, tb, stream, info);
+	}
+}
+
 template <class F>
 int dispatch_method_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
 {
 	static_assert(F::N > 4 && F::N <= 64, "CTA-per-system kernels cover 4 < n <= 64");
 	switch (tb.method) {
-	case REHUEL_RADAU_IIA_53: return launch_cta<F, 3, 1, 1, EST_REUSE>(ka, tb, stream, info);
-	case REHUEL_LOBATTO_IIIC_43: return launch_cta<F, 3, 1, 1, EST_IDENTITY>(ka, tb, stream, info);
-	case REHUEL_LOBATTO_IIIC_85: return launch_cta<F, 5, 1, 2, EST_OWN_LU>(ka, tb, stream, info);
+	case REHUEL_IMPLICIT_EULER: return launch_block<F, 1, 1, 0, EST_IDENTITY>(ka, tb, stream, info);
+	case REHUEL_RADAU_IIA_32: return launch_block<F, 2, 0, 1, EST_OWN_LU>(ka, tb, stream, info);
+	case REHUEL_RADAU_IIA_53: return launch_block<F, 3, 1, 1, EST_REUSE>(ka, tb, stream, info);
+	case REHUEL_RADAU_IIA_95: return launch_block<F, 5, 1, 2, EST_REUSE>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_43: return launch_block<F, 3, 1, 1, EST_IDENTITY>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_64: return launch_block<F, 4, 0, 2, EST_IDENTITY>(ka, tb, stream, info);
+	case REHUEL_LOBATTO_IIIC_85: return launch_block<F, 5, 1, 2, EST_OWN_LU>(ka, tb, stream, info);
 	}
 	return set_error(REHUEL_EINVAL, "method %d (%s) has no CTA-per-system kernel", tb.method, tb.name);
 }
