@@ -76,6 +76,16 @@ typedef struct rehuel_options {
 	int newton_refresh_jac;         /* newton.hpp:59    default 10 */
 	int output_mode;                /* options.hpp:96-103 bit 0: store samples (STORE_IN_VECTORS); default 1 */
 	unsigned long long output_interval; /* options.hpp:104 every k-th ACCEPTED step is a sample; default 1 */
+	int keep_state;                 /* NEW: != 0 makes the host-buffer entry points return the controller state at exit
+	                                   (rehuel_result.state) so that rehuel_irk_ensemble_continue can carry on where
+	                                   this call stopped.  Fills in irk::restore_state, an empty stub in the reference
+	                                   (irk.cpp:786-803).  Default 0. */
+	unsigned long long dense_samples; /* NEW: dense output.  > 0: every member's solution is also
+	                                   sampled on the uniform grid t_k = dense_t0 + k*dense_dt, k = 0..dense_samples-1,
+	                                   from the collocation polynomial of the accepted step that covers t_k
+	                                   (b_j(theta) of irk::project_b, irk.cpp:731-747); only for methods that carry
+	                                   b_interp (the Radau IIA family and LOBATTO_IIIC_85).  Default 0. */
+	double dense_t0, dense_dt;
 	int handout_order;              /* NEW (scheduling of the batched overload, no reference counterpart): order in which
 	                                   the host-buffer entry points hand members to the GPU lanes.  REHUEL_ORDER_INDEX,
 	                                   REHUEL_ORDER_LOCALITY (default) or REHUEL_ORDER_LOCALITY_DESC.  Results do not
@@ -137,6 +147,9 @@ typedef struct rehuel_result {
 	double *t_samples;      /* [cap][M]    sample 0 is (t0, y0), irk.hpp:581-585 */
 	double *y_samples;      /* [cap][n][M] */
 	double *err_samples;    /* [cap][M] */
+	double *state;          /* [REHUEL_NSTATE][M] controller state at exit (options.keep_state), else NULL */
+	size_t n_dense;         /* options.dense_samples, 0 if none */
+	double *y_dense;        /* [n_dense][n][M] dense-output samples; grid points the member never reached are NaN */
 	double elapsed_ms;      /* host wall time of the call (rk_output::elapsed_time is in ms, my_timer.hpp:142-149) */
 	double kernel_ms;       /* device time of the integration kernel(s), max over GPUs */
 	double accept_frac;     /* sum(steps)/sum(attempt)  (irk.hpp:864) */
@@ -195,10 +208,27 @@ typedef struct rehuel_device_io {
 	unsigned *trace_len;   /* [1] */
 	const double *rtol, *atol, *newton_tol; /* [M] each or NULL: per-member rel_tol / abs_tol / newton tol overriding
 	                          the options (mixed-tolerance ensembles); all three or none */
+	const double *t_start;  /* [M] or NULL: per-member start time instead of t0 (continuing a stopped ensemble) */
+	const double *state_in; /* [REHUEL_NSTATE][M] or NULL: controller state to continue from (rows REHUEL_STATE_*) */
+	double *state_out;      /* [REHUEL_NSTATE][M] or NULL: controller state at exit */
+	size_t n_dense;         /* dense output: number of grid times t_k = dense_t0 + k*dense_dt (0 = off) */
+	double dense_t0, dense_dt;
+	double *y_dense;        /* [n_dense][n][M]; the caller pre-fills it (e.g. with NaN): only reached grid points are written */
 	const unsigned *order; /* [M] or NULL: queue position q -> member index order[q].  Lets the caller hand out
 	                          expensive members first (longest-processing-time-first) when cost correlates with a
 	                          parameter; results do not depend on it. */
 } rehuel_device_io;
+
+/* rows of the controller state (loop variables of irk_guts at exit, irk.hpp:560-590) */
+#define REHUEL_STATE_DT          0 /* step size the next attempt would use */
+#define REHUEL_STATE_DTS0        1 /* dts[0], dts[1]: step-size history of the controller (irk.hpp:853-855) */
+#define REHUEL_STATE_DTS1        2
+#define REHUEL_STATE_ERRQ        3 /* errs[1]^(1/(1+min(order,order2))): error history as the kernels carry it */
+#define REHUEL_STATE_ALT         4 /* alternative_error_formula flag (irk.hpp:587,763,845) */
+#define REHUEL_STATE_MAXIT       5 /* current Newton iteration budget (irk.hpp:644-648) */
+#define REHUEL_STATE_STEP        6 /* accepted steps so far */
+#define REHUEL_STATE_LAST_RELAX  7 /* step at which the budget was last raised */
+#define REHUEL_NSTATE            8
 
 #define REHUEL_CNT_ATTEMPT             0
 #define REHUEL_CNT_REJECT_NEWTON       1
@@ -225,6 +255,15 @@ int rehuel_irk_ensemble_device(int problem, int method, double t0, double t1, do
 size_t rehuel_locality_order_workspace(size_t M);
 int rehuel_locality_order(const double *params, int p, size_t M, int descending, unsigned *order,
                           void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* Continues a stopped ensemble to a later end time: every member starts from prev->t_final[i],
+ * prev->y[.][i] and the controller state prev->state (the previous call must have run with
+ * options.keep_state != 0), i.e. the time loop carries on as if its end time had been t1 all along
+ * -- no restart transient from dt0.  What irk::restore_state (irk.cpp:786-803, an empty stub) was
+ * meant for; combine the legs with rehuel_result_merge.  Counters in `out` are those of this leg. */
+int rehuel_irk_ensemble_continue(int problem, int method, double t1, int n_hint, const double *params,
+                                 const rehuel_options *opts, size_t n_samples_cap, int n_gpus,
+                                 const rehuel_result *prev, rehuel_result *out);
 
 /* Batched irk::merge_rk_output (irk.cpp:750-783): concatenates two legs of a restarted ensemble
  * into `a` (counters added -- fun_evals/jac_evals are NOT, exactly like the reference --, status

@@ -61,6 +61,9 @@ struct output_options {
 	std::size_t output_mode = STORE_IN_VECTORS;
 	std::size_t output_interval = 1;
 	std::size_t max_samples = 0; // NEW: rows of sample storage per member (0 = final state only)
+	// NEW: dense output on the uniform grid dense_t0 + k*dense_dt, k < dense_samples (project_b, irk.cpp:731-747)
+	std::size_t dense_samples = 0;
+	double dense_t0 = 0.0, dense_dt = 0.0;
 	bool store_in_vectors() const { return output_mode & 1; }
 	void enable_store_in_vectors() { output_mode |= 1; }
 	void disable_store_in_vectors() { output_mode &= ~std::size_t(1); }
@@ -77,8 +80,9 @@ enum rk_methods {
 
 struct solver_options : common_solver_options {
 	solver_options() : adaptive_step_size(true), use_newton_iters_adaptive_step(true), verbose_newton(false),
-	                   extrapolate_stage(false), handout_order(REHUEL_ORDER_LOCALITY) {}
+	                   extrapolate_stage(false), keep_state(false), handout_order(REHUEL_ORDER_LOCALITY) {}
 	bool adaptive_step_size, use_newton_iters_adaptive_step, verbose_newton, extrapolate_stage;
+	bool keep_state; // NEW: keep the controller state so that irk::odeint_continue can carry on (restore_state, irk.cpp:786)
 	int handout_order; // NEW: REHUEL_ORDER_* (scheduling of the batched overload only; results do not depend on it)
 };
 inline solver_options default_solver_options() { return solver_options(); }
@@ -103,6 +107,10 @@ inline rehuel_options to_c_options(const solver_options &so, const output_option
 	o.newton_refresh_jac = so.newton_opts->refresh_jac;
 	o.output_mode = (int)oo.output_mode;
 	o.output_interval = oo.output_interval;
+	o.keep_state = so.keep_state ? 1 : 0;
+	o.dense_samples = oo.dense_samples;
+	o.dense_t0 = oo.dense_t0;
+	o.dense_dt = oo.dense_dt;
 	o.handout_order = so.handout_order;
 	return o;
 }
@@ -147,6 +155,9 @@ public:
 	double t_vals(std::size_t i, std::size_t s) const { return r_.t_samples[s * r_.M + i]; }
 	double y_vals(std::size_t i, std::size_t s, int k) const { return r_.y_samples[(s * r_.n + k) * r_.M + i]; }
 	double err(std::size_t i, std::size_t s) const { return r_.err_samples[s * r_.M + i]; }
+	// dense output of member i at grid time dense_t0 + g*dense_dt (NaN where the member never got)
+	std::size_t n_dense() const { return r_.n_dense; }
+	double y_dense(std::size_t i, std::size_t g, int k) const { return r_.y_dense[(g * r_.n + k) * r_.M + i]; }
 	double elapsed_time() const { return r_.elapsed_ms; } // ms, my_timer.hpp:142-149
 	double kernel_time() const { return r_.kernel_ms; }
 	double accept_frac() const { return r_.accept_frac; }
@@ -190,6 +201,19 @@ inline ensemble_output odeint(int problem, double t0, double t1, const double *y
 	s_opts.newton_opts = &n_opts;
 	output_options output_opts;
 	return odeint(problem, t0, t1, y0, y0_broadcast, params, M, s_opts, output_opts);
+}
+
+// What irk::restore_state (irk.cpp:786-803, an empty stub) was meant for: carry an ensemble that ran with
+// solver_opts.keep_state on to a later end time, every member from its own (t, y, controller state).
+inline ensemble_output odeint_continue(int problem, const ensemble_output &prev, double t1, const double *params,
+                                       solver_options solver_opts, const output_options &output_opts,
+                                       int method = RADAU_IIA_53, int n_gpus = 1, int n_hint = 0)
+{
+	rehuel_options o = to_c_options(solver_opts, output_opts);
+	ensemble_output out;
+	check(rehuel_irk_ensemble_continue(problem, method, t1, n_hint, params, &o,
+	                                   output_opts.store_in_vectors() ? output_opts.max_samples : 0, n_gpus, &prev.raw(), &out.raw()));
+	return out;
 }
 
 // irk::merge_rk_output (irk.cpp:750-783), batched: appends leg 2 to leg 1.

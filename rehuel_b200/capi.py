@@ -38,11 +38,13 @@ class Options(C.Structure):
         ("newton_tol", C.c_double), ("newton_dx_delta", C.c_double),
         ("newton_maxit", C.c_int), ("newton_refresh_jac", C.c_int),
         ("output_mode", C.c_int), ("output_interval", C.c_ulonglong),
+        ("keep_state", C.c_int), ("dense_samples", C.c_ulonglong), ("dense_t0", C.c_double), ("dense_dt", C.c_double),
         ("handout_order", C.c_int),
     ]
 
 
 ORDER_INDEX, ORDER_LOCALITY, ORDER_LOCALITY_DESC = 0, 1, 2
+NSTATE = 8  # rows of the controller state (REHUEL_STATE_*)
 
 
 class Stats(C.Structure):
@@ -66,6 +68,7 @@ class Result(C.Structure):
         ("steps", _PU),
         ("n_samples_cap", C.c_size_t), ("n_samples", _PU),
         ("t_samples", _PD), ("y_samples", _PD), ("err_samples", _PD),
+        ("state", _PD), ("n_dense", C.c_size_t), ("y_dense", _PD),
         ("elapsed_ms", C.c_double), ("kernel_ms", C.c_double), ("accept_frac", C.c_double),
         ("sum", Stats), ("impl", C.c_void_p),
     ]
@@ -81,6 +84,8 @@ class DeviceIO(C.Structure):
         ("queue", C.c_void_p),
         ("trace", C.c_void_p), ("trace_cap", C.c_size_t), ("trace_member", C.c_size_t),
         ("trace_len", C.c_void_p), ("rtol", C.c_void_p), ("atol", C.c_void_p), ("newton_tol", C.c_void_p),
+        ("t_start", C.c_void_p), ("state_in", C.c_void_p), ("state_out", C.c_void_p),
+        ("n_dense", C.c_size_t), ("dense_t0", C.c_double), ("dense_dt", C.c_double), ("y_dense", C.c_void_p),
         ("order", C.c_void_p),
     ]
 
@@ -113,6 +118,9 @@ def _load() -> C.CDLL:
     lib.rehuel_locality_order_workspace.argtypes = [C.c_size_t]
     lib.rehuel_locality_order.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.c_void_p]
+    lib.rehuel_irk_ensemble_continue.argtypes = [
+        C.c_int, C.c_int, C.c_double, C.c_int, _PD, C.POINTER(Options), C.c_size_t, C.c_int, C.POINTER(Result),
+        C.POINTER(Result)]
     lib.rehuel_result_free.argtypes = [C.POINTER(Result)]
     lib.rehuel_result_merge.argtypes = [C.POINTER(Result), C.POINTER(Result)]
     return lib
@@ -126,7 +134,7 @@ EXPORTS = (
     "rehuel_problem_dims", "rehuel_get_coefficients", "rehuel_irk_ensemble", "rehuel_result_free",
     "rehuel_irk_single", "rehuel_irk_ensemble_device", "rehuel_result_merge", "rehuel_kernel_launches",
     "rehuel_kernel_info", "rehuel_last_error", "rehuel_version", "rehuel_fp64_peak", "rehuel_release_cached_memory",
-    "rehuel_locality_order_workspace", "rehuel_locality_order",
+    "rehuel_locality_order_workspace", "rehuel_locality_order", "rehuel_irk_ensemble_continue",
 )
 
 
@@ -147,7 +155,8 @@ def default_options() -> Options:
 
 def make_options(rel_tol=1e-4, abs_tol=None, max_dt=0.0, max_steps=-1, adaptive=True, out_interval=0,
                  newton_tol=None, newton_dx_delta=1e-4, newton_maxit=5000, newton_refresh_jac=10,
-                 output_mode=1, output_interval=1, handout_order=ORDER_LOCALITY) -> Options:
+                 output_mode=1, output_interval=1, handout_order=ORDER_LOCALITY, keep_state=False,
+                 dense_samples=0, dense_t0=0.0, dense_dt=0.0) -> Options:
     """Reference defaults, with newton_tol = 0.1*min(rtol, atol) unless given -- what the example
     driver and the 4-argument odeint do (examples/example_equations.cpp:220, irk.hpp:921)."""
     if abs_tol is None:
@@ -155,7 +164,8 @@ def make_options(rel_tol=1e-4, abs_tol=None, max_dt=0.0, max_steps=-1, adaptive=
     if newton_tol is None:
         newton_tol = 0.1 * min(rel_tol, abs_tol)
     return Options(rel_tol, abs_tol, max_dt, max_steps, int(adaptive), out_interval, newton_tol,
-                   newton_dx_delta, newton_maxit, newton_refresh_jac, output_mode, output_interval, handout_order)
+                   newton_dx_delta, newton_maxit, newton_refresh_jac, output_mode, output_interval, int(keep_state),
+                   dense_samples, dense_t0, dense_dt, handout_order)
 
 
 def name_to_method(name: str) -> int:
@@ -238,6 +248,8 @@ class EnsembleOutput:
     kernel_ms: float
     accept_frac: float
     sum: dict
+    state: np.ndarray | None = None    # [NSTATE, M] controller state at exit (options.keep_state)
+    y_dense: np.ndarray | None = None  # [n_dense, n, M] dense-output samples (options.dense_samples)
 
 
 def _as_np(ptr, shape, dtype):
@@ -263,20 +275,47 @@ def irk_ensemble(problem: int, method: int, t0: float, t1: float, dt0: float, y0
     if raw:
         return res
     try:
-        cap = res.n_samples_cap
-        out = EnsembleOutput(
-            y=_as_np(res.y, (n, M), np.float64), t_final=_as_np(res.t_final, (M,), np.float64),
-            err_last=_as_np(res.err_last, (M,), np.float64), status=_as_np(res.status, (M,), np.int32),
-            counters={k: _as_np(getattr(res, k), (M,), np.uint32) for k in COUNTER_ROWS},
-            n_samples=_as_np(res.n_samples, (M,), np.uint32),
-            t_samples=_as_np(res.t_samples, (cap, M), np.float64) if cap else None,
-            y_samples=_as_np(res.y_samples, (cap, n, M), np.float64) if cap else None,
-            err_samples=_as_np(res.err_samples, (cap, M), np.float64) if cap else None,
-            elapsed_ms=res.elapsed_ms, kernel_ms=res.kernel_ms, accept_frac=res.accept_frac,
-            sum={k: int(getattr(res.sum, k)) for k, _ in Stats._fields_})
+        out = to_output(res)
     finally:
         lib.rehuel_result_free(C.byref(res))
     return out
+
+
+def to_output(res: Result) -> EnsembleOutput:
+    """Copy a raw ``rehuel_result`` into numpy arrays (the C result stays owned by the caller)."""
+    n, M, cap = res.n, res.M, res.n_samples_cap
+    return EnsembleOutput(
+        y=_as_np(res.y, (n, M), np.float64), t_final=_as_np(res.t_final, (M,), np.float64),
+        err_last=_as_np(res.err_last, (M,), np.float64), status=_as_np(res.status, (M,), np.int32),
+        counters={k: _as_np(getattr(res, k), (M,), np.uint32) for k in COUNTER_ROWS},
+        n_samples=_as_np(res.n_samples, (M,), np.uint32),
+        t_samples=_as_np(res.t_samples, (cap, M), np.float64) if cap else None,
+        y_samples=_as_np(res.y_samples, (cap, n, M), np.float64) if cap else None,
+        err_samples=_as_np(res.err_samples, (cap, M), np.float64) if cap else None,
+        elapsed_ms=res.elapsed_ms, kernel_ms=res.kernel_ms, accept_frac=res.accept_frac,
+        sum={k: int(getattr(res.sum, k)) for k, _ in Stats._fields_},
+        state=_as_np(res.state, (NSTATE, M), np.float64) if res.state else None,
+        y_dense=_as_np(res.y_dense, (res.n_dense, n, M), np.float64) if res.n_dense else None)
+
+
+def irk_ensemble_continue(problem: int, method: int, t1: float, params, opts: Options, prev: Result,
+                          n_samples_cap: int = 0, n_gpus: int = 1, n_hint: int = 0) -> Result:
+    """rehuel_irk_ensemble_continue: carry a stopped ensemble (raw result of a keep_state run) on to t1.
+    Returns the RAW result of the new leg (free it with result_free; merge legs with result_merge)."""
+    n, p = problem_dims(problem, n_hint or prev.n)
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(p, -1) if p else np.zeros((1, 1))
+    res = Result()
+    check(lib.rehuel_irk_ensemble_continue(problem, method, t1, n_hint or n, params.ctypes.data_as(_PD), C.byref(opts),
+                                           n_samples_cap, n_gpus, C.byref(prev), C.byref(res)))
+    return res
+
+
+def result_merge(a: Result, b: Result) -> None:
+    check(lib.rehuel_result_merge(C.byref(a), C.byref(b)))
+
+
+def result_free(res: Result) -> None:
+    lib.rehuel_result_free(C.byref(res))
 
 
 def irk_single(problem: int, method: int, t0: float, t1: float, dt0: float, y0, params, opts: Options,

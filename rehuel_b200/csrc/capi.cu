@@ -419,6 +419,14 @@ int ensemble_device(LaunchFn launch, int n, int p, int method, double t0, double
 		ka.io.trace_len = nullptr;
 	}
 	if (ka.io.n_samples_cap == 0 && !ka.io.n_samples) ka.store_samples = 0; // nobody looks at the sample count
+	if (!ka.io.y_dense || ka.io.n_dense == 0) {
+		ka.io.n_dense = 0;
+		ka.io.y_dense = nullptr;
+	} else if (!tb.has_interp) {
+		return fail(REHUEL_EINVAL, "Chosen method does not have dense output!"); // irk.cpp:733
+	} else if (!(ka.io.dense_dt > 0.0)) {
+		return fail(REHUEL_EINVAL, "dense_dt must be > 0");
+	}
 	if ((ka.io.rtol || ka.io.atol || ka.io.newton_tol) && !(ka.io.rtol && ka.io.atol && ka.io.newton_tol))
 		return fail(REHUEL_EINVAL, "per-member tolerances: rtol, atol and newton_tol must all be given");
 	return launch(ka, tb, stream, nullptr);
@@ -427,6 +435,21 @@ int ensemble_device(LaunchFn launch, int n, int p, int method, double t0, double
 int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
                   const double *y0, int y0_broadcast, const double *params, const rehuel_options *opts,
                   size_t n_samples_cap, int n_gpus, rehuel_result *out)
+{
+	return ensemble_host_from(launch, n, p, method, t0, t1, dt0, M, y0, y0_broadcast, params, opts, n_samples_cap, n_gpus,
+	                          nullptr, nullptr, out);
+}
+
+// NaN fill for the dense-output block: grid times a member never reaches stay NaN
+__global__ void __launch_bounds__(256) fill_nan_kernel(double *x, size_t count)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+		x[i] = __longlong_as_double(0x7ff8000000000000ll);
+}
+
+int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
+                       const double *y0, int y0_broadcast, const double *params, const rehuel_options *opts,
+                       size_t n_samples_cap, int n_gpus, const double *t_start, const double *state_in, rehuel_result *out)
 {
 	auto tic = std::chrono::steady_clock::now();
 	if (!out) return fail(REHUEL_EINVAL, "out must not be NULL");
@@ -441,6 +464,10 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 	if (n_gpus < 1) n_gpus = 1;
 	if (n_gpus > ndev) return fail(REHUEL_EINVAL, "n_gpus=%d but only %d CUDA devices are visible", n_gpus, ndev);
 	if (!ka.store_samples) n_samples_cap = 0;
+	const size_t n_dense = (size_t)opts->dense_samples;
+	const bool keep_state = opts->keep_state != 0;
+	if (n_dense && !tb.has_interp) return fail(REHUEL_EINVAL, "Chosen method does not have dense output!"); // irk.cpp:733
+	if (n_dense && !(opts->dense_dt > 0.0)) return fail(REHUEL_EINVAL, "dense_dt must be > 0");
 	int cur_dev = 0;
 	CUDA_TRY(cudaGetDevice(&cur_dev));
 	const int dev0 = (n_gpus == 1) ? cur_dev : 0;
@@ -455,7 +482,8 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 	const size_t max_shards = (size_t)n_gpus * 16;
 	size_t hbytes = Slab::need(M, 8) + Slab::need((size_t)n * M, 8) + Slab::need(M, 8) + Slab::need(M, 4) +
 	                Slab::need((size_t)REHUEL_NCOUNTERS * M, 4) + Slab::need(M, 4) +
-	                Slab::need(max_shards * kStatWords, 8) + 3 * Slab::need(n_samples_cap * M, 8) * (size_t)(n > 1 ? n : 1);
+	                Slab::need(max_shards * kStatWords, 8) + 3 * Slab::need(n_samples_cap * M, 8) * (size_t)(n > 1 ? n : 1) +
+	                (keep_state ? Slab::need((size_t)REHUEL_NSTATE * M, 8) : 0) + Slab::need(n_dense * n * M, 8);
 	Slab hs;
 	hs.base = static_cast<char *>(g_cache.get(-1, hbytes));
 	hs.size = hbytes;
@@ -480,6 +508,11 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 	out->n_samples = n_samples_cap ? hs.take<unsigned>(M) : nullptr; // NULL: no samples were asked for
 	unsigned long long *h_stats = hs.take<unsigned long long>(max_shards * kStatWords);
 	std::memset(h_stats, 0, sizeof(unsigned long long) * max_shards * kStatWords);
+	if (keep_state) out->state = hs.take<double>((size_t)REHUEL_NSTATE * M);
+	if (n_dense) {
+		out->y_dense = hs.take<double>(n_dense * n * M);
+		out->n_dense = n_dense;
+	}
 	if (n_samples_cap) {
 		out->t_samples = hs.take<double>(n_samples_cap * M);
 		out->y_samples = hs.take<double>(n_samples_cap * n * M);
@@ -562,7 +595,9 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			const size_t dbytes = Slab::need(y0_broadcast ? (size_t)n : (size_t)n * m, 8) + Slab::need((size_t)p * m, 8) +
 			                      Slab::need((size_t)(n + 2) * m, 8) + Slab::need((size_t)(1 + REHUEL_NCOUNTERS) * m, 4) +
 			                      Slab::need(m, 4) + Slab::need(1, 8) + Slab::need(kStatWords, 8) +
-			                      3 * Slab::need(n_samples_cap * m, 8) * (size_t)(n > 1 ? n : 1);
+			                      3 * Slab::need(n_samples_cap * m, 8) * (size_t)(n > 1 ? n : 1) +
+			                      (t_start ? Slab::need(m, 8) : 0) + (state_in ? Slab::need((size_t)REHUEL_NSTATE * m, 8) : 0) +
+			                      (keep_state ? Slab::need((size_t)REHUEL_NSTATE * m, 8) : 0) + Slab::need(n_dense * n * m, 8);
 			// hand-out order (order.cu): only pays where the lanes of a warp integrate different members
 			const bool reorder = opts->handout_order != REHUEL_ORDER_INDEX && p > 0 && n <= 4 && m >= 4096;
 			const size_t order_ws = reorder ? locality_order_workspace(m) : 0;
@@ -585,6 +620,17 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			sh.io.n_samples = ds.take<unsigned>(m);
 			sh.io.queue = ds.take<unsigned long long>(1);
 			sh.d_stats = ds.take<unsigned long long>(kStatWords);
+			double *d_tstart = t_start ? ds.take<double>(m) : nullptr;
+			double *d_state_in = state_in ? ds.take<double>((size_t)REHUEL_NSTATE * m) : nullptr;
+			sh.io.state_out = keep_state ? ds.take<double>((size_t)REHUEL_NSTATE * m) : nullptr;
+			sh.io.t_start = d_tstart;
+			sh.io.state_in = d_state_in;
+			if (n_dense) {
+				sh.io.n_dense = n_dense;
+				sh.io.dense_t0 = opts->dense_t0;
+				sh.io.dense_dt = opts->dense_dt;
+				sh.io.y_dense = ds.take<double>(n_dense * n * m);
+			}
 			if (n_samples_cap) {
 				sh.io.t_samples = ds.take<double>(n_samples_cap * m);
 				sh.io.y_samples = ds.take<double>(n_samples_cap * n * m);
@@ -604,6 +650,15 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			if (p)
 				CUDA_TRY(cudaMemcpy2DAsync(d_par, sizeof(double) * m, params + sh.off, sizeof(double) * M,
 				                           sizeof(double) * m, p, cudaMemcpyHostToDevice, sh.stream));
+			if (d_tstart) CUDA_TRY(cudaMemcpyAsync(d_tstart, t_start + sh.off, sizeof(double) * m, cudaMemcpyHostToDevice, sh.stream));
+			if (d_state_in)
+				CUDA_TRY(cudaMemcpy2DAsync(d_state_in, sizeof(double) * m, state_in + sh.off, sizeof(double) * M,
+				                           sizeof(double) * m, REHUEL_NSTATE, cudaMemcpyHostToDevice, sh.stream));
+			if (n_dense) {
+				fill_nan_kernel<<<296, 256, 0, sh.stream>>>(sh.io.y_dense, n_dense * n * m);
+				CUDA_TRY(cudaGetLastError());
+				g_launches.fetch_add(1);
+			}
 			CUDA_TRY(cudaMemsetAsync(sh.d_stats, 0, sizeof(unsigned long long) * kStatWords, sh.stream));
 			if (reorder) {
 				unsigned *d_order = ds.take<unsigned>(m);
@@ -627,6 +682,12 @@ int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t
 			                           (size_t)n + 2, cudaMemcpyDeviceToHost, sh.stream));
 			CUDA_TRY(cudaMemcpy2DAsync(hint + sh.off, sizeof(int) * M, dint, sizeof(int) * m, sizeof(int) * m,
 			                           (size_t)1 + REHUEL_NCOUNTERS, cudaMemcpyDeviceToHost, sh.stream));
+			if (keep_state)
+				CUDA_TRY(cudaMemcpy2DAsync(out->state + sh.off, sizeof(double) * M, sh.io.state_out, sizeof(double) * m,
+				                           sizeof(double) * m, REHUEL_NSTATE, cudaMemcpyDeviceToHost, sh.stream));
+			if (n_dense)
+				CUDA_TRY(cudaMemcpy2DAsync(out->y_dense + sh.off, sizeof(double) * M, sh.io.y_dense, sizeof(double) * m,
+				                           sizeof(double) * m, n_dense * n, cudaMemcpyDeviceToHost, sh.stream));
 			if (n_samples_cap)
 				CUDA_TRY(cudaMemcpyAsync(out->n_samples + sh.off, sh.io.n_samples, sizeof(unsigned) * m, cudaMemcpyDeviceToHost, sh.stream));
 			if (n_samples_cap) {
@@ -784,6 +845,10 @@ void rehuel_default_options(rehuel_options *o)
 	o->newton_refresh_jac = 10;        // newton.hpp:59
 	o->output_mode = 1;                // options.hpp:103 STORE_IN_VECTORS
 	o->output_interval = 1;            // options.hpp:104
+	o->keep_state = 0;
+	o->dense_samples = 0;
+	o->dense_t0 = 0.0;
+	o->dense_dt = 0.0;
 	o->handout_order = REHUEL_ORDER_LOCALITY;
 }
 
@@ -903,6 +968,22 @@ int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt
 	return ensemble_host(launch, n, p, method, t0, t1, dt0, M, y0, y0_broadcast, params, opts, n_samples_cap, n_gpus, out);
 }
 
+int rehuel_irk_ensemble_continue(int problem, int method, double t1, int n_hint, const double *params,
+                                 const rehuel_options *opts, size_t n_samples_cap, int n_gpus,
+                                 const rehuel_result *prev, rehuel_result *out)
+{
+	if (!prev || !prev->y || !prev->t_final) return fail(REHUEL_EINVAL, "continue: `prev` must be a result of this library");
+	if (!prev->state) return fail(REHUEL_EINVAL, "continue: the previous call must run with options.keep_state != 0");
+	int n = 0, p = 0;
+	if (rehuel_problem_dims(problem, n_hint ? n_hint : prev->n, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
+	if (n != prev->n) return fail(REHUEL_EINVAL, "continue: problem has n = %d but `prev` holds n = %d", n, prev->n);
+	LaunchFn launch = find_launcher(problem, n);
+	if (!launch) return REHUEL_EINVAL;
+	// dt0 is only a placeholder here: every member's step size comes from its state
+	return ensemble_host_from(launch, n, p, method, prev->t_final[0], t1, 1e-6, prev->M, prev->y, 0, params, opts, n_samples_cap,
+	                          n_gpus, prev->t_final, prev->state, out);
+}
+
 void rehuel_release_cached_memory(void)
 {
 	g_cache.trim();
@@ -997,6 +1078,14 @@ int rehuel_result_merge(rehuel_result *a, const rehuel_result *b)
 		a->t_final[i] = b->t_final[i];
 		a->err_last[i] = b->err_last[i];
 		for (int c = 0; c < n; ++c) a->y[c * M + i] = b->y[c * M + i];
+	}
+	// controller state: the merged run stopped where leg 2 stopped
+	if (a->state && b->state) std::memcpy(a->state, b->state, sizeof(double) * REHUEL_NSTATE * M);
+	// dense output on a common grid: each leg filled the grid times it covered, the rest is NaN
+	if (a->y_dense && b->y_dense && a->n_dense == b->n_dense) {
+		const size_t cnt = a->n_dense * (size_t)n * M;
+		for (size_t i = 0; i < cnt; ++i)
+			if (a->y_dense[i] != a->y_dense[i]) a->y_dense[i] = b->y_dense[i];
 	}
 	a->n_samples = ns;
 	a->t_samples = ts;

@@ -307,8 +307,22 @@ __device__ __forceinline__ double propose_dt(double dt, double err, double &q_pr
 	return new_dt;
 }
 
+// Dense-output weights of one grid time inside an accepted step:
+// w_i(theta) = sum_k Wd[i][k] theta^(S-k) by Horner, so that y(t + theta dt) = y + sum_i w_i Y_i.
+template <int S, int NC>
+__device__ __forceinline__ void dense_weights(const DevTableau<S, NC> &tb, double theta, double (&w)[S])
+{
+#pragma unroll
+	for (int i = 0; i < S; ++i) {
+		double acc = tb.Wd[i][0];
+#pragma unroll
+		for (int k = 1; k < S; ++k) acc = fma(acc, theta, tb.Wd[i][k]);
+		w[i] = acc * theta;
+	}
+}
+
 // ------------------------------------------------------------------ the kernel
-template <class F, int S, int NR, int NC, int EST, int BLOCK, int MIN_BLOCKS, bool TOLV = false>
+template <class F, int S, int NR, int NC, int EST, int BLOCK, int MIN_BLOCKS, bool TOLV = false, bool DENSE = false>
 #ifdef REHUEL_MAXNREG
 __global__ void __maxnreg__(REHUEL_MAXNREG)
 #else
@@ -339,6 +353,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	int status = REHUEL_SUCCESS;
 	unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0,
 	         c_iters = 0, n_stored = 0;
+	unsigned kd = 0; // dense output: index of the next grid time (DENSE kernels only)
 	// per-member tolerances (TOLV kernels only; otherwise the uniform values of the options)
 	double m_rtol = a.rtol, m_atol = a.atol, m_Rtol2 = a.Rtol2;
 
@@ -365,7 +380,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						const double nt = io.newton_tol[mem];
 						m_Rtol2 = nt * nt;
 					}
-					t = a.t0;
+					t = io.t_start ? io.t_start[mem] : a.t0;
 					dt = a.dt0;
 					if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
 					dts0 = dts1 = dt;                 // irk.hpp:572
@@ -375,6 +390,26 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					maxit = a.maxit0;
 					step = 0;
 					last_relax = 0;
+					if (io.state_in) { // continue a stopped integration: the loop variables as they were at exit
+						const double *si = io.state_in + mem;
+						dt = si[REHUEL_STATE_DT * M];
+						dts0 = si[REHUEL_STATE_DTS0 * M];
+						dts1 = si[REHUEL_STATE_DTS1 * M];
+						q_prev = si[REHUEL_STATE_ERRQ * M];
+						alt = si[REHUEL_STATE_ALT * M] != 0.0;
+						maxit = (int)si[REHUEL_STATE_MAXIT * M];
+						step = (long long)si[REHUEL_STATE_STEP * M];
+						last_relax = (long long)si[REHUEL_STATE_LAST_RELAX * M];
+					}
+					if (DENSE) { // grid times before the start are not this call's; one AT the start is the initial state
+						kd = 0;
+						while (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) < t) ++kd;
+						if (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) == t) {
+#pragma unroll
+							for (int k = 0; k < N; ++k) io.y_dense[((size_t)kd * N + k) * M + mem] = y[k];
+							++kd;
+						}
+					}
 					status = REHUEL_SUCCESS;
 					c_attempt = c_rej_newton = c_rej_err = c_newton_ok = c_fun = c_jac = c_iters = 0;
 					n_stored = 0;
@@ -722,6 +757,23 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						}
 					}
 					if (!rejected) { // irk.hpp:813-846
+						if (DENSE) { // grid times inside (t, t + dt] from this step's collocation polynomial
+							const double t_new = t + dt;
+							while (kd < io.n_dense) {
+								const double tk = fma((double)kd, io.dense_dt, io.dense_t0);
+								if (tk > t_new) break;
+								double w[S];
+								dense_weights<S, NC>(tb, (tk - t) * rdt, w);
+#pragma unroll
+								for (int k = 0; k < N; ++k) {
+									double acc = y[k];
+#pragma unroll
+									for (int i = 0; i < S; ++i) acc = fma(w[i], Y[i][k], acc);
+									io.y_dense[((size_t)kd * N + k) * M + mem] = (tk == t_new) ? yn[k] : acc;
+								}
+								++kd;
+							}
+						}
 #pragma unroll
 						for (int k = 0; k < N; ++k) y[k] = yn[k];
 						const double t_old = t;
@@ -769,6 +821,17 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				io.counters[REHUEL_CNT_STEPS * M + mem] = (unsigned)step;
 			}
 			if (io.n_samples) io.n_samples[mem] = n_stored;
+			if (io.state_out) {
+				double *so = io.state_out + mem;
+				so[REHUEL_STATE_DT * M] = dt;
+				so[REHUEL_STATE_DTS0 * M] = dts0;
+				so[REHUEL_STATE_DTS1 * M] = dts1;
+				so[REHUEL_STATE_ERRQ * M] = q_prev;
+				so[REHUEL_STATE_ALT * M] = alt ? 1.0 : 0.0;
+				so[REHUEL_STATE_MAXIT * M] = (double)maxit;
+				so[REHUEL_STATE_STEP * M] = (double)step;
+				so[REHUEL_STATE_LAST_RELAX * M] = (double)last_relax;
+			}
 			have = false;
 		}
 	}

@@ -325,7 +325,7 @@ __device__ __forceinline__ void band_solve_cplx(const double *abr, const double 
 }
 
 // ------------------------------------------------------------------ the kernel: one warp per block
-template <class F, int S, int NR, int NC, int EST>
+template <class F, int S, int NR, int NC, int EST, bool DENSE = false>
 __global__ void __launch_bounds__(32)
 ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ DevTableau<S, NC> tb)
 {
@@ -358,7 +358,7 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 		__syncwarp();
 
 		// ---------------- per-member scalar state (identical in every lane)
-		double t = a.t0, dt = a.dt0;
+		double t = io.t_start ? io.t_start[mem] : a.t0, dt = a.dt0;
 		if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
 		double dts0 = dt, dts1 = dt, q_prev = tb.q_init, err = 0.0; // q_prev: see propose_dt (irk_thread.cuh)
 		bool alt = true;
@@ -367,6 +367,25 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 		int status = REHUEL_SUCCESS;
 		unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0, c_iters = 0,
 		         n_stored = 0;
+		if (io.state_in) { // continue a stopped integration: the loop variables as they were at exit
+			const double *si = io.state_in + mem;
+			dt = si[REHUEL_STATE_DT * M];
+			dts0 = si[REHUEL_STATE_DTS0 * M];
+			dts1 = si[REHUEL_STATE_DTS1 * M];
+			q_prev = si[REHUEL_STATE_ERRQ * M];
+			alt = si[REHUEL_STATE_ALT * M] != 0.0;
+			maxit = (int)si[REHUEL_STATE_MAXIT * M];
+			step = (long long)si[REHUEL_STATE_STEP * M];
+			last_relax = (long long)si[REHUEL_STATE_LAST_RELAX * M];
+		}
+		unsigned kd = 0; // dense output: next grid time (see irk_thread.cuh)
+		if (DENSE) {
+			while (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) < t) ++kd;
+			if (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) == t) {
+				for (int k = lane; k < N; k += 32) io.y_dense[((size_t)kd * N + k) * M + mem] = y[k];
+				++kd;
+			}
+		}
 		if (a.store_samples) {
 			if (io.n_samples_cap) {
 				if (lane == 0) {
@@ -592,6 +611,22 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			const double new_dt = propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
 			bool stuck = false;
 			if (!rejected) { // irk.hpp:813-846
+				if (DENSE) { // grid times inside (t, t + dt] from this step's collocation polynomial
+					const double t_new = t + dt;
+					while (kd < io.n_dense) {
+						const double tk = fma((double)kd, io.dense_dt, io.dense_t0);
+						if (tk > t_new) break;
+						double w[S];
+						dense_weights<S, NC>(tb, (tk - t) * rdt, w);
+						for (int i = lane; i < N; i += 32) {
+							double acc = y[i];
+#pragma unroll
+							for (int s = 0; s < S; ++s) acc = fma(w[s], Y[s * N + i], acc);
+							io.y_dense[((size_t)kd * N + i) * M + mem] = (tk == t_new) ? yn[i] : acc;
+						}
+						++kd;
+					}
+				}
 				for (int i = lane; i < N; i += 32) y[i] = yn[i];
 				const double t_old = t;
 				t += dt;
@@ -639,6 +674,17 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 				io.counters[REHUEL_CNT_STEPS * M + mem] = (unsigned)step;
 			}
 			if (io.n_samples) io.n_samples[mem] = n_stored;
+			if (io.state_out) {
+				double *so = io.state_out + mem;
+				so[REHUEL_STATE_DT * M] = dt;
+				so[REHUEL_STATE_DTS0 * M] = dts0;
+				so[REHUEL_STATE_DTS1 * M] = dts1;
+				so[REHUEL_STATE_ERRQ * M] = q_prev;
+				so[REHUEL_STATE_ALT * M] = alt ? 1.0 : 0.0;
+				so[REHUEL_STATE_MAXIT * M] = (double)maxit;
+				so[REHUEL_STATE_STEP * M] = (double)step;
+				so[REHUEL_STATE_LAST_RELAX * M] = (double)last_relax;
+			}
 		}
 		__syncwarp();
 	}

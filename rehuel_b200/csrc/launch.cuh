@@ -34,6 +34,10 @@ using LaunchFn = int (*)(const KernelArgs &, const Tableau &, cudaStream_t, Kern
 int ensemble_host(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
                   const double *y0, int y0_broadcast, const double *params, const rehuel_options *opts,
                   size_t n_samples_cap, int n_gpus, rehuel_result *out);
+// The same, continuing from per-member start times and controller state (host arrays [M], [REHUEL_NSTATE][M]; NULL = fresh start).
+int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
+                       const double *y0, int y0_broadcast, const double *params, const rehuel_options *opts,
+                       size_t n_samples_cap, int n_gpus, const double *t_start, const double *state_in, rehuel_result *out);
 // Device-resident variant; same semantics as rehuel_irk_ensemble_device.
 int ensemble_device(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
                     const rehuel_options *opts, const rehuel_device_io *io, cudaStream_t stream);
@@ -73,6 +77,14 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 			return set_error(REHUEL_EINVAL, "per-member tolerances are built for the 3-stage methods only");
 		}
 	}
+	if (ka.io.n_dense) { // dense output: separate instantiation (the stage values stay live to the end of the attempt)
+		if (ka.io.rtol) return set_error(REHUEL_EINVAL, "dense output and per-member tolerances cannot be combined");
+		if constexpr (EST != EST_IDENTITY) { // exactly the tableaux that carry b_interp
+			kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS, false, true>;
+		} else {
+			return set_error(REHUEL_EINVAL, "Chosen method does not have dense output!"); // irk.cpp:733
+		}
+	}
 	if (tb.s != S || tb.n_real != NR || tb.n_cplx != NC || tb.est_mode != EST)
 		return set_error(REHUEL_EINVAL, "internal: tableau %s does not have the structure its kernel was built for", tb.name);
 	int dev = 0, sms = 0, per_sm = 0;
@@ -80,8 +92,8 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 	{
 		// SM count and occupancy per (kernel instantiation, device), queried once: three driver calls per launch
 		// are noticeable when a host call issues 8 chunk launches back to back.  Benign race: same values.
-		static int cache_sms[2][64], cache_per_sm[2][64];
-		const int v = ka.io.rtol ? 1 : 0;
+		static int cache_sms[3][64], cache_per_sm[3][64];
+		const int v = ka.io.rtol ? 1 : (ka.io.n_dense ? 2 : 0);
 		if (dev < 64 && cache_per_sm[v][dev] > 0) {
 			sms = cache_sms[v][dev];
 			per_sm = cache_per_sm[v][dev];
@@ -142,7 +154,14 @@ template <class F, int S, int NR, int NC, int EST>
 int launch_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
 {
 	constexpr int THREADS = (F::N <= 16) ? 128 : 256;
-	auto kern = ensemble_irk_cta<F, S, NR, NC, EST, THREADS>;
+	void (*kern)(const KernelArgs, const DevTableau<S, NC>) = ensemble_irk_cta<F, S, NR, NC, EST, THREADS, false>;
+	if (ka.io.n_dense) {
+		if constexpr (EST != EST_IDENTITY) {
+			kern = ensemble_irk_cta<F, S, NR, NC, EST, THREADS, true>;
+		} else {
+			return set_error(REHUEL_EINVAL, "Chosen method does not have dense output!"); // irk.cpp:733
+		}
+	}
 	const size_t smem = CtaSmem<F, S, NC>::bytes;
 	int dev = 0, sms = 0, per_sm = 0;
 	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
@@ -176,7 +195,14 @@ int launch_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ker
 template <class F, int S, int NR, int NC, int EST>
 int launch_warp(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
 {
-	auto kern = ensemble_irk_warp<F, S, NR, NC, EST>;
+	void (*kern)(const KernelArgs, const DevTableau<S, NC>) = ensemble_irk_warp<F, S, NR, NC, EST, false>;
+	if (ka.io.n_dense) {
+		if constexpr (EST != EST_IDENTITY) {
+			kern = ensemble_irk_warp<F, S, NR, NC, EST, true>;
+		} else {
+			return set_error(REHUEL_EINVAL, "Chosen method does not have dense output!"); // irk.cpp:733
+		}
+	}
 	const size_t smem = WarpSmem<F, S, NC, EST>::bytes;
 	if (tb.s != S || tb.n_real != NR || tb.n_cplx != NC || tb.est_mode != EST)
 		return set_error(REHUEL_EINVAL, "internal: tableau %s does not have the structure its kernel was built for", tb.name);

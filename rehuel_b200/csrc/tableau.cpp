@@ -269,7 +269,16 @@ bool get_coefficients(int method, Tableau &tb)
 		if (tb.gamma == 0.0) tb.est_mode = EST_IDENTITY;
 		else if (tb.n_real && std::fabs(tb.gamma * tb.gamma_hat - 1.0) < 1e-13) tb.est_mode = EST_REUSE;
 		else tb.est_mode = EST_OWN_LU;
-		if (interp) build_interpolant(tb);
+		if (interp) {
+			build_interpolant(tb);
+			// w_interp[:, k] = A^-T b_interp[:, k]
+			for (int k = 0; k < tb.s; ++k) {
+				double col[MAX_S], w[MAX_S];
+				for (int j = 0; j < tb.s; ++j) col[j] = tb.b_interp[j][k];
+				if (!solve_transposed(tb, col, w)) return false;
+				for (int i = 0; i < tb.s; ++i) tb.w_interp[i][k] = w[i];
+			}
+		}
 		return true;
 	}
 	return false;

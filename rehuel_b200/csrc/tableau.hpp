@@ -35,6 +35,9 @@ struct Tableau {
 	// dense output: b_j(theta) = sum_k b_interp[j][k] theta^(s-k)  (irk.cpp:111-210, 731-747)
 	bool has_interp = false;
 	double b_interp[MAX_S][MAX_S] = {};
+	// dense output in terms of the stage increments Y_i the kernels hold:  y(t + theta dt) = y + sum_i w_i(theta) Y_i,
+	// w(theta) = A^-T b(theta)  =>  w_i(theta) = sum_k w_interp[i][k] theta^(s-k)   (w(1) = d)
+	double w_interp[MAX_S][MAX_S] = {};
 };
 
 // Returns false if the method id is unknown / unsupported by the GPU path.
@@ -59,6 +62,7 @@ struct DevTableau {
 	double rgamma;    // 1/gamma (0 if gamma == 0)
 	double gamma_hat; // real eigenvalue of inv(A) (0 if none)
 	double alpha[NC > 0 ? NC : 1], beta[NC > 0 ? NC : 1];
+	double Wd[S][S];  // dense output: w_i(theta) = sum_k Wd[i][k] theta^(S-k), y(t + theta dt) = y + sum_i w_i Y_i
 	double expo;      // 1/(1+min(order,order2))  (irk.hpp:588, 774)
 	double q_init;    // 0.9^expo: the controller's initial error history (irk.hpp:573) as propose_dt carries it
 	int min_order;
@@ -73,6 +77,7 @@ inline DevTableau<S, NC> make_dev_tableau(const Tableau &tb)
 			dt.A[i][j] = tb.A[i][j];
 			dt.T[i][j] = tb.T[i][j];
 			dt.Ti[i][j] = tb.Ti[i][j];
+			dt.Wd[i][j] = tb.w_interp[i][j];
 		}
 		for (int j = 0; j < S; ++j) dt.Asum[i] += tb.A[i][j];
 		dt.c[i] = tb.c[i];

@@ -424,6 +424,108 @@ def test_brusselator_mol_64_equations_warp_and_cta_per_system(capi, port):
     assert abs(int(g.counters["attempt"].sum()) - int(r.counters["attempt"].sum())) <= 0.02 * r.counters["attempt"].sum()
 
 
+def test_continue_with_controller_state(capi, port):
+    """rehuel_irk_ensemble_continue (what irk::restore_state, an empty stub at irk.cpp:786-803, was meant for):
+    [0,10] with keep_state, then on to 40, against one leg [0,40] and against the oracle; the continued leg must not
+    pay the restart transient a cold second call pays; rehuel_result_merge adds the legs up."""
+    from rehuel_b200 import ensembles
+    M = 4096
+    P = ensembles.robertson_params(M)
+    o = capi.make_options(1e-6, 1e-6, keep_state=True)
+    one = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, o)
+    leg1 = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 10.0, 1e-6, ensembles.ROBERTSON_Y0, P, o, raw=True)
+    l1 = capi.to_output(leg1)
+    assert l1.state is not None and l1.state.shape == (capi.NSTATE, M) and np.all(l1.state[0] > 0)
+    leg2 = capi.irk_ensemble_continue(capi.ROBERTSON, 211, 40.0, P, o, leg1)
+    l2 = capi.to_output(leg2)
+    cold = capi.irk_ensemble(capi.ROBERTSON, 211, 10.0, 40.0, 1e-6, l1.y, P, o)
+    assert np.all(l2.status == 0) and np.all(l2.t_final == 40.0)
+    assert scaled_err(l2.y, one.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+    r = port.solve("robertson", 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, :256].copy(), ref_options(1e-6, 1e-6))
+    assert scaled_err(l2.y[:, :256], r.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+    a1, a2, a_one, a_cold = (x.counters["attempt"].astype(np.int64) for x in (l1, l2, one, cold))
+    print(f"\nattempts/member: one leg {a_one.mean():.2f}; two legs {a1.mean():.2f} + {a2.mean():.2f} (continued) vs + {a_cold.mean():.2f} (cold restart)")
+    assert (a1 + a2).mean() <= a_one.mean() + 2.5          # the stop at t = 10 costs about one clamped step
+    assert a_cold.mean() >= a2.mean() + 5                   # dt0 = 1e-6 has to grow back by factors of <= 8
+    capi.result_merge(leg1, leg2)
+    m = capi.to_output(leg1)
+    assert np.array_equal(m.counters["attempt"], (a1 + a2).astype(np.uint32)) and np.all(m.t_final == 40.0)
+    assert np.array_equal(m.y, l2.y) and np.array_equal(m.state, l2.state)
+    capi.result_free(leg1)
+    capi.result_free(leg2)
+    # without keep_state there is nothing to continue from: loud error
+    plain = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 1.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, :8].copy(),
+                              capi.make_options(1e-6, 1e-6), raw=True)
+    with pytest.raises(capi.RehuelError):
+        capi.irk_ensemble_continue(capi.ROBERTSON, 211, 2.0, P[:, :8].copy(), o, plain)
+    capi.result_free(plain)
+    # the warp-per-system kernel carries state the same way
+    Pb, yb = ensembles.bruss1d_params(4), ensembles.bruss1d_y0(32)
+    b_one = capi.irk_ensemble(capi.BRUSSELATOR_1D, 211, 0.0, 4.0, 1e-6, yb, Pb, o)
+    b1 = capi.irk_ensemble(capi.BRUSSELATOR_1D, 211, 0.0, 1.5, 1e-6, yb, Pb, o, raw=True)
+    b2 = capi.to_output(capi.irk_ensemble_continue(capi.BRUSSELATOR_1D, 211, 4.0, Pb, o, b1, n_hint=64))
+    assert np.all(b2.status == 0) and scaled_err(b2.y, b_one.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+    assert capi.to_output(b1).counters["attempt"].sum() + b2.counters["attempt"].sum() <= b_one.counters["attempt"].sum() + 3 * 4
+
+
+def test_dense_output_on_a_uniform_grid(capi, port):
+    """Dense output: y(t_n + theta dt) = y_n + sum_j b_j(theta) dt k_j with the b_j(theta) of
+    irk::project_b (irk.cpp:731-747, pinned by golden vectors in test_capi_host.py).
+    (a) exact check on y' = l y, where the collocation polynomial of a step can be restated in numpy from (t_n, y_n);
+    (b) Robertson against the oracle integrated to every grid time; (c) unreachable grid times stay NaN,
+    methods without b_interp are refused, the warp-per-system kernel samples the same way."""
+    from rehuel_b200 import ensembles
+    lam = np.array([[-0.4, -3.0, -25.0, 0.7]])
+    K, Dt = 21, 0.1
+    for method in (210, 211, 212, 232):
+        o = capi.make_options(1e-6, 1e-6, dense_samples=K, dense_t0=0.0, dense_dt=Dt)
+        g = capi.irk_ensemble(capi.EXPONENTIAL, method, 0.0, 2.0, 1e-3, np.array([1.0]), lam, o, n_samples_cap=4096)
+        assert np.all(g.status == 0) and g.y_dense.shape == (K, 1, 4) and np.all(np.isfinite(g.y_dense))
+        tab = capi.get_coefficients(method)
+        A, s = tab["A"], tab["s"]
+        worst = 0.0
+        for i in range(4):
+            ns = int(g.n_samples[i])
+            tn, yn = g.t_samples[:ns, i], g.y_samples[:ns, 0, i]
+            for k in range(K):
+                tk = 0.0 + k * Dt
+                j = np.searchsorted(tn, tk, side="left")  # step (tn[j-1], tn[j]] covers tk
+                if j == 0:
+                    want = 1.0
+                else:
+                    h = tn[j] - tn[j - 1]
+                    theta = (tk - tn[j - 1]) / h
+                    z = h * lam[0, i]
+                    Y = np.linalg.solve(np.eye(s) - z * A, z * A @ np.ones(s)) * yn[j - 1]  # stage increments
+                    w = np.linalg.solve(A.T, capi.project_b(method, theta))
+                    want = yn[j - 1] + w @ Y
+                worst = max(worst, abs(g.y_dense[k, 0, i] - want) / abs(want))
+        print(f"\ndense output, y' = l y, method {method}: max rel. deviation from the numpy collocation polynomial {worst:.2e}")
+        assert worst <= 2e-9  # the Newton iteration stops at |R| < 1e-7 * tolerance scale, not at rounding
+    # (b) Robertson, 8 members, grid of 9 times
+    M, K, Dt = 8, 9, 5.0
+    P = ensembles.robertson_params(M)
+    o = capi.make_options(1e-6, 1e-6, dense_samples=K, dense_t0=0.0, dense_dt=Dt)
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, o)
+    assert np.array_equal(g.y_dense[0], np.tile(ensembles.ROBERTSON_Y0[:, None], (1, M)))
+    assert np.array_equal(g.y_dense[8], g.y)  # t = 40 is the end point itself
+    for k in range(1, K):
+        r = port.solve("robertson", 211, 0.0, k * Dt, 1e-6, ensembles.ROBERTSON_Y0, P, ref_options(1e-8, 1e-8))
+        se = scaled_err(g.y_dense[k], r.y, 1e-6, 1e-6).max()
+        assert se <= 50.0, (k, se)  # a 3-stage collocation polynomial is O(h^4) inside the step, the step end O(h^6)
+    # (c)
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 12.0, 1e-6, ensembles.ROBERTSON_Y0, P, o)
+    assert np.all(np.isfinite(g.y_dense[:3])) and np.all(np.isnan(g.y_dense[3:]))
+    with pytest.raises(capi.RehuelError):
+        capi.irk_ensemble(capi.ROBERTSON, 230, 0.0, 1.0, 1e-6, ensembles.ROBERTSON_Y0, P, o)
+    Pb, yb = ensembles.bruss1d_params(3), ensembles.bruss1d_y0(32)
+    ob = capi.make_options(1e-6, 1e-6, dense_samples=5, dense_t0=0.0, dense_dt=0.5)
+    gw = capi.irk_ensemble(capi.BRUSSELATOR_1D, 211, 0.0, 2.0, 1e-6, yb, Pb, ob)
+    gc = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, 211, 0.0, 2.0, 1e-6, yb, Pb, ob)
+    assert np.all(np.isfinite(gw.y_dense)) and np.array_equal(gw.y_dense[4], gw.y)
+    assert scaled_err(gw.y_dense.reshape(-1, 3), gc.y_dense.reshape(-1, 3), 1e-6, 1e-6).max() <= PARITY_BOUND
+
+
 def test_mixed_stiffness_mixed_tolerance_ensemble(capi, port):
     """Config-5 shape: even members Robertson (config-2 sweep), odd members Van der Pol (config-3
     sweep), per-member rtol = atol = 10^(-3-6v), newton tol = 0.1 rtol.  The two problem classes
