@@ -14,7 +14,11 @@ NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC
              --expt-relaxed-constexpr -Xptxas -v
 SRC       := rehuel_b200/csrc
 LIB       := rehuel_b200/librehuel_b200.so
-OBJS      := build/capi.o build/order.o build/tableau.o
+INST      := robertson van_der_pol exponential stiff_eq brusselator lorenz harmonic dimer kinetic4 \
+             bruss1d_64 bruss1d_8 bruss1d_dense_64 bruss1d_dense_8
+OBJS      := build/capi.o build/order.o build/tableau.o $(INST:%=build/inst_%.o)
+KHDRS     := $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/irk_warp.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh \
+             $(SRC)/tableau.hpp include/rehuel_b200.h
 
 .PHONY: all oracle clean sass examples tableaux
 all: $(LIB)
@@ -22,8 +26,12 @@ all: $(LIB)
 build:
 	mkdir -p build
 
-build/capi.o: $(SRC)/capi.cu $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/irk_warp.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh $(SRC)/tableau.hpp include/rehuel_b200.h | build
+build/capi.o: $(SRC)/capi.cu $(KHDRS) | build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/capi.ptxas.log || (cat build/capi.ptxas.log; false)
+
+# one translation unit per built-in functor: `make -j` compiles the kernel instantiations in parallel
+build/inst_%.o: $(SRC)/instances/inst_%.cu $(KHDRS) | build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/inst_$*.ptxas.log || (cat build/inst_$*.ptxas.log; false)
 
 build/order.o: $(SRC)/order.cu $(SRC)/launch.cuh include/rehuel_b200.h | build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/order.ptxas.log || (cat build/order.ptxas.log; false)
@@ -40,10 +48,12 @@ tableaux:
 	python tools/gen_tableaux.py
 
 # Programs on the three faces of the boundary: C ABI, C++ API (built-in problem), C++ user functor.
-examples: build/c_interface_test build/cpp_api build/user_functor
+examples: build/c_interface_test build/cpp_api build/user_functor build/rehuel_example
 build/c_interface_test: examples/c_interface_test.c include/rehuel_b200.h $(LIB)
 	/usr/bin/gcc -std=c11 -O2 -Wall -Iinclude $< -o $@ -Lrehuel_b200 -lrehuel_b200 -lm -Wl,-rpath,'$$ORIGIN/../rehuel_b200'
 build/cpp_api: examples/cpp_api.cpp include/rehuel_b200/irk.hpp $(LIB)
+	$(HOSTCXX) -std=c++11 -O2 -Wall -Iinclude $< -o $@ -Lrehuel_b200 -lrehuel_b200 -Wl,-rpath,'$$ORIGIN/../rehuel_b200'
+build/rehuel_example: examples/rehuel_example.cpp include/rehuel_b200/irk.hpp include/rehuel_b200.h $(LIB)
 	$(HOSTCXX) -std=c++11 -O2 -Wall -Iinclude $< -o $@ -Lrehuel_b200 -lrehuel_b200 -Wl,-rpath,'$$ORIGIN/../rehuel_b200'
 build/user_functor: examples/user_functor.cu include/rehuel_b200/irk.cuh $(SRC)/launch.cuh $(SRC)/irk_thread.cuh $(LIB)
 	$(NVCC) -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) --expt-relaxed-constexpr -Iinclude $< -o $@ \
@@ -55,7 +65,7 @@ oracle:
 sass: $(LIB)
 	mkdir -p profiles
 	/usr/local/cuda/bin/cuobjdump -sass $(LIB) > profiles/librehuel_b200.sass
-	cp build/capi.ptxas.log profiles/ptxas_v.log
+	cat build/inst_*.ptxas.log > profiles/ptxas_v.log
 
 clean:
 	rm -rf build $(LIB)

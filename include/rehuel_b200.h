@@ -59,6 +59,10 @@ extern "C" {
 #define REHUEL_PROBLEM_EXPONENTIAL    5 /* n=1, params (lambda);   test_equations.hpp:37-59 */
 #define REHUEL_PROBLEM_STIFF_EQ       6 /* n=2, no params;         test_equations.hpp:207-250 */
 #define REHUEL_PROBLEM_BRUSSELATOR    7 /* n=2, params (a,b);      test_equations.hpp:120-145 */
+#define REHUEL_PROBLEM_LORENZ         8 /* n=3, params (sigma,rho,beta); test_equations.hpp:519-543 */
+#define REHUEL_PROBLEM_HARMONIC       9 /* n=2, params (w);        test_equations.hpp:63-84 */
+#define REHUEL_PROBLEM_DIMER         10 /* n=2, params (rate);     test_equations.hpp:180-203 */
+#define REHUEL_PROBLEM_KINETIC_4     11 /* n=4, params (b2,b3,b4); test_equations.hpp:484-517 */
 
 /* Solver options.  Replaces irk::solver_options (irk.hpp:95-124) : common_solver_options
  * (options.hpp:40-85), the newton::options it points to (newton.hpp:57-78; only tol, dx_delta,
@@ -106,8 +110,8 @@ void rehuel_default_options(rehuel_options *opts);
 int rehuel_name_to_method(const char *name);
 const char *rehuel_method_to_name(int method);
 
-/* Problem registry ("robertson", "van-der-pol", "brusselator-1d", "exponential",
- * "stiff-equation", "brusselator").  Unknown -> 0. */
+/* Problem registry ("robertson", "van-der-pol", "brusselator-1d", "brusselator-1d-dense", "exponential",
+ * "stiff-equation", "brusselator", "lorenz", "harmonic", "dimer", "kinetic-4").  Unknown -> 0. */
 int rehuel_name_to_problem(const char *name);
 /* n = number of equations, p = number of parameters.  n_hint selects n for size-generic
  * problems (brusselator-1d: n = 2*Ng), ignored otherwise.  Returns REHUEL_EINVAL if unknown. */

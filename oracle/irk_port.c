@@ -244,7 +244,8 @@ static void inv_transpose_times(const tableau *tb, const double *w, double *d)
 
 /* ------------------------------------------------------------------ problems (functor concept) */
 enum { REF_ROBERTSON = 1, REF_VDPOL = 2, REF_BRUSS1D = 3, REF_ROBER_HARDCODED = 4,
-       REF_EXPONENTIAL = 5, REF_STIFF_EQ = 6, REF_BRUSS2 = 7 };
+       REF_EXPONENTIAL = 5, REF_STIFF_EQ = 6, REF_BRUSS2 = 7, REF_LORENZ = 8, REF_HARMONIC = 9, REF_DIMER = 10,
+       REF_KINETIC4 = 11 };
 
 typedef struct {
 	int id, n;
@@ -286,6 +287,33 @@ static void fun(const problem *pr, double t, const double *y, double *f)
 		const double a = pr->p[0], b = pr->p[1];
 		f[0] = a + y[0]*y[0]*y[1] - b*y[0] - y[0];
 		f[1] = b*y[0] - y[0]*y[0]*y[1];
+		break;
+	}
+	case REF_LORENZ: { /* test_equations.hpp:526-532 */
+		const double s = pr->p[0], r = pr->p[1], b = pr->p[2];
+		f[0] = s*(y[1] - y[0]);
+		f[1] = y[0]*(r - y[2]) - y[1];
+		f[2] = y[0]*y[1] - b*y[2];
+		break;
+	}
+	case REF_HARMONIC: /* test_equations.hpp:73-76 */
+		f[0] = pr->p[0]*y[1];
+		f[1] = -pr->p[0]*y[0];
+		break;
+	case REF_DIMER: { /* test_equations.hpp:185-189; irate = 1.0/rate as in the constructor */
+		const double rate = pr->p[0], irate = 1.0/rate;
+		f[0] = -2*rate*y[0]*y[0] + 2*irate*y[1];
+		f[1] = rate*y[0]*y[0] - irate*y[1];
+		break;
+	}
+	case REF_KINETIC4: { /* test_equations.hpp:492-502 */
+		const double b2 = pr->p[0], b3 = pr->p[1], b4 = pr->p[2];
+		double r0 = -2*y[0]*y[0] - y[0]*(y[1] + y[2]);
+		r0 += 2*b2*y[1] + b3*y[2] + b4*y[3];
+		f[0] = r0;
+		f[1] = y[0]*y[0] - y[0]*y[1] + b3*y[2] - b2*y[1];
+		f[2] = y[0]*y[1] - y[0]*y[2] + b4*y[3] - b3*y[2];
+		f[3] = y[0]*y[2] - b4*y[3];
 		break;
 	}
 	case REF_BRUSS1D: { /* ours; twin of bruss1d in ref_driver.cpp */
@@ -344,6 +372,30 @@ static void jac(const problem *pr, double t, const double *y, double *J)
 		AT(J,n,1,0) = b - 2*y[0]*y[1]; AT(J,n,1,1) = -y[0]*y[0];
 		break;
 	}
+	case REF_LORENZ: { /* test_equations.hpp:534-540 */
+		const double s = pr->p[0], r = pr->p[1], b = pr->p[2];
+		AT(J,n,0,0) = -s; AT(J,n,0,1) = s; AT(J,n,0,2) = 0;
+		AT(J,n,1,0) = r - y[2]; AT(J,n,1,1) = -1.0; AT(J,n,1,2) = -y[0];
+		AT(J,n,2,0) = y[1]; AT(J,n,2,1) = y[0]; AT(J,n,2,2) = -b;
+		break;
+	}
+	case REF_HARMONIC: /* test_equations.hpp:78-81 */
+		AT(J,n,0,0) = 0; AT(J,n,0,1) = pr->p[0]; AT(J,n,1,0) = -pr->p[0]; AT(J,n,1,1) = 0;
+		break;
+	case REF_DIMER: { /* test_equations.hpp:191-200 */
+		const double rate = pr->p[0], irate = 1.0/rate;
+		AT(J,n,0,0) = -4*rate*y[0]; AT(J,n,0,1) = 2*irate;
+		AT(J,n,1,0) = 2*rate*y[0]; AT(J,n,1,1) = -irate;
+		break;
+	}
+	case REF_KINETIC4: { /* test_equations.hpp:508-512 */
+		const double b2 = pr->p[0], b3 = pr->p[1], b4 = pr->p[2];
+		AT(J,n,0,0) = -4*y[0] - y[1] - y[2]; AT(J,n,0,1) = -y[0] + 2*b2; AT(J,n,0,2) = -y[0] + b3; AT(J,n,0,3) = b4;
+		AT(J,n,1,0) = 2*y[0] - y[1]; AT(J,n,1,1) = -y[0] - b2; AT(J,n,1,2) = b3; AT(J,n,1,3) = 0.0;
+		AT(J,n,2,0) = y[1] - y[2]; AT(J,n,2,1) = y[0]; AT(J,n,2,2) = -y[0] - b3; AT(J,n,2,3) = b4;
+		AT(J,n,3,0) = y[2]; AT(J,n,3,1) = 0; AT(J,n,3,2) = y[0]; AT(J,n,3,3) = -b4;
+		break;
+	}
 	case REF_BRUSS1D: {
 		const int Ng = n / 2;
 		const double alpha = pr->p[0], B = pr->p[2];
@@ -372,6 +424,10 @@ int ref_problem_dims(int id, int n_hint, int *n, int *p)
 	case REF_EXPONENTIAL: *n = 1; *p = 1; return 0;
 	case REF_STIFF_EQ: *n = 2; *p = 0; return 0;
 	case REF_BRUSS2: *n = 2; *p = 2; return 0;
+	case REF_LORENZ: *n = 3; *p = 3; return 0;
+	case REF_HARMONIC: *n = 2; *p = 1; return 0;
+	case REF_DIMER: *n = 2; *p = 1; return 0;
+	case REF_KINETIC4: *n = 4; *p = 3; return 0;
 	}
 	return -1;
 }

@@ -112,7 +112,8 @@ struct ref_options {
 };
 
 enum { REF_ROBERTSON = 1, REF_VDPOL = 2, REF_BRUSS1D = 3, REF_ROBER_HARDCODED = 4,
-       REF_EXPONENTIAL = 5, REF_STIFF_EQ = 6, REF_BRUSS2 = 7 };
+       REF_EXPONENTIAL = 5, REF_STIFF_EQ = 6, REF_BRUSS2 = 7, REF_LORENZ = 8, REF_HARMONIC = 9, REF_DIMER = 10,
+       REF_KINETIC4 = 11 };
 
 int ref_problem_dims(int problem, int n_hint, int *n, int *p)
 {
@@ -124,6 +125,10 @@ int ref_problem_dims(int problem, int n_hint, int *n, int *p)
 	case REF_EXPONENTIAL: *n = 1; *p = 1; return 0;
 	case REF_STIFF_EQ: *n = 2; *p = 0; return 0;
 	case REF_BRUSS2: *n = 2; *p = 2; return 0;
+	case REF_LORENZ: *n = 3; *p = 3; return 0;
+	case REF_HARMONIC: *n = 2; *p = 1; return 0;
+	case REF_DIMER: *n = 2; *p = 1; return 0;
+	case REF_KINETIC4: *n = 4; *p = 3; return 0;
 	}
 	return -1;
 }
@@ -276,6 +281,10 @@ int ref_irk_ensemble(int problem, int method, double t0, double t1, double dt0,
 			case REF_EXPONENTIAL: { test_equations::exponential f(par(0)); RUN(f); break; }
 			case REF_STIFF_EQ: { test_equations::stiff_eq f; RUN(f); break; }
 			case REF_BRUSS2: { test_equations::bruss f(par(0), par(1)); RUN(f); break; }
+			case REF_LORENZ: { test_equations::lorenz f(par(0), par(1), par(2)); RUN(f); break; }
+			case REF_HARMONIC: { test_equations::harmonic f(par(0)); RUN(f); break; }
+			case REF_DIMER: { test_equations::dimer f(par(0)); RUN(f); break; }
+			case REF_KINETIC4: { test_equations::kinetic_4 f(par(0), par(1), par(2)); RUN(f); break; }
 			}
 #undef RUN
 		}
@@ -328,6 +337,10 @@ int ref_newton_solve_stages(int problem, int method, int variant, int n_hint, co
 		case REF_EXPONENTIAL: { test_equations::exponential f(params[0]); CALL(f); break; }
 		case REF_STIFF_EQ: { test_equations::stiff_eq f; CALL(f); break; }
 		case REF_BRUSS2: { test_equations::bruss f(params[0], params[1]); CALL(f); break; }
+		case REF_LORENZ: { test_equations::lorenz f(params[0], params[1], params[2]); CALL(f); break; }
+		case REF_HARMONIC: { test_equations::harmonic f(params[0]); CALL(f); break; }
+		case REF_DIMER: { test_equations::dimer f(params[0]); CALL(f); break; }
+		case REF_KINETIC4: { test_equations::kinetic_4 f(params[0], params[1], params[2]); CALL(f); break; }
 		}
 #undef CALL
 	} catch (std::exception &e) {
@@ -383,6 +396,10 @@ int ref_fixed_step(int problem, int method, int n_hint, const double *params, co
 			case REF_EXPONENTIAL: { test_equations::exponential f(params[0]); CALL(f); break; }
 			case REF_STIFF_EQ: { test_equations::stiff_eq f; CALL(f); break; }
 			case REF_BRUSS2: { test_equations::bruss f(params[0], params[1]); CALL(f); break; }
+			case REF_LORENZ: { test_equations::lorenz f(params[0], params[1], params[2]); CALL(f); break; }
+			case REF_HARMONIC: { test_equations::harmonic f(params[0]); CALL(f); break; }
+			case REF_DIMER: { test_equations::dimer f(params[0]); CALL(f); break; }
+			case REF_KINETIC4: { test_equations::kinetic_4 f(params[0], params[1], params[2]); CALL(f); break; }
 			}
 #undef CALL
 			if (status != newton::SUCCESS) ++failed;

@@ -24,10 +24,12 @@ LIB_PATHS = {
 
 # problem ids shared by ref_driver.cpp and irk_port.c (NOT the product's ids)
 ROBERTSON, VDPOL, BRUSS1D, ROBER_HARDCODED, EXPONENTIAL, STIFF_EQ, BRUSS2 = 1, 2, 3, 4, 5, 6, 7
+LORENZ, HARMONIC, DIMER, KINETIC4 = 8, 9, 10, 11
 PROBLEM_IDS = {
     "robertson": ROBERTSON, "van-der-pol": VDPOL, "brusselator-1d": BRUSS1D,
     "robertson-hardcoded": ROBER_HARDCODED, "exponential": EXPONENTIAL,
-    "stiff-equation": STIFF_EQ, "brusselator": BRUSS2,
+    "stiff-equation": STIFF_EQ, "brusselator": BRUSS2, "lorenz": LORENZ, "harmonic": HARMONIC, "dimer": DIMER,
+    "kinetic-4": KINETIC4,
 }
 COUNTER_NAMES = ("attempt", "reject_newton", "reject_err", "newton_success", "newton_incr_diverge",
                  "newton_iter_error_too_large", "newton_maxit_exceed", "fun_evals", "jac_evals")

@@ -22,7 +22,6 @@
 #include <vector>
 
 #include "../../include/rehuel_b200.h"
-#include "functors.cuh"
 #include "irk_thread.cuh"
 #include "launch.cuh"
 #include "tableau.hpp"
@@ -78,6 +77,10 @@ static const ProblemInfo kProblems[] = {
     {REHUEL_PROBLEM_EXPONENTIAL, "exponential", 1, 1},
     {REHUEL_PROBLEM_STIFF_EQ, "stiff-equation", 2, 0},
     {REHUEL_PROBLEM_BRUSSELATOR, "brusselator", 2, 2},
+    {REHUEL_PROBLEM_LORENZ, "lorenz", 3, 3},
+    {REHUEL_PROBLEM_HARMONIC, "harmonic", 2, 1},
+    {REHUEL_PROBLEM_DIMER, "dimer", 2, 1},
+    {REHUEL_PROBLEM_KINETIC_4, "kinetic-4", 4, 3},
 };
 static const ProblemInfo *find_problem(int id)
 {
@@ -86,27 +89,41 @@ static const ProblemInfo *find_problem(int id)
 	return nullptr;
 }
 
-// ------------------------------------------------------------------ kernel dispatch (templates: launch.cuh)
+// ------------------------------------------------------------------ kernel dispatch
+// The kernel templates (launch.cuh) are instantiated per functor in instances/inst_*.cu.
+LaunchFn launcher_robertson();
+LaunchFn launcher_van_der_pol();
+LaunchFn launcher_exponential();
+LaunchFn launcher_stiff_eq();
+LaunchFn launcher_brusselator();
+LaunchFn launcher_lorenz();
+LaunchFn launcher_harmonic();
+LaunchFn launcher_dimer();
+LaunchFn launcher_kinetic4();
+LaunchFn launcher_bruss1d_64();
+LaunchFn launcher_bruss1d_8();
+LaunchFn launcher_bruss1d_dense_64();
+LaunchFn launcher_bruss1d_dense_8();
+
 static LaunchFn find_launcher(int problem, int n)
 {
-	if (problem == REHUEL_PROBLEM_BRUSSELATOR_1D) {
-		if (n == 64) return &dispatch_method_cta<Brusselator1dF<32>>;
-		if (n == 8) return &dispatch_method_cta<Brusselator1dF<4>>;
+	if (problem == REHUEL_PROBLEM_BRUSSELATOR_1D || problem == REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE) {
+		const bool dense = problem == REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE;
+		if (n == 64) return dense ? launcher_bruss1d_dense_64() : launcher_bruss1d_64();
+		if (n == 8) return dense ? launcher_bruss1d_dense_8() : launcher_bruss1d_8();
 		set_error(REHUEL_EINVAL, "brusselator-1d is built for n = 64 (Ng = 32) and n = 8 (Ng = 4), got n = %d", n);
 		return nullptr;
 	}
-	if (problem == REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE) {
-		if (n == 64) return &dispatch_method_cta<Brusselator1dDenseF<32>>;
-		if (n == 8) return &dispatch_method_cta<Brusselator1dDenseF<4>>;
-		set_error(REHUEL_EINVAL, "brusselator-1d-dense is built for n = 64 (Ng = 32) and n = 8 (Ng = 4), got n = %d", n);
-		return nullptr;
-	}
 	switch (problem) {
-	case REHUEL_PROBLEM_ROBERTSON: return &dispatch_method<RobertsonF>;
-	case REHUEL_PROBLEM_VAN_DER_POL: return &dispatch_method<VanDerPolF>;
-	case REHUEL_PROBLEM_EXPONENTIAL: return &dispatch_method<ExponentialF>;
-	case REHUEL_PROBLEM_STIFF_EQ: return &dispatch_method<StiffEqF>;
-	case REHUEL_PROBLEM_BRUSSELATOR: return &dispatch_method<BrusselatorF>;
+	case REHUEL_PROBLEM_ROBERTSON: return launcher_robertson();
+	case REHUEL_PROBLEM_VAN_DER_POL: return launcher_van_der_pol();
+	case REHUEL_PROBLEM_EXPONENTIAL: return launcher_exponential();
+	case REHUEL_PROBLEM_STIFF_EQ: return launcher_stiff_eq();
+	case REHUEL_PROBLEM_BRUSSELATOR: return launcher_brusselator();
+	case REHUEL_PROBLEM_LORENZ: return launcher_lorenz();
+	case REHUEL_PROBLEM_HARMONIC: return launcher_harmonic();
+	case REHUEL_PROBLEM_DIMER: return launcher_dimer();
+	case REHUEL_PROBLEM_KINETIC_4: return launcher_kinetic4();
 	}
 	set_error(REHUEL_EINVAL, "problem %d has no GPU kernel", problem);
 	return nullptr;

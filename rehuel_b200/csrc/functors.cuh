@@ -112,6 +112,107 @@ struct BrusselatorF {
 	}
 };
 
+// Lorenz system; test_equations.hpp:519-543.  p = (sigma, rho, beta).
+struct LorenzF {
+	static constexpr int N = 3;
+	static constexpr int P = 3;
+	static constexpr bool kAutonomous = true;
+	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&p)[P], double (&f)[N])
+	{
+		f[0] = p[0] * (y[1] - y[0]);
+		f[1] = y[0] * (p[1] - y[2]) - y[1];
+		f[2] = y[0] * y[1] - p[2] * y[2];
+	}
+	__device__ __forceinline__ static void jac(double, const double (&y)[N], const double (&p)[P], double (&J)[N][N])
+	{
+		J[0][0] = -p[0];
+		J[0][1] = p[0];
+		J[0][2] = 0.0;
+		J[1][0] = p[1] - y[2];
+		J[1][1] = -1.0;
+		J[1][2] = -y[0];
+		J[2][0] = y[1];
+		J[2][1] = y[0];
+		J[2][2] = -p[2];
+	}
+};
+
+// Harmonic oscillator; test_equations.hpp:63-84.  p = (w).
+struct HarmonicF {
+	static constexpr int N = 2;
+	static constexpr int P = 1;
+	static constexpr bool kAutonomous = true;
+	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&p)[P], double (&f)[N])
+	{
+		f[0] = p[0] * y[1];
+		f[1] = -p[0] * y[0];
+	}
+	__device__ __forceinline__ static void jac(double, const double (&)[N], const double (&p)[P], double (&J)[N][N])
+	{
+		J[0][0] = 0.0;
+		J[0][1] = p[0];
+		J[1][0] = -p[0];
+		J[1][1] = 0.0;
+	}
+};
+
+// Dimerisation reaction; test_equations.hpp:180-203.  p = (rate); irate = 1/rate like the reference's constructor.
+struct DimerF {
+	static constexpr int N = 2;
+	static constexpr int P = 1;
+	static constexpr bool kAutonomous = true;
+	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&p)[P], double (&f)[N])
+	{
+		const double rate = p[0], irate = 1.0 / p[0];
+		f[0] = -2 * rate * y[0] * y[0] + 2 * irate * y[1];
+		f[1] = rate * y[0] * y[0] - irate * y[1];
+	}
+	__device__ __forceinline__ static void jac(double, const double (&y)[N], const double (&p)[P], double (&J)[N][N])
+	{
+		const double rate = p[0], irate = 1.0 / p[0];
+		J[0][0] = -4 * rate * y[0];
+		J[0][1] = 2 * irate;
+		J[1][0] = 2 * rate * y[0];
+		J[1][1] = -irate;
+	}
+};
+
+// Four-species reversible polymerisation kinetics; test_equations.hpp:484-517.  p = (b2, b3, b4).
+// The one built-in system with n = 4, the largest the thread-per-system kernels take.
+struct Kinetic4F {
+	static constexpr int N = 4;
+	static constexpr int P = 3;
+	static constexpr bool kAutonomous = true;
+	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&p)[P], double (&f)[N])
+	{
+		const double b2 = p[0], b3 = p[1], b4 = p[2];
+		f[0] = (-2 * y[0] * y[0] - y[0] * (y[1] + y[2])) + (2 * b2 * y[1] + b3 * y[2] + b4 * y[3]);
+		f[1] = y[0] * y[0] - y[0] * y[1] + b3 * y[2] - b2 * y[1];
+		f[2] = y[0] * y[1] - y[0] * y[2] + b4 * y[3] - b3 * y[2];
+		f[3] = y[0] * y[2] - b4 * y[3];
+	}
+	__device__ __forceinline__ static void jac(double, const double (&y)[N], const double (&p)[P], double (&J)[N][N])
+	{
+		const double b2 = p[0], b3 = p[1], b4 = p[2];
+		J[0][0] = -4 * y[0] - y[1] - y[2];
+		J[0][1] = -y[0] + 2 * b2;
+		J[0][2] = -y[0] + b3;
+		J[0][3] = b4;
+		J[1][0] = 2 * y[0] - y[1];
+		J[1][1] = -y[0] - b2;
+		J[1][2] = b3;
+		J[1][3] = 0.0;
+		J[2][0] = y[1] - y[2];
+		J[2][1] = y[0];
+		J[2][2] = -y[0] - b3;
+		J[2][3] = b4;
+		J[3][0] = y[2];
+		J[3][1] = 0.0;
+		J[3][2] = y[0];
+		J[3][3] = -b4;
+	}
+};
+
 // 1-D Brusselator, method of lines on NG interior grid points, interleaved (u_i, v_i), boundary
 // values u = 1, v = 3 (the reference only has a "TODO: Discretization of a
 // PDE", test_equations.hpp:546).  p = (alpha, A, B).  Componentwise functor for the CTA-per-system

@@ -1,0 +1,7 @@
+// Kernel instantiations for one built-in device functor (own translation unit: the builds run in parallel).
+#include "../functors.cuh"
+#include "../launch.cuh"
+
+namespace rehuel {
+LaunchFn launcher_bruss1d_64() { return &dispatch_method_cta<Brusselator1dF<32>>; }
+} // namespace rehuel

@@ -1,0 +1,7 @@
+// Kernel instantiations for one built-in device functor (own translation unit: the builds run in parallel).
+#include "../functors.cuh"
+#include "../launch.cuh"
+
+namespace rehuel {
+LaunchFn launcher_lorenz() { return &dispatch_method<LorenzF>; }
+} // namespace rehuel

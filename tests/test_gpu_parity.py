@@ -27,7 +27,8 @@ def capi():
     return m
 
 
-PROBLEM_ID = {"robertson": 1, "van-der-pol": 2, "brusselator-1d": 3, "exponential": 5, "stiff-equation": 6, "brusselator": 7}
+PROBLEM_ID = {"robertson": 1, "van-der-pol": 2, "brusselator-1d": 3, "exponential": 5, "stiff-equation": 6, "brusselator": 7,
+              "lorenz": 8, "harmonic": 9, "dimer": 10, "kinetic-4": 11}
 
 
 def _gpu_single(capi, c, **kw):
@@ -68,7 +69,7 @@ def test_golden_single_systems(capi, golden):
     print("\nname | scaled_err | attempts gpu/ref | rejE gpu/ref | rejN gpu/ref | fun gpu/ref | jac gpu/ref")
     for r in rows:
         print("%-28s %.3e  %d/%d  %d/%d  %d/%d  %d/%d  %d/%d" % r)
-    assert len(rows) >= 16
+    assert len(rows) >= 30
 
 
 def test_golden_ensembles(capi, golden):
@@ -298,6 +299,47 @@ def test_boundary_programs_c_abi_cpp_api_user_functor(capi):
         r = subprocess.run([path], capture_output=True, text=True, timeout=120)
         print("\n" + r.stdout.strip())
         assert r.returncode == 0, (exe, r.stdout, r.stderr)
+
+
+def test_example_driver_cli_single_and_ensemble(capi, port, golden, tmp_path):
+    """examples/rehuel_example.cpp, the reference's example driver (examples/example_equations.cpp) on this library:
+    same options, trajectory as "t y0 y1 ..." lines (irk.hpp:837-843), summary on stderr in the reference's words.
+    Single system against the golden trajectory of the unmodified reference; --ensemble / --dense / --output-file."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "build", "rehuel_example")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", ROOT, "examples"])
+    c = next(c for c in cases_of(golden, "single") if c["name"] == "robertson_211_t40")
+    r = subprocess.run([exe, "--equation", "robertson", "--method", "RADAU_IIA_53", "--time-span", "0", "40", "--dt", "1e-6",
+                        "--rel-tol", "1e-6", "--abs-tol", "1e-6"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    rows = np.array([[float(x) for x in line.split()] for line in r.stdout.strip().splitlines()])
+    assert rows.shape == (c["traj_len"], 4)                      # (t0, y0) + one row per accepted step
+    L = min(64, c["traj_len"])
+    ref_t, ref_y = unhex(c["traj_t"])[:L], unhex(c["traj_y"]).reshape(-1, 3)[:L]
+    np.testing.assert_allclose(rows[:L, 0], ref_t, rtol=1e-5)    # default stream precision: 6 digits
+    np.testing.assert_allclose(rows[:L, 1:], ref_y, rtol=1e-5, atol=1e-11)
+    for key in ("Solved equation in", "Accepted", "function evaluations.", "Jacobi matrix evaluations."):
+        assert key in r.stderr
+    assert f"{c['counters']['jac_evals']} Jacobi matrix evaluations." in r.stderr
+    # ensemble of 4096 swept members, dense output of member 17 on a grid, written to a file
+    out = tmp_path / "traj.txt"
+    r = subprocess.run([exe, "--equation", "robertson", "--method", "RADAU_IIA_53", "--time-span", "0", "40", "--dt", "1e-6",
+                        "--rel-tol", "1e-6", "--abs-tol", "1e-6", "--ensemble", "4096", "--sweep", "1", "--member", "17",
+                        "--dense", "9", "5", "--output-file", str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Solved 4096 equations" in r.stderr and "systems/s" in r.stderr, r.stderr
+    rows = np.loadtxt(out)
+    assert rows.shape == (9, 4) and np.allclose(rows[:, 0], np.arange(9) * 5.0)
+    from rehuel_b200 import ensembles
+    P = ensembles.robertson_params(4096)[:, 17:18].copy()
+    ro = port.solve("robertson", 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, ref_options(1e-6, 1e-6))
+    np.testing.assert_allclose(rows[-1, 1:], ro.y[:, 0], rtol=2e-5, atol=1e-11)
+    np.testing.assert_allclose(rows[:, 1:].sum(1), 1.0, rtol=1e-5)  # mass conservation along the dense output
+    # bad input is refused like the reference does (example_equations.cpp:310, 498)
+    assert subprocess.run([exe, "--equation", "nope"], capture_output=True).returncode != 0
+    assert subprocess.run([exe, "--equation", "robertson", "--method", "RK4"], capture_output=True).returncode != 0
 
 
 def test_handout_order_and_slow_lane_parking_do_not_change_results(capi, port):

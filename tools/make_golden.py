@@ -74,6 +74,15 @@ def main():
         ("van-der-pol", [1e-2], [2.0, 0.0], 213, 0.0, 2.0, 1e-6, o6),
         ("brusselator", [1.0, 3.0], [1.0, 1.0], 212, 0.0, 20.0, 1e-6, o6),
         ("exponential", [-0.4], [1.0], 213, 0.0, 2.0, 1e-6, dict(rel_tol=1e-4)),
+        # the remaining small test functors of test_equations.hpp (kinetic-4 is the n = 4 case)
+        ("lorenz", [10.0, 28.0, 8.0 / 3.0], [1.0, 1.0, 1.0], 211, 0.0, 2.0, 1e-6, o6),
+        ("lorenz", [10.0, 28.0, 8.0 / 3.0], [1.0, 1.0, 1.0], 230, 0.0, 1.0, 1e-6, o6),
+        ("harmonic", [3.0], [0.0, 1.0], 211, 0.0, 5.0, 1e-6, o6),
+        ("dimer", [5.0], [1.0, 0.0], 230, 0.0, 3.0, 1e-6, o6),
+        ("kinetic-4", [0.5, 0.3, 0.2], [1.0, 0.0, 0.0, 0.0], 211, 0.0, 10.0, 1e-6, o6),
+        ("kinetic-4", [0.5, 0.3, 0.2], [1.0, 0.0, 0.0, 0.0], 230, 0.0, 10.0, 1e-6, o6),
+        ("kinetic-4", [0.5, 0.3, 0.2], [1.0, 0.0, 0.0, 0.0], 232, 0.0, 2.0, 1e-6, o6),
+        ("kinetic-4", [0.5, 0.3, 0.2], [1.0, 0.0, 0.0, 0.0], 212, 0.0, 10.0, 1e-6, o6),
         ("brusselator-1d", [0.02, 1.0, 3.0], list(ensembles.bruss1d_y0(4)), 211, 0.0, 1.0, 1e-6, o6),
         ("brusselator-1d", [0.02, 1.0, 3.0], list(ensembles.bruss1d_y0(4)), 232, 0.0, 1.0, 1e-6, o6),
     ]
