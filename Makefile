@@ -16,7 +16,7 @@ SRC       := rehuel_b200/csrc
 LIB       := rehuel_b200/librehuel_b200.so
 INST      := robertson van_der_pol exponential stiff_eq brusselator lorenz harmonic dimer kinetic4 \
              bruss1d_64 bruss1d_8 bruss1d_dense_64 bruss1d_dense_8
-OBJS      := build/capi.o build/order.o build/tableau.o $(INST:%=build/inst_%.o)
+OBJS      := build/capi.o build/order.o build/selftest.o build/tableau.o $(INST:%=build/inst_%.o)
 KHDRS     := $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/irk_warp.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh \
              $(SRC)/tableau.hpp include/rehuel_b200.h
 
@@ -35,6 +35,9 @@ build/inst_%.o: $(SRC)/instances/inst_%.cu $(KHDRS) | build
 
 build/order.o: $(SRC)/order.cu $(SRC)/launch.cuh include/rehuel_b200.h | build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/order.ptxas.log || (cat build/order.ptxas.log; false)
+
+build/selftest.o: $(SRC)/selftest.cu $(KHDRS) | build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/selftest.ptxas.log || (cat build/selftest.ptxas.log; false)
 
 build/tableau.o: $(SRC)/tableau.cpp $(SRC)/tableau.hpp $(SRC)/tableau_eig.inc $(SRC)/tableau_dec.inc | build
 	$(HOSTCXX) -O2 -std=c++17 -fPIC -Wall -Wextra -c $< -o $@

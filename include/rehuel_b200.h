@@ -287,6 +287,14 @@ int rehuel_kernel_info(int problem, int method, int n_hint, int *regs, int *loca
  * MEASURED_PEAKS.json carries no FP64 figure. */
 int rehuel_fp64_peak(double *tflops, double *ms);
 
+/* Diagnostic: the warp-per-system kernel's band LU + band solve (n = 64, half bandwidth 2) on caller-given
+ * matrices, 4 per problem (lane m <-> matrix m as in the integrator).  ab: [n_problems][4][2 (re,im)][66][7] band
+ * rows (slot 2 + j - i holds A(i,j), rows 64..65 zero); rhs, x: [n_problems][4][2][64]; is_cplx, flags:
+ * [n_problems][4].  pivot != 0: dgbtf2-style row pivoting; pivot == 0: plain elimination, flags[] = "partial
+ * pivoting would have exchanged rows".  HOST pointers; for the test-suite. */
+int rehuel_selftest_band(int n_problems, int pivot, const double *ab, const double *rhs, const int *is_cplx,
+                         double *x, int *flags);
+
 /* Last error text of the calling thread (the reference reports through free-text log_out). */
 const char *rehuel_last_error(void);
 const char *rehuel_version(void);

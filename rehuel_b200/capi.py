@@ -135,7 +135,7 @@ EXPORTS = (
     "rehuel_problem_dims", "rehuel_get_coefficients", "rehuel_irk_ensemble", "rehuel_result_free",
     "rehuel_irk_single", "rehuel_irk_ensemble_device", "rehuel_result_merge", "rehuel_kernel_launches",
     "rehuel_kernel_info", "rehuel_last_error", "rehuel_version", "rehuel_fp64_peak", "rehuel_release_cached_memory",
-    "rehuel_locality_order_workspace", "rehuel_locality_order", "rehuel_irk_ensemble_continue",
+    "rehuel_locality_order_workspace", "rehuel_locality_order", "rehuel_irk_ensemble_continue", "rehuel_selftest_band",
 )
 
 

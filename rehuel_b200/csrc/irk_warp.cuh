@@ -51,10 +51,11 @@ struct WarpSmem {
 	static constexpr int o_dy = o_e + N;
 	static constexpr int o_dalt = o_dy + N;
 	static constexpr int o_fy = o_dalt + N;
-	static constexpr int o_abr = o_fy + N;                    // real band factors [NREAL][N][W]
-	static constexpr int o_rdr = o_abr + NREAL * N * W;       // reciprocal pivots [NREAL][N]
-	static constexpr int o_abc = o_rdr + NREAL * N;           // complex band factors [NC][2][N][W]
-	static constexpr int o_rdc = o_abc + NC * 2 * N * W;      // reciprocal pivots [NC][2][N]
+	static constexpr int PL = (N + KB) * W;                   // one band plane: N rows + KB zero rows of padding
+	static constexpr int o_abr = o_fy + N;                    // real band factors [NREAL][N + KB][W]
+	static constexpr int o_rdr = o_abr + NREAL * PL;          // reciprocal pivots [NREAL][N]
+	static constexpr int o_abc = o_rdr + NREAL * N;           // complex band factors [NC][2][N + KB][W]
+	static constexpr int o_rdc = o_abc + NC * 2 * PL;         // reciprocal pivots [NC][2][N]
 	static constexpr int o_piv = o_rdc + NC * 2 * N;          // interchange offsets, bytes: [NREAL + NC][N]
 	static constexpr size_t bytes = (size_t)o_piv * 8 + (((size_t)(NREAL + NC) * N + 15) & ~size_t(15));
 };
@@ -67,124 +68,81 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // ------------------------------------------------------------------ band LU, one lane per matrix
-// In:  ab[i*W + KB + (j-i)] = A(i,j) for |i-j| <= KB, zero elsewhere.
+// ONE routine for real and complex matrices, so that the lanes that factorise the matrices of an
+// attempt side by side execute the same instructions (a real matrix is a complex one whose
+// imaginary plane is never loaded or stored: `is_c` predicates those accesses).
+//
+// In:  ab[i*W + KB + (j-i)] = A(i,j) for |i-j| <= KB, zero elsewhere; each plane carries KB extra
+//      zero rows below row N-1, so no step of the recurrence needs a bounds check.
 // Out: U(k,k..k+2KB) in ab[k*W + KB ..], multipliers L(k+r,k) in ab[(k+r)*W + KB - r], reciprocal
-//      pivots in rd[k], interchange offsets p-k in piv[k] (dgbtf2: only the not yet eliminated
-//      part of the rows is exchanged, the solves apply the interchanges step by step).
-template <int N, int KB>
-__device__ __forceinline__ void band_lu_real(double *ab, double *rd, signed char *piv)
+//      pivots in rd[k].
+// PIVOT = false: plain elimination; returns true if row partial pivoting WOULD have exchanged rows
+//                somewhere (the caller then redoes the factorisation with PIVOT = true -- where no
+//                exchange is needed the two perform the same operations);
+// PIVOT = true:  dgbtf2's pivoting: only the not yet eliminated part of the rows is exchanged, the
+//                exchange offsets p-k go to piv[k] and the solves apply them step by step.
+template <int N, int KB, bool PIVOT>
+__device__ __forceinline__ bool band_lu(double *abr, double *abi, bool is_c, double *rdr, double *rdi, signed char *piv)
 {
-	constexpr int W = 3 * KB + 1, WW = 2 * KB + 1;
-	double w[KB + 1][WW]; // rows k..k+KB, columns k..k+2KB
-#pragma unroll
-	for (int r = 0; r <= KB; ++r)
-#pragma unroll
-		for (int c = 0; c < WW; ++c) w[r][c] = (r < N && c < N && c - r <= KB && r - c <= KB) ? ab[r * W + KB + c - r] : 0.0;
-#pragma unroll 2
-	for (int k = 0; k < N; ++k) {
-		int p = 0;
-		double best = fabs(w[0][0]);
-#pragma unroll
-		for (int r = 1; r <= KB; ++r) {
-			const double v = fabs(w[r][0]); // rows beyond N hold zeros and never win
-			if (v > best) {
-				best = v;
-				p = r;
-			}
-		}
-		piv[k] = (signed char)p;
-#pragma unroll
-		for (int r = 1; r <= KB; ++r) {
-			const bool sw = (p == r);
-#pragma unroll
-			for (int c = 0; c < WW; ++c) {
-				const double u = w[0][c], v = w[r][c];
-				w[0][c] = sw ? v : u;
-				w[r][c] = sw ? u : v;
-			}
-		}
-		const double rp = fast_rcp(w[0][0]);
-		rd[k] = rp;
-#pragma unroll
-		for (int c = 0; c < WW; ++c) ab[k * W + KB + c] = w[0][c];
-#pragma unroll
-		for (int r = 1; r <= KB; ++r) {
-			const double l = w[r][0] * rp;
-			if (k + r < N) ab[(k + r) * W + KB - r] = l;
-#pragma unroll
-			for (int c = 1; c < WW; ++c) w[r][c] = fma(-l, w[0][c], w[r][c]);
-		}
-		// slide: rows k+1..k+KB+1, columns k+1..k+2KB+1
-		const int in = k + 1 + KB; // new row
-#pragma unroll
-		for (int r = 0; r < KB; ++r) {
-#pragma unroll
-			for (int c = 0; c + 1 < WW; ++c) w[r][c] = w[r + 1][c + 1];
-			w[r][WW - 1] = 0.0;
-		}
-#pragma unroll
-		for (int c = 0; c < WW; ++c) w[KB][c] = (in < N && k + 1 + c < N) ? ab[in * W + c] : 0.0; // column k+1+c sits in slot c
-	}
-}
-
-template <int N, int KB>
-__device__ __forceinline__ void band_lu_cplx(double *abr, double *abi, double *rdr, double *rdi, signed char *piv)
-{
-	constexpr int W = 3 * KB + 1, WW = 2 * KB + 1;
-	double wr[KB + 1][WW], wi[KB + 1][WW];
+	// without interchanges U keeps the band of A (KB superdiagonals); with them it fills in up to 2*KB
+	constexpr int W = 3 * KB + 1, WW = (PIVOT ? 2 * KB : KB) + 1;
+	double wr[KB + 1][WW], wi[KB + 1][WW]; // rows k..k+KB, columns k..k+WW-1
 #pragma unroll
 	for (int r = 0; r <= KB; ++r)
 #pragma unroll
 		for (int c = 0; c < WW; ++c) {
-			const bool in = (r < N && c < N && c - r <= KB && r - c <= KB);
+			const bool in = (c - r <= KB && r - c <= KB);
 			wr[r][c] = in ? abr[r * W + KB + c - r] : 0.0;
-			wi[r][c] = in ? abi[r * W + KB + c - r] : 0.0;
+			wi[r][c] = (in && is_c) ? abi[r * W + KB + c - r] : 0.0;
 		}
-#pragma unroll 2
+	bool would_swap = false;
+#pragma unroll 1
 	for (int k = 0; k < N; ++k) {
 		int p = 0;
-		double best = fabs(wr[0][0]) + fabs(wi[0][0]); // izamax's |re|+|im|
+		double best = fabs(wr[0][0]) + fabs(wi[0][0]); // izamax's |re|+|im|; plain |re| for a real matrix
 #pragma unroll
 		for (int r = 1; r <= KB; ++r) {
-			const double v = fabs(wr[r][0]) + fabs(wi[r][0]);
+			const double v = fabs(wr[r][0]) + fabs(wi[r][0]); // the padding rows hold zeros and never win
 			if (v > best) {
 				best = v;
 				p = r;
 			}
 		}
-		piv[k] = (signed char)p;
+		would_swap |= (p != 0);
+		if (PIVOT) {
+			piv[k] = (signed char)p;
 #pragma unroll
-		for (int r = 1; r <= KB; ++r) {
-			const bool sw = (p == r);
+			for (int r = 1; r <= KB; ++r) {
+				const bool sw = (p == r);
 #pragma unroll
-			for (int c = 0; c < WW; ++c) {
-				double u = wr[0][c], v = wr[r][c];
-				wr[0][c] = sw ? v : u;
-				wr[r][c] = sw ? u : v;
-				u = wi[0][c];
-				v = wi[r][c];
-				wi[0][c] = sw ? v : u;
-				wi[r][c] = sw ? u : v;
+				for (int c = 0; c < WW; ++c) {
+					double u = wr[0][c], v = wr[r][c];
+					wr[0][c] = sw ? v : u;
+					wr[r][c] = sw ? u : v;
+					u = wi[0][c];
+					v = wi[r][c];
+					wi[0][c] = sw ? v : u;
+					wi[r][c] = sw ? u : v;
+				}
 			}
 		}
+		// reciprocal pivot 1/(a+ib) = (a-ib)/(a^2+b^2)
 		const double pr = wr[0][0], pi = wi[0][0];
 		const double rden = fast_rcp(fma(pr, pr, pi * pi));
 		const double rr = pr * rden, ri = -pi * rden;
 		rdr[k] = rr;
-		rdi[k] = ri;
+		if (is_c) rdi[k] = ri;
 #pragma unroll
 		for (int c = 0; c < WW; ++c) {
 			abr[k * W + KB + c] = wr[0][c];
-			abi[k * W + KB + c] = wi[0][c];
+			if (is_c) abi[k * W + KB + c] = wi[0][c];
 		}
 #pragma unroll
 		for (int r = 1; r <= KB; ++r) {
 			const double lr = fma(wr[r][0], rr, -wi[r][0] * ri);
 			const double li = fma(wr[r][0], ri, wi[r][0] * rr);
-			if (k + r < N) {
-				abr[(k + r) * W + KB - r] = lr;
-				abi[(k + r) * W + KB - r] = li;
-			}
+			abr[(k + r) * W + KB - r] = lr; // rows >= N are padding
+			if (is_c) abi[(k + r) * W + KB - r] = li;
 #pragma unroll
 			for (int c = 1; c < WW; ++c) {
 				const double ur = wr[0][c], ui = wi[0][c];
@@ -192,6 +150,7 @@ __device__ __forceinline__ void band_lu_cplx(double *abr, double *abi, double *r
 				wi[r][c] = fma(-lr, ui, fma(-li, ur, wi[r][c]));
 			}
 		}
+		// slide: rows k+1..k+KB+1, columns k+1..k+WW (column k+1+c of the new row sits in slot c)
 		const int in = k + 1 + KB;
 #pragma unroll
 		for (int r = 0; r < KB; ++r) {
@@ -200,122 +159,94 @@ __device__ __forceinline__ void band_lu_cplx(double *abr, double *abi, double *r
 				wr[r][c] = wr[r + 1][c + 1];
 				wi[r][c] = wi[r + 1][c + 1];
 			}
-			wr[r][WW - 1] = 0.0;
-			wi[r][WW - 1] = 0.0;
+			// the column that enters the window: beyond every older row's band when U is 2*KB wide (fill-in only
+			// comes from interchanges); with the narrow window it is the row's own, still untouched, last band entry
+			wr[r][WW - 1] = PIVOT ? 0.0 : abr[(k + 1 + r) * W + 2 * KB - r];
+			wi[r][WW - 1] = (PIVOT || !is_c) ? 0.0 : abi[(k + 1 + r) * W + 2 * KB - r];
 		}
+		if (in < N + KB) { // warp-uniform (k is)
 #pragma unroll
-		for (int c = 0; c < WW; ++c) {
-			const bool ok = (in < N && k + 1 + c < N);
-			wr[KB][c] = ok ? abr[in * W + c] : 0.0;
-			wi[KB][c] = ok ? abi[in * W + c] : 0.0;
+			for (int c = 0; c < WW; ++c) {
+				wr[KB][c] = abr[in * W + c];
+				wi[KB][c] = is_c ? abi[in * W + c] : 0.0;
+			}
+		} else {
+#pragma unroll
+			for (int c = 0; c < WW; ++c) wr[KB][c] = wi[KB][c] = 0.0;
 		}
 	}
+	return would_swap;
 }
 
 // ------------------------------------------------------------------ band solves, one lane per right-hand side
-// x <- U^-1 L^-1 P x with the factors above; x in shared memory, the recurrence in registers.
-template <int N, int KB>
-__device__ __forceinline__ void band_solve_real(const double *ab, const double *rd, const signed char *piv, double *x)
-{
-	constexpr int W = 3 * KB + 1;
-	double w[KB + 1];
-#pragma unroll
-	for (int r = 0; r <= KB; ++r) w[r] = (r < N) ? x[r] : 0.0;
-#pragma unroll 4
-	for (int k = 0; k < N; ++k) { // forward: interchange, then eliminate with the unit lower factor
-		const int p = piv[k];
-#pragma unroll
-		for (int r = 1; r <= KB; ++r) {
-			const bool sw = (p == r);
-			const double u = w[0], v = w[r];
-			w[0] = sw ? v : u;
-			w[r] = sw ? u : v;
-		}
-#pragma unroll
-		for (int r = 1; r <= KB; ++r)
-			if (k + r < N) w[r] = fma(-ab[(k + r) * W + KB - r], w[0], w[r]);
-		x[k] = w[0];
-#pragma unroll
-		for (int r = 0; r < KB; ++r) w[r] = w[r + 1];
-		w[KB] = (k + 1 + KB < N) ? x[k + 1 + KB] : 0.0;
-	}
-	double u[2 * KB + 1]; // u[c] = x[k + c]
-#pragma unroll
-	for (int c = 0; c <= 2 * KB; ++c) u[c] = 0.0;
-#pragma unroll 4
-	for (int k = N - 1; k >= 0; --k) { // backward; the newest unknown enters the chain last
-		double acc = x[k];
-#pragma unroll
-		for (int c = 2 * KB; c >= 1; --c) acc = fma(-ab[k * W + KB + c], u[c], acc); // entries beyond column N-1 are stored zeros
-		const double xk = acc * rd[k];
-		x[k] = xk;
-#pragma unroll
-		for (int c = 2 * KB; c >= 2; --c) u[c] = u[c - 1];
-		u[1] = xk;
-	}
-}
-
-template <int N, int KB>
-__device__ __forceinline__ void band_solve_cplx(const double *abr, const double *abi, const double *rdr, const double *rdi,
-                                                const signed char *piv, double *xr, double *xi)
+// x <- U^-1 L^-1 P x with the factors above (P only when PIVOT); x in shared memory, the recurrence in
+// registers.  Real and complex systems share the routine like the factorisations do.  The forward
+// window may read up to KB entries past x[N-1]: they only ever combine with the zero multipliers
+// of the padding rows and are never stored.
+template <int N, int KB, bool PIVOT>
+__device__ __forceinline__ void band_solve(const double *abr, const double *abi, bool is_c, const double *rdr, const double *rdi,
+                                           const signed char *piv, double *xr, double *xi)
 {
 	constexpr int W = 3 * KB + 1;
 	double wr[KB + 1], wi[KB + 1];
 #pragma unroll
 	for (int r = 0; r <= KB; ++r) {
-		wr[r] = (r < N) ? xr[r] : 0.0;
-		wi[r] = (r < N) ? xi[r] : 0.0;
+		wr[r] = xr[r];
+		wi[r] = is_c ? xi[r] : 0.0;
 	}
-#pragma unroll 4
-	for (int k = 0; k < N; ++k) {
-		const int p = piv[k];
+#pragma unroll 2
+	for (int k = 0; k < N; ++k) { // forward: (interchange, then) eliminate with the unit lower factor
+		if (PIVOT) {
+			const int p = piv[k];
 #pragma unroll
-		for (int r = 1; r <= KB; ++r) {
-			const bool sw = (p == r);
-			double u = wr[0], v = wr[r];
-			wr[0] = sw ? v : u;
-			wr[r] = sw ? u : v;
-			u = wi[0];
-			v = wi[r];
-			wi[0] = sw ? v : u;
-			wi[r] = sw ? u : v;
+			for (int r = 1; r <= KB; ++r) {
+				const bool sw = (p == r);
+				double u = wr[0], v = wr[r];
+				wr[0] = sw ? v : u;
+				wr[r] = sw ? u : v;
+				u = wi[0];
+				v = wi[r];
+				wi[0] = sw ? v : u;
+				wi[r] = sw ? u : v;
+			}
 		}
 #pragma unroll
-		for (int r = 1; r <= KB; ++r)
-			if (k + r < N) {
-				const double lr = abr[(k + r) * W + KB - r], li = abi[(k + r) * W + KB - r];
-				const double a = wr[r], b = wi[r];
-				wr[r] = fma(-lr, wr[0], fma(li, wi[0], a));
-				wi[r] = fma(-lr, wi[0], fma(-li, wr[0], b));
-			}
+		for (int r = 1; r <= KB; ++r) {
+			const double lr = abr[(k + r) * W + KB - r], li = is_c ? abi[(k + r) * W + KB - r] : 0.0;
+			const double a = wr[r], b = wi[r];
+			wr[r] = fma(-lr, wr[0], fma(li, wi[0], a));
+			wi[r] = fma(-lr, wi[0], fma(-li, wr[0], b));
+		}
 		xr[k] = wr[0];
-		xi[k] = wi[0];
+		if (is_c) xi[k] = wi[0];
 #pragma unroll
 		for (int r = 0; r < KB; ++r) {
 			wr[r] = wr[r + 1];
 			wi[r] = wi[r + 1];
 		}
-		wr[KB] = (k + 1 + KB < N) ? xr[k + 1 + KB] : 0.0;
-		wi[KB] = (k + 1 + KB < N) ? xi[k + 1 + KB] : 0.0;
+		wr[KB] = xr[k + 1 + KB];
+		wi[KB] = is_c ? xi[k + 1 + KB] : 0.0;
 	}
-	double ur[2 * KB + 1], ui[2 * KB + 1];
+	constexpr int UB = PIVOT ? 2 * KB : KB; // superdiagonals of U (see band_lu)
+	double ur[UB + 1], ui[UB + 1]; // u[c] = x[k + c]
 #pragma unroll
-	for (int c = 0; c <= 2 * KB; ++c) ur[c] = ui[c] = 0.0;
-#pragma unroll 4
-	for (int k = N - 1; k >= 0; --k) {
-		double ar = xr[k], ai = xi[k];
+	for (int c = 0; c <= UB; ++c) ur[c] = ui[c] = 0.0;
+#pragma unroll 2
+	for (int k = N - 1; k >= 0; --k) { // backward; the newest unknown enters the chain last
+		double ar = xr[k], ai = is_c ? xi[k] : 0.0;
 #pragma unroll
-		for (int c = 2 * KB; c >= 1; --c) {
-			const double er = abr[k * W + KB + c], ei = abi[k * W + KB + c];
+		for (int c = UB; c >= 1; --c) {
+			const double er = abr[k * W + KB + c], ei = is_c ? abi[k * W + KB + c] : 0.0; // beyond column N-1: stored zeros
 			ar = fma(-er, ur[c], fma(ei, ui[c], ar));
 			ai = fma(-er, ui[c], fma(-ei, ur[c], ai));
 		}
-		const double kr = fma(ar, rdr[k], -ai * rdi[k]);
-		const double ki = fma(ar, rdi[k], ai * rdr[k]);
+		const double dr = rdr[k], di = is_c ? rdi[k] : 0.0;
+		const double kr = fma(ar, dr, -ai * di);
+		const double ki = fma(ar, di, ai * dr);
 		xr[k] = kr;
-		xi[k] = ki;
+		if (is_c) xi[k] = ki;
 #pragma unroll
-		for (int c = 2 * KB; c >= 2; --c) {
+		for (int c = UB; c >= 2; --c) {
 			ur[c] = ur[c - 1];
 			ui[c] = ui[c - 1];
 		}
@@ -343,6 +274,21 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 	const int lane = threadIdx.x;
 	const unsigned long long M = a.M;
 	const rehuel_device_io &io = a.io;
+	constexpr int PL = L::PL;
+	// lane -> matrix: lane 0 the real Newton block, lanes 1..NC the complex ones, lane NC+1 the estimator's own
+	const bool m_cplx = lane >= 1 && lane <= NC;
+	const bool m_est = (EST == EST_OWN_LU) && lane == NC + 1;
+	const bool has_matrix = (NR && lane == 0) || m_cplx || m_est;
+	const int m_c = m_cplx ? lane - 1 : 0;
+	double *m_abr = m_cplx ? abc + (m_c * 2) * PL : (m_est ? abr + PL : abr);
+	double *m_abi = m_cplx ? abc + (m_c * 2 + 1) * PL : m_abr;
+	double *m_rdr = m_cplx ? rdc + (m_c * 2) * N : (m_est ? rdr + N : rdr);
+	double *m_rdi = m_cplx ? rdc + (m_c * 2 + 1) * N : m_rdr;
+	signed char *m_piv = m_cplx ? pivc + m_c * N : (m_est ? piv + N : piv);
+	// lane -> right-hand side of a Newton update: the same lanes, estimator excluded
+	const bool has_rhs = (NR && lane == 0) || m_cplx;
+	double *m_xr = m_cplx ? Z + (NR + 2 * m_c) * N : Z;
+	double *m_xi = m_cplx ? Z + (NR + 2 * m_c + 1) * N : Z;
 
 	for (;;) {
 		// ---------------- next member
@@ -436,36 +382,47 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			const double rdt = 1.0 / dt;
 			const double mur = (EST == EST_REUSE) ? 1.0 / (tb.gamma * dt) : tb.gamma_hat * rdt;
 			const double mue = (EST == EST_OWN_LU) ? 1.0 / (tb.gamma * dt) : 0.0;
-			for (int i = lane; i < N; i += 32) {
-				double row[N];
+			auto build_matrices = [&]() {
+				for (int i = lane; i < N; i += 32) {
+					double row[N];
 #pragma unroll
-				for (int j = 0; j < N; ++j) row[j] = 0.0;
-				F::jac_row(i, t, y, par, row);
+					for (int j = 0; j < N; ++j) row[j] = 0.0;
+					F::jac_row(i, t, y, par, row);
 #pragma unroll
-				for (int d = -KB; d <= 2 * KB; ++d) {
-					const int j = i + d;
-					const double jv = (d <= KB && j >= 0 && j < N) ? row[j] : 0.0;
-					const double dg = (d == 0) ? 1.0 : 0.0;
-					if (NR) abr[i * W + KB + d] = dg * mur - jv;
-					if (EST == EST_OWN_LU) abr[N * W + i * W + KB + d] = dg * mue - jv;
+					for (int d = -KB; d <= 2 * KB; ++d) {
+						const int j = i + d;
+						const double jv = (d <= KB && j >= 0 && j < N) ? row[j] : 0.0;
+						const double dg = (d == 0) ? 1.0 : 0.0;
+						if (NR) abr[i * W + KB + d] = dg * mur - jv;
+						if (EST == EST_OWN_LU) abr[PL + i * W + KB + d] = dg * mue - jv;
 #pragma unroll
-					for (int c = 0; c < NC; ++c) {
-						abc[(c * 2 + 0) * N * W + i * W + KB + d] = dg * (tb.alpha[c] * rdt) - jv;
-						abc[(c * 2 + 1) * N * W + i * W + KB + d] = dg * (tb.beta[c] * rdt);
+						for (int c = 0; c < NC; ++c) {
+							abc[(c * 2 + 0) * PL + i * W + KB + d] = dg * (tb.alpha[c] * rdt) - jv;
+							abc[(c * 2 + 1) * PL + i * W + KB + d] = dg * (tb.beta[c] * rdt);
+						}
 					}
 				}
-			}
+				for (int e = lane; e < KB * W; e += 32) { // the zero rows below row N-1 of every plane
+					if (NR) abr[N * W + e] = 0.0;
+					if (EST == EST_OWN_LU) abr[PL + N * W + e] = 0.0;
+#pragma unroll
+					for (int c = 0; c < 2 * NC; ++c) abc[c * PL + N * W + e] = 0.0;
+				}
+				__syncwarp();
+			};
 			++c_jac;
+			// -------- all factorisations side by side, one lane per matrix, one routine for all of them:
+			// plain elimination first; if pivoting would have exchanged rows anywhere, redo them pivoted
+			build_matrices();
+			bool flag = false;
+			if (has_matrix) flag = band_lu<N, KB, false>(m_abr, m_abi, m_cplx, m_rdr, m_rdi, m_piv);
 			__syncwarp();
-			// -------- all factorisations side by side: lane 0 real, lanes 1..NC complex, lane NC+1 estimator
-			if (NR && lane == 0) band_lu_real<N, KB>(abr, rdr, piv);
-			if (lane >= 1 && lane <= NC) {
-				const int c = lane - 1;
-				band_lu_cplx<N, KB>(abc + (c * 2) * N * W, abc + (c * 2 + 1) * N * W, rdc + (c * 2) * N, rdc + (c * 2 + 1) * N,
-				                    pivc + c * N);
+			const bool piv_any = __any_sync(0xffffffffu, flag);
+			if (piv_any) {
+				build_matrices();
+				if (has_matrix) band_lu<N, KB, true>(m_abr, m_abi, m_cplx, m_rdr, m_rdi, m_piv);
+				__syncwarp();
 			}
-			if (EST == EST_OWN_LU && lane == NC + 1) band_lu_real<N, KB>(abr + N * W, rdr + N, piv + N);
-			__syncwarp();
 
 			// -------- simplified Newton (irk.hpp:398-493)
 			for (int e = lane; e < S * N; e += 32) Y[e] = 0.0; // irk.hpp:415
@@ -482,11 +439,9 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 					Z[e] = acc;
 				}
 				__syncwarp();
-				if (NR && lane == 0) band_solve_real<N, KB>(abr, rdr, piv, Z);
-				if (lane >= 1 && lane <= NC) {
-					const int c = lane - 1;
-					band_solve_cplx<N, KB>(abc + (c * 2) * N * W, abc + (c * 2 + 1) * N * W, rdc + (c * 2) * N,
-					                       rdc + (c * 2 + 1) * N, pivc + c * N, Z + (NR + 2 * c) * N, Z + (NR + 2 * c + 1) * N);
+				if (has_rhs) { // all right-hand sides side by side, one lane each
+					if (piv_any) band_solve<N, KB, true>(m_abr, m_abi, m_cplx, m_rdr, m_rdi, m_piv, m_xr, m_xi);
+					else band_solve<N, KB, false>(m_abr, m_abi, m_cplx, m_rdr, m_rdi, m_piv, m_xr, m_xi);
 				}
 				__syncwarp();
 				if (NR)
@@ -569,8 +524,9 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			auto apply_Einv_dt = [&]() {
 				if (EST != EST_IDENTITY) {
 					if (lane == 0) {
-						if (EST == EST_REUSE) band_solve_real<N, KB>(abr, rdr, piv, ev);
-						else band_solve_real<N, KB>(abr + N * W, rdr + N, piv + N, ev);
+						const int o = (EST == EST_REUSE) ? 0 : 1; // which real plane holds E's factors
+						if (piv_any) band_solve<N, KB, true>(abr + o * PL, abr, false, rdr + o * N, rdr, piv + o * N, ev, ev);
+						else band_solve<N, KB, false>(abr + o * PL, abr, false, rdr + o * N, rdr, piv + o * N, ev, ev);
 					}
 					__syncwarp();
 				}

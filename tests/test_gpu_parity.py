@@ -568,6 +568,52 @@ def test_dense_output_on_a_uniform_grid(capi, port):
     assert scaled_err(gw.y_dense.reshape(-1, 3), gc.y_dense.reshape(-1, 3), 1e-6, 1e-6).max() <= PARITY_BOUND
 
 
+def test_band_lu_and_solve_against_lapack(capi):
+    """The warp kernel's band routines (irk_warp.cuh) on matrices the ODE problems never produce: random banded
+    matrices NEED row interchanges (pivoted variant, fill-in up to 2*kBand) and diagonally dominant ones do not
+    (plain variant; its flag must say so).  Real and complex matrices side by side in the lanes of one warp, like
+    in the integrator; checked against numpy's dense LAPACK solve."""
+    rng = np.random.default_rng(11)
+    n, kb, W, P = 64, 2, 7, 24
+    def run(dominant, pivot):
+        A = np.zeros((P, 4, n, n), dtype=np.complex128)
+        cplx = np.zeros((P, 4), dtype=np.int32)
+        cplx[:, 1:3] = 1  # lanes 1, 2 complex; 0, 3 real -- the LOBATTO_IIIC_85 set
+        for p in range(P):
+            for m in range(4):
+                for i in range(n):
+                    for j in range(max(0, i - kb), min(n, i + kb + 1)):
+                        A[p, m, i, j] = rng.standard_normal() + (1j * rng.standard_normal() if cplx[p, m] else 0)
+                    if dominant:
+                        A[p, m, i, i] += 8.0
+        b = rng.standard_normal((P, 4, n)) + 1j * rng.standard_normal((P, 4, n)) * cplx[:, :, None]
+        ab = np.zeros((P, 4, 2, n + kb, W))
+        for i in range(n):
+            for j in range(max(0, i - kb), min(n, i + kb + 1)):
+                ab[:, :, 0, i, kb + j - i] = A[:, :, i, j].real
+                ab[:, :, 1, i, kb + j - i] = A[:, :, i, j].imag
+        rhs = np.stack([b.real, b.imag], axis=2).copy()
+        x = np.zeros_like(rhs)
+        flags = np.zeros((P, 4), dtype=np.int32)
+        pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        capi.check(capi.lib.rehuel_selftest_band(P, int(pivot), pd(ab), pd(rhs), pi(cplx), pd(x), pi(flags)))
+        want = np.linalg.solve(A.reshape(-1, n, n), b.reshape(-1, n, 1)).reshape(P, 4, n)
+        got = x[:, :, 0] + 1j * x[:, :, 1]
+        scale = np.abs(want).max(axis=2, keepdims=True)
+        return np.abs(got - want).max() if not np.isfinite(got).all() else (np.abs(got - want) / scale).max(), flags
+    err, flags = run(dominant=False, pivot=True)
+    print(f"\nband LU, random matrices, pivoted: max rel. error vs LAPACK {err:.2e}; interchanges in {flags.mean():.0%} of them")
+    assert err < 1e-9 and flags.all()           # every random matrix interchanges rows somewhere
+    _, flags = run(dominant=False, pivot=False)
+    assert flags.all()                          # ... and the plain variant notices that it would have had to
+    err, flags = run(dominant=True, pivot=False)
+    print(f"band LU, diagonally dominant, plain: max rel. error {err:.2e}")
+    assert err < 1e-12 and not flags.any()
+    err2, _ = run(dominant=True, pivot=True)
+    assert err2 < 1e-12
+
+
 def test_mixed_stiffness_mixed_tolerance_ensemble(capi, port):
     """Config-5 shape: even members Robertson (config-2 sweep), odd members Van der Pol (config-3
     sweep), per-member rtol = atol = 10^(-3-6v), newton tol = 0.1 rtol.  The two problem classes
