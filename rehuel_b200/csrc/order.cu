@@ -199,7 +199,7 @@ int locality_order(const double *params, int p, size_t M, int descending, unsign
 	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 	const unsigned long long want = (M + 255) / 256;
 	const unsigned grid = (unsigned)(want < (unsigned long long)sms * 8 ? want : (unsigned long long)sms * 8);
-	const unsigned grid_mm = (unsigned)(want < (unsigned long long)sms * 2 ? want : (unsigned long long)sms * 2);
+	const unsigned grid_mm = grid; // one atomic pair per block and parameter: a few thousand in all
 	order_minmax_kernel<<<grid_mm, 256, 0, stream>>>(params, M, dims, minmax);
 	REHUEL_CUDA_TRY(cudaGetLastError());
 	count_launch();
