@@ -577,6 +577,11 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				int nstat = kNewtonMaxit;
 				int it = 1;
 				const int cap = (slow_trip || maxit <= kFastIters) ? maxit : kFastIters + 1;
+				// The iteration loop exists twice: the common instance knows at compile time that no row was
+				// interchanged; the rare one permutes the right-hand sides.  (One loop with a run-time test
+				// costs ~25 register moves per iteration around the skipped block.)
+				auto newton_loop = [&](auto swaps_tag) {
+				constexpr bool SWAPS = decltype(swaps_tag)::value;
 				for (; it < cap; ++it) { // irk.hpp:458 (cap == maxit unless this is a fast trip)
 					// dY = -(I - dt A(x)J)^-1 R through the decoupled blocks
 					double Z[S][N];
@@ -589,7 +594,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							for (int j = 0; j < S; ++j) acc = fma(tb.Ti[i][j], R[j][k], acc);
 							Z[i][k] = acc;
 						}
-					if (piv_any) { // rare: the right-hand sides follow the recorded row interchanges
+					if (SWAPS) { // the right-hand sides follow the recorded row interchanges
 						if (NR) apply_row_swaps(pivs, 0, Z[0]);
 #pragma unroll
 						for (int c = 0; c < NC; ++c) {
@@ -640,6 +645,9 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						break;
 					}
 				}
+				};
+				if (piv_any) newton_loop(std::true_type());
+				else newton_loop(std::false_type());
 
 				__syncwarp(amask);
 
