@@ -12,6 +12,16 @@
 //   };
 //   auto sol = irk::odeint(my_ode{}, t0, t1, y0, /*broadcast*/true, params, M, s_opts, out_opts, irk::RADAU_IIA_53);
 //
+// Larger systems (4 < N <= 64) are worked on by a whole warp or thread block, so their functor is
+// COMPONENTWISE (irk_cta.cuh / irk_warp.cuh):
+//
+//   struct my_pde {
+//       static constexpr int N = 64, P = 3;
+//       static constexpr int kBand = 2;   // optional: J(i,j) == 0 for |i-j| > kBand  ->  warp-per-system band kernels
+//       __device__ static double fun(int i, double t, const double *y, const double *p);                 // f_i(t, y)
+//       __device__ static void jac_row(int i, double t, const double *y, const double *p, double *row);  // row i of J, pre-zeroed
+//   };
+//
 // The kernel template is instantiated HERE, in the user's translation unit; the host pipeline
 // (uploads, chunked launches, result download, statistics) is rehuel::ensemble_host in the library.
 #ifndef REHUEL_B200_IRK_CUH
@@ -29,7 +39,10 @@ ensemble_output odeint(F, double t0, double t1, const double *y0, bool y0_broadc
 {
 	rehuel_options o = to_c_options(solver_opts, output_opts);
 	ensemble_output out;
-	check(rehuel::ensemble_host(&rehuel::dispatch_method<F>, F::N, F::P, method, t0, t1, dt, M, y0, y0_broadcast ? 1 : 0,
+	rehuel::LaunchFn launch;
+	if constexpr (F::N <= 4) launch = &rehuel::dispatch_method<F>; // thread-per-system
+	else launch = &rehuel::dispatch_method_cta<F>;                 // warp- or CTA-per-system
+	check(rehuel::ensemble_host(launch, F::N, F::P, method, t0, t1, dt, M, y0, y0_broadcast ? 1 : 0,
 	                            params, &o, output_opts.store_in_vectors() ? output_opts.max_samples : 0, n_gpus,
 	                            &out.raw()));
 	return out;
