@@ -19,9 +19,11 @@ class DeviceEnsemble:
                  n_samples_cap: int = 0, n_hint: int = 0, trace_cap: int = 0, trace_member: int = 0,
                  order: torch.Tensor | None = None, rtol: torch.Tensor | None = None,
                  atol: torch.Tensor | None = None, newton_tol: torch.Tensor | None = None,
-                 handout_order: int = capi.ORDER_INDEX):
+                 handout_order: int = capi.ORDER_INDEX, handout_keys: torch.Tensor | None = None):
         """``order``: caller-supplied hand-out order (int32 [M]).  ``handout_order``: ORDER_LOCALITY(_DESC) makes
-        every ``solve`` recompute the parameter-locality order on the device first (rehuel_locality_order)."""
+        every ``solve`` recompute the parameter-locality order on the device first (rehuel_locality_order), from
+        ``handout_keys`` ([k, M] float64: whatever the cost of a member depends on, e.g. parameters AND tolerance)
+        or, by default, from the parameters."""
         assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
         dev = y0.device
         n, p = capi.problem_dims(problem, n_hint or y0.shape[0])
@@ -67,7 +69,11 @@ class DeviceEnsemble:
             self.order = order.contiguous()
             io.order = self.order.data_ptr()
         self.handout_order = capi.ORDER_INDEX
-        if order is None and handout_order != capi.ORDER_INDEX and p:
+        self.keys = handout_keys if handout_keys is not None else (params if p else None)
+        if handout_keys is not None:
+            assert handout_keys.is_cuda and handout_keys.dtype == torch.float64 and handout_keys.is_contiguous()
+            assert handout_keys.dim() == 2 and handout_keys.shape[1] == M
+        if order is None and handout_order != capi.ORDER_INDEX and self.keys is not None:
             self.handout_order = handout_order
             self.order = torch.empty(M, dtype=torch.int32, device=dev)
             ws = capi.lib.rehuel_locality_order_workspace(M)
