@@ -476,15 +476,15 @@ int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, dou
 	int rc = prepare(method, t0, t1, dt0, M, opts, tb, ka);
 	if (rc) return rc;
 	if (!y0 || (p && !params)) return fail(REHUEL_EINVAL, "y0/params must not be NULL");
+	const size_t n_dense = (size_t)opts->dense_samples;
+	const bool keep_state = opts->keep_state != 0;
+	if (n_dense && !tb.has_interp) return fail(REHUEL_EINVAL, "Chosen method does not have dense output!"); // irk.cpp:733
+	if (n_dense && !(opts->dense_dt > 0.0)) return fail(REHUEL_EINVAL, "dense_dt must be > 0");
 	int ndev = 0;
 	CUDA_TRY(cudaGetDeviceCount(&ndev));
 	if (n_gpus < 1) n_gpus = 1;
 	if (n_gpus > ndev) return fail(REHUEL_EINVAL, "n_gpus=%d but only %d CUDA devices are visible", n_gpus, ndev);
 	if (!ka.store_samples) n_samples_cap = 0;
-	const size_t n_dense = (size_t)opts->dense_samples;
-	const bool keep_state = opts->keep_state != 0;
-	if (n_dense && !tb.has_interp) return fail(REHUEL_EINVAL, "Chosen method does not have dense output!"); // irk.cpp:733
-	if (n_dense && !(opts->dense_dt > 0.0)) return fail(REHUEL_EINVAL, "dense_dt must be > 0");
 	int cur_dev = 0;
 	CUDA_TRY(cudaGetDevice(&cur_dev));
 	const int dev0 = (n_gpus == 1) ? cur_dev : 0;
@@ -989,7 +989,8 @@ int rehuel_irk_ensemble_continue(int problem, int method, double t1, int n_hint,
                                  const rehuel_options *opts, size_t n_samples_cap, int n_gpus,
                                  const rehuel_result *prev, rehuel_result *out)
 {
-	if (!prev || !prev->y || !prev->t_final) return fail(REHUEL_EINVAL, "continue: `prev` must be a result of this library");
+	if (!prev || !prev->y || !prev->t_final || prev->M == 0)
+		return fail(REHUEL_EINVAL, "continue: `prev` must be a (non-empty) result of this library");
 	if (!prev->state) return fail(REHUEL_EINVAL, "continue: the previous call must run with options.keep_state != 0");
 	int n = 0, p = 0;
 	if (rehuel_problem_dims(problem, n_hint ? n_hint : prev->n, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);

@@ -128,6 +128,25 @@ def test_project_b_matches_reference_and_identities(capi, golden):
     assert capi.project_b(230, 0.5) is None  # no b_interp for LOBATTO_IIIC_43 (irk.cpp:261-272)
 
 
+def test_argument_errors_are_reported_before_any_gpu_work(capi):
+    """Bad arguments come back as REHUEL_EINVAL with a message (no GPU needed to find out)."""
+    from rehuel_b200 import ensembles
+    P = ensembles.robertson_params(4)
+    for kw, needle in ((dict(dense_samples=4, dense_t0=0.0, dense_dt=1.0, method=230), "dense output"),  # no b_interp (irk.cpp:733)
+                       (dict(dense_samples=4, dense_t0=0.0, dense_dt=0.0, method=211), "dense_dt"),
+                       (dict(handout_order=7, method=211), "handout_order"),
+                       (dict(newton_refresh_jac=0, method=211), "refresh_jac"),
+                       (dict(method=220), "not supported")):  # LOBATTO_IIIA_43: singular A
+        method = kw.pop("method")
+        with pytest.raises(capi.RehuelError) as ei:
+            capi.irk_ensemble(capi.ROBERTSON, method, 0.0, 1.0, 1e-6, ensembles.ROBERTSON_Y0, P, capi.make_options(1e-6, 1e-6, **kw))
+        assert ei.value.code == -1 and needle in str(ei.value), (needle, str(ei.value))
+    with pytest.raises(capi.RehuelError) as ei:  # nothing to continue from
+        capi.irk_ensemble_continue(capi.ROBERTSON, 211, 2.0, P, capi.make_options(1e-6, 1e-6), capi.Result())
+    assert ei.value.code == -1 and "continue" in str(ei.value)
+    assert capi.lib.rehuel_locality_order(None, 3, 16, 0, None, None, 0, None) == -1
+
+
 def test_no_gpu_means_loud_failure_not_a_fallback(capi):
     import torch
     if torch.cuda.is_available():
