@@ -155,6 +155,32 @@ def test_fixed_step_mode_1e12(capi, golden):
         assert c["nsteps"] <= int(g.counters["steps"][0]) <= c["nsteps"] + 1
 
 
+def test_fixed_step_convergence_orders(capi):
+    """The reference's manual order check (test_orders/main.cpp:47-90: y' = l y with fixed steps, error against exp,
+    slopes read off a plot) as an assertion, for every tableau the library builds: the observed order between
+    successive step sizes must reach the nominal one (irk.cpp `sc.order`).  One ensemble per method, members = rates."""
+    lam = np.array([[-0.25, -0.5, -1.0]])
+    nominal = {200: 1, 210: 3, 211: 5, 212: 9, 213: 13, 230: 4, 231: 6, 232: 8}
+    for method, order in nominal.items():
+        assert capi.get_coefficients(method)["order"] == order
+        o = capi.make_options(1e-6, 1e-6, adaptive=False, newton_tol=1e-15, newton_dx_delta=1e-15, newton_maxit=50)
+        # binary fractions, so that 8/dt steps land on t1 exactly
+        dts = {1: (0.125, 0.0625, 0.03125), 3: (0.5, 0.25, 0.125), 4: (0.5, 0.25, 0.125), 5: (1.0, 0.5, 0.25), 6: (1.0, 0.5, 0.25),
+               8: (2.0, 1.0, 0.5), 9: (2.0, 1.0, 0.5), 13: (4.0, 2.0, 1.0)}[order]
+        errs = []
+        for dt in dts:
+            g = capi.irk_ensemble(capi.EXPONENTIAL, method, 0.0, 8.0, dt, np.array([1.0]), lam, o)
+            assert np.all(g.status == 0) and np.all(g.counters["steps"] == round(8.0 / dt))
+            errs.append(np.abs(g.y[0] - np.exp(8.0 * lam[0])))
+        errs = np.array(errs)
+        observed = np.log2(errs[:-1] / errs[1:])
+        usable = errs[1:] > 1e-13                       # below that the differences are rounding
+        print(f"\nmethod {method} (order {order}): errors {errs[:, -1]}, observed orders {observed[:, -1]}")
+        assert usable.any(), (method, errs)
+        assert np.all(observed[usable] >= order - 0.6), (method, observed)
+        assert np.all(observed[usable] <= order + 1.6), (method, observed)
+
+
 def test_trajectory_samples_and_trace(capi, golden):
     """rk_output::t_vals / y_vals / err (irk.hpp:581-585, 825-832) through rehuel_irk_single."""
     c = [c for c in cases_of(golden, "single") if c["name"] == "robertson_211_t40"][0]
