@@ -287,6 +287,11 @@ int rehuel_kernel_info(int problem, int method, int n_hint, int *regs, int *loca
  * MEASURED_PEAKS.json carries no FP64 figure. */
 int rehuel_fp64_peak(double *tflops, double *ms);
 
+/* Diagnostic: evaluates a built-in device functor once on the GPU: f[n] = fun(t, y), J[n*n] (row-major) = jac(t, y).
+ * HOST pointers.  The reference checks its analytic Jacobians against finite differences in test/test_test_equations.cpp
+ * (vacuously: newton.hpp:235-242 never updates the maximum); tests/test_gpu_parity.py does it for real through this. */
+int rehuel_eval_functor(int problem, int n_hint, double t, const double *y, const double *params, double *f, double *J);
+
 /* Diagnostic: the warp-per-system kernel's band LU + band solve (n = 64, half bandwidth 2) on caller-given
  * matrices, 4 per problem (lane m <-> matrix m as in the integrator).  ab: [n_problems][4][2 (re,im)][66][7] band
  * rows (slot 2 + j - i holds A(i,j), rows 64..65 zero); rhs, x: [n_problems][4][2][64]; is_cplx, flags:

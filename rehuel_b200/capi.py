@@ -136,6 +136,7 @@ EXPORTS = (
     "rehuel_irk_single", "rehuel_irk_ensemble_device", "rehuel_result_merge", "rehuel_kernel_launches",
     "rehuel_kernel_info", "rehuel_last_error", "rehuel_version", "rehuel_fp64_peak", "rehuel_release_cached_memory",
     "rehuel_locality_order_workspace", "rehuel_locality_order", "rehuel_irk_ensemble_continue", "rehuel_selftest_band",
+    "rehuel_eval_functor",
 )
 
 
@@ -214,6 +215,17 @@ def project_b(method: int, theta: float):
     out = np.zeros(7)
     s = lib.rehuel_project_b(C.c_int(method), C.c_double(theta), out.ctypes.data_as(_PD))
     return out[:s].copy() if s > 0 else None
+
+
+def eval_functor(problem: int, t: float, y, params, n_hint: int = 0):
+    """f(t, y) and J(t, y) of a built-in device functor, evaluated on the GPU (diagnostic)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n, p = problem_dims(problem, n_hint or y.shape[0])
+    par = np.ascontiguousarray(params if p else [0.0], dtype=np.float64)
+    f = np.zeros(n); J = np.zeros((n, n))
+    pd = lambda a: a.ctypes.data_as(_PD)
+    check(lib.rehuel_eval_functor(C.c_int(problem), C.c_int(n_hint or n), C.c_double(t), pd(y), pd(par), pd(f), pd(J)))
+    return f, J
 
 
 def kernel_info(problem: int, method: int, n_hint: int = 0) -> dict:

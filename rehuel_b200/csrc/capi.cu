@@ -105,6 +105,20 @@ LaunchFn launcher_bruss1d_8();
 LaunchFn launcher_bruss1d_dense_64();
 LaunchFn launcher_bruss1d_dense_8();
 
+EvalFn evaluator_robertson();
+EvalFn evaluator_van_der_pol();
+EvalFn evaluator_exponential();
+EvalFn evaluator_stiff_eq();
+EvalFn evaluator_brusselator();
+EvalFn evaluator_lorenz();
+EvalFn evaluator_harmonic();
+EvalFn evaluator_dimer();
+EvalFn evaluator_kinetic4();
+EvalFn evaluator_bruss1d_64();
+EvalFn evaluator_bruss1d_8();
+EvalFn evaluator_bruss1d_dense_64();
+EvalFn evaluator_bruss1d_dense_8();
+
 static LaunchFn find_launcher(int problem, int n)
 {
 	if (problem == REHUEL_PROBLEM_BRUSSELATOR_1D || problem == REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE) {
@@ -126,6 +140,24 @@ static LaunchFn find_launcher(int problem, int n)
 	case REHUEL_PROBLEM_KINETIC_4: return launcher_kinetic4();
 	}
 	set_error(REHUEL_EINVAL, "problem %d has no GPU kernel", problem);
+	return nullptr;
+}
+
+static EvalFn find_evaluator(int problem, int n)
+{
+	switch (problem) {
+	case REHUEL_PROBLEM_ROBERTSON: return evaluator_robertson();
+	case REHUEL_PROBLEM_VAN_DER_POL: return evaluator_van_der_pol();
+	case REHUEL_PROBLEM_EXPONENTIAL: return evaluator_exponential();
+	case REHUEL_PROBLEM_STIFF_EQ: return evaluator_stiff_eq();
+	case REHUEL_PROBLEM_BRUSSELATOR: return evaluator_brusselator();
+	case REHUEL_PROBLEM_LORENZ: return evaluator_lorenz();
+	case REHUEL_PROBLEM_HARMONIC: return evaluator_harmonic();
+	case REHUEL_PROBLEM_DIMER: return evaluator_dimer();
+	case REHUEL_PROBLEM_KINETIC_4: return evaluator_kinetic4();
+	case REHUEL_PROBLEM_BRUSSELATOR_1D: return n == 64 ? evaluator_bruss1d_64() : (n == 8 ? evaluator_bruss1d_8() : nullptr);
+	case REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE: return n == 64 ? evaluator_bruss1d_dense_64() : (n == 8 ? evaluator_bruss1d_dense_8() : nullptr);
+	}
 	return nullptr;
 }
 
@@ -1000,6 +1032,16 @@ int rehuel_irk_ensemble_continue(int problem, int method, double t1, int n_hint,
 	// dt0 is only a placeholder here: every member's step size comes from its state
 	return ensemble_host_from(launch, n, p, method, prev->t_final[0], t1, 1e-6, prev->M, prev->y, 0, params, opts, n_samples_cap,
 	                          n_gpus, prev->t_final, prev->state, out);
+}
+
+int rehuel_eval_functor(int problem, int n_hint, double t, const double *y, const double *params, double *f, double *J)
+{
+	int n = 0, p = 0;
+	if (rehuel_problem_dims(problem, n_hint, &n, &p) != REHUEL_OK) return fail(REHUEL_EINVAL, "unknown problem id %d", problem);
+	if (!y || (p && !params) || !f || !J) return fail(REHUEL_EINVAL, "eval: y, params, f and J are required");
+	EvalFn ev = find_evaluator(problem, n);
+	if (!ev) return fail(REHUEL_EINVAL, "problem %d has no device functor for n = %d", problem, n);
+	return ev(t, y, params, f, J);
 }
 
 void rehuel_release_cached_memory(void)

@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_bruss1d_64() { return &dispatch_method_cta<Brusselator1dF<32>>; }
+EvalFn evaluator_bruss1d_64() { return &eval_functor<Brusselator1dF<32>, true>; }
 } // namespace rehuel

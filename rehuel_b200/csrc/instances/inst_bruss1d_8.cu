@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_bruss1d_8() { return &dispatch_method_cta<Brusselator1dF<4>>; }
+EvalFn evaluator_bruss1d_8() { return &eval_functor<Brusselator1dF<4>, true>; }
 } // namespace rehuel

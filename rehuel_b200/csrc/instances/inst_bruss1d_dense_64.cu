@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_bruss1d_dense_64() { return &dispatch_method_cta<Brusselator1dDenseF<32>>; }
+EvalFn evaluator_bruss1d_dense_64() { return &eval_functor<Brusselator1dDenseF<32>, true>; }
 } // namespace rehuel

@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_bruss1d_dense_8() { return &dispatch_method_cta<Brusselator1dDenseF<4>>; }
+EvalFn evaluator_bruss1d_dense_8() { return &eval_functor<Brusselator1dDenseF<4>, true>; }
 } // namespace rehuel

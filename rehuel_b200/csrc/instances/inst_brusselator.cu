@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_brusselator() { return &dispatch_method<BrusselatorF>; }
+EvalFn evaluator_brusselator() { return &eval_functor<BrusselatorF, false>; }
 } // namespace rehuel

@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_dimer() { return &dispatch_method<DimerF>; }
+EvalFn evaluator_dimer() { return &eval_functor<DimerF, false>; }
 } // namespace rehuel

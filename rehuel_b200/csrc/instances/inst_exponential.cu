@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_exponential() { return &dispatch_method<ExponentialF>; }
+EvalFn evaluator_exponential() { return &eval_functor<ExponentialF, false>; }
 } // namespace rehuel

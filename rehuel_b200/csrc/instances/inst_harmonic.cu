@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_harmonic() { return &dispatch_method<HarmonicF>; }
+EvalFn evaluator_harmonic() { return &eval_functor<HarmonicF, false>; }
 } // namespace rehuel

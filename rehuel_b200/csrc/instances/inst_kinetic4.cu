@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_kinetic4() { return &dispatch_method<Kinetic4F>; }
+EvalFn evaluator_kinetic4() { return &eval_functor<Kinetic4F, false>; }
 } // namespace rehuel

@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_lorenz() { return &dispatch_method<LorenzF>; }
+EvalFn evaluator_lorenz() { return &eval_functor<LorenzF, false>; }
 } // namespace rehuel

@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_robertson() { return &dispatch_method<RobertsonF>; }
+EvalFn evaluator_robertson() { return &eval_functor<RobertsonF, false>; }
 } // namespace rehuel

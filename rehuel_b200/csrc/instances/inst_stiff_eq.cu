@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_stiff_eq() { return &dispatch_method<StiffEqF>; }
+EvalFn evaluator_stiff_eq() { return &eval_functor<StiffEqF, false>; }
 } // namespace rehuel

@@ -4,4 +4,5 @@
 
 namespace rehuel {
 LaunchFn launcher_van_der_pol() { return &dispatch_method<VanDerPolF>; }
+EvalFn evaluator_van_der_pol() { return &eval_functor<VanDerPolF, false>; }
 } // namespace rehuel

@@ -131,6 +131,55 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 	return REHUEL_OK;
 }
 
+// ---- diagnostic: evaluate a functor's f(t,y) and J(t,y) on the device (rehuel_eval_functor)
+using EvalFn = int (*)(double t, const double *y, const double *p, double *f, double *J /* row-major n x n */);
+
+template <class F>
+__global__ void eval_functor_kernel(double t, const double *y, const double *p, double *f, double *J)
+{
+	constexpr int N = F::N, PA = F::P > 0 ? F::P : 1;
+	double yy[N], pp[PA], ff[N], JJ[N][N];
+	for (int k = 0; k < N; ++k) yy[k] = y[k];
+	for (int k = 0; k < PA; ++k) pp[k] = (k < F::P) ? p[k] : 0.0;
+	F::fun(t, yy, pp, ff);
+	F::jac(t, yy, pp, JJ);
+	for (int i = 0; i < N; ++i) {
+		f[i] = ff[i];
+		for (int j = 0; j < N; ++j) J[i * N + j] = JJ[i][j];
+	}
+}
+
+template <class F>
+__global__ void eval_functor_rows_kernel(double t, const double *y, const double *p, double *f, double *J)
+{
+	constexpr int N = F::N;
+	for (int i = threadIdx.x; i < N; i += blockDim.x) {
+		f[i] = F::fun(i, t, y, p);
+		for (int j = 0; j < N; ++j) J[i * N + j] = 0.0;
+		F::jac_row(i, t, y, p, J + i * N);
+	}
+}
+
+// host pointers in, host pointers out (a test hook, not a fast path)
+template <class F, bool COMPONENTWISE>
+int eval_functor(double t, const double *y, const double *p, double *f, double *J)
+{
+	constexpr int N = F::N, PA = F::P > 0 ? F::P : 1;
+	double *d = nullptr;
+	REHUEL_CUDA_TRY(cudaMalloc(&d, sizeof(double) * (N + PA + N + N * N)));
+	double *dy = d, *dp = d + N, *df = dp + PA, *dJ = df + N;
+	REHUEL_CUDA_TRY(cudaMemcpy(dy, y, sizeof(double) * N, cudaMemcpyHostToDevice));
+	if (F::P > 0) REHUEL_CUDA_TRY(cudaMemcpy(dp, p, sizeof(double) * F::P, cudaMemcpyHostToDevice));
+	if constexpr (COMPONENTWISE) eval_functor_rows_kernel<F><<<1, 64>>>(t, dy, dp, df, dJ);
+	else eval_functor_kernel<F><<<1, 1>>>(t, dy, dp, df, dJ);
+	REHUEL_CUDA_TRY(cudaGetLastError());
+	count_launch();
+	REHUEL_CUDA_TRY(cudaMemcpy(f, df, sizeof(double) * N, cudaMemcpyDeviceToHost));
+	REHUEL_CUDA_TRY(cudaMemcpy(J, dJ, sizeof(double) * N * N, cudaMemcpyDeviceToHost));
+	cudaFree(d);
+	return REHUEL_OK;
+}
+
 // Method id -> kernel instantiation (stage count and eigen-structure are compile-time).
 template <class F>
 int dispatch_method(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)

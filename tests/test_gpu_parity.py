@@ -155,6 +155,34 @@ def test_fixed_step_mode_1e12(capi, golden):
         assert c["nsteps"] <= int(g.counters["steps"][0]) <= c["nsteps"] + 1
 
 
+def test_analytic_jacobians_match_finite_differences(capi):
+    """test/test_test_equations.cpp:8-82 compares every test equation's analytic Jacobian with finite differences --
+    vacuously, because verify_jacobi_matrix never updates its maximum (newton.hpp:235-242).  Done for real here, on
+    the DEVICE functors (rehuel_eval_functor), at several states each."""
+    from rehuel_b200 import ensembles
+    rng = np.random.default_rng(5)
+    cases = [(capi.ROBERTSON, [0.04, 1e4, 3e7], 3, 0), (capi.VAN_DER_POL, [1e-2], 2, 0), (capi.EXPONENTIAL, [-0.4], 1, 0),
+             (capi.STIFF_EQ, None, 2, 0), (capi.BRUSSELATOR, [1.0, 3.5], 2, 0), (capi.LORENZ, [10.0, 28.0, 8.0 / 3.0], 3, 0),
+             (capi.HARMONIC, [3.0], 2, 0), (capi.DIMER, [5.0], 2, 0), (capi.KINETIC_4, [0.5, 0.3, 0.2], 4, 0),
+             (capi.BRUSSELATOR_1D, [0.02, 1.0, 3.0], 64, 64), (capi.BRUSSELATOR_1D_DENSE, [0.02, 1.0, 3.0], 8, 8)]
+    for prob, par, n, hint in cases:
+        for trial in range(3):
+            y = rng.uniform(0.2, 1.5, n)
+            f0, J = capi.eval_functor(prob, 0.3, y, par, n_hint=hint)
+            fd = np.zeros((n, n))
+            for j in range(n):
+                h = 1e-6 * max(1.0, abs(y[j]))
+                yp, ym = y.copy(), y.copy()
+                yp[j] += h
+                ym[j] -= h
+                fd[:, j] = (capi.eval_functor(prob, 0.3, yp, par, n_hint=hint)[0] - capi.eval_functor(prob, 0.3, ym, par, n_hint=hint)[0]) / (2 * h)
+            scale = max(1.0, np.abs(J).max())
+            assert np.abs(J - fd).max() <= 1e-6 * scale, (prob, trial, np.abs(J - fd).max(), scale)
+    # and the right-hand side itself against the host-side restatement used for the ensembles' initial data
+    f, _ = capi.eval_functor(capi.ROBERTSON, 0.0, [1.0, 2e-5, 0.1], [0.04, 1e4, 3e7])
+    np.testing.assert_allclose(f, [-0.04 + 1e4 * 2e-5 * 0.1, 0.04 - 1e4 * 2e-5 * 0.1 - 3e7 * 4e-10, 3e7 * 4e-10], rtol=1e-14)
+
+
 def test_fixed_step_convergence_orders(capi):
     """The reference's manual order check (test_orders/main.cpp:47-90: y' = l y with fixed steps, error against exp,
     slopes read off a plot) as an assertion, for every tableau the library builds: the observed order between
