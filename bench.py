@@ -225,7 +225,7 @@ def run_gpu_arm(args) -> None:
 
     M = args.members
     t0, t1 = SPANS[args.span]
-    handout = {"index": capi.ORDER_INDEX, "locality": capi.ORDER_LOCALITY}[args.handout]
+    handout = {"index": capi.ORDER_INDEX, "locality": capi.ORDER_LOCALITY, "locality_desc": capi.ORDER_LOCALITY_DESC}[args.handout]
     opts = capi.make_options(RTOL, ATOL, handout_order=handout)
     # rank r owns members [r*M, (r+1)*M) of the sweep (weak scaling; any rank can generate its slice)
     P_host = torch.from_numpy(ensembles.robertson_params(M, start=rank * M)).pin_memory()
@@ -336,7 +336,9 @@ def run_gpu_arm(args) -> None:
                        "parallelism": f"member-sharded x{world} (no data-path collective)",
                        "l2": "flushed between timed steps (256 MiB fill, outside the per-step event pair)",
                        "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
-                       "handout_order": args.handout + (" (Morton order of the rate constants, recomputed on the device inside every timed step)" if handout else ""),
+                       "handout_order": args.handout + (" (Morton order of the rate constants, recomputed on the device inside every timed step"
+                                                       + ("; walked from the large-k1 end, whose members need up to 39 attempts against 23, so the "
+                                                          "queue drains on cheap members" if args.handout == "locality_desc" else "") + ")" if handout else ""),
                        "wall_s_timed_region_rank0": wall, "host_binding_rank0": numa_note},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P_host.numel() * 8 + 24),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * et.item() / args.steps,
@@ -380,7 +382,7 @@ def main() -> None:
     ap.add_argument("--span", choices=tuple(SPANS), default="short")
     ap.add_argument("--members", type=int, default=M_PER_GPU, help="members per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--handout", choices=("index", "locality"), default="locality",
+    ap.add_argument("--handout", choices=("index", "locality", "locality_desc"), default="locality_desc",
                     help="order in which members are handed to the GPU lanes (results do not depend on it)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
