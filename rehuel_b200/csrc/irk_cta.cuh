@@ -494,6 +494,11 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 					Y[e] += acc;
 				}
 				const double xnorm2 = block_sum<THREADS>(x2, red); // irk.hpp:466 (also orders Z reads before reuse)
+				if (REHUEL_SKIP_DEAD_RESIDUAL && xnorm2 < a.xtol2) { // the residual of irk.hpp:469-472 would never be looked at
+					c_fun += S;                                       // (see irk_thread.cuh); its evaluations are booked
+					nstat = kNewtonSuccess;
+					break;
+				}
 				Rnorm2 = residual();
 				if (Rnorm2 < a.Rtol2) { nstat = kNewtonSuccess; break; }
 				if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; }

@@ -266,6 +266,9 @@ __device__ __forceinline__ void lu_solve(const LuCplx<N> &m, double (&xr)[N], do
 // evaluations of the first residual are the same f(t + c_i dt, y) = f(y): the kernel then evaluates
 // it once (the evaluation counters still book the S calls the reference makes) and reuses it for
 // the gamma*dt*f(t, y) term of the error estimate (irk.hpp:702).
+#ifndef REHUEL_SKIP_DEAD_RESIDUAL
+#define REHUEL_SKIP_DEAD_RESIDUAL 1
+#endif
 #ifndef REHUEL_AUTONOMOUS_OPT
 #define REHUEL_AUTONOMOUS_OPT 2 // 0: off, 1: first residual only, 2: + error estimate
 #endif
@@ -354,6 +357,9 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0,
 	         c_iters = 0, n_stored = 0;
 	unsigned kd = 0; // dense output: index of the next grid time (DENSE kernels only)
+#ifdef REHUEL_COUNT_SKIPS
+	unsigned c_skips = 0;
+#endif
 	// per-member tolerances (TOLV kernels only; otherwise the uniform values of the options)
 	double m_rtol = a.rtol, m_atol = a.atol, m_Rtol2 = a.Rtol2;
 
@@ -629,6 +635,19 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							xnorm2 = fma(acc, acc, xnorm2); // irk.hpp:466
 							Y[i][k] += acc;                 // irk.hpp:468 (step == 1)
 						}
+					// The reference evaluates R(Y) (irk.hpp:469-472) and then stops on |R|^2 < tol^2 (473-476) OR
+					// |dY|^2 < dx_delta^2 (477-480), both with the same status and iteration count, and never
+					// looks at that residual again.  When the step test already holds -- with the default
+					// dx_delta = 1e-4 against tol ~ 1e-7 it almost always fires first -- the evaluation is
+					// dead work: skip it, book its function calls.
+					if (REHUEL_SKIP_DEAD_RESIDUAL && xnorm2 < a.xtol2) {
+#ifdef REHUEL_COUNT_SKIPS
+						++c_skips; // dev builds: how often the step test fires first (reported in the MAXIT_EXCEED row)
+#endif
+						c_fun += S;
+						nstat = kNewtonSuccess;
+						break;
+					}
 					Rnorm2 = residual();                    // irk.hpp:469-472
 					if (Rnorm2 < (TOLV ? m_Rtol2 : a.Rtol2)) { nstat = kNewtonSuccess; break; } // irk.hpp:473-476
 					if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; } // irk.hpp:477-480
@@ -822,7 +841,12 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				io.counters[REHUEL_CNT_REJECT_NEWTON * M + mem] = c_rej_newton;
 				io.counters[REHUEL_CNT_REJECT_ERR * M + mem] = c_rej_err;
 				io.counters[REHUEL_CNT_NEWTON_SUCCESS * M + mem] = c_newton_ok;
+#ifdef REHUEL_COUNT_SKIPS
+				io.counters[REHUEL_CNT_NEWTON_MAXIT_EXCEED * M + mem] = c_skips;
+				c_skips = 0;
+#else
 				io.counters[REHUEL_CNT_NEWTON_MAXIT_EXCEED * M + mem] = c_rej_newton;
+#endif
 				io.counters[REHUEL_CNT_FUN_EVALS * M + mem] = c_fun;
 				io.counters[REHUEL_CNT_JAC_EVALS * M + mem] = c_jac;
 				io.counters[REHUEL_CNT_NEWTON_ITERS * M + mem] = c_iters;

@@ -468,6 +468,11 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 				}
 				__syncwarp();
 				const double xnorm2 = warp_sum(x2); // irk.hpp:466
+				if (REHUEL_SKIP_DEAD_RESIDUAL && xnorm2 < a.xtol2) { // the residual of irk.hpp:469-472 would never be looked at
+					c_fun += S;                                       // (see irk_thread.cuh); its evaluations are booked
+					nstat = kNewtonSuccess;
+					break;
+				}
 				Rnorm2 = residual();
 				if (Rnorm2 < a.Rtol2) { nstat = kNewtonSuccess; break; }
 				if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; }
