@@ -58,7 +58,7 @@ build/cpp_api: examples/cpp_api.cpp include/rehuel_b200/irk.hpp $(LIB)
 	$(HOSTCXX) -std=c++11 -O2 -Wall -Iinclude $< -o $@ -Lrehuel_b200 -lrehuel_b200 -Wl,-rpath,'$$ORIGIN/../rehuel_b200'
 build/rehuel_example: examples/rehuel_example.cpp include/rehuel_b200/irk.hpp include/rehuel_b200.h $(LIB)
 	$(HOSTCXX) -std=c++11 -O2 -Wall -Iinclude $< -o $@ -Lrehuel_b200 -lrehuel_b200 -Wl,-rpath,'$$ORIGIN/../rehuel_b200'
-build/user_functor: examples/user_functor.cu include/rehuel_b200/irk.cuh $(SRC)/launch.cuh $(SRC)/irk_thread.cuh $(LIB)
+build/user_functor: examples/user_functor.cu include/rehuel_b200/irk.cuh include/rehuel_b200/irk.hpp $(KHDRS) $(LIB)
 	$(NVCC) -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) --expt-relaxed-constexpr -Iinclude $< -o $@ \
 	    -Lrehuel_b200 -lrehuel_b200 -cudart shared -Xlinker -rpath,'$$ORIGIN/../rehuel_b200'
 

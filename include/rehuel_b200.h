@@ -218,6 +218,9 @@ typedef struct rehuel_device_io {
 	size_t n_dense;         /* dense output: number of grid times t_k = dense_t0 + k*dense_dt (0 = off) */
 	double dense_t0, dense_dt;
 	double *y_dense;        /* [n_dense][n][M]; the caller pre-fills it (e.g. with NaN): only reached grid points are written */
+	unsigned long long *stats; /* [REHUEL_NSTATS] or NULL: ensemble sums accumulated by the kernel itself (the caller zeroes
+	                          them): words 0..8 the counters in REHUEL_CNT_* order, 9 members with status != 0,
+	                          10 the maximum number of attempts of any member */
 	const unsigned *order; /* [M] or NULL: queue position q -> member index order[q].  Lets the caller hand out
 	                          expensive members first (longest-processing-time-first) when cost correlates with a
 	                          parameter; results do not depend on it. */
@@ -244,6 +247,7 @@ typedef struct rehuel_device_io {
 #define REHUEL_CNT_NEWTON_ITERS        7
 #define REHUEL_CNT_STEPS               8
 #define REHUEL_NCOUNTERS               9
+#define REHUEL_NSTATS                  11
 
 int rehuel_irk_ensemble_device(int problem, int method, double t0, double t1, double dt0, size_t M,
                                int n_hint, const rehuel_options *opts, const rehuel_device_io *io,

@@ -87,7 +87,7 @@ class DeviceIO(C.Structure):
         ("trace_len", C.c_void_p), ("rtol", C.c_void_p), ("atol", C.c_void_p), ("newton_tol", C.c_void_p),
         ("t_start", C.c_void_p), ("state_in", C.c_void_p), ("state_out", C.c_void_p),
         ("n_dense", C.c_size_t), ("dense_t0", C.c_double), ("dense_dt", C.c_double), ("y_dense", C.c_void_p),
-        ("order", C.c_void_p),
+        ("stats", C.c_void_p), ("order", C.c_void_p),
     ]
 
 

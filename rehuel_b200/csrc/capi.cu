@@ -416,38 +416,9 @@ static void free_result(rehuel_result *r)
 	std::memset(r, 0, sizeof *r);
 }
 
-// ------------------------------------------------------------------ stats reduction epilogue
-// Ensemble sums of the per-member counters (the role merge_rk_output's counter adds play in the
-// reference, irk.cpp:773-780): one pass over counters[9][m] + status[m] -> 13 words.
+// Ensemble sums of the per-member counters (the role merge_rk_output's counter adds play in the reference,
+// irk.cpp:773-780) are accumulated by the integration kernels themselves (rehuel_device_io.stats).
 constexpr int kStatWords = 13;
-__global__ void __launch_bounds__(256) ensemble_stats_kernel(const unsigned *__restrict__ counters,
-                                                            const int *__restrict__ status, size_t m,
-                                                            unsigned long long *__restrict__ out)
-{
-	unsigned long long acc[REHUEL_NCOUNTERS] = {};
-	unsigned long long failed = 0, maxatt = 0;
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x) {
-#pragma unroll
-		for (int c = 0; c < REHUEL_NCOUNTERS; ++c) acc[c] += counters[c * m + i];
-		failed += status[i] != 0;
-		const unsigned long long a = counters[REHUEL_CNT_ATTEMPT * m + i];
-		maxatt = a > maxatt ? a : maxatt;
-	}
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-		for (int c = 0; c < REHUEL_NCOUNTERS; ++c) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], o);
-		failed += __shfl_down_sync(0xffffffffu, failed, o);
-		const unsigned long long other = __shfl_down_sync(0xffffffffu, maxatt, o);
-		maxatt = other > maxatt ? other : maxatt;
-	}
-	if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-		for (int c = 0; c < REHUEL_NCOUNTERS; ++c) atomicAdd(out + c, acc[c]);
-		atomicAdd(out + REHUEL_NCOUNTERS, failed);
-		atomicMax(out + REHUEL_NCOUNTERS + 1, maxatt);
-	}
-}
 
 int ensemble_device(LaunchFn launch, int n, int p, int method, double t0, double t1, double dt0, size_t M,
                     const rehuel_options *opts, const rehuel_device_io *io, cudaStream_t stream)
@@ -716,17 +687,22 @@ int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, dou
 				if (ro) return ro;
 				sh.io.order = d_order;
 			}
+			sh.io.stats = sh.d_stats;
 			KernelArgs k = ka;
 			k.M = m;
 			k.io = sh.io;
 			if (n_samples_cap == 0) k.store_samples = 0; // final state only: skip the per-step sample bookkeeping
+			// at most `inflight` integration kernels of a device run side by side: kernel i waits for kernel i - inflight
+			// (tuning aid REHUEL_INFLIGHT; 0 = no limit)
+			static const long inflight = std::getenv("REHUEL_INFLIGHT") ? std::atol(std::getenv("REHUEL_INFLIGHT")) : 0;
+			if (inflight > 0 && si >= (size_t)inflight && shards[si - inflight].dev == sh.dev && shards[si - inflight].m)
+				CUDA_TRY(cudaStreamWaitEvent(sh.stream, shards[si - inflight].ev1, 0));
 			CUDA_TRY(cudaEventRecord(sh.ev0, sh.stream));
 			int rr = launch(k, tb, sh.stream, nullptr);
 			if (rr) return rr;
 			CUDA_TRY(cudaEventRecord(sh.ev1, sh.stream));
-			// D2H of the per-member results first: the statistics kernel below has to wait for free
-			// SM slots behind the persistent kernels of the following chunks, and must not hold the
-			// bulk copies back with it (measured: without this order no copy overlapped any kernel)
+			CUDA_TRY(cudaMemcpyAsync(h_stats + si * kStatWords, sh.d_stats, sizeof(unsigned long long) * kStatWords,
+			                         cudaMemcpyDeviceToHost, sh.stream));
 			CUDA_TRY(cudaMemcpy2DAsync(hdbl + sh.off, sizeof(double) * M, ddbl, sizeof(double) * m, sizeof(double) * m,
 			                           (size_t)n + 2, cudaMemcpyDeviceToHost, sh.stream));
 			CUDA_TRY(cudaMemcpy2DAsync(hint + sh.off, sizeof(int) * M, dint, sizeof(int) * m, sizeof(int) * m,
@@ -748,16 +724,6 @@ int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, dou
 				                           sizeof(double) * m, n_samples_cap * n, cudaMemcpyDeviceToHost, sh.stream));
 			}
 			t_mark[si + 1] = now_ms();
-		}
-		for (size_t si = 0; si < shards.size(); ++si) { // statistics epilogue, after every bulk copy is queued
-			DeviceShard &sh = shards[si];
-			if (sh.m == 0) continue;
-			CUDA_TRY(cudaSetDevice(sh.dev));
-			ensemble_stats_kernel<<<148, 256, 0, sh.stream>>>(sh.io.counters, sh.io.status, sh.m, sh.d_stats);
-			CUDA_TRY(cudaGetLastError());
-			g_launches.fetch_add(1);
-			CUDA_TRY(cudaMemcpyAsync(h_stats + si * kStatWords, sh.d_stats, sizeof(unsigned long long) * kStatWords,
-			                         cudaMemcpyDeviceToHost, sh.stream));
 		}
 		const bool timing = std::getenv("REHUEL_TIMING") != nullptr;
 		const double t_issued = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();

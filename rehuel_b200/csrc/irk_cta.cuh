@@ -654,6 +654,7 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 			io.t_final[mem] = t;
 			if (io.err_last) io.err_last[mem] = err;
 			io.status[mem] = status;
+			const unsigned steps_here = (unsigned)(step - (io.state_in ? (long long)io.state_in[REHUEL_STATE_STEP * M + mem] : 0ll));
 			if (io.counters) {
 				io.counters[REHUEL_CNT_ATTEMPT * M + mem] = c_attempt;
 				io.counters[REHUEL_CNT_REJECT_NEWTON * M + mem] = c_rej_newton;
@@ -663,7 +664,20 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 				io.counters[REHUEL_CNT_FUN_EVALS * M + mem] = c_fun;
 				io.counters[REHUEL_CNT_JAC_EVALS * M + mem] = c_jac;
 				io.counters[REHUEL_CNT_NEWTON_ITERS * M + mem] = c_iters;
-				io.counters[REHUEL_CNT_STEPS * M + mem] = (unsigned)step;
+				io.counters[REHUEL_CNT_STEPS * M + mem] = steps_here;
+			}
+			if (io.stats) { // ensemble sums; members are few on this path, so straight to global memory
+				atomicAdd(io.stats + REHUEL_CNT_ATTEMPT, (unsigned long long)c_attempt);
+				atomicAdd(io.stats + REHUEL_CNT_REJECT_NEWTON, (unsigned long long)c_rej_newton);
+				atomicAdd(io.stats + REHUEL_CNT_REJECT_ERR, (unsigned long long)c_rej_err);
+				atomicAdd(io.stats + REHUEL_CNT_NEWTON_SUCCESS, (unsigned long long)c_newton_ok);
+				atomicAdd(io.stats + REHUEL_CNT_NEWTON_MAXIT_EXCEED, (unsigned long long)c_rej_newton);
+				atomicAdd(io.stats + REHUEL_CNT_FUN_EVALS, (unsigned long long)c_fun);
+				atomicAdd(io.stats + REHUEL_CNT_JAC_EVALS, (unsigned long long)c_jac);
+				atomicAdd(io.stats + REHUEL_CNT_NEWTON_ITERS, (unsigned long long)c_iters);
+				atomicAdd(io.stats + REHUEL_CNT_STEPS, (unsigned long long)steps_here);
+				if (status != 0) atomicAdd(io.stats + REHUEL_NCOUNTERS, 1ull);
+				atomicMax(io.stats + REHUEL_NCOUNTERS + 1, (unsigned long long)c_attempt);
 			}
 			if (io.n_samples) io.n_samples[mem] = n_stored;
 			if (io.state_out) {

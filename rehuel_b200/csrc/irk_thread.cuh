@@ -341,6 +341,11 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned long long M = a.M;
 	const rehuel_device_io &io = a.io;
+	// ensemble sums (io.stats): a finishing member adds its counters to the CTA's shared-memory totals, the CTA adds
+	// them to global memory once at the end -- no separate reduction pass over the counter arrays
+	__shared__ unsigned s_stats[REHUEL_NSTATS];
+	if (threadIdx.x < REHUEL_NSTATS) s_stats[threadIdx.x] = 0u;
+	__syncthreads();
 
 	// ---- lane-persistent member state
 	bool have = false, exhausted = false;
@@ -836,6 +841,8 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 			io.t_final[mem] = t;
 			if (io.err_last) io.err_last[mem] = err;
 			io.status[mem] = status;
+			// accepted steps of THIS call (a continued member's `step` also counts the earlier legs)
+			const unsigned steps_here = (unsigned)(step - (io.state_in ? (long long)io.state_in[REHUEL_STATE_STEP * M + mem] : 0ll));
 			if (io.counters) {
 				io.counters[REHUEL_CNT_ATTEMPT * M + mem] = c_attempt;
 				io.counters[REHUEL_CNT_REJECT_NEWTON * M + mem] = c_rej_newton;
@@ -850,7 +857,28 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				io.counters[REHUEL_CNT_FUN_EVALS * M + mem] = c_fun;
 				io.counters[REHUEL_CNT_JAC_EVALS * M + mem] = c_jac;
 				io.counters[REHUEL_CNT_NEWTON_ITERS * M + mem] = c_iters;
-				io.counters[REHUEL_CNT_STEPS * M + mem] = (unsigned)step;
+				io.counters[REHUEL_CNT_STEPS * M + mem] = steps_here;
+			}
+			if (io.stats) {
+				// the lanes that finish a member in this trip add up first (one REDUX each), their leader adds the
+				// sums to the CTA's 32-bit shared-memory totals (native atomics); the totals move on to the
+				// 64-bit global words before they can overflow, and at the end of the kernel
+				const unsigned fm = __activemask();
+				unsigned v[REHUEL_NCOUNTERS] = {c_attempt, c_rej_newton, c_rej_err, c_newton_ok, c_rej_newton, c_fun, c_jac, c_iters, steps_here};
+#pragma unroll
+				for (int c = 0; c < REHUEL_NCOUNTERS; ++c) v[c] = __reduce_add_sync(fm, v[c]);
+				const unsigned nfail = __reduce_add_sync(fm, status != 0 ? 1u : 0u);
+				const unsigned amax = __reduce_max_sync(fm, c_attempt);
+				if ((int)lane == __ffs(fm) - 1) {
+#pragma unroll
+					for (int c = 0; c < REHUEL_NCOUNTERS; ++c) atomicAdd(&s_stats[c], v[c]);
+					atomicAdd(&s_stats[REHUEL_NCOUNTERS], nfail);
+					atomicMax(&s_stats[REHUEL_NCOUNTERS + 1], amax);
+					if (s_stats[REHUEL_CNT_FUN_EVALS] > 0x40000000u) { // the fastest-growing total: hand everything on
+#pragma unroll
+						for (int c = 0; c <= REHUEL_NCOUNTERS; ++c) atomicAdd(io.stats + c, (unsigned long long)atomicExch(&s_stats[c], 0u));
+					}
+				}
 			}
 			if (io.n_samples) io.n_samples[mem] = n_stored;
 			if (io.state_out) {
@@ -866,6 +894,11 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 			}
 			have = false;
 		}
+	}
+	__syncthreads(); // every warp of the CTA has left the loop
+	if (io.stats && threadIdx.x < REHUEL_NSTATS && s_stats[threadIdx.x]) {
+		if (threadIdx.x == REHUEL_NCOUNTERS + 1) atomicMax(io.stats + threadIdx.x, (unsigned long long)s_stats[threadIdx.x]);
+		else atomicAdd(io.stats + threadIdx.x, (unsigned long long)s_stats[threadIdx.x]);
 	}
 }
 

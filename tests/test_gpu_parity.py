@@ -546,6 +546,13 @@ def test_continue_with_controller_state(capi, port):
     capi.result_merge(leg1, leg2)
     m = capi.to_output(leg1)
     assert np.array_equal(m.counters["attempt"], (a1 + a2).astype(np.uint32)) and np.all(m.t_final == 40.0)
+    # accepted steps are per leg (a continued member's step counter carries on, its `steps` row must not)
+    assert np.array_equal(m.counters["steps"], l1.counters["steps"] + l2.counters["steps"])
+    assert np.all(m.counters["steps"] == m.counters["attempt"] - m.counters["reject_err"] - m.counters["reject_newton"])
+    for leg in (l1, l2, one):  # the kernel's own ensemble sums equal the sums of the per-member rows
+        for k in ("attempt", "reject_err", "reject_newton", "newton_success", "fun_evals", "jac_evals", "newton_iters", "steps"):
+            assert leg.sum[k] == int(leg.counters[k].astype(np.int64).sum()), k
+        assert leg.sum["max_attempt"] == int(leg.counters["attempt"].max()) and leg.sum["n_failed"] == 0
     assert np.array_equal(m.y, l2.y) and np.array_equal(m.state, l2.state)
     capi.result_free(leg1)
     capi.result_free(leg2)
