@@ -692,11 +692,6 @@ int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, dou
 			k.M = m;
 			k.io = sh.io;
 			if (n_samples_cap == 0) k.store_samples = 0; // final state only: skip the per-step sample bookkeeping
-			// at most `inflight` integration kernels of a device run side by side: kernel i waits for kernel i - inflight
-			// (tuning aid REHUEL_INFLIGHT; 0 = no limit)
-			static const long inflight = std::getenv("REHUEL_INFLIGHT") ? std::atol(std::getenv("REHUEL_INFLIGHT")) : 0;
-			if (inflight > 0 && si >= (size_t)inflight && shards[si - inflight].dev == sh.dev && shards[si - inflight].m)
-				CUDA_TRY(cudaStreamWaitEvent(sh.stream, shards[si - inflight].ev1, 0));
 			CUDA_TRY(cudaEventRecord(sh.ev0, sh.stream));
 			int rr = launch(k, tb, sh.stream, nullptr);
 			if (rr) return rr;
