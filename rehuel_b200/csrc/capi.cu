@@ -587,6 +587,7 @@ int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, dou
 			// boundaries on multiples of 1024 members: every row of every chunk then starts 4 KiB-aligned on both
 			// sides of the pitched copies (unaligned rows cost ~8 % of the whole call)
 			auto cut = [&](size_t w) -> size_t {
+				if (w == 0) return lo;
 				if (w >= wsum) return hi;
 				const size_t x = lo + (hi - lo) * w / wsum;
 				const size_t r = (x + 512) & ~size_t(1023);
@@ -595,6 +596,20 @@ int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, dou
 			sh.off = cut(wacc);
 			wacc += weight(c);
 			sh.m = cut(wacc) - sh.off;
+		}
+	}
+	{ // the work units must tile [0, M) exactly: a gap would leave members silently unsolved
+		size_t next = 0;
+		for (const DeviceShard &sh : shards) {
+			if (sh.off != next) {
+				free_result(out);
+				return fail(REHUEL_EINVAL, "internal: chunk layout leaves a gap at member %zu", next);
+			}
+			next += sh.m;
+		}
+		if (next != M) {
+			free_result(out);
+			return fail(REHUEL_EINVAL, "internal: chunk layout covers %zu of %zu members", next, M);
 		}
 	}
 	std::vector<double> t_mark(shards.size() + 1, 0.0); // host time at which each shard's work was issued (REHUEL_TIMING)
