@@ -675,6 +675,37 @@ def test_band_lu_and_solve_against_lapack(capi):
     assert err2 < 1e-12
 
 
+def test_chunked_host_pipeline_is_transparent(capi, monkeypatch):
+    """The host-buffer entry point cuts large ensembles into chunks on separate streams (H2D / ordering / kernel / D2H
+    overlap).  Every output -- final states, counters, ensemble sums, controller state, dense output, the continued
+    leg -- must be bit-identical to the unchunked call."""
+    from rehuel_b200 import ensembles
+    M = 300000  # 2 chunks by default (>= 128 Ki members each); odd split sizes via REHUEL_CHUNK_WEIGHTS
+    P = ensembles.robertson_params(M)
+    o = capi.make_options(1e-6, 1e-6, keep_state=True, dense_samples=3, dense_t0=0.0, dense_dt=2.0)
+    outs = {}
+    for name, env in (("one", {"REHUEL_CHUNKS": "1"}), ("default", {}), ("odd", {"REHUEL_CHUNK_WEIGHTS": "3,1,2,5,1"})):
+        for k in ("REHUEL_CHUNKS", "REHUEL_CHUNK_WEIGHTS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        leg1 = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 4.0, 1e-6, ensembles.ROBERTSON_Y0, P, o, raw=True)
+        leg2 = capi.irk_ensemble_continue(capi.ROBERTSON, 211, 6.0, P, o, leg1)
+        outs[name] = (capi.to_output(leg1), capi.to_output(leg2))
+        capi.result_free(leg1)
+        capi.result_free(leg2)
+    for name in ("default", "odd"):
+        for a, b in zip(outs[name], outs["one"]):
+            assert np.array_equal(a.y, b.y) and np.array_equal(a.t_final, b.t_final) and np.array_equal(a.status, b.status)
+            assert np.array_equal(a.state, b.state) and np.array_equal(a.err_last, b.err_last)
+            assert np.array_equal(np.nan_to_num(a.y_dense, nan=-1.0), np.nan_to_num(b.y_dense, nan=-1.0))
+            assert all(np.array_equal(a.counters[k], b.counters[k]) for k in a.counters)
+            assert a.sum == b.sum
+    one1, one2 = outs["one"]
+    assert np.all(one1.t_final == 4.0) and np.all(one2.t_final == 6.0) and one1.sum["n_failed"] == 0
+    assert np.all(np.isfinite(one1.y_dense)) and np.all(np.isnan(one2.y_dense[:2])) and np.all(np.isfinite(one2.y_dense[2]))
+
+
 def test_mixed_stiffness_mixed_tolerance_ensemble(capi, port):
     """Config-5 shape: even members Robertson (config-2 sweep), odd members Van der Pol (config-3
     sweep), per-member rtol = atol = 10^(-3-6v), newton tol = 0.1 rtol.  The two problem classes
