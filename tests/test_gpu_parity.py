@@ -675,6 +675,35 @@ def test_band_lu_and_solve_against_lapack(capi):
     assert err2 < 1e-12
 
 
+def test_concurrent_calls_from_several_host_threads(capi):
+    """The reference is re-entrant; the replacement must be callable from several host threads at once:
+    four threads solve different ensembles concurrently (ctypes drops the GIL), each result equals its solo run."""
+    import threading
+    from rehuel_b200 import ensembles
+    jobs = [(capi.ROBERTSON, 211, 40.0, ensembles.ROBERTSON_Y0, ensembles.robertson_params(150000)),
+            (capi.VAN_DER_POL, 230, 2.0, ensembles.VDPOL_Y0, ensembles.vdpol_params(4096)),
+            (capi.ROBERTSON, 232, 5.0, ensembles.ROBERTSON_Y0, ensembles.robertson_params(20000, start=777)),
+            (capi.BRUSSELATOR_1D, 211, 2.0, ensembles.bruss1d_y0(32), ensembles.bruss1d_params(64))]
+    o = capi.make_options(1e-6, 1e-6)
+    solo = [capi.irk_ensemble(p, m, 0.0, t1, 1e-6, y0, P, o) for p, m, t1, y0, P in jobs]
+    for rep in range(3):
+        got, errs = [None] * len(jobs), []
+        def work(k):
+            try:
+                p, m, t1, y0, P = jobs[k]
+                got[k] = capi.irk_ensemble(p, m, 0.0, t1, 1e-6, y0, P, o)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        assert not errs, errs
+        for a, b in zip(got, solo):
+            assert np.array_equal(a.y, b.y) and np.array_equal(a.counters["attempt"], b.counters["attempt"]) and a.sum == b.sum
+
+
 def test_chunked_host_pipeline_is_transparent(capi, monkeypatch):
     """The host-buffer entry point cuts large ensembles into chunks on separate streams (H2D / ordering / kernel / D2H
     overlap).  Every output -- final states, counters, ensemble sums, controller state, dense output, the continued
