@@ -594,6 +594,9 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				auto newton_loop = [&](auto swaps_tag) {
 				constexpr bool SWAPS = decltype(swaps_tag)::value;
 				for (; it < cap; ++it) { // irk.hpp:458 (cap == maxit unless this is a fast trip)
+#if defined(REHUEL_COUNT_SKIPS) && REHUEL_COUNT_SKIPS == 2
+					if (slow_trip) ++c_skips; // dev builds (mode 2): Newton iterations actually EXECUTED in slow trips
+#endif
 					// dY = -(I - dt A(x)J)^-1 R through the decoupled blocks
 					double Z[S][N];
 #pragma unroll
@@ -646,8 +649,8 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					// dx_delta = 1e-4 against tol ~ 1e-7 it almost always fires first -- the evaluation is
 					// dead work: skip it, book its function calls.
 					if (REHUEL_SKIP_DEAD_RESIDUAL && xnorm2 < a.xtol2) {
-#ifdef REHUEL_COUNT_SKIPS
-						++c_skips; // dev builds: how often the step test fires first (reported in the MAXIT_EXCEED row)
+#if defined(REHUEL_COUNT_SKIPS) && REHUEL_COUNT_SKIPS == 1
+						++c_skips; // dev builds (mode 1): how often the step test fires first (reported in the MAXIT_EXCEED row)
 #endif
 						c_fun += S;
 						nstat = kNewtonSuccess;
