@@ -198,8 +198,8 @@ def bind_to_gpu_numa_node(local_rank: int) -> str:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ensemble_irk_thread<RobertsonF,...> at 2^20 members, t in [0,40]
-# (profiles/r1_v7_ncu_summary.txt: 241.76 MB + 283.03 MB)
-NCU_DRAM_BYTES_PER_LAUNCH = 524.79e6
+# (profiles/r1_v8_ncu_summary.txt: 248.26 MB + 290.20 MB)
+NCU_DRAM_BYTES_PER_LAUNCH = 538.46e6
 
 
 def run_gpu_arm(args) -> None:
@@ -352,7 +352,7 @@ def run_gpu_arm(args) -> None:
                 "bound": "fp64", "achieved": ach_dense, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": ach_dense / peak_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                 "traffic_note": "DRAM bytes read + written per launch of this kernel, ncu --set full capture of this command "
-                                "(profiles/r1_v7_ncu_summary.txt): 5x the 109 MB of algorithmic I/O because members are handed "
+                                "(profiles/r1_v8_ncu_summary.txt): 5x the 109 MB of algorithmic I/O because members are handed "
                                 "out in parameter order, so every 8-byte result lands in its own 32-byte sector; 2% of HBM peak",
                 "kernel_ms_per_launch": kernel_ms_max / args.steps,
                 "model": "SURVEY.md 8(d) dense-algorithm flops: 873*attempts + 321*newton_iters + 41*uses_of_8.20, from the kernel's per-member counters",
