@@ -94,7 +94,15 @@ typedef struct rehuel_options {
 	                                   the host-buffer entry points hand members to the GPU lanes.  REHUEL_ORDER_INDEX,
 	                                   REHUEL_ORDER_LOCALITY (default) or REHUEL_ORDER_LOCALITY_DESC.  Results do not
 	                                   depend on it. */
+	int shard_mode;                 /* NEW: how rehuel_irk_ensemble(..., n_gpus > 1) deals members to the GPUs:
+	                                   REHUEL_SHARD_CONTIGUOUS (default): GPU g owns members [M g/G, M (g+1)/G);
+	                                   REHUEL_SHARD_INTERLEAVED: chunks of >= 16 Ki members go to the GPUs in turn, for
+	                                   ensembles whose cost grows along the index (a stiffness sweep).  Results do not
+	                                   depend on it. */
 } rehuel_options;
+
+#define REHUEL_SHARD_CONTIGUOUS  0
+#define REHUEL_SHARD_INTERLEAVED 1
 
 #define REHUEL_ORDER_INDEX          0 /* member i is the i-th to be handed out */
 #define REHUEL_ORDER_LOCALITY       1 /* space-filling-curve order of the parameter vectors: members with nearby

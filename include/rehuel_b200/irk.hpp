@@ -80,10 +80,12 @@ enum rk_methods {
 
 struct solver_options : common_solver_options {
 	solver_options() : adaptive_step_size(true), use_newton_iters_adaptive_step(true), verbose_newton(false),
-	                   extrapolate_stage(false), keep_state(false), handout_order(REHUEL_ORDER_LOCALITY) {}
+	                   extrapolate_stage(false), keep_state(false), handout_order(REHUEL_ORDER_LOCALITY),
+	                   shard_mode(REHUEL_SHARD_CONTIGUOUS) {}
 	bool adaptive_step_size, use_newton_iters_adaptive_step, verbose_newton, extrapolate_stage;
 	bool keep_state; // NEW: keep the controller state so that irk::odeint_continue can carry on (restore_state, irk.cpp:786)
 	int handout_order; // NEW: REHUEL_ORDER_* (scheduling of the batched overload only; results do not depend on it)
+	int shard_mode;    // NEW: REHUEL_SHARD_* (how n_gpus > 1 deals members to the devices)
 };
 inline solver_options default_solver_options() { return solver_options(); }
 
@@ -112,6 +114,7 @@ inline rehuel_options to_c_options(const solver_options &so, const output_option
 	o.dense_t0 = oo.dense_t0;
 	o.dense_dt = oo.dense_dt;
 	o.handout_order = so.handout_order;
+	o.shard_mode = so.shard_mode;
 	return o;
 }
 

@@ -40,11 +40,12 @@ class Options(C.Structure):
         ("newton_maxit", C.c_int), ("newton_refresh_jac", C.c_int),
         ("output_mode", C.c_int), ("output_interval", C.c_ulonglong),
         ("keep_state", C.c_int), ("dense_samples", C.c_ulonglong), ("dense_t0", C.c_double), ("dense_dt", C.c_double),
-        ("handout_order", C.c_int),
+        ("handout_order", C.c_int), ("shard_mode", C.c_int),
     ]
 
 
 ORDER_INDEX, ORDER_LOCALITY, ORDER_LOCALITY_DESC = 0, 1, 2
+SHARD_CONTIGUOUS, SHARD_INTERLEAVED = 0, 1
 NSTATE = 8  # rows of the controller state (REHUEL_STATE_*)
 
 
@@ -158,7 +159,7 @@ def default_options() -> Options:
 def make_options(rel_tol=1e-4, abs_tol=None, max_dt=0.0, max_steps=-1, adaptive=True, out_interval=0,
                  newton_tol=None, newton_dx_delta=1e-4, newton_maxit=5000, newton_refresh_jac=10,
                  output_mode=1, output_interval=1, handout_order=ORDER_LOCALITY, keep_state=False,
-                 dense_samples=0, dense_t0=0.0, dense_dt=0.0) -> Options:
+                 dense_samples=0, dense_t0=0.0, dense_dt=0.0, shard_mode=0) -> Options:
     """Reference defaults, with newton_tol = 0.1*min(rtol, atol) unless given -- what the example
     driver and the 4-argument odeint do (examples/example_equations.cpp:220, irk.hpp:921)."""
     if abs_tol is None:
@@ -167,7 +168,7 @@ def make_options(rel_tol=1e-4, abs_tol=None, max_dt=0.0, max_steps=-1, adaptive=
         newton_tol = 0.1 * min(rel_tol, abs_tol)
     return Options(rel_tol, abs_tol, max_dt, max_steps, int(adaptive), out_interval, newton_tol,
                    newton_dx_delta, newton_maxit, newton_refresh_jac, output_mode, output_interval, int(keep_state),
-                   dense_samples, dense_t0, dense_dt, handout_order)
+                   dense_samples, dense_t0, dense_dt, handout_order, shard_mode)
 
 
 def name_to_method(name: str) -> int:

@@ -171,6 +171,8 @@ static int prepare(int method, double t0, double t1, double dt0, size_t M, const
 	if (o->newton_maxit < 1) return fail(REHUEL_EINVAL, "newton_maxit must be >= 1");
 	if (o->newton_refresh_jac <= 0) return fail(REHUEL_EINVAL, "newton_refresh_jac must be > 0 (the reference divides by it, irk.hpp:485)");
 	if (o->output_interval == 0) return fail(REHUEL_EINVAL, "output_interval must be > 0 (irk.hpp:825 takes step %% output_interval)");
+	if (o->shard_mode != REHUEL_SHARD_CONTIGUOUS && o->shard_mode != REHUEL_SHARD_INTERLEAVED)
+		return fail(REHUEL_EINVAL, "shard_mode must be REHUEL_SHARD_CONTIGUOUS or REHUEL_SHARD_INTERLEAVED");
 	if (o->handout_order < REHUEL_ORDER_INDEX || o->handout_order > REHUEL_ORDER_LOCALITY_DESC)
 		return fail(REHUEL_EINVAL, "handout_order must be REHUEL_ORDER_INDEX, _LOCALITY or _LOCALITY_DESC");
 	std::memset(&ka, 0, sizeof ka);
@@ -552,51 +554,52 @@ int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, dou
 	// into up to 8 chunks on separate streams so that the H2D copy of chunk i+1 and the D2H copies
 	// of chunk i-1 overlap the kernel of chunk i.  Chunk sizes taper off at the end (see `weight`).
 	std::deque<DeviceShard> shards; // deque: elements are never moved (DeviceShard owns CUDA handles)
-	for (int g = 0; g < n_gpus; ++g) {
-		const size_t lo = M * (size_t)g / (size_t)n_gpus, hi = M * (size_t)(g + 1) / (size_t)n_gpus;
-		size_t chunks = (hi - lo) / (128u << 10);
-		chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
-		bool taper = true;
-		if (const char *e = std::getenv("REHUEL_CHUNKS")) { // tuning aids
-			const long v = std::atol(e);
-			if (v >= 1 && v <= 16) chunks = (size_t)v;
+	// tuning aids: REHUEL_CHUNKS=k (chunks per GPU), REHUEL_CHUNK_WEIGHTS="1,2,4,4,2,1" (relative chunk sizes)
+	long env_chunks = 0;
+	if (const char *e = std::getenv("REHUEL_CHUNKS")) env_chunks = std::atol(e);
+	size_t wts[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1}, n_wts = 0;
+	if (const char *e = std::getenv("REHUEL_CHUNK_WEIGHTS")) {
+		for (const char *q = e; *q && n_wts < 16;) {
+			char *end = nullptr;
+			const long v = std::strtol(q, &end, 10);
+			if (end == q) break;
+			wts[n_wts++] = v > 0 ? (size_t)v : 1;
+			q = (*end == ',') ? end + 1 : end;
 		}
-		if (const char *e = std::getenv("REHUEL_CHUNK_TAPER")) taper = std::atol(e) != 0;
+	}
+	// members [lo, hi) cut into chunks that are dealt to `owners` devices in turn (1 owner: all to dev_first)
+	auto add_chunks = [&](size_t lo, size_t hi, int dev_first, int owners) {
+		size_t chunks = (hi - lo) / owners / (128u << 10);
+		chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks); // per device; 8 equal chunks measured best at 2^20 members
+		if (env_chunks >= 1 && env_chunks <= 16) chunks = (size_t)env_chunks;
+		if (n_wts >= 1) chunks = n_wts;
 		if (n_samples_cap) chunks = 1;
-		// chunk weights: equal by default; REHUEL_CHUNK_WEIGHTS="1,2,4,4,4,2,1" (tuning aid) sets them explicitly
-		size_t wts[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
-		(void)taper;
-		if (const char *e = std::getenv("REHUEL_CHUNK_WEIGHTS")) {
-			size_t k = 0;
-			for (const char *q = e; *q && k < 16;) {
-				char *end = nullptr;
-				const long v = std::strtol(q, &end, 10);
-				if (end == q) break;
-				wts[k++] = v > 0 ? (size_t)v : 1;
-				q = (*end == ',') ? end + 1 : end;
-			}
-			if (k >= 1 && !n_samples_cap) chunks = k;
-		}
-		auto weight = [&](size_t c) -> size_t { return wts[c]; };
+		const bool weighted = n_wts >= 1 && !n_samples_cap && owners == 1;
+		chunks *= (size_t)owners;
 		size_t wsum = 0, wacc = 0;
-		for (size_t c = 0; c < chunks; ++c) wsum += weight(c);
+		for (size_t c = 0; c < chunks; ++c) wsum += weighted ? wts[c] : 1;
+		// boundaries on multiples of 1024 members: every row of every chunk then starts 4 KiB-aligned on both
+		// sides of the pitched copies (unaligned rows cost ~8 % of the whole call)
+		auto cut = [&](size_t w) -> size_t {
+			if (w == 0) return lo;
+			if (w >= wsum) return hi;
+			const size_t x = lo + (hi - lo) * w / wsum;
+			const size_t r = (x + 512) & ~size_t(1023);
+			return r < lo ? lo : (r > hi ? hi : r);
+		};
 		for (size_t c = 0; c < chunks; ++c) {
 			shards.emplace_back();
 			DeviceShard &sh = shards.back();
-			sh.dev = dev0 + g;
-			// boundaries on multiples of 1024 members: every row of every chunk then starts 4 KiB-aligned on both
-			// sides of the pitched copies (unaligned rows cost ~8 % of the whole call)
-			auto cut = [&](size_t w) -> size_t {
-				if (w == 0) return lo;
-				if (w >= wsum) return hi;
-				const size_t x = lo + (hi - lo) * w / wsum;
-				const size_t r = (x + 512) & ~size_t(1023);
-				return r < lo ? lo : (r > hi ? hi : r);
-			};
+			sh.dev = dev_first + (int)(c % (size_t)owners);
 			sh.off = cut(wacc);
-			wacc += weight(c);
+			wacc += weighted ? wts[c] : 1;
 			sh.m = cut(wacc) - sh.off;
 		}
+	};
+	if (opts->shard_mode == REHUEL_SHARD_INTERLEAVED && n_gpus > 1) {
+		add_chunks(0, M, dev0, n_gpus); // chunk k -> GPU k mod G: balances ensembles whose cost grows with the index
+	} else {
+		for (int g = 0; g < n_gpus; ++g) add_chunks(M * (size_t)g / (size_t)n_gpus, M * (size_t)(g + 1) / (size_t)n_gpus, dev0 + g, 1);
 	}
 	{ // the work units must tile [0, M) exactly: a gap would leave members silently unsolved
 		size_t next = 0;
@@ -875,6 +878,7 @@ void rehuel_default_options(rehuel_options *o)
 	o->dense_t0 = 0.0;
 	o->dense_dt = 0.0;
 	o->handout_order = REHUEL_ORDER_LOCALITY;
+	o->shard_mode = REHUEL_SHARD_CONTIGUOUS;
 }
 
 int rehuel_name_to_method(const char *name) { return name_to_method(name); }

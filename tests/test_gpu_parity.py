@@ -791,8 +791,22 @@ def test_c_abi_multi_gpu_sharding_is_bit_identical(capi):
     o = capi.make_options(1e-6, 1e-6)
     one = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, o, n_gpus=1)
     for g in sorted({2, G}):
-        many = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, o, n_gpus=g)
-        assert np.array_equal(one.y, many.y) and np.array_equal(one.status, many.status)
-        for k in one.counters:
-            assert np.array_equal(one.counters[k], many.counters[k]), k
-        assert one.sum == many.sum
+        for mode in (capi.SHARD_CONTIGUOUS, capi.SHARD_INTERLEAVED):
+            om = capi.make_options(1e-6, 1e-6, shard_mode=mode)
+            many = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, om, n_gpus=g)
+            assert np.array_equal(one.y, many.y) and np.array_equal(one.status, many.status)
+            for k in one.counters:
+                assert np.array_equal(one.counters[k], many.counters[k]), k
+            assert one.sum == many.sum
+    # a stiffness sweep (cost grows along the index): interleaved sharding balances the devices
+    Mv = 1 << 18
+    Pv = ensembles.vdpol_params(Mv)
+    times = {}
+    for mode in (capi.SHARD_CONTIGUOUS, capi.SHARD_INTERLEAVED):
+        om = capi.make_options(1e-6, 1e-6, shard_mode=mode)
+        r = [capi.irk_ensemble(capi.VAN_DER_POL, 230, 0.0, 2.0, 1e-6, ensembles.VDPOL_Y0, Pv, om, n_gpus=2) for _ in range(2)][-1]
+        times[mode] = r.kernel_ms
+        assert r.sum["n_failed"] == 0
+    print(f"\nVan der Pol 2^18 on 2 GPUs: kernel {times[0]:.1f} ms contiguous, {times[1]:.1f} ms interleaved")
+    # (both are close to the ~24 ms a lane needs for two of the stiffest members)
+    assert times[capi.SHARD_INTERLEAVED] <= 1.05 * times[capi.SHARD_CONTIGUOUS]
