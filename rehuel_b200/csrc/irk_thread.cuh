@@ -51,7 +51,10 @@ constexpr int kNewtonSuccess = 0, kNewtonMaxit = 3; // newton.hpp:45-51
 #define REHUEL_FAST_ITERS 64
 #endif
 constexpr int kFastIters = REHUEL_FAST_ITERS; // Newton iterations a lane may take before it is parked for a slow trip
-constexpr int kParkLanes = 16; // parked lanes per warp that trigger a slow trip
+#ifndef REHUEL_PARK_LANES
+#define REHUEL_PARK_LANES 16
+#endif
+constexpr int kParkLanes = REHUEL_PARK_LANES; // parked lanes per warp that trigger a slow trip
 
 // Reciprocal for LU pivots and 1/dt: MUFU.RCP64H seed (~20 bits) + two Newton steps (quadratic:
 // 20 -> 40 -> 80 bits, i.e. correctly rounded up to ~1 ulp), 5 instructions and no slow path
