@@ -10,7 +10,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 # use the distro compiler as nvcc's host compiler so the .so links libstdc++.so.6 dynamically.
 HOSTCXX   := /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-Wextra \
+NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unknown-pragmas \
              --expt-relaxed-constexpr -Xptxas -v
 SRC       := rehuel_b200/csrc
 LIB       := rehuel_b200/librehuel_b200.so

@@ -305,12 +305,16 @@ int rehuel_fp64_peak(double *tflops, double *ms);
 int rehuel_eval_functor(int problem, int n_hint, double t, const double *y, const double *params, double *f, double *J);
 
 /* Diagnostic: the warp-per-system kernel's band LU + band solve (n = 64, half bandwidth 2) on caller-given
- * matrices, 4 per problem (lane m <-> matrix m as in the integrator).  ab: [n_problems][4][2 (re,im)][66][7] band
- * rows (slot 2 + j - i holds A(i,j), rows 64..65 zero); rhs, x: [n_problems][4][2][64]; is_cplx, flags:
- * [n_problems][4].  pivot != 0: dgbtf2-style row pivoting; pivot == 0: plain elimination, flags[] = "partial
- * pivoting would have exchanged rows".  HOST pointers; for the test-suite. */
+ * matrices, 4 per problem, side by side in the lanes of one warp as in the integrator.  ab: [n_problems][4][2
+ * (re,im)][66][7] band rows (slot 2 + j - i holds A(i,j), rows 64..65 zero); rhs, x: [n_problems][4][2][64]; is_cplx,
+ * flags: [n_problems][4].  pivot != 0: the fallback, dgbtf2-style row pivoting, one lane per matrix; pivot == 0: the
+ * twisted factorisation without interchanges the integrator normally runs, one lane pair per matrix, flags[] =
+ * "partial pivoting would have exchanged rows".  HOST pointers; for the test-suite. */
 int rehuel_selftest_band(int n_problems, int pivot, const double *ab, const double *rhs, const int *is_cplx,
                          double *x, int *flags);
+/* Diagnostic: on != 0 sends every attempt of the warp-per-system kernels through their pivoted band fallback
+ * (which real problems practically never take), so that the test-suite can compare the two paths.  Process-wide. */
+void rehuel_debug_force_pivot(int on);
 
 /* Last error text of the calling thread (the reference reports through free-text log_out). */
 const char *rehuel_last_error(void);

@@ -137,7 +137,7 @@ EXPORTS = (
     "rehuel_irk_single", "rehuel_irk_ensemble_device", "rehuel_result_merge", "rehuel_kernel_launches",
     "rehuel_kernel_info", "rehuel_last_error", "rehuel_version", "rehuel_fp64_peak", "rehuel_release_cached_memory",
     "rehuel_locality_order_workspace", "rehuel_locality_order", "rehuel_irk_ensemble_continue", "rehuel_selftest_band",
-    "rehuel_eval_functor",
+    "rehuel_eval_functor", "rehuel_debug_force_pivot",
 )
 
 
@@ -233,6 +233,11 @@ def kernel_info(problem: int, method: int, n_hint: int = 0) -> dict:
     v = [C.c_int() for _ in range(5)]
     check(lib.rehuel_kernel_info(C.c_int(problem), C.c_int(method), C.c_int(n_hint), *[C.byref(x) for x in v]))
     return dict(zip(("regs", "local_bytes", "smem_bytes", "ctas_per_sm", "block"), [x.value for x in v]))
+
+
+def debug_force_pivot(on: bool) -> None:
+    """Test hook: every attempt of the warp-per-system kernels takes the pivoted band fallback."""
+    lib.rehuel_debug_force_pivot(C.c_int(1 if on else 0))
 
 
 def fp64_peak_tflops() -> float:

@@ -44,6 +44,23 @@ int set_error(int code, const char *fmt, ...)
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1); }
 
+static std::atomic<int> g_force_pivot{0};
+int debug_force_pivot() { return g_force_pivot.load(); }
+
+// cudaMallocAsync's default pool gives freed blocks back to the driver at the next synchronisation unless told to keep
+// them; launch_warp allocates its fallback slabs from it on every launch.
+int retain_async_pool(int dev)
+{
+	static std::atomic<unsigned long long> done{0};
+	if (dev >= 0 && dev < 64 && (done.load() >> dev & 1ull)) return REHUEL_OK;
+	cudaMemPool_t pool;
+	REHUEL_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+	unsigned long long keep = ~0ull;
+	REHUEL_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev);
+	return REHUEL_OK;
+}
+
 // ------------------------------------------------------------------ FP64 FMA peak probe
 // Register-resident DFMA chains: 8 independent accumulators per thread, no memory traffic.
 // Gives the achievable FP64 FMA rate of THIS device at its current clocks = the roofline
@@ -1028,7 +1045,12 @@ void rehuel_release_cached_memory(void)
 {
 	g_cache.trim();
 	g_streams.trim();
+	int dev = 0;
+	cudaMemPool_t pool;
+	if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
 }
+
+void rehuel_debug_force_pivot(int on) { rehuel::g_force_pivot.store(on ? 1 : 0); }
 
 void rehuel_result_free(rehuel_result *out) { free_result(out); }
 

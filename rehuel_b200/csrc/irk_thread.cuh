@@ -43,6 +43,10 @@ struct KernelArgs {
 	unsigned long long output_interval;
 	unsigned long long M;
 	rehuel_device_io io;
+	// warp-per-system kernels only (filled in by launch_warp): global slabs for the pivoted band fallback, one per
+	// warp of the grid; force_pivot != 0 sends every attempt through that fallback (rehuel_debug_force_pivot)
+	double *pivot_scratch;
+	int force_pivot;
 };
 
 constexpr double kMachinePrecision = 1e-17; // enums.hpp:129

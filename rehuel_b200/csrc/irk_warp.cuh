@@ -5,20 +5,26 @@
 // Same algorithm, statement for statement, as the other two kernels (irk_thread.cuh,
 // irk_cta.cuh) and hence as the reference loop irk.hpp:604-860 / newton_solve_stages
 // irk.hpp:398-493.  What the band buys: the decoupled Newton matrices  mu I - J  keep the band of
-// J, their LU (row partial pivoting, dgbtf2's pattern: L within kBand below the diagonal, U within
-// 2*kBand above it) costs O(n*kBand^2) instead of O(n^3), and a factorisation or a triangular
-// solve is a short SEQUENTIAL recurrence -- no work for a whole thread block.  So:
-//   * state vectors (y, Y, R, Z/F) and the band factors live in the warp's slice of shared memory
-//     (~35 KB for n = 64, S = 5: six independent warps per SM instead of one 256-thread CTA);
-//   * vector work (stage evaluations, the (Ti (x) I) / (T (x) I) transforms, norms) is spread over
-//     the 32 lanes, reductions are shuffle butterflies (identical on every lane);
-//   * every matrix is factorised by ONE lane, all matrices side by side (lane m <-> matrix m),
-//     with a sliding window of kBand+1 rows in registers; every right-hand side is solved by ONE
-//     lane, all of them side by side, with a sliding window of the solution in registers, so the
-//     recurrence runs at register latency;
+// J, their LU costs O(n*kBand^2) instead of O(n^3), and a factorisation or a triangular solve is a
+// short SEQUENTIAL recurrence -- no work for a whole thread block.  What bounds the kernel is the
+// LATENCY of those recurrences times the number of members an SM can hold, so:
+//   * the recurrences are halved: every matrix is factorised, every right-hand side solved, by a
+//     PAIR of lanes with the twisted factorisation of band_twisted.cuh (one lane top-down, its
+//     neighbour bottom-up, meeting on kBand separator rows); all matrices of an attempt side by
+//     side (lanes 2m, 2m+1 <-> matrix m), one routine for real and complex ones;
+//   * shared memory per member is what caps the resident warps, so it only holds what lanes
+//     must see of each other: y, one set of work vectors (stage states -> right-hand sides of the
+//     solves) and the band factors in the narrow twisted layout (~20 KB for n = 64, S = 5: eleven
+//     warps per SM).  The stage increments Y, the residual R and everything of the update /
+//     estimator phase live in REGISTERS, component i on lane i mod 32: the (Ti (x) I), (T (x) I)
+//     and (A (x) I) transforms never leave the lane;
+//   * the twisted routines do not interchange rows; they report whether partial pivoting would
+//     have, and then the attempt's matrices are rebuilt in the wide pivoted layout (dgbtf2's
+//     pattern: L within kBand below the diagonal, U within 2*kBand above it) in a per-warp slab of
+//     GLOBAL memory and factorised / solved by the one-lane-per-matrix routines below.  mu I - J
+//     practically never needs it (the 1-D Brusselator never does), so its cost does not matter,
+//     but it keeps the kernel correct for any banded functor;
 //   * scalar control (dt, controller history, counters) is kept redundantly by every lane.
-// For the 64-equation Brusselator (kBand = 2) with LOBATTO_IIIC_85 an attempt costs ~10 us of one
-// warp instead of ~120 us of one SM.
 //
 // Functor concept: the componentwise one of irk_cta.cuh plus `static constexpr int kBand`.
 #pragma once
@@ -27,6 +33,7 @@
 #include <math.h>
 
 #include "../../include/rehuel_b200.h"
+#include "band_twisted.cuh"
 #include "irk_cta.cuh"
 #include "irk_thread.cuh"
 #include "tableau.hpp"
@@ -37,27 +44,28 @@ template <class F, int S, int NC, int EST>
 struct WarpSmem {
 	static constexpr int N = F::N;
 	static constexpr int KB = jac_band<F>::value;
-	static constexpr int W = 3 * KB + 1; // band row: KB multipliers | diagonal | 2*KB of U
+	using G = Tw<N, KB>;
 	static constexpr int PA = ((F::P > 0 ? F::P : 1) + 1) & ~1;
 	static constexpr int NREAL = 1 + (EST == EST_OWN_LU ? 1 : 0); // slot 0: real Newton block, slot 1: estimator
-	// offsets in doubles
+	static constexpr int NMAT = NREAL + NC;
+	// ---- shared memory, offsets in doubles
 	static constexpr int o_y = 0;
-	static constexpr int o_yn = o_y + N;
-	static constexpr int o_p = o_yn + N;
-	static constexpr int o_Y = o_p + PA;
-	static constexpr int o_R = o_Y + S * N;
-	static constexpr int o_Z = o_R + S * N;     // Z of the Newton update; doubles as F of the residual
-	static constexpr int o_e = o_Z + S * N;
-	static constexpr int o_dy = o_e + N;
-	static constexpr int o_dalt = o_dy + N;
-	static constexpr int o_fy = o_dalt + N;
-	static constexpr int PL = (N + KB) * W;                   // one band plane: N rows + KB zero rows of padding
-	static constexpr int o_abr = o_fy + N;                    // real band factors [NREAL][N + KB][W]
-	static constexpr int o_rdr = o_abr + NREAL * PL;          // reciprocal pivots [NREAL][N]
-	static constexpr int o_abc = o_rdr + NREAL * N;           // complex band factors [NC][2][N + KB][W]
-	static constexpr int o_rdc = o_abc + NC * 2 * PL;         // reciprocal pivots [NC][2][N]
-	static constexpr int o_piv = o_rdc + NC * 2 * N;          // interchange offsets, bytes: [NREAL + NC][N]
-	static constexpr size_t bytes = (size_t)o_piv * 8 + (((size_t)(NREAL + NC) * N + 15) & ~size_t(15));
+	static constexpr int o_p = o_y + N;
+	static constexpr int o_w = o_p + PA;                          // work vectors [S][N] (+ KB entries the pivoted forward sweep may look at)
+	static constexpr int o_fr = o_w + S * N + KB;                 // real twisted factors    [NREAL][half][HP]
+	static constexpr int o_fc = o_fr + NREAL * 2 * G::HP;         // complex twisted factors [NC][half][re|im][HP]
+	static constexpr int o_q = o_fc + NC * 2 * 2 * G::HP;         // inverse separator blocks [NMAT][half][re|im][KB*KB]
+	static constexpr int total = o_q + NMAT * 2 * 2 * KB * KB;
+	static constexpr size_t bytes = (size_t)total * 8;
+	// ---- per-warp slab in global memory for the pivoted fallback, offsets in doubles
+	static constexpr int W = 3 * KB + 1;                          // band row: KB multipliers | diagonal | 2*KB of U
+	static constexpr int PL = (N + KB) * W;                       // one band plane: N rows + KB zero rows of padding
+	static constexpr int g_abr = 0;                               // real band factors [NREAL][N + KB][W]
+	static constexpr int g_rdr = g_abr + NREAL * PL;              // reciprocal pivots [NREAL][N]
+	static constexpr int g_abc = g_rdr + NREAL * N;               // complex band factors [NC][2][N + KB][W]
+	static constexpr int g_rdc = g_abc + NC * 2 * PL;             // reciprocal pivots [NC][2][N]
+	static constexpr int g_piv = g_rdc + NC * 2 * N;              // interchange offsets, bytes: [NMAT][N]
+	static constexpr size_t slab_doubles = (size_t)g_piv + ((size_t)NMAT * N + 7) / 8;
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -67,7 +75,52 @@ __device__ __forceinline__ double warp_sum(double v)
 	return v;
 }
 
-// ------------------------------------------------------------------ band LU, one lane per matrix
+// ------------------------------------------------------------------ twisted band LU / solve, one lane PAIR per matrix
+// `mask`: the lanes that execute the call together (whole pairs).  The sweeps are band_twisted.cuh's; here the two
+// halves exchange their separator data with one shuffle per number.
+template <int N, int KB>
+__device__ __forceinline__ bool tw_factor_pair(unsigned mask, double *pr, double *pi, bool is_c, int np, double *qr, double *qi)
+{
+	double sr[KB][KB], si[KB][KB], tr[KB][KB], ti[KB][KB];
+	bool flag = tw_lu_sweep<N, KB>(pr, pi, is_c, np, sr, si);
+	__syncwarp(mask);
+#pragma unroll
+	for (int j = 0; j < KB; ++j)
+#pragma unroll
+		for (int c = 0; c < KB; ++c) { // the partner's block, turned into this half's orientation
+			tr[j][c] = __shfl_xor_sync(mask, sr[KB - 1 - j][KB - 1 - c], 1);
+			ti[j][c] = __shfl_xor_sync(mask, si[KB - 1 - j][KB - 1 - c], 1);
+		}
+	flag |= tw_separator<N, KB>(pr, pi, is_c, np, sr, si, tr, ti, qr, qi);
+	return flag;
+}
+
+// x <- A^-1 x.  xr/xi point at this half's first unknown, xs = +1 / -1 (see tw_forward).
+template <int N, int KB>
+__device__ __forceinline__ void tw_solve_pair(unsigned mask, const double *pr, const double *pi, bool is_c, int np, const double *qr,
+                                              const double *qi, double *xr, double *xi, int xs)
+{
+	double gr[KB], gi[KB], hr[KB], hi[KB], sr[KB], si[KB];
+	tw_forward<N, KB>(pr, pi, is_c, np, xr, xi, xs, gr, gi);
+	__syncwarp(mask);
+#pragma unroll
+	for (int j = 0; j < KB; ++j) {
+		hr[j] = __shfl_xor_sync(mask, gr[KB - 1 - j], 1);
+		hi[j] = __shfl_xor_sync(mask, gi[KB - 1 - j], 1);
+	}
+	tw_separator_solve<N, KB>(qr, qi, is_c, np, xr, xi, xs, gr, gi, hr, hi, sr, si);
+	tw_backward<N, KB>(pr, pi, is_c, np, xr, xi, xs, sr, si);
+	__syncwarp(mask); // both halves have read the separator's right-hand side
+	if (xs > 0) {
+#pragma unroll
+		for (int j = 0; j < KB; ++j) {
+			xr[np + j] = sr[j];
+			if (is_c) xi[np + j] = si[j];
+		}
+	}
+}
+
+// ------------------------------------------------------------------ pivoted band LU, one lane per matrix (fallback)
 // ONE routine for real and complex matrices, so that the lanes that factorise the matrices of an
 // attempt side by side execute the same instructions (a real matrix is a complex one whose
 // imaginary plane is never loaded or stored: `is_c` predicates those accesses).
@@ -257,38 +310,61 @@ __device__ __forceinline__ void band_solve(const double *abr, const double *abi,
 
 // ------------------------------------------------------------------ the kernel: one warp per block
 template <class F, int S, int NR, int NC, int EST, bool DENSE = false>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 11)
 ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ DevTableau<S, NC> tb)
 {
 	static_assert(S == NR + 2 * NC && NR <= 1, "eigen-structure");
 	using L = WarpSmem<F, S, NC, EST>;
-	constexpr int N = F::N, KB = L::KB, W = L::W;
+	using G = typename L::G;
+	constexpr int N = F::N, KB = L::KB, W = L::W, HP = G::HP;
+	constexpr int NPL = (N + 31) / 32;     // components per lane: i = lane + 32*j
+	constexpr bool FULL = (N % 32 == 0);   // every lane owns NPL components
 	static_assert(KB >= 1 && KB <= 4, "band kernels are built for half bandwidths 1..4");
-	static_assert(1 + NC + 1 <= 32, "one lane per matrix");
+	static_assert(2 * (1 + NC + 1) <= 32, "one lane pair per matrix");
+	static_assert(EST != EST_REUSE || NR == 1, "E's factors are the real Newton block's");
 	extern __shared__ double sm[];
-	double *y = sm + L::o_y, *yn = sm + L::o_yn, *par = sm + L::o_p, *Y = sm + L::o_Y, *R = sm + L::o_R, *Z = sm + L::o_Z,
-	       *Fv = sm + L::o_Z, *ev = sm + L::o_e, *dyv = sm + L::o_dy, *dalt = sm + L::o_dalt, *fy = sm + L::o_fy,
-	       *abr = sm + L::o_abr, *rdr = sm + L::o_rdr, *abc = sm + L::o_abc, *rdc = sm + L::o_rdc;
-	signed char *piv = reinterpret_cast<signed char *>(sm + L::o_piv); // [real slots][N] then [NC][N]
-	signed char *pivc = piv + L::NREAL * N;
+	double *y = sm + L::o_y, *par = sm + L::o_p, *work = sm + L::o_w;
 	const int lane = threadIdx.x;
 	const unsigned long long M = a.M;
 	const rehuel_device_io &io = a.io;
+	// ---- twisted roles: lanes 2m, 2m+1 <-> matrix m (0: real Newton block, 1..NC: complex ones, NC+1: estimator's own),
+	//      even lane = top half, odd lane = bottom half
+	const int tm = lane >> 1, th = lane & 1;
+	const bool t_real = NR && tm == 0;
+	const bool t_cplx = tm >= 1 && tm <= NC;
+	const bool t_est = (EST == EST_OWN_LU) && tm == NC + 1;
+	const bool t_has = t_real || t_cplx || t_est;
+	const int t_c = t_cplx ? tm - 1 : 0;
+	double *t_pr = t_cplx ? sm + L::o_fc + ((t_c * 2 + th) * 2) * HP : sm + L::o_fr + ((t_est ? 1 : 0) * 2 + th) * HP;
+	double *t_pi = t_cplx ? t_pr + HP : t_pr;
+	const int t_slot = t_cplx ? L::NREAL + t_c : (t_est ? 1 : 0);
+	double *t_qr = sm + L::o_q + ((t_slot * 2 + th) * 2) * KB * KB, *t_qi = t_qr + KB * KB;
+	const int t_np = th ? G::NP1 : G::NP0, t_xs = th ? -1 : 1;
+	const bool t_rhs = t_real || t_cplx;                       // right-hand sides of a Newton update
+	double *t_xr = (t_cplx ? work + (NR + 2 * t_c) * N : work) + (th ? N - 1 : 0);
+	double *t_xi = t_cplx ? t_xr + N : t_xr;
+	const bool t_E = (EST == EST_REUSE) ? t_real : t_est;      // the pair that holds the factors of E = I - gamma dt J
+	double *t_er = work + (th ? N - 1 : 0);                    // E's right-hand side is work[0..N)
+	const unsigned m_has = __ballot_sync(0xffffffffu, t_has), m_rhs = __ballot_sync(0xffffffffu, t_rhs),
+	               m_E = __ballot_sync(0xffffffffu, t_E);
+	// ---- pivoted fallback roles: lane m <-> matrix m, factors in this warp's global slab
+	double *slab = a.pivot_scratch ? a.pivot_scratch + (size_t)blockIdx.x * L::slab_doubles : nullptr;
+	double *abr = slab + L::g_abr, *rdr = slab + L::g_rdr, *abc = slab + L::g_abc, *rdc = slab + L::g_rdc;
+	signed char *piv = reinterpret_cast<signed char *>(slab + L::g_piv); // [real slots][N] then [NC][N]
+	signed char *pivc = piv + L::NREAL * N;
 	constexpr int PL = L::PL;
-	// lane -> matrix: lane 0 the real Newton block, lanes 1..NC the complex ones, lane NC+1 the estimator's own
-	const bool m_cplx = lane >= 1 && lane <= NC;
-	const bool m_est = (EST == EST_OWN_LU) && lane == NC + 1;
-	const bool has_matrix = (NR && lane == 0) || m_cplx || m_est;
-	const int m_c = m_cplx ? lane - 1 : 0;
-	double *m_abr = m_cplx ? abc + (m_c * 2) * PL : (m_est ? abr + PL : abr);
-	double *m_abi = m_cplx ? abc + (m_c * 2 + 1) * PL : m_abr;
-	double *m_rdr = m_cplx ? rdc + (m_c * 2) * N : (m_est ? rdr + N : rdr);
-	double *m_rdi = m_cplx ? rdc + (m_c * 2 + 1) * N : m_rdr;
-	signed char *m_piv = m_cplx ? pivc + m_c * N : (m_est ? piv + N : piv);
-	// lane -> right-hand side of a Newton update: the same lanes, estimator excluded
-	const bool has_rhs = (NR && lane == 0) || m_cplx;
-	double *m_xr = m_cplx ? Z + (NR + 2 * m_c) * N : Z;
-	double *m_xi = m_cplx ? Z + (NR + 2 * m_c + 1) * N : Z;
+	const bool p_cplx = lane >= 1 && lane <= NC;
+	const bool p_est = (EST == EST_OWN_LU) && lane == NC + 1;
+	const bool p_has = (NR && lane == 0) || p_cplx || p_est;
+	const int p_c = p_cplx ? lane - 1 : 0;
+	double *p_abr = p_cplx ? abc + (p_c * 2) * PL : (p_est ? abr + PL : abr);
+	double *p_abi = p_cplx ? abc + (p_c * 2 + 1) * PL : p_abr;
+	double *p_rdr = p_cplx ? rdc + (p_c * 2) * N : (p_est ? rdr + N : rdr);
+	double *p_rdi = p_cplx ? rdc + (p_c * 2 + 1) * N : p_rdr;
+	signed char *p_piv = p_cplx ? pivc + p_c * N : (p_est ? piv + N : piv);
+	const bool p_rhs = (NR && lane == 0) || p_cplx;
+	double *p_xr = p_cplx ? work + (NR + 2 * p_c) * N : work;
+	double *p_xi = p_cplx ? work + (NR + 2 * p_c + 1) * N : work;
 
 	for (;;) {
 		// ---------------- next member
@@ -299,7 +375,16 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 		}
 		mem = __shfl_sync(0xffffffffu, mem, 0);
 		if (mem >= M) break;
-		for (int k = lane; k < N; k += 32) y[k] = io.y0_broadcast ? io.y0[k] : io.y0[k * M + mem];
+		double yr[NPL]; // y, component lane + 32 j; the shared copy is for the neighbours (f and J couple components)
+#pragma unroll
+		for (int j = 0; j < NPL; ++j) {
+			const int i = lane + 32 * j;
+			yr[j] = 0.0;
+			if (FULL || i < N) {
+				yr[j] = io.y0_broadcast ? io.y0[i] : io.y0[i * M + mem];
+				y[i] = yr[j];
+			}
+		}
 		for (int k = lane; k < F::P; k += 32) par[k] = io.params[k * M + mem];
 		__syncwarp();
 
@@ -328,7 +413,11 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 		if (DENSE) {
 			while (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) < t) ++kd;
 			if (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) == t) {
-				for (int k = lane; k < N; k += 32) io.y_dense[((size_t)kd * N + k) * M + mem] = y[k];
+#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int i = lane + 32 * j;
+					if (FULL || i < N) io.y_dense[((size_t)kd * N + i) * M + mem] = yr[j];
+				}
 				++kd;
 			}
 		}
@@ -338,32 +427,48 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 					io.t_samples[mem] = t;
 					if (io.err_samples) io.err_samples[mem] = 0.0;
 				}
-				for (int k = lane; k < N; k += 32) io.y_samples[k * M + mem] = y[k];
+#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int i = lane + 32 * j;
+					if (FULL || i < N) io.y_samples[i * M + mem] = yr[j];
+				}
 			}
 			n_stored = 1;
 		}
 
+		double Yr[S][NPL], Rr[S][NPL]; // stage increments and residual, component lane + 32 j of every stage
 		// residual R = Y - dt*(A (x) I) F(y+Y), returns |R|^2   (irk.hpp:366-386)
 		auto residual = [&]() -> double {
-			for (int e = lane; e < S * N; e += 32) R[e] = y[e % N] + Y[e]; // stage states (R is free here)
+#pragma unroll
+			for (int s = 0; s < S; ++s)
+#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int i = lane + 32 * j;
+					if (FULL || i < N) work[s * N + i] = yr[j] + Yr[s][j]; // stage states, for the neighbours
+				}
 			__syncwarp();
-			for (int e = lane; e < S * N; e += 32) {
-				const int s = e / N, i = e % N;
-				Fv[e] = F::fun(i, fma(tb.c[s], dt, t), R + s * N, par);
-			}
-			__syncwarp();
+			double Fr[S][NPL];
+#pragma unroll
+			for (int s = 0; s < S; ++s)
+#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int i = lane + 32 * j;
+					Fr[s][j] = (FULL || i < N) ? F::fun(i, fma(tb.c[s], dt, t), work + s * N, par) : 0.0;
+				}
+			__syncwarp(); // the work vectors are free again
 			c_fun += S;
 			double r2 = 0.0;
-			for (int e = lane; e < S * N; e += 32) {
-				const int s = e / N, i = e % N;
-				double acc = 0.0;
 #pragma unroll
-				for (int j = 0; j < S; ++j) acc = fma(tb.A[s][j], Fv[j * N + i], acc);
-				const double r = fma(-dt, acc, Y[e]);
-				R[e] = r;
-				r2 = fma(r, r, r2);
-			}
-			__syncwarp();
+			for (int s = 0; s < S; ++s)
+#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					double acc = 0.0;
+#pragma unroll
+					for (int k = 0; k < S; ++k) acc = fma(tb.A[s][k], Fr[k][j], acc);
+					const double r = fma(-dt, acc, Yr[s][j]);
+					Rr[s][j] = r;
+					r2 = fma(r, r, r2);
+				}
 			return warp_sum(r2);
 		};
 
@@ -382,7 +487,34 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			const double rdt = 1.0 / dt;
 			const double mur = (EST == EST_REUSE) ? 1.0 / (tb.gamma * dt) : tb.gamma_hat * rdt;
 			const double mue = (EST == EST_OWN_LU) ? 1.0 / (tb.gamma * dt) : 0.0;
-			auto build_matrices = [&]() {
+			auto build_twisted = [&]() {
+#pragma unroll
+				for (int jj = 0; jj < NPL; ++jj) {
+					const int i = lane + 32 * jj;
+					if (FULL || i < N) {
+						double row[N];
+#pragma unroll
+						for (int j = 0; j < N; ++j) row[j] = 0.0;
+						F::jac_row(i, t, y, par, row);
+#pragma unroll
+						for (int d = -KB; d <= KB; ++d) {
+							const int j = i + d;
+							const double jv = (j >= 0 && j < N) ? row[j] : 0.0;
+							const double dg = (d == 0) ? 1.0 : 0.0;
+							if (NR) tw_put<N, KB>(sm + L::o_fr, sm + L::o_fr + HP, i, d, dg * mur - jv);
+							if (EST == EST_OWN_LU) tw_put<N, KB>(sm + L::o_fr + 2 * HP, sm + L::o_fr + 3 * HP, i, d, dg * mue - jv);
+#pragma unroll
+							for (int c = 0; c < NC; ++c) {
+								double *top = sm + L::o_fc + (c * 4) * HP, *bot = top + 2 * HP;
+								tw_put<N, KB>(top, bot, i, d, dg * (tb.alpha[c] * rdt) - jv);
+								tw_put<N, KB>(top + HP, bot + HP, i, d, dg * (tb.beta[c] * rdt));
+							}
+						}
+					}
+				}
+				__syncwarp();
+			};
+			auto build_pivoted = [&]() {
 				for (int i = lane; i < N; i += 32) {
 					double row[N];
 #pragma unroll
@@ -411,62 +543,75 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 				__syncwarp();
 			};
 			++c_jac;
-			// -------- all factorisations side by side, one lane per matrix, one routine for all of them:
-			// plain elimination first; if pivoting would have exchanged rows anywhere, redo them pivoted
-			build_matrices();
+			// -------- all factorisations side by side, one lane pair per matrix, one routine for all of them;
+			// if partial pivoting would have exchanged rows anywhere, redo them pivoted (one lane per matrix)
+			build_twisted();
 			bool flag = false;
-			if (has_matrix) flag = band_lu<N, KB, false>(m_abr, m_abi, m_cplx, m_rdr, m_rdi, m_piv);
+			if (t_has) flag = tw_factor_pair<N, KB>(m_has, t_pr, t_pi, t_cplx, t_np, t_qr, t_qi);
 			__syncwarp();
-			const bool piv_any = __any_sync(0xffffffffu, flag);
+			const bool piv_any = __any_sync(0xffffffffu, flag) || a.force_pivot;
 			if (piv_any) {
-				build_matrices();
-				if (has_matrix) band_lu<N, KB, true>(m_abr, m_abi, m_cplx, m_rdr, m_rdi, m_piv);
+				if (!slab) { // launch_warp always provides one
+					status = REHUEL_GENERAL_ERROR;
+					break;
+				}
+				build_pivoted();
+				if (p_has) band_lu<N, KB, true>(p_abr, p_abi, p_cplx, p_rdr, p_rdi, p_piv);
 				__syncwarp();
 			}
 
 			// -------- simplified Newton (irk.hpp:398-493)
-			for (int e = lane; e < S * N; e += 32) Y[e] = 0.0; // irk.hpp:415
-			__syncwarp();
+#pragma unroll
+			for (int s = 0; s < S; ++s)
+#pragma unroll
+				for (int j = 0; j < NPL; ++j) Yr[s][j] = 0.0; // irk.hpp:415
 			double Rnorm2 = residual();
 			int nstat = kNewtonMaxit;
 			int it = 1;
 			for (; it < maxit; ++it) { // irk.hpp:458
-				for (int e = lane; e < S * N; e += 32) { // Z = (Ti (x) I) R
-					const int s = e / N, i = e % N;
-					double acc = 0.0;
 #pragma unroll
-					for (int j = 0; j < S; ++j) acc = fma(tb.Ti[s][j], R[j * N + i], acc);
-					Z[e] = acc;
+				for (int s = 0; s < S; ++s)
+#pragma unroll
+					for (int j = 0; j < NPL; ++j) { // Z = (Ti (x) I) R
+						const int i = lane + 32 * j;
+						double acc = 0.0;
+#pragma unroll
+						for (int k = 0; k < S; ++k) acc = fma(tb.Ti[s][k], Rr[k][j], acc);
+						if (FULL || i < N) work[s * N + i] = acc;
+					}
+				__syncwarp();
+				if (!piv_any) { // all right-hand sides side by side, one lane pair each
+					if (t_rhs) tw_solve_pair<N, KB>(m_rhs, t_pr, t_pi, t_cplx, t_np, t_qr, t_qi, t_xr, t_xi, t_xs);
+				} else {
+					if (p_rhs) band_solve<N, KB, true>(p_abr, p_abi, p_cplx, p_rdr, p_rdi, p_piv, p_xr, p_xi);
 				}
 				__syncwarp();
-				if (has_rhs) { // all right-hand sides side by side, one lane each
-					if (piv_any) band_solve<N, KB, true>(m_abr, m_abi, m_cplx, m_rdr, m_rdi, m_piv, m_xr, m_xi);
-					else band_solve<N, KB, false>(m_abr, m_abi, m_cplx, m_rdr, m_rdi, m_piv, m_xr, m_xi);
-				}
-				__syncwarp();
-				if (NR)
-					for (int i = lane; i < N; i += 32) Z[i] *= -mur;
+				double z[NPL][S]; // W = -mu Z, componentwise
 #pragma unroll
-				for (int c = 0; c < NC; ++c) {
-					double *zr = Z + (NR + 2 * c) * N, *zi = zr + N;
-					const double mr = tb.alpha[c] * rdt, mi = tb.beta[c] * rdt;
-					for (int i = lane; i < N; i += 32) { // w = -(mr + i mi) w
-						const double wr = zr[i], wi = zi[i];
-						zr[i] = fma(-mr, wr, mi * wi);
-						zi[i] = fma(-mr, wi, -mi * wr);
+				for (int j = 0; j < NPL; ++j) {
+					const int i = lane + 32 * j;
+#pragma unroll
+					for (int k = 0; k < S; ++k) z[j][k] = (FULL || i < N) ? work[k * N + i] : 0.0;
+					if (NR) z[j][0] *= -mur;
+#pragma unroll
+					for (int c = 0; c < NC; ++c) { // w = -(mr + i mi) w
+						const double mr = tb.alpha[c] * rdt, mi = tb.beta[c] * rdt;
+						const double wr = z[j][NR + 2 * c], wi = z[j][NR + 2 * c + 1];
+						z[j][NR + 2 * c] = fma(-mr, wr, mi * wi);
+						z[j][NR + 2 * c + 1] = fma(-mr, wi, -mi * wr);
 					}
 				}
-				__syncwarp();
 				double x2 = 0.0;
-				for (int e = lane; e < S * N; e += 32) { // dY = (T (x) I) W ; Y += dY
-					const int s = e / N, i = e % N;
-					double acc = 0.0;
 #pragma unroll
-					for (int j = 0; j < S; ++j) acc = fma(tb.T[s][j], Z[j * N + i], acc);
-					x2 = fma(acc, acc, x2);
-					Y[e] += acc;
-				}
-				__syncwarp();
+				for (int s = 0; s < S; ++s)
+#pragma unroll
+					for (int j = 0; j < NPL; ++j) { // dY = (T (x) I) W ; Y += dY
+						double acc = 0.0;
+#pragma unroll
+						for (int k = 0; k < S; ++k) acc = fma(tb.T[s][k], z[j][k], acc);
+						x2 = fma(acc, acc, x2);
+						Yr[s][j] += acc;
+					}
 				const double xnorm2 = warp_sum(x2); // irk.hpp:466
 				if (REHUEL_SKIP_DEAD_RESIDUAL && xnorm2 < a.xtol2) { // the residual of irk.hpp:469-472 would never be looked at
 					c_fun += S;                                       // (see irk_thread.cuh); its evaluations are booked
@@ -504,60 +649,80 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			++c_newton_ok;
 			c_iters += (unsigned)it;
 
-			// -------- new solution + embedded error (irk.hpp:691-731)
+			// -------- new solution + embedded error (irk.hpp:691-731), componentwise in registers
 			const double gam = tb.gamma * dt;
-			for (int i = lane; i < N; i += 32) {
+			double dyv[NPL], dalt[NPL], yn[NPL], ev[NPL];
+#pragma unroll
+			for (int j = 0; j < NPL; ++j) {
+				const int i = lane + 32 * j;
 				double s1 = 0.0, s2 = 0.0;
 #pragma unroll
 				for (int s = 0; s < S; ++s) {
-					s1 = fma(Y[s * N + i], tb.d[s], s1);
-					s2 = fma(Y[s * N + i], tb.d2[s], s2);
+					s1 = fma(Yr[s][j], tb.d[s], s1);
+					s2 = fma(Yr[s][j], tb.d2[s], s2);
 				}
-				dyv[i] = s1;
-				dalt[i] = s2;
-				yn[i] = y[i] + s1;
-				if (EST != EST_IDENTITY) fy[i] = F::fun(i, t, y, par); // irk.hpp:702
+				dyv[j] = s1;
+				dalt[j] = s2;
+				yn[j] = yr[j] + s1;
+				double dyalt = s2;
+				if (EST != EST_IDENTITY && (FULL || i < N)) dyalt = fma(gam, F::fun(i, t, y, par), s2); // irk.hpp:702
+				ev[j] = dyalt - s1;
 			}
 			++c_fun;
-			__syncwarp();
-			for (int i = lane; i < N; i += 32) {
-				const double dyalt = (EST != EST_IDENTITY) ? fma(gam, fy[i], dalt[i]) : dalt[i];
-				ev[i] = dyalt - dyv[i];
-			}
-			__syncwarp();
 			const double esc = (EST == EST_IDENTITY) ? dt : 1.0 / tb.gamma; // dt*E^-1 = (1/gamma)(mu I - J)^-1
 			auto apply_Einv_dt = [&]() {
 				if (EST != EST_IDENTITY) {
-					if (lane == 0) {
-						const int o = (EST == EST_REUSE) ? 0 : 1; // which real plane holds E's factors
-						if (piv_any) band_solve<N, KB, true>(abr + o * PL, abr, false, rdr + o * N, rdr, piv + o * N, ev, ev);
-						else band_solve<N, KB, false>(abr + o * PL, abr, false, rdr + o * N, rdr, piv + o * N, ev, ev);
+#pragma unroll
+					for (int j = 0; j < NPL; ++j) {
+						const int i = lane + 32 * j;
+						if (FULL || i < N) work[i] = ev[j];
 					}
 					__syncwarp();
+					if (!piv_any) {
+						if (t_E) tw_solve_pair<N, KB>(m_E, t_pr, t_pr, false, t_np, t_qr, t_qi, t_er, t_er, t_xs);
+					} else if (lane == 0) {
+						const int o = (EST == EST_REUSE) ? 0 : 1; // which real plane holds E's factors
+						band_solve<N, KB, true>(abr + o * PL, abr, false, rdr + o * N, rdr, piv + o * N, work, work);
+					}
+					__syncwarp();
+#pragma unroll
+					for (int j = 0; j < NPL; ++j) {
+						const int i = lane + 32 * j;
+						ev[j] = (FULL || i < N) ? work[i] : 0.0;
+					}
 				}
-				for (int i = lane; i < N; i += 32) ev[i] *= esc;
-				__syncwarp();
+#pragma unroll
+				for (int j = 0; j < NPL; ++j) ev[j] *= esc;
 			};
 			apply_Einv_dt(); // 8.19
 			if (alt) {       // 8.20, irk.hpp:722-731
 				if (EST != EST_IDENTITY) {
-					for (int i = lane; i < N; i += 32) Z[i] = y[i] + ev[i];
+					static_assert(EST == EST_IDENTITY || S >= 2, "the trial state of 8.20 uses the second work vector");
+#pragma unroll
+					for (int j = 0; j < NPL; ++j) {
+						const int i = lane + 32 * j;
+						if (FULL || i < N) work[N + i] = yr[j] + ev[j];
+					}
 					__syncwarp();
-					for (int i = lane; i < N; i += 32) fy[i] = F::fun(i, t, Z, par);
-					__syncwarp();
+#pragma unroll
+					for (int j = 0; j < NPL; ++j) {
+						const int i = lane + 32 * j;
+						const double fy = (FULL || i < N) ? F::fun(i, t, work + N, par) : 0.0;
+						ev[j] = fma(gam, fy, dalt[j]) - dyv[j];
+					}
+				} else {
+#pragma unroll
+					for (int j = 0; j < NPL; ++j) ev[j] = dalt[j] - dyv[j];
 				}
 				++c_fun;
-				for (int i = lane; i < N; i += 32) {
-					const double v = (EST != EST_IDENTITY) ? fma(gam, fy[i], dalt[i]) : dalt[i];
-					ev[i] = v - dyv[i];
-				}
-				__syncwarp();
 				apply_Einv_dt();
 			}
 			double tot = 0.0;
-			for (int i = lane; i < N; i += 32) { // irk.hpp:733-746
-				const double sc = fma(a.rtol, fmax(fabs(y[i]), fabs(yn[i])), a.atol);
-				const double q = ev[i] / sc;
+#pragma unroll
+			for (int j = 0; j < NPL; ++j) { // irk.hpp:733-746
+				const int i = lane + 32 * j;
+				const double sc = fma(a.rtol, fmax(fabs(yr[j]), fabs(yn[j])), a.atol);
+				const double q = (FULL || i < N) ? ev[j] / sc : 0.0;
 				tot = fma(q, q, tot);
 			}
 			tot = warp_sum(tot);
@@ -579,16 +744,23 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 						if (tk > t_new) break;
 						double w[S];
 						dense_weights<S, NC>(tb, (tk - t) * rdt, w);
-						for (int i = lane; i < N; i += 32) {
-							double acc = y[i];
 #pragma unroll
-							for (int s = 0; s < S; ++s) acc = fma(w[s], Y[s * N + i], acc);
-							io.y_dense[((size_t)kd * N + i) * M + mem] = (tk == t_new) ? yn[i] : acc;
+						for (int j = 0; j < NPL; ++j) {
+							const int i = lane + 32 * j;
+							double acc = yr[j];
+#pragma unroll
+							for (int s = 0; s < S; ++s) acc = fma(w[s], Yr[s][j], acc);
+							if (FULL || i < N) io.y_dense[((size_t)kd * N + i) * M + mem] = (tk == t_new) ? yn[j] : acc;
 						}
 						++kd;
 					}
 				}
-				for (int i = lane; i < N; i += 32) y[i] = yn[i];
+#pragma unroll
+				for (int j = 0; j < NPL; ++j) {
+					const int i = lane + 32 * j;
+					yr[j] = yn[j];
+					if (FULL || i < N) y[i] = yn[j];
+				}
 				const double t_old = t;
 				t += dt;
 				++step;
@@ -600,7 +772,11 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 							io.t_samples[row * M + mem] = t;
 							if (io.err_samples) io.err_samples[row * M + mem] = err;
 						}
-						for (int i = lane; i < N; i += 32) io.y_samples[(row * N + i) * M + mem] = yn[i];
+#pragma unroll
+						for (int j = 0; j < NPL; ++j) {
+							const int i = lane + 32 * j;
+							if (FULL || i < N) io.y_samples[(row * N + i) * M + mem] = yn[j];
+						}
 					}
 					++n_stored;
 				}
@@ -618,7 +794,11 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 
 		// ---------------- results
 		__syncwarp();
-		for (int k = lane; k < N; k += 32) io.y[k * M + mem] = y[k];
+#pragma unroll
+		for (int j = 0; j < NPL; ++j) {
+			const int i = lane + 32 * j;
+			if (FULL || i < N) io.y[i * M + mem] = yr[j];
+		}
 		if (lane == 0) {
 			io.t_final[mem] = t;
 			if (io.err_last) io.err_last[mem] = err;

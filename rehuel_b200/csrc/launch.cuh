@@ -22,6 +22,8 @@ namespace rehuel {
 // ---- exported by librehuel_b200.so (capi.cu)
 int set_error(int code, const char *fmt, ...); // records the thread's last error text, returns code
 void count_launch();                            // bumps rehuel_kernel_launches()
+int debug_force_pivot();                        // rehuel_debug_force_pivot()'s switch
+int retain_async_pool(int dev);                 // once per device: the stream-ordered pool keeps freed blocks
 
 struct KernelInfo {
 	int regs, local_bytes, smem_bytes, ctas_per_sm, block;
@@ -277,8 +279,16 @@ int launch_warp(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ke
 	unsigned grid = (unsigned)(ka.M < cap ? ka.M : cap);
 	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
 	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
-	kern<<<grid, 32, smem, stream>>>(ka, dtb);
+	// one slab per warp for the pivoted band fallback (irk_warp.cuh); stream-ordered, so concurrent launches on other
+	// streams get their own and the block goes back to the (retained) pool as soon as this kernel is done
+	KernelArgs k = ka;
+	int rp = retain_async_pool(dev);
+	if (rp) return rp;
+	REHUEL_CUDA_TRY(cudaMallocAsync((void **)&k.pivot_scratch, WarpSmem<F, S, NC, EST>::slab_doubles * sizeof(double) * grid, stream));
+	k.force_pivot = debug_force_pivot();
+	kern<<<grid, 32, smem, stream>>>(k, dtb);
 	REHUEL_CUDA_TRY(cudaGetLastError());
+	REHUEL_CUDA_TRY(cudaFreeAsync(k.pivot_scratch, stream));
 	count_launch();
 	return REHUEL_OK;
 }

@@ -191,3 +191,23 @@ def test_c_program_fails_loudly_without_gpu():
         subprocess.check_call(["make", "-C", ROOT, "build/c_interface_test"], stdout=subprocess.DEVNULL)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 2 and "failed" in r.stderr
+
+
+def test_twisted_band_factorisation_on_the_host(tmp_path):
+    """rehuel_b200/csrc/band_twisted.cuh (the lane-pair band LU / solve of the warp-per-system kernel) is
+    __host__ __device__: tests/band_twisted_host.cu runs those sweeps on the CPU, the two lanes one after the other,
+    against a dense complex solve with partial pivoting -- real and complex, n = 8 ... 64, half bandwidths 1 ... 4,
+    odd and even splits; matrices that need interchanges must raise the would-pivot flag."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    exe = tmp_path / "band_twisted_host"
+    cmd = [nvcc, "-O1", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", str(exe), os.path.join(ROOT, "tests", "band_twisted_host.cu")]
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    subprocess.check_call(cmd)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    print(out.stdout)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK")

@@ -630,10 +630,10 @@ def test_dense_output_on_a_uniform_grid(capi, port):
 
 
 def test_band_lu_and_solve_against_lapack(capi):
-    """The warp kernel's band routines (irk_warp.cuh) on matrices the ODE problems never produce: random banded
-    matrices NEED row interchanges (pivoted variant, fill-in up to 2*kBand) and diagonally dominant ones do not
-    (plain variant; its flag must say so).  Real and complex matrices side by side in the lanes of one warp, like
-    in the integrator; checked against numpy's dense LAPACK solve."""
+    """The warp kernel's band routines (irk_warp.cuh, band_twisted.cuh) on matrices the ODE problems never produce:
+    random banded matrices NEED row interchanges (pivoted one-lane variant, fill-in up to 2*kBand) and diagonally
+    dominant ones do not (twisted lane-pair variant; its flag must say so).  Real and complex matrices side by side
+    in the lanes of one warp, like in the integrator; checked against numpy's dense LAPACK solve."""
     rng = np.random.default_rng(11)
     n, kb, W, P = 64, 2, 7, 24
     def run(dominant, pivot):
@@ -673,6 +673,40 @@ def test_band_lu_and_solve_against_lapack(capi):
     assert err < 1e-12 and not flags.any()
     err2, _ = run(dominant=True, pivot=True)
     assert err2 < 1e-12
+
+
+def test_warp_kernel_pivoted_fallback_agrees_with_the_twisted_path(capi, port):
+    """The warp-per-system kernels factorise with the twisted elimination (lane pairs, no interchanges) and fall back
+    to pivoted band LUs in a global slab when partial pivoting would have exchanged rows -- which mu I - J of the
+    Brusselator never asks for.  rehuel_debug_force_pivot sends every attempt through the fallback: both paths must
+    agree with the oracle and, to rounding, with each other (different elimination orders, same Newton iterates)."""
+    from rehuel_b200 import ensembles
+    P, y0 = ensembles.bruss1d_params(5), ensembles.bruss1d_y0(32)
+    o, ro = capi.make_options(1e-6, 1e-6), ref_options(1e-6, 1e-6)
+    for method, t1 in ((capi.RADAU_IIA_53, 4.0), (capi.LOBATTO_IIIC_85, 0.25), (capi.RADAU_IIA_32, 0.5), (capi.LOBATTO_IIIC_64, 0.25)):
+        fast = capi.irk_ensemble(capi.BRUSSELATOR_1D, method, 0.0, t1, 1e-6, y0, P, o)
+        capi.debug_force_pivot(True)
+        try:
+            slow = capi.irk_ensemble(capi.BRUSSELATOR_1D, method, 0.0, t1, 1e-6, y0, P, o)
+        finally:
+            capi.debug_force_pivot(False)
+        r = port.solve("brusselator-1d", method, 0.0, t1, 1e-6, y0, P, ro)
+        assert np.all(fast.status == 0) and np.all(slow.status == 0)
+        d = np.abs(fast.y - slow.y).max() / np.abs(slow.y).max()
+        print(f"\nmethod {method}: twisted vs pivoted fallback max rel. difference {d:.2e}; attempts {fast.counters['attempt'].sum()}/"
+              f"{slow.counters['attempt'].sum()}/{r.counters['attempt'].sum()} (twisted/pivoted/oracle); kernel {fast.kernel_ms:.2f} / {slow.kernel_ms:.2f} ms")
+        assert scaled_err(fast.y, r.y, 1e-6, 1e-6).max() <= PARITY_BOUND and scaled_err(slow.y, r.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+        assert scaled_err(fast.y, slow.y, 1e-6, 1e-6).max() <= 1.0
+        assert abs(int(fast.counters["attempt"].sum()) - int(slow.counters["attempt"].sum())) <= max(2, 0.02 * slow.counters["attempt"].sum())
+    # the 8-equation instance: lanes without a component, three pivot rows per half
+    P8, y8 = ensembles.bruss1d_params(16), ensembles.bruss1d_y0(4)
+    fast = capi.irk_ensemble(capi.BRUSSELATOR_1D, capi.LOBATTO_IIIC_85, 0.0, 1.0, 1e-6, y8, P8, o, n_hint=8)
+    capi.debug_force_pivot(True)
+    try:
+        slow = capi.irk_ensemble(capi.BRUSSELATOR_1D, capi.LOBATTO_IIIC_85, 0.0, 1.0, 1e-6, y8, P8, o, n_hint=8)
+    finally:
+        capi.debug_force_pivot(False)
+    assert np.all(fast.status == 0) and scaled_err(fast.y, slow.y, 1e-6, 1e-6).max() <= 1.0
 
 
 def test_concurrent_calls_from_several_host_threads(capi):
