@@ -20,6 +20,8 @@
 //       static constexpr int kBand = 2;   // optional: J(i,j) == 0 for |i-j| > kBand  ->  warp-per-system band kernels
 //       __device__ static double fun(int i, double t, const double *y, const double *p);                 // f_i(t, y)
 //       __device__ static void jac_row(int i, double t, const double *y, const double *p, double *row);  // row i of J, pre-zeroed
+//       // optional with kBand, faster: band[kBand + o] = J(i, i + o), o = -kBand .. kBand, statically indexed
+//       __device__ static void jac_band(int i, double t, const double *y, const double *p, double (&band)[2 * kBand + 1]);
 //   };
 //
 // The kernel template is instantiated HERE, in the user's translation unit; the host pipeline

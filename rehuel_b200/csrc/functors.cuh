@@ -255,6 +255,22 @@ struct Brusselator1dF {
 			if (g < NG - 1) row[2 * (g + 1) + 1] = d;
 		}
 	}
+	// Optional for banded functors: row i of J as its band, band[kBand + o] = J(i, i + o) (entries beyond the matrix: 0).
+	// Statically indexed, so the warp-per-system kernel keeps it in registers instead of a dense row in local memory.
+	// Same expressions as jac_row.
+	__device__ __forceinline__ static void jac_band(int i, double, const double *y, const double *p, double (&band)[2 * kBand + 1])
+	{
+		const int g = i >> 1;
+		const double alpha = p[0], B = p[2];
+		const double d = alpha * (NG + 1.0) * (NG + 1.0);
+		const double u = y[2 * g], v = y[2 * g + 1];
+		const bool is_u = (i & 1) == 0;
+		band[0] = (g > 0) ? d : 0.0;
+		band[1] = is_u ? 0.0 : B - 2.0 * u * v;
+		band[2] = is_u ? 2.0 * u * v - (B + 1.0) - 2.0 * d : -u * u - 2.0 * d;
+		band[3] = is_u ? u * u : 0.0;
+		band[4] = (g < NG - 1) ? d : 0.0;
+	}
 };
 
 // The same equations with the Jacobian treated as DENSE (no kBand trait): takes the general

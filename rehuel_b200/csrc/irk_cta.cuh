@@ -42,6 +42,13 @@ struct jac_band { static constexpr int value = F::N - 1; };
 template <class F>
 struct jac_band<F, decltype((void)F::kBand)> { static constexpr int value = F::kBand < F::N - 1 ? F::kBand : F::N - 1; };
 
+// Optional functor member for banded Jacobians: jac_band(i, t, y, p, double (&band)[2*kBand+1]) fills
+// band[kBand + o] = J(i, i + o), o = -kBand .. kBand (entries beyond the matrix: 0), with static indices.
+template <class F, class = void>
+struct has_jac_band { static constexpr bool value = false; };
+template <class F>
+struct has_jac_band<F, decltype((void)&F::jac_band)> { static constexpr bool value = true; };
+
 template <class F, int S, int NC>
 struct CtaSmem {
 	static constexpr int N = F::N;

@@ -75,6 +75,27 @@ __device__ __forceinline__ double warp_sum(double v)
 	return v;
 }
 
+// Row i of the Jacobian as its band, band[KB + o] = J(i, i + o): straight from the functor's jac_band if it has one
+// (registers), else cut out of a dense row (local memory: measurably slower, but every componentwise functor works).
+template <class F, int KB>
+__device__ __forceinline__ void jacobian_band(int i, double t, const double *y, const double *par, double (&band)[2 * KB + 1])
+{
+	if constexpr (has_jac_band<F>::value) {
+		F::jac_band(i, t, y, par, band);
+	} else {
+		constexpr int N = F::N;
+		double row[N];
+#pragma unroll
+		for (int j = 0; j < N; ++j) row[j] = 0.0;
+		F::jac_row(i, t, y, par, row);
+#pragma unroll
+		for (int o = -KB; o <= KB; ++o) {
+			const int j = i + o;
+			band[KB + o] = (j >= 0 && j < N) ? row[j] : 0.0;
+		}
+	}
+}
+
 // ------------------------------------------------------------------ twisted band LU / solve, one lane PAIR per matrix
 // `mask`: the lanes that execute the call together (whole pairs).  The sweeps are band_twisted.cuh's; here the two
 // halves exchange their separator data with one shuffle per number.
@@ -492,14 +513,11 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 				for (int jj = 0; jj < NPL; ++jj) {
 					const int i = lane + 32 * jj;
 					if (FULL || i < N) {
-						double row[N];
-#pragma unroll
-						for (int j = 0; j < N; ++j) row[j] = 0.0;
-						F::jac_row(i, t, y, par, row);
+						double band[2 * KB + 1]; // J(i, i-KB .. i+KB)
+						jacobian_band<F, KB>(i, t, y, par, band);
 #pragma unroll
 						for (int d = -KB; d <= KB; ++d) {
-							const int j = i + d;
-							const double jv = (j >= 0 && j < N) ? row[j] : 0.0;
+							const double jv = band[KB + d];
 							const double dg = (d == 0) ? 1.0 : 0.0;
 							if (NR) tw_put<N, KB>(sm + L::o_fr, sm + L::o_fr + HP, i, d, dg * mur - jv);
 							if (EST == EST_OWN_LU) tw_put<N, KB>(sm + L::o_fr + 2 * HP, sm + L::o_fr + 3 * HP, i, d, dg * mue - jv);
@@ -516,14 +534,11 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			};
 			auto build_pivoted = [&]() {
 				for (int i = lane; i < N; i += 32) {
-					double row[N];
-#pragma unroll
-					for (int j = 0; j < N; ++j) row[j] = 0.0;
-					F::jac_row(i, t, y, par, row);
+					double band[2 * KB + 1];
+					jacobian_band<F, KB>(i, t, y, par, band);
 #pragma unroll
 					for (int d = -KB; d <= 2 * KB; ++d) {
-						const int j = i + d;
-						const double jv = (d <= KB && j >= 0 && j < N) ? row[j] : 0.0;
+						const double jv = (d <= KB) ? band[KB + (d <= KB ? d : 0)] : 0.0;
 						const double dg = (d == 0) ? 1.0 : 0.0;
 						if (NR) abr[i * W + KB + d] = dg * mur - jv;
 						if (EST == EST_OWN_LU) abr[PL + i * W + KB + d] = dg * mue - jv;

@@ -158,7 +158,15 @@ __global__ void eval_functor_rows_kernel(double t, const double *y, const double
 	for (int i = threadIdx.x; i < N; i += blockDim.x) {
 		f[i] = F::fun(i, t, y, p);
 		for (int j = 0; j < N; ++j) J[i * N + j] = 0.0;
-		F::jac_row(i, t, y, p, J + i * N);
+		if constexpr (has_jac_band<F>::value) { // what the warp-per-system kernel calls
+			constexpr int KB = jac_band<F>::value;
+			double band[2 * KB + 1];
+			F::jac_band(i, t, y, p, band);
+			for (int o = -KB; o <= KB; ++o)
+				if (i + o >= 0 && i + o < N) J[i * N + i + o] = band[KB + o];
+		} else {
+			F::jac_row(i, t, y, p, J + i * N);
+		}
 	}
 }
 
