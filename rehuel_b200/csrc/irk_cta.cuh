@@ -69,11 +69,12 @@ struct CtaSmem {
 	static constexpr int o_red = o_fy + N;           // 64 doubles of reduction scratch
 	static constexpr int o_rdr = o_red + 64;         // reciprocal pivots, real matrix
 	static constexpr int o_rdc = o_rdr + N;          // reciprocal pivots, complex matrices (re, im)
-	static constexpr int o_J = o_rdc + 2 * N * (NC > 0 ? NC : 1);
-	static constexpr int o_LUr = o_J + N * N;
+	static constexpr int o_rde = o_rdc + 2 * N * (NC > 0 ? NC : 1); // reciprocal pivots, the estimator's own matrix
+	static constexpr int o_J = o_rde + N;            // Jacobian, leading dimension LD: the estimator's own matrix
+	static constexpr int o_LUr = o_J + N * LD;       // (1/gamma dt) I - J is built over it and factorised in place
 	static constexpr int o_LUc = o_LUr + N * LD;
-	static constexpr int o_int = o_LUc + 2 * N * LD * NC; // int region: perm arrays
-	static constexpr int n_int = N * (1 + NC) + 8;
+	static constexpr int o_int = o_LUc + 2 * N * LD * NC; // int region: perm arrays (real, complex, estimator)
+	static constexpr int n_int = N * (2 + NC) + 1 + 8;
 	static constexpr size_t bytes = (size_t)o_int * 8 + (size_t)n_int * 4;
 };
 
@@ -93,20 +94,24 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 	return s;
 }
 
-// Fused LU of NRm real (0 or 1) and NCm complex N x N matrices in shared memory; matrix m is
-// piloted by warp m.  perm[m][k] = row exchanged with row k at step k (ipiv); reciprocal pivots go
-// to rdr / rdc so that the solves multiply.
-template <int N, int LD, int NRm, int NCm, int THREADS, int KB>
-__device__ __forceinline__ void lu_factor_set(double *Ar, double *Ac, double *rdr, double *rdc, int *permr, int *permc)
+// Fused LU of NRm (0 or 1) + NEm (0 or 1) real and NCm complex N x N matrices in shared memory; matrix m is
+// piloted by warp m (real Newton block, complex ones, then the estimator's own real matrix Ae).  perm[m][k] = row
+// exchanged with row k at step k (ipiv); reciprocal pivots go to rdr / rdc / rde so that the solves multiply.
+// A step is two block barriers and a chain (pivot search -> reciprocal -> multipliers -> rank-1 update) that
+// nothing overlaps, so what counts is the NUMBER of steps: all matrices of an attempt share the N steps.
+template <int N, int LD, int NRm, int NCm, int NEm, int THREADS, int KB>
+__device__ __forceinline__ void lu_factor_set(double *Ar, double *Ac, double *Ae, double *rdr, double *rdc, double *rde, int *permr,
+                                              int *permc, int *perme)
 {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	constexpr int NM = NRm + NCm;
+	constexpr int NM = NRm + NCm + NEm;
 	static_assert(NM <= THREADS / 32, "one pilot warp per matrix");
 	for (int k = 0; k < N; ++k) {
 		if (warp < NM) {
-			const bool is_real = warp < NRm;
-			const int c = warp - NRm;
-			double *are = is_real ? Ar : Ac + (size_t)c * 2 * N * LD;
+			const bool is_est = NEm && warp == NRm + NCm;
+			const bool is_real = warp < NRm || is_est;
+			const int c = is_real ? 0 : warp - NRm;
+			double *are = is_est ? Ae : (is_real ? Ar : Ac + (size_t)c * 2 * N * LD);
 			double *aim = are + N * LD; // only for complex
 			// ---- pivot search: first row of maximal magnitude in column k (izamax: |re|+|im|)
 			double best = -1.0;
@@ -122,15 +127,15 @@ __device__ __forceinline__ void lu_factor_set(double *Ar, double *Ac, double *rd
 			}
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) {
-				const double ob = __shfl_down_sync(0xffffffffu, best, o);
-				const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+				const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+				const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
 				if (ob > best || (ob == best && oi < bi)) {
 					best = ob;
 					bi = oi;
 				}
 			}
-			const int p = __shfl_sync(0xffffffffu, bi, 0);
-			if (lane == 0) (is_real ? permr : permc + c * N)[k] = p; // interchange list, as ipiv of dgetrf
+			const int p = bi; // the butterfly leaves the same (value, first index) in every lane
+			if (lane == 0) (is_est ? perme : (is_real ? permr : permc + c * N))[k] = p; // interchange list, as ipiv of dgetrf
 			if (p != k) {
 				// like dgbtrf, only the not yet eliminated part of the rows is exchanged; the
 				// solves apply the interchanges step by step, so the multipliers stay put
@@ -146,14 +151,14 @@ __device__ __forceinline__ void lu_factor_set(double *Ar, double *Ac, double *rd
 				}
 			}
 			__syncwarp();
-			// ---- reciprocal pivot, multipliers
+			// ---- reciprocal pivot (fast_rcp: see irk_thread.cuh), multipliers
 			if (is_real) {
-				const double rp = 1.0 / are[k * LD + k];
-				if (lane == 0) rdr[k] = rp;
+				const double rp = fast_rcp(are[k * LD + k]);
+				if (lane == 0) (is_est ? rde : rdr)[k] = rp;
 				for (int r = k + 1 + lane; r < rmax; r += 32) are[r * LD + k] *= rp;
 			} else {
 				const double pr = are[k * LD + k], pi = aim[k * LD + k];
-				const double rden = 1.0 / fma(pr, pr, pi * pi);
+				const double rden = fast_rcp(fma(pr, pr, pi * pi));
 				const double rr = pr * rden, ri = -pi * rden;
 				if (lane == 0) {
 					rdc[(c * 2 + 0) * N + k] = rr;
@@ -167,27 +172,56 @@ __device__ __forceinline__ void lu_factor_set(double *Ar, double *Ac, double *rd
 			}
 		}
 		__syncthreads();
-		// ---- rank-1 update of every trailing block: 16x16 thread tiles, strided
-		const int m = N - k - 1;
-		if (m > 0) {
-			constexpr int TX = 16, TY = THREADS / 16;
+		// ---- rank-1 update of every trailing block: 16 x (THREADS/16) thread grid, strided; a thread keeps its (up to CB)
+		// pivot-row entries of every matrix in registers while it walks down its rows
+		if (k + 1 < N) {
+			constexpr int TX = 16, TY = THREADS / 16, CB = (N + TX - 1) / TX;
 			const int tx = tid % TX, ty = tid / TX;
 			const int rmax = (k + KB + 1 < N) ? k + KB + 1 : N;
 			const int cmax = (k + 2 * KB + 1 < N) ? k + 2 * KB + 1 : N;
-			for (int i = k + 1 + ty; i < rmax; i += TY) {
-				if (NRm) {
-					const double l = Ar[i * LD + k];
-					for (int j = k + 1 + tx; j < cmax; j += TX) Ar[i * LD + j] = fma(-l, Ar[k * LD + j], Ar[i * LD + j]);
-				}
+			const int j0 = k + 1 + tx;
+			if (NRm) {
+				double u[CB];
 #pragma unroll
-				for (int c = 0; c < NCm; ++c) {
-					double *are = Ac + (size_t)c * 2 * N * LD;
-					double *aim = are + N * LD;
+				for (int b = 0; b < CB; ++b) u[b] = (j0 + TX * b < cmax) ? Ar[k * LD + j0 + TX * b] : 0.0;
+				for (int i = k + 1 + ty; i < rmax; i += TY) {
+					const double l = Ar[i * LD + k];
+#pragma unroll
+					for (int b = 0; b < CB; ++b)
+						if (j0 + TX * b < cmax) Ar[i * LD + j0 + TX * b] = fma(-l, u[b], Ar[i * LD + j0 + TX * b]);
+				}
+			}
+			if (NEm) {
+				double u[CB];
+#pragma unroll
+				for (int b = 0; b < CB; ++b) u[b] = (j0 + TX * b < cmax) ? Ae[k * LD + j0 + TX * b] : 0.0;
+				for (int i = k + 1 + ty; i < rmax; i += TY) {
+					const double l = Ae[i * LD + k];
+#pragma unroll
+					for (int b = 0; b < CB; ++b)
+						if (j0 + TX * b < cmax) Ae[i * LD + j0 + TX * b] = fma(-l, u[b], Ae[i * LD + j0 + TX * b]);
+				}
+			}
+#pragma unroll
+			for (int c = 0; c < NCm; ++c) {
+				double *are = Ac + (size_t)c * 2 * N * LD;
+				double *aim = are + N * LD;
+				double ur[CB], ui[CB];
+#pragma unroll
+				for (int b = 0; b < CB; ++b) {
+					const bool in = j0 + TX * b < cmax;
+					ur[b] = in ? are[k * LD + j0 + TX * b] : 0.0;
+					ui[b] = in ? aim[k * LD + j0 + TX * b] : 0.0;
+				}
+				for (int i = k + 1 + ty; i < rmax; i += TY) {
 					const double lr = are[i * LD + k], li = aim[i * LD + k];
-					for (int j = k + 1 + tx; j < cmax; j += TX) {
-						const double ur = are[k * LD + j], ui = aim[k * LD + j];
-						are[i * LD + j] = fma(-lr, ur, fma(li, ui, are[i * LD + j]));
-						aim[i * LD + j] = fma(-lr, ui, fma(-li, ur, aim[i * LD + j]));
+#pragma unroll
+					for (int b = 0; b < CB; ++b) {
+						const int j = j0 + TX * b;
+						if (j < cmax) {
+							are[i * LD + j] = fma(-lr, ur[b], fma(li, ui[b], are[i * LD + j]));
+							aim[i * LD + j] = fma(-lr, ui[b], fma(-li, ur[b], aim[i * LD + j]));
+						}
 					}
 				}
 			}
@@ -341,11 +375,12 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 	extern __shared__ double sm[];
 	double *y = sm + L::o_y, *yn = sm + L::o_yn, *par = sm + L::o_p, *Y = sm + L::o_Y, *R = sm + L::o_R,
 	       *Z = sm + L::o_Z, *Fv = sm + L::o_F, *ev = sm + L::o_e, *dyv = sm + L::o_dy, *dalt = sm + L::o_dalt,
-	       *fy = sm + L::o_fy, *red = sm + L::o_red, *rdr = sm + L::o_rdr, *rdc = sm + L::o_rdc, *J = sm + L::o_J,
-	       *LUr = sm + L::o_LUr, *LUc = sm + L::o_LUc;
+	       *fy = sm + L::o_fy, *red = sm + L::o_red, *rdr = sm + L::o_rdr, *rdc = sm + L::o_rdc, *rde = sm + L::o_rde,
+	       *J = sm + L::o_J, *LUr = sm + L::o_LUr, *LUc = sm + L::o_LUc;
 	int *permr = reinterpret_cast<int *>(sm + L::o_int);
 	int *permc = permr + N;
-	int *s_ctl = permc + N * NC; // [0..1]: member index (64 bit)
+	int *perme = permc + N * NC;
+	int *s_ctl = permr + ((N * (2 + NC) + 1) & ~1); // [0..1]: member index (64 bit, hence the even offset)
 	const int tid = threadIdx.x, warp = tid >> 5;
 	const unsigned long long M = a.M;
 	const rehuel_device_io &io = a.io;
@@ -441,23 +476,27 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 			// -------- Jacobian and the decoupled Newton matrices (irk.hpp:422-436)
 			const double rdt = 1.0 / dt;
 			const double mur = (EST == EST_REUSE) ? 1.0 / (tb.gamma * dt) : tb.gamma_hat * rdt;
-			for (int e = tid; e < N * N; e += THREADS) J[e] = 0.0;
+			const double mue = (EST == EST_OWN_LU) ? 1.0 / (tb.gamma * dt) : 0.0;
+			for (int e = tid; e < N * LD; e += THREADS) J[e] = 0.0;
 			__syncthreads();
-			for (int i = tid; i < N; i += THREADS) F::jac_row(i, t, y, par, J + i * N);
+			for (int i = tid; i < N; i += THREADS) F::jac_row(i, t, y, par, J + i * LD);
 			++c_jac;
 			__syncthreads();
 			for (int e = tid; e < N * N; e += THREADS) {
 				const int i = e / N, j = e % N;
-				const double jv = J[e];
+				const double jv = J[i * LD + j];
 				if (NR) LUr[i * LD + j] = (i == j ? mur : 0.0) - jv;
 #pragma unroll
 				for (int c = 0; c < NC; ++c) {
 					LUc[(size_t)c * 2 * N * LD + i * LD + j] = (i == j ? tb.alpha[c] * rdt : 0.0) - jv;
 					LUc[(size_t)c * 2 * N * LD + N * LD + i * LD + j] = (i == j ? tb.beta[c] * rdt : 0.0);
 				}
+				// E/gam = (1/gam) I - J of the error estimate gets its own factors, in place of J (read above by this thread)
+				if (EST == EST_OWN_LU) J[i * LD + j] = (i == j ? mue : 0.0) - jv;
 			}
 			__syncthreads();
-			lu_factor_set<N, LD, NR, NC, THREADS, KB>(LUr, LUc, rdr, rdc, permr, permc);
+			// all factorisations of the attempt in the same N steps, the estimator's included
+			lu_factor_set<N, LD, NR, NC, (EST == EST_OWN_LU ? 1 : 0), THREADS, KB>(LUr, LUc, J, rdr, rdc, rde, permr, permc, perme);
 
 			// -------- simplified Newton (irk.hpp:398-493)
 			for (int e = tid; e < S * N; e += THREADS) Y[e] = 0.0; // irk.hpp:415
@@ -553,15 +592,6 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 			}
 			++c_fun;
 			__syncthreads();
-			if (EST == EST_OWN_LU) { // E/gam = (1/gam) I - J gets its own factors (in the real slot)
-				const double mue = 1.0 / gam;
-				for (int e = tid; e < N * N; e += THREADS) {
-					const int i = e / N, j = e % N;
-					LUr[i * LD + j] = (i == j ? mue : 0.0) - J[e];
-				}
-				__syncthreads();
-				lu_factor_set<N, LD, 1, 0, THREADS, KB>(LUr, nullptr, rdr, nullptr, permr, nullptr);
-			}
 			for (int i = tid; i < N; i += THREADS) {
 				const double dyalt = (EST != EST_IDENTITY) ? fma(gam, fy[i], dalt[i]) : dalt[i];
 				ev[i] = dyalt - dyv[i];
@@ -570,7 +600,10 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 			const double esc = (EST == EST_IDENTITY) ? dt : 1.0 / tb.gamma; // dt*E^-1 = (1/gamma)(mu I - J)^-1
 			auto apply_Einv_dt = [&]() {
 				if (EST != EST_IDENTITY) {
-					if (warp == 0) lu_solve_real_warp<N, LD, KB>(LUr, rdr, permr, ev);
+					if (warp == 0) {
+						if (EST == EST_OWN_LU) lu_solve_real_warp<N, LD, KB>(J, rde, perme, ev);
+						else lu_solve_real_warp<N, LD, KB>(LUr, rdr, permr, ev);
+					}
 					__syncthreads();
 				}
 				for (int i = tid; i < N; i += THREADS) ev[i] *= esc;
