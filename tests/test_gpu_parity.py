@@ -316,6 +316,57 @@ def test_full_size_properties_1M(capi, port):
     assert se.max() <= PARITY_BOUND
 
 
+def test_full_size_configs_3_and_4(capi, port):
+    """BASELINE configs 3 and 4 at FULL size.  Config 3: 2^20 Van der Pol members (mu_ref = 1 .. 1e-6, LOBATTO_IIIC_43,
+    thread-per-system; the stiff end runs into Newton failures) -- counter identities on every member, a strided
+    sample against the oracle.  Config 4: 65 536 members of the 64-equation Brusselator (LOBATTO_IIIC_85, t in [0,10],
+    ~2150 attempts per member, warp-per-system) -- the CPU oracle needs ~90 s per member there, so: counter identities
+    on every member, a sample re-run alone must be bit-identical (results do not depend on placement), and a few members
+    against the CTA-per-system kernel, whose dense LUs share no linear-algebra code with the twisted band solves."""
+    from rehuel_b200 import ensembles
+    o, ro = capi.make_options(1e-6, 1e-6), ref_options(1e-6, 1e-6)
+    # ---- config 3
+    M = 1 << 20
+    P = ensembles.vdpol_params(M)
+    g = capi.irk_ensemble(capi.VAN_DER_POL, 230, 0.0, 2.0, 1e-6, ensembles.VDPOL_Y0, P, o)
+    c = g.counters
+    assert np.all(g.status == 0) and np.all(g.t_final == 2.0) and np.all(np.isfinite(g.y))
+    assert np.array_equal(c["attempt"], c["steps"] + c["reject_err"] + c["reject_newton"])
+    assert np.array_equal(c["newton_success"], c["attempt"] - c["reject_newton"])
+    assert g.sum["attempt"] == int(c["attempt"].astype(np.int64).sum()) and g.sum["n_failed"] == 0
+    assert c["reject_newton"].sum() > 100000                       # the stiff tenth of the sweep fails Newton solves
+    idx = np.arange(0, M, M // 256)
+    r = port.solve("van-der-pol", 230, 0.0, 2.0, 1e-6, ensembles.VDPOL_Y0, P[:, idx].copy(), ro)
+    se = scaled_err(g.y[:, idx], r.y, 1e-6, 1e-6)
+    same = float(np.mean(c["attempt"][idx] == r.counters["attempt"]))
+    print(f"\nconfig 3, 2^20 members: kernel {g.kernel_ms:.1f} ms; sample of {len(idx)} vs oracle: max scaled err {se.max():.3e}, "
+          f"identical attempt counts {same:.3f}, newton rejections gpu/ref {c['reject_newton'][idx].sum()}/{r.counters['reject_newton'].sum()}")
+    assert se.max() <= PARITY_BOUND and same >= 0.98
+    # ---- config 4
+    M = 1 << 16
+    P = ensembles.bruss1d_params(M)
+    y0 = ensembles.bruss1d_y0(32)
+    g = capi.irk_ensemble(capi.BRUSSELATOR_1D, capi.LOBATTO_IIIC_85, 0.0, 10.0, 1e-6, y0, P, o, n_hint=64)
+    c = g.counters
+    assert np.all(g.status == 0) and np.all(g.t_final == 10.0) and np.all(np.isfinite(g.y))
+    assert np.array_equal(c["attempt"], c["steps"] + c["reject_err"] + c["reject_newton"])
+    assert np.array_equal(c["newton_success"], c["attempt"] - c["reject_newton"])
+    assert g.sum["attempt"] == int(c["attempt"].astype(np.int64).sum()) and g.sum["n_failed"] == 0
+    idx = np.arange(0, M, M // 96)
+    solo = capi.irk_ensemble(capi.BRUSSELATOR_1D, capi.LOBATTO_IIIC_85, 0.0, 10.0, 1e-6, y0, P[:, idx].copy(), o, n_hint=64)
+    assert np.array_equal(solo.y, g.y[:, idx])
+    for k in c:
+        assert np.array_equal(solo.counters[k], c[k][idx]), k
+    few = idx[::24]
+    d = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 0.0, 10.0, 1e-6, y0, P[:, few].copy(), o, n_hint=64)
+    se = scaled_err(g.y[:, few], d.y, 1e-6, 1e-6)
+    print(f"config 4, 65536 members: kernel {g.kernel_ms:.0f} ms = {M / g.kernel_ms * 1e3:.3g} systems/s, {c['attempt'].mean():.0f} attempts per member; "
+          f"{len(idx)} members re-run alone: bit-identical; {len(few)} members vs the dense CTA kernel: max scaled err {se.max():.3e}, "
+          f"attempts {c['attempt'][few].tolist()} / {d.counters['attempt'].tolist()}")
+    assert se.max() <= PARITY_BOUND
+    assert np.abs(c["attempt"][few].astype(np.int64) - d.counters["attempt"].astype(np.int64)).max() <= 0.02 * c["attempt"][few].max()
+
+
 def test_merge_two_legs(capi):
     """merge_rk_output semantics (irk.cpp:750-783; test/irk.cpp:218-244): integrate [0,2] then [2,4]."""
     lam = np.array([[-0.4, -0.4]])
