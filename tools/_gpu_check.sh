@@ -1,2 +1,6 @@
 cd $GRAFT_REPO_ROOT
-timeout 1200 python -m pytest tests -m gpu -x -q -s -k "full_size_configs" 2>&1 | grep -v "^$" | tail -12
+mkdir -p gpurun_out
+ID=$(python -c "from rehuel_b200 import capi; print(capi.BRUSSELATOR_1D_DENSE)")
+python tools/run_config4.py 148 1.0 232 $ID 2>&1 | tail -1
+python tools/run_config4.py 148 1.0 211 $ID 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -x -q -s -k "bruss or dense or user_functor or jacobians" 2>&1 | grep "cta \|passed\|failed\|Error\|error" | tail -25
