@@ -13,7 +13,7 @@
 //   auto sol = irk::odeint(my_ode{}, t0, t1, y0, /*broadcast*/true, params, M, s_opts, out_opts, irk::RADAU_IIA_53);
 //
 // Larger systems (4 < N <= 64) are worked on by a whole warp or thread block, so their functor is
-// COMPONENTWISE (irk_cta.cuh / irk_warp.cuh):
+// COMPONENTWISE (irk_warp.cuh: banded; irk_wdense.cuh: dense, N <= 16; irk_cta.cuh: dense, N > 16):
 //
 //   struct my_pde {
 //       static constexpr int N = 64, P = 3;

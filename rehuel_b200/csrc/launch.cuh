@@ -15,6 +15,7 @@
 #include "irk_cta.cuh"
 #include "irk_thread.cuh"
 #include "irk_warp.cuh"
+#include "irk_wdense.cuh"
 #include "tableau.hpp"
 
 namespace rehuel {
@@ -301,12 +302,58 @@ int launch_warp(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ke
 	return REHUEL_OK;
 }
 
-// 4 < n <= 64: banded functors (kBand <= 4) go warp-per-system, everything else CTA-per-system
+// ---- warp-per-system path for small dense systems (4 < n <= 16), irk_wdense.cuh
+template <class F, int S, int NR, int NC, int EST>
+int launch_wdense(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	void (*kern)(const KernelArgs, const DevTableau<S, NC>) = ensemble_irk_wdense<F, S, NR, NC, EST, false>;
+	if (ka.io.n_dense) {
+		if constexpr (EST != EST_IDENTITY) {
+			kern = ensemble_irk_wdense<F, S, NR, NC, EST, true>;
+		} else {
+			return set_error(REHUEL_EINVAL, "Chosen method does not have dense output!"); // irk.cpp:733
+		}
+	}
+	const size_t smem = WdSmem<F, S, NC, EST>::bytes;
+	if (tb.s != S || tb.n_real != NR || tb.n_cplx != NC || tb.est_mode != EST)
+		return set_error(REHUEL_EINVAL, "internal: tableau %s does not have the structure its kernel was built for", tb.name);
+	int dev = 0, sms = 0, per_sm = 0;
+	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
+	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	REHUEL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+	if (per_sm < 1) return set_error(REHUEL_ECUDA, "warp-per-system kernel does not fit on an SM");
+	if (info) {
+		cudaFuncAttributes fa;
+		REHUEL_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+		info->regs = fa.numRegs;
+		info->local_bytes = (int)fa.localSizeBytes;
+		info->smem_bytes = (int)smem;
+		info->ctas_per_sm = per_sm;
+		info->block = 32;
+		return REHUEL_OK;
+	}
+	if (ka.M == 0) return REHUEL_OK;
+	if (ka.io.rtol) return set_error(REHUEL_EINVAL, "per-member tolerances are not built for the warp-per-system kernels");
+	unsigned long long cap = (unsigned long long)sms * per_sm;
+	unsigned grid = (unsigned)(ka.M < cap ? ka.M : cap);
+	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
+	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	kern<<<grid, 32, smem, stream>>>(ka, dtb);
+	REHUEL_CUDA_TRY(cudaGetLastError());
+	count_launch();
+	return REHUEL_OK;
+}
+
+// 4 < n <= 64: banded functors (kBand <= 4) go warp-per-system with band factors in shared memory, small dense
+// systems (n <= 16) warp-per-system with the matrices in registers, everything else CTA-per-system
 template <class F, int S, int NR, int NC, int EST>
 int launch_block(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
 {
-	if constexpr (jac_band<F>::value <= 4) {
+	constexpr int KB = jac_band<F>::value;
+	if constexpr (KB <= 4 && F::N >= 2 * KB + 2) {
 		return launch_warp<F, S, NR, NC, EST>(ka, tb, stream, info);
+	} else if constexpr (F::N <= 16) {
+		return launch_wdense<F, S, NR, NC, EST>(ka, tb, stream, info);
 	} else {
 		return launch_cta<F, S, NR, NC, EST>(ka, tb, stream, info);
 	}

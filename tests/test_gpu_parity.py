@@ -760,6 +760,56 @@ def test_warp_kernel_pivoted_fallback_agrees_with_the_twisted_path(capi, port):
     assert np.all(fast.status == 0) and scaled_err(fast.y, slow.y, 1e-6, 1e-6).max() <= 1.0
 
 
+def test_small_dense_systems_warp_per_system_register_lu(capi, port):
+    """Dense Jacobians with 4 < n <= 16 run warp-per-system with the decoupled Newton matrices in REGISTERS (one row
+    per lane, 2..4 matrices side by side in 8- or 16-lane segments, irk_wdense.cuh) instead of a whole CTA per member.
+    The 1-D Brusselator declared dense, n = 8 and n = 16, every tableau the block kernels are built for: against the
+    oracle (dense LAPACK-style LU of the full stage matrix), against the band kernel on the same equations, and with
+    dense output / continuation, which share the frame of the band kernel."""
+    from rehuel_b200 import ensembles
+    o, ro = capi.make_options(1e-6, 1e-6), ref_options(1e-6, 1e-6)
+    assert capi.kernel_info(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 8)["block"] == 32
+    assert capi.kernel_info(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 16)["block"] == 32
+    assert capi.kernel_info(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 64)["block"] == 256
+    for n in (8, 16):
+        M = 24
+        P, y0 = ensembles.bruss1d_params(M), ensembles.bruss1d_y0(n // 2)
+        for method, t1 in ((capi.RADAU_IIA_53, 10.0), (capi.LOBATTO_IIIC_43, 2.0), (capi.LOBATTO_IIIC_85, 1.0), (capi.RADAU_IIA_95, 4.0),
+                           (capi.RADAU_IIA_32, 2.0), (capi.LOBATTO_IIIC_64, 1.0)):
+            r = port.solve("brusselator-1d", method, 0.0, t1, 1e-6, y0, P, ro)
+            d = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, method, 0.0, t1, 1e-6, y0, P, o, n_hint=n)
+            b = capi.irk_ensemble(capi.BRUSSELATOR_1D, method, 0.0, t1, 1e-6, y0, P, o, n_hint=n)
+            se = scaled_err(d.y, r.y, 1e-6, 1e-6)
+            print(f"\nbruss1d n={n} dense-warp method {method} t1={t1}: max scaled err {se.max():.3e}; attempts dense/band/ref "
+                  f"{d.counters['attempt'].sum()}/{b.counters['attempt'].sum()}/{r.counters['attempt'].sum()}; "
+                  f"fun {d.counters['fun_evals'].sum()}/{r.counters['fun_evals'].sum()}; kernel {d.kernel_ms:.2f} ms")
+            assert np.all(d.status == 0) and np.all(d.t_final == t1)
+            assert se.max() <= PARITY_BOUND and scaled_err(d.y, b.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+            slack = 0.20 if method == capi.RADAU_IIA_95 else 0.02
+            assert abs(int(d.counters["attempt"].sum()) - int(r.counters["attempt"].sum())) <= max(3, slack * r.counters["attempt"].sum())
+    # dense output and continuation through the dense-warp kernel
+    P, y0 = ensembles.bruss1d_params(6), ensembles.bruss1d_y0(4)
+    od = capi.make_options(1e-6, 1e-6, dense_samples=5, dense_t0=0.0, dense_dt=0.5)
+    gd = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, 211, 0.0, 2.0, 1e-6, y0, P, od, n_hint=8)
+    gb = capi.irk_ensemble(capi.BRUSSELATOR_1D, 211, 0.0, 2.0, 1e-6, y0, P, od, n_hint=8)
+    assert np.all(np.isfinite(gd.y_dense)) and np.array_equal(gd.y_dense[4], gd.y)
+    assert scaled_err(gd.y_dense.reshape(-1, 6), gb.y_dense.reshape(-1, 6), 1e-6, 1e-6).max() <= PARITY_BOUND
+    ok = capi.make_options(1e-6, 1e-6, keep_state=True)
+    one = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, 211, 0.0, 4.0, 1e-6, y0, P, ok, n_hint=8)
+    leg1 = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, 211, 0.0, 1.5, 1e-6, y0, P, ok, n_hint=8, raw=True)
+    leg2 = capi.to_output(capi.irk_ensemble_continue(capi.BRUSSELATOR_1D_DENSE, 211, 4.0, P, ok, leg1, n_hint=8))
+    assert np.all(leg2.status == 0) and scaled_err(leg2.y, one.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+    capi.result_free(leg1)
+    # a few thousand members: what the register LU buys over a CTA per member
+    M = 4096
+    P = ensembles.bruss1d_params(M)
+    for n in (8, 16):
+        g = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, capi.RADAU_IIA_53, 0.0, 10.0, 1e-6, ensembles.bruss1d_y0(n // 2), P, o, n_hint=n)
+        att = int(g.counters["attempt"].astype(np.int64).sum())
+        print(f"dense-warp n={n}: {M} members, {att / M:.0f} attempts each: kernel {g.kernel_ms:.2f} ms = {att / g.kernel_ms * 1e-3:.1f} M attempts/s")
+        assert np.all(g.status == 0)
+
+
 def test_concurrent_calls_from_several_host_threads(capi):
     """The reference is re-entrant; the replacement must be callable from several host threads at once:
     four threads solve different ensembles concurrently (ctypes drops the GIL), each result equals its solo run."""
