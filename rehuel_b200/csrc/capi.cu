@@ -119,9 +119,11 @@ LaunchFn launcher_dimer();
 LaunchFn launcher_kinetic4();
 LaunchFn launcher_bruss1d_64();
 LaunchFn launcher_bruss1d_8();
+LaunchFn launcher_bruss1d_32();
 LaunchFn launcher_bruss1d_16();
 LaunchFn launcher_bruss1d_dense_64();
 LaunchFn launcher_bruss1d_dense_8();
+LaunchFn launcher_bruss1d_dense_32();
 LaunchFn launcher_bruss1d_dense_16();
 
 EvalFn evaluator_robertson();
@@ -135,9 +137,11 @@ EvalFn evaluator_dimer();
 EvalFn evaluator_kinetic4();
 EvalFn evaluator_bruss1d_64();
 EvalFn evaluator_bruss1d_8();
+EvalFn evaluator_bruss1d_32();
 EvalFn evaluator_bruss1d_16();
 EvalFn evaluator_bruss1d_dense_64();
 EvalFn evaluator_bruss1d_dense_8();
+EvalFn evaluator_bruss1d_dense_32();
 EvalFn evaluator_bruss1d_dense_16();
 
 static LaunchFn find_launcher(int problem, int n)
@@ -145,9 +149,10 @@ static LaunchFn find_launcher(int problem, int n)
 	if (problem == REHUEL_PROBLEM_BRUSSELATOR_1D || problem == REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE) {
 		const bool dense = problem == REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE;
 		if (n == 64) return dense ? launcher_bruss1d_dense_64() : launcher_bruss1d_64();
+		if (n == 32) return dense ? launcher_bruss1d_dense_32() : launcher_bruss1d_32();
 		if (n == 16) return dense ? launcher_bruss1d_dense_16() : launcher_bruss1d_16();
 		if (n == 8) return dense ? launcher_bruss1d_dense_8() : launcher_bruss1d_8();
-		set_error(REHUEL_EINVAL, "brusselator-1d is built for n = 64, 16 and 8 (Ng = 32, 8, 4), got n = %d", n);
+		set_error(REHUEL_EINVAL, "brusselator-1d is built for n = 64, 32, 16 and 8 (Ng = 32, 16, 8, 4), got n = %d", n);
 		return nullptr;
 	}
 	switch (problem) {
@@ -177,9 +182,10 @@ static EvalFn find_evaluator(int problem, int n)
 	case REHUEL_PROBLEM_HARMONIC: return evaluator_harmonic();
 	case REHUEL_PROBLEM_DIMER: return evaluator_dimer();
 	case REHUEL_PROBLEM_KINETIC_4: return evaluator_kinetic4();
-	case REHUEL_PROBLEM_BRUSSELATOR_1D: return n == 64 ? evaluator_bruss1d_64() : (n == 16 ? evaluator_bruss1d_16() : (n == 8 ? evaluator_bruss1d_8() : nullptr));
+	case REHUEL_PROBLEM_BRUSSELATOR_1D: return n == 64 ? evaluator_bruss1d_64() : (n == 32 ? evaluator_bruss1d_32() : (n == 16 ? evaluator_bruss1d_16() : (n == 8 ? evaluator_bruss1d_8() : nullptr)));
 	case REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE:
-		return n == 64 ? evaluator_bruss1d_dense_64() : (n == 16 ? evaluator_bruss1d_dense_16() : (n == 8 ? evaluator_bruss1d_dense_8() : nullptr));
+		return n == 64 ? evaluator_bruss1d_dense_64()
+		               : (n == 32 ? evaluator_bruss1d_dense_32() : (n == 16 ? evaluator_bruss1d_dense_16() : (n == 8 ? evaluator_bruss1d_dense_8() : nullptr)));
 	}
 	return nullptr;
 }

@@ -365,7 +365,7 @@ __device__ __forceinline__ void lu_solve_cplx_warp(const double *Are, const doub
 }
 
 template <class F, int S, int NR, int NC, int EST, int THREADS, bool DENSE = false>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 1)
 ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ DevTableau<S, NC> tb)
 {
 	static_assert(S == NR + 2 * NC && NR <= 1, "eigen-structure");

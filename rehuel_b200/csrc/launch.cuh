@@ -58,6 +58,9 @@ int locality_order(const double *params, int p, size_t M, int descending, unsign
 			                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
 	} while (0)
 
+#ifndef REHUEL_CTA_SMALL_THREADS
+#define REHUEL_CTA_SMALL_THREADS 128
+#endif
 #ifndef REHUEL_BLOCK
 #define REHUEL_BLOCK 128
 #endif
@@ -213,7 +216,8 @@ int dispatch_method(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream
 template <class F, int S, int NR, int NC, int EST>
 int launch_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
 {
-	constexpr int THREADS = (F::N <= 16) ? 128 : 256;
+	// up to n = 32 a member's matrices take a quarter of an SM's shared memory: smaller blocks, several per SM
+	constexpr int THREADS = (F::N <= 32) ? REHUEL_CTA_SMALL_THREADS : 256;
 	void (*kern)(const KernelArgs, const DevTableau<S, NC>) = ensemble_irk_cta<F, S, NR, NC, EST, THREADS, false>;
 	if (ka.io.n_dense) {
 		if constexpr (EST != EST_IDENTITY) {

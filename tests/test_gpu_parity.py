@@ -800,6 +800,16 @@ def test_small_dense_systems_warp_per_system_register_lu(capi, port):
     leg2 = capi.to_output(capi.irk_ensemble_continue(capi.BRUSSELATOR_1D_DENSE, 211, 4.0, P, ok, leg1, n_hint=8))
     assert np.all(leg2.status == 0) and scaled_err(leg2.y, one.y, 1e-6, 1e-6).max() <= PARITY_BOUND
     capi.result_free(leg1)
+    # n = 32: too big for register rows -> CTA-per-system, 128-thread blocks, several members per SM
+    assert capi.kernel_info(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 32)["block"] == 128
+    P, y0 = ensembles.bruss1d_params(12), ensembles.bruss1d_y0(16)
+    for method, t1 in ((capi.RADAU_IIA_53, 4.0), (capi.LOBATTO_IIIC_85, 0.5)):
+        r = port.solve("brusselator-1d", method, 0.0, t1, 1e-6, y0, P, ro)
+        d = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, method, 0.0, t1, 1e-6, y0, P, o, n_hint=32)
+        b = capi.irk_ensemble(capi.BRUSSELATOR_1D, method, 0.0, t1, 1e-6, y0, P, o, n_hint=32)
+        assert np.all(d.status == 0) and np.all(b.status == 0)
+        assert scaled_err(d.y, r.y, 1e-6, 1e-6).max() <= PARITY_BOUND and scaled_err(b.y, r.y, 1e-6, 1e-6).max() <= PARITY_BOUND
+        assert int(d.counters["attempt"].sum()) == int(r.counters["attempt"].sum()) == int(b.counters["attempt"].sum())
     # a few thousand members: what the register LU buys over a CTA per member
     M = 4096
     P = ensembles.bruss1d_params(M)
