@@ -1,2 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q -k "small_dense or bruss" 2>&1 | tail -3
+mkdir -p gpurun_out
+nvidia-smi -L | wc -l
+python tools/config4_multi_gpu.py > gpurun_out/config4_multi_gpu.json 2> gpurun_out/config4_multi_gpu.err; cat gpurun_out/config4_multi_gpu.json; tail -3 gpurun_out/config4_multi_gpu.err
