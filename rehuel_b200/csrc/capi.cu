@@ -121,10 +121,12 @@ LaunchFn launcher_bruss1d_64();
 LaunchFn launcher_bruss1d_8();
 LaunchFn launcher_bruss1d_32();
 LaunchFn launcher_bruss1d_16();
+LaunchFn launcher_bruss1d_12();
 LaunchFn launcher_bruss1d_dense_64();
 LaunchFn launcher_bruss1d_dense_8();
 LaunchFn launcher_bruss1d_dense_32();
 LaunchFn launcher_bruss1d_dense_16();
+LaunchFn launcher_bruss1d_dense_12();
 
 EvalFn evaluator_robertson();
 EvalFn evaluator_van_der_pol();
@@ -139,10 +141,12 @@ EvalFn evaluator_bruss1d_64();
 EvalFn evaluator_bruss1d_8();
 EvalFn evaluator_bruss1d_32();
 EvalFn evaluator_bruss1d_16();
+EvalFn evaluator_bruss1d_12();
 EvalFn evaluator_bruss1d_dense_64();
 EvalFn evaluator_bruss1d_dense_8();
 EvalFn evaluator_bruss1d_dense_32();
 EvalFn evaluator_bruss1d_dense_16();
+EvalFn evaluator_bruss1d_dense_12();
 
 static LaunchFn find_launcher(int problem, int n)
 {
@@ -151,8 +155,9 @@ static LaunchFn find_launcher(int problem, int n)
 		if (n == 64) return dense ? launcher_bruss1d_dense_64() : launcher_bruss1d_64();
 		if (n == 32) return dense ? launcher_bruss1d_dense_32() : launcher_bruss1d_32();
 		if (n == 16) return dense ? launcher_bruss1d_dense_16() : launcher_bruss1d_16();
+		if (n == 12) return dense ? launcher_bruss1d_dense_12() : launcher_bruss1d_12();
 		if (n == 8) return dense ? launcher_bruss1d_dense_8() : launcher_bruss1d_8();
-		set_error(REHUEL_EINVAL, "brusselator-1d is built for n = 64, 32, 16 and 8 (Ng = 32, 16, 8, 4), got n = %d", n);
+		set_error(REHUEL_EINVAL, "brusselator-1d is built for n = 64, 32, 16, 12 and 8 (Ng = 32, 16, 8, 6, 4), got n = %d", n);
 		return nullptr;
 	}
 	switch (problem) {
@@ -182,10 +187,10 @@ static EvalFn find_evaluator(int problem, int n)
 	case REHUEL_PROBLEM_HARMONIC: return evaluator_harmonic();
 	case REHUEL_PROBLEM_DIMER: return evaluator_dimer();
 	case REHUEL_PROBLEM_KINETIC_4: return evaluator_kinetic4();
-	case REHUEL_PROBLEM_BRUSSELATOR_1D: return n == 64 ? evaluator_bruss1d_64() : (n == 32 ? evaluator_bruss1d_32() : (n == 16 ? evaluator_bruss1d_16() : (n == 8 ? evaluator_bruss1d_8() : nullptr)));
+	case REHUEL_PROBLEM_BRUSSELATOR_1D: return n == 64 ? evaluator_bruss1d_64() : (n == 32 ? evaluator_bruss1d_32() : (n == 16 ? evaluator_bruss1d_16() : (n == 12 ? evaluator_bruss1d_12() : (n == 8 ? evaluator_bruss1d_8() : nullptr))));
 	case REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE:
 		return n == 64 ? evaluator_bruss1d_dense_64()
-		               : (n == 32 ? evaluator_bruss1d_dense_32() : (n == 16 ? evaluator_bruss1d_dense_16() : (n == 8 ? evaluator_bruss1d_dense_8() : nullptr)));
+		               : (n == 32 ? evaluator_bruss1d_dense_32() : (n == 16 ? evaluator_bruss1d_dense_16() : (n == 12 ? evaluator_bruss1d_dense_12() : (n == 8 ? evaluator_bruss1d_dense_8() : nullptr))));
 	}
 	return nullptr;
 }

@@ -770,8 +770,9 @@ def test_small_dense_systems_warp_per_system_register_lu(capi, port):
     o, ro = capi.make_options(1e-6, 1e-6), ref_options(1e-6, 1e-6)
     assert capi.kernel_info(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 8)["block"] == 32
     assert capi.kernel_info(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 16)["block"] == 32
+    assert capi.kernel_info(capi.BRUSSELATOR_1D_DENSE, capi.RADAU_IIA_53, 12)["block"] == 32
     assert capi.kernel_info(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 64)["block"] == 256
-    for n in (8, 16):
+    for n in (8, 12, 16):  # 12: rows that do not fill their lane segment, band halves of 5 pivot rows
         M = 24
         P, y0 = ensembles.bruss1d_params(M), ensembles.bruss1d_y0(n // 2)
         for method, t1 in ((capi.RADAU_IIA_53, 10.0), (capi.LOBATTO_IIIC_43, 2.0), (capi.LOBATTO_IIIC_85, 1.0), (capi.RADAU_IIA_95, 4.0),
