@@ -28,6 +28,13 @@
 #include "irk_warp.cuh"
 #include "tableau.hpp"
 
+#ifndef REHUEL_WD_MINB8
+#define REHUEL_WD_MINB8 12
+#endif
+#ifndef REHUEL_WD_MINB16
+#define REHUEL_WD_MINB16 12
+#endif
+
 namespace rehuel {
 
 template <class F, int S, int NC, int EST>
@@ -142,7 +149,7 @@ __device__ __forceinline__ void wd_solve(const double (&ar)[N], const double (&a
 
 // ------------------------------------------------------------------ the kernel: one warp per block
 template <class F, int S, int NR, int NC, int EST, bool DENSE = false>
-__global__ void __launch_bounds__(32, 8)
+__global__ void __launch_bounds__(32, (F::N <= 8) ? REHUEL_WD_MINB8 : REHUEL_WD_MINB16)
 ensemble_irk_wdense(const __grid_constant__ KernelArgs a, const __grid_constant__ DevTableau<S, NC> tb)
 {
 	static_assert(S == NR + 2 * NC && NR <= 1, "eigen-structure");
