@@ -17,7 +17,7 @@ LIB       := rehuel_b200/librehuel_b200.so
 INST      := robertson van_der_pol exponential stiff_eq brusselator lorenz harmonic dimer kinetic4 \
              bruss1d_64 bruss1d_32 bruss1d_16 bruss1d_12 bruss1d_8 bruss1d_dense_64 bruss1d_dense_32 bruss1d_dense_16 bruss1d_dense_12 bruss1d_dense_8
 OBJS      := build/capi.o build/order.o build/selftest.o build/tableau.o $(INST:%=build/inst_%.o)
-KHDRS     := $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/irk_warp.cuh $(SRC)/irk_wdense.cuh $(SRC)/band_twisted.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh \
+KHDRS     := $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/irk_warp.cuh $(SRC)/irk_wdense.cuh $(SRC)/irk_wseg.cuh $(SRC)/band_twisted.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh \
              $(SRC)/tableau.hpp include/rehuel_b200.h
 
 .PHONY: all oracle clean sass examples tableaux

@@ -16,6 +16,7 @@
 #include "irk_thread.cuh"
 #include "irk_warp.cuh"
 #include "irk_wdense.cuh"
+#include "irk_wseg.cuh"
 #include "tableau.hpp"
 
 namespace rehuel {
@@ -348,14 +349,54 @@ int launch_wdense(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 	return REHUEL_OK;
 }
 
+// ---- segment-per-system path for the smallest dense systems (4 < n <= 8, four members per warp), irk_wseg.cuh
+template <class F, int S, int NR, int NC, int EST>
+int launch_wseg(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
+{
+	void (*kern)(const KernelArgs, const DevTableau<S, NC>) = ensemble_irk_wseg<F, S, NR, NC, EST>;
+	const size_t smem = WsSmem<F, S>::bytes;
+	if (tb.s != S || tb.n_real != NR || tb.n_cplx != NC || tb.est_mode != EST)
+		return set_error(REHUEL_EINVAL, "internal: tableau %s does not have the structure its kernel was built for", tb.name);
+	int dev = 0, sms = 0, per_sm = 0;
+	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
+	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	REHUEL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+	if (per_sm < 1) return set_error(REHUEL_ECUDA, "segment-per-system kernel does not fit on an SM");
+	if (info) {
+		cudaFuncAttributes fa;
+		REHUEL_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+		info->regs = fa.numRegs;
+		info->local_bytes = (int)fa.localSizeBytes;
+		info->smem_bytes = (int)smem;
+		info->ctas_per_sm = per_sm;
+		info->block = 32;
+		return REHUEL_OK;
+	}
+	if (ka.M == 0) return REHUEL_OK;
+	if (ka.io.rtol) return set_error(REHUEL_EINVAL, "per-member tolerances are not built for the warp-per-system kernels");
+	const unsigned long long want = (ka.M + 3) / 4, cap = (unsigned long long)sms * per_sm;
+	unsigned grid = (unsigned)(want < cap ? want : cap);
+	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
+	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	kern<<<grid, 32, smem, stream>>>(ka, dtb);
+	REHUEL_CUDA_TRY(cudaGetLastError());
+	count_launch();
+	return REHUEL_OK;
+}
+
 // 4 < n <= 64: banded functors (kBand <= 4) go warp-per-system with band factors in shared memory, small dense
-// systems (n <= 16) warp-per-system with the matrices in registers, everything else CTA-per-system
+// systems (n <= 16) warp-per-system with the matrices in registers (n <= 8: four members per warp), everything else
+// CTA-per-system
 template <class F, int S, int NR, int NC, int EST>
 int launch_block(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, KernelInfo *info)
 {
 	constexpr int KB = jac_band<F>::value;
 	if constexpr (KB <= 4 && F::N >= 2 * KB + 2) {
 		return launch_warp<F, S, NR, NC, EST>(ka, tb, stream, info);
+	} else if constexpr (F::N <= 8) {
+		// four members per warp; dense output and stored samples are only built into the one-member-per-warp kernel
+		if (ka.io.n_dense || (ka.store_samples && ka.io.n_samples_cap)) return launch_wdense<F, S, NR, NC, EST>(ka, tb, stream, info);
+		return launch_wseg<F, S, NR, NC, EST>(ka, tb, stream, info);
 	} else if constexpr (F::N <= 16) {
 		return launch_wdense<F, S, NR, NC, EST>(ka, tb, stream, info);
 	} else {

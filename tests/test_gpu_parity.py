@@ -801,6 +801,28 @@ def test_small_dense_systems_warp_per_system_register_lu(capi, port):
     leg2 = capi.to_output(capi.irk_ensemble_continue(capi.BRUSSELATOR_1D_DENSE, 211, 4.0, P, ok, leg1, n_hint=8))
     assert np.all(leg2.status == 0) and scaled_err(leg2.y, one.y, 1e-6, 1e-6).max() <= PARITY_BOUND
     capi.result_free(leg1)
+    # n <= 8 runs FOUR members per warp in lockstep (irk_wseg.cuh); a call that stores samples takes the one-member-per-warp
+    # kernel (irk_wdense.cuh): the same steps (the real blocks go through a real-only LU there, so the last bits may differ),
+    # and inside one kernel a member's result must not depend on its neighbours or on the member count
+    P, y0 = ensembles.bruss1d_params(23), ensembles.bruss1d_y0(4)
+    for method, t1 in ((capi.RADAU_IIA_53, 6.0), (capi.LOBATTO_IIIC_85, 0.5), (capi.LOBATTO_IIIC_43, 1.0), (capi.RADAU_IIA_32, 0.5)):
+        four = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, method, 0.0, t1, 1e-6, y0, P, o, n_hint=8)
+        one = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, method, 0.0, t1, 1e-6, y0, P, o, n_hint=8, n_samples_cap=2)
+        assert np.all(four.status == 0) and np.allclose(four.y, one.y, rtol=1e-10, atol=0.0) and np.array_equal(four.t_final, one.t_final)
+        for k in four.counters:
+            assert np.array_equal(four.counters[k], one.counters[k]), (method, k)
+        for m in (1, 3, 5):
+            part = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, method, 0.0, t1, 1e-6, y0, P[:, 7:7 + m].copy(), o, n_hint=8)
+            assert np.array_equal(part.y, four.y[:, 7:7 + m]) and np.array_equal(part.counters["attempt"], four.counters["attempt"][7:7 + m])
+    # ... with a member that fails (max_steps) next to members that go on, and in fixed-step mode
+    om = capi.make_options(1e-6, 1e-6, max_steps=20)
+    gm = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, 211, 0.0, 6.0, 1e-6, y0, P, om, n_hint=8)
+    gw = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, 211, 0.0, 6.0, 1e-6, y0, P, om, n_hint=8, n_samples_cap=2)
+    assert np.array_equal(gm.status, gw.status) and np.allclose(gm.y, gw.y, rtol=1e-10, atol=0.0) and np.allclose(gm.t_final, gw.t_final, rtol=1e-12) and gm.status.max() != 0
+    of = capi.make_options(1e-6, 1e-6, adaptive=False)
+    gf = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, 211, 0.0, 0.01, 1e-4, y0, P, of, n_hint=8)
+    gfw = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, 211, 0.0, 0.01, 1e-4, y0, P, of, n_hint=8, n_samples_cap=2)
+    assert np.all(gf.status == 0) and np.allclose(gf.y, gfw.y, rtol=1e-10, atol=0.0) and np.array_equal(gf.counters["attempt"], gfw.counters["attempt"]) and gf.counters["attempt"].min() >= 100
     # n = 32: too big for register rows -> CTA-per-system, 128-thread blocks, several members per SM
     assert capi.kernel_info(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 32)["block"] == 128
     P, y0 = ensembles.bruss1d_params(12), ensembles.bruss1d_y0(16)
