@@ -1,20 +1,22 @@
-// Segment-per-system ensemble integrator for the SMALLEST dense systems beyond the thread kernel (4 < n <= 8):
-// FOUR members share a warp, each in its own segment of 8 lanes, persistent warps pull members from the global queue.
+// Segment-per-system ensemble integrator for the SMALLEST dense systems beyond the thread kernel: FOUR members
+// (4 < n <= 8) or TWO (8 < n <= 16, three-stage methods) share a warp, each in its own segment of 8 or 16 lanes;
+// persistent warps pull members from the global queue.
 //
 // Same algorithm, statement for statement, as the other kernels (irk_thread.cuh, irk_warp.cuh, irk_wdense.cuh,
 // irk_cta.cuh) and hence as the reference loop irk.hpp:604-860 / newton_solve_stages irk.hpp:398-493; the linear
 // algebra is irk_wdense.cuh's (a matrix lives in the registers of its segment, row i on lane i of the segment, LU
 // and solves by segmented shuffles).  What changes is who sits next to whom: in irk_wdense.cuh the 2..4 matrices of
-// ONE member sit side by side and the componentwise work (stage functions, transforms, norms) uses 8 of 32 lanes;
-// here the same matrix of FOUR members sits side by side and every phase uses the whole warp (real matrices go
+// ONE member sit side by side and the componentwise work (stage functions, transforms, norms) uses n of 32 lanes;
+// here the same matrix of the four (two) members sits side by side and every phase uses the whole warp (real matrices go
 // through a real-only routine, since a pass holds one kind of matrix).
 //
-// The four members advance in LOCKSTEP, one attempt per trip of the outer loop, like the lanes of the thread
+// The members of a warp advance in LOCKSTEP, one attempt per trip of the outer loop, like the lanes of the thread
 // kernel: every collective step (shuffles, __syncwarp) is executed by all lanes, a segment that has nothing to do in
 // it (no member left, Newton iteration already converged, attempt failed) is switched off by a predicate, and a
 // segment whose member is finished writes its results and takes the next member from the queue.  The Newton loop
-// runs until the slowest of the four has converged (or hit maxit).  Results are those of the single-member kernels
-// bit for bit: which lanes integrate a member does not enter the arithmetic.
+// runs until the slowest of them has converged (or hit maxit).  Which lanes integrate a member, and next to whom,
+// does not enter the arithmetic: a member's result is bit-identical wherever it runs in this kernel, and equal to
+// irk_wdense.cuh's up to the rounding of the real-only LU.
 //
 // Not built here (launch.cuh routes those calls to irk_wdense.cuh): dense output, stored trajectory samples.
 #pragma once
@@ -32,8 +34,8 @@ namespace rehuel {
 template <class F, int S>
 struct WsSmem {
 	static constexpr int N = F::N;
-	static_assert(N > 4 && N <= 8, "one member per segment of 8 lanes");
-	static constexpr int SEG = 8, MPW = 4;
+	static_assert(N > 4 && N <= 16, "one member per segment of 8 or 16 lanes");
+	static constexpr int SEG = (N <= 8) ? 8 : 16, MPW = 32 / SEG;
 	static constexpr int PA = ((F::P > 0 ? F::P : 1) + 1) & ~1;
 	static constexpr int o_y = 0;
 	static constexpr int o_p = o_y + N;
@@ -99,14 +101,15 @@ __device__ __forceinline__ void wd_solve_real(const double (&ar)[N], int rsrc, d
 	if (mine) x[wi] = v;
 }
 
-__device__ __forceinline__ double seg8_sum(double v)
+template <int SEG>
+__device__ __forceinline__ double seg_sum(double v)
 {
 #pragma unroll
-	for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 8);
+	for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, SEG);
 	return v;
 }
 
-// ------------------------------------------------------------------ the kernel: one warp per block, four members per warp
+// ------------------------------------------------------------------ the kernel: one warp per block, 32/SEG members per warp
 template <class F, int S, int NR, int NC, int EST>
 __global__ void __launch_bounds__(32, 10)
 ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ DevTableau<S, NC> tb)
@@ -114,16 +117,16 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 	static_assert(S == NR + 2 * NC && NR <= 1, "eigen-structure");
 	static_assert(EST != EST_REUSE || NR == 1, "E's factors are the real Newton block's");
 	using L = WsSmem<F, S>;
-	constexpr int N = F::N, SEG = 8, NCA = NC > 0 ? NC : 1;
+	constexpr int N = F::N, SEG = L::SEG, NCA = NC > 0 ? NC : 1;
 	constexpr unsigned FULLM = 0xffffffffu;
 	extern __shared__ double sm[];
-	const int lane = threadIdx.x, seg = lane >> 3, wi = lane & 7;
+	const int lane = threadIdx.x, seg = lane / SEG, wi = lane % SEG;
 	double *y = sm + seg * L::stride + L::o_y, *par = sm + seg * L::stride + L::o_p, *work = sm + seg * L::stride + L::o_w;
 	const bool row = wi < N; // this lane owns component wi of its member and row wi of its matrices
 	const unsigned long long M = a.M;
 	const rehuel_device_io &io = a.io;
 
-	// ---- per-member state, identical in the 8 lanes of a segment
+	// ---- per-member state, identical in the lanes of a segment
 	bool has = false, exhausted = false;
 	unsigned long long mem = 0;
 	double yr = 0.0; // y, component wi; the shared copy is for the other lanes (f and J couple components)
@@ -155,7 +158,7 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 					yr = row ? (io.y0_broadcast ? io.y0[wi] : io.y0[wi * M + mem]) : 0.0;
 					if (row) y[wi] = yr;
 					if (wi < F::P) par[wi] = io.params[wi * M + mem];
-					static_assert(F::P <= 8, "parameters are loaded by the lanes of the segment");
+					static_assert(F::P <= SEG, "parameters are loaded by the lanes of the segment");
 					t = io.t_start ? io.t_start[mem] : a.t0;
 					dt = a.dt0;
 					if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
@@ -253,7 +256,7 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 				Rr[s] = r;
 				r2 = fma(r, r, r2);
 			}
-			return seg8_sum(r2);
+			return seg_sum<SEG>(r2);
 		};
 #pragma unroll
 		for (int s = 0; s < S; ++s) Yr[s] = 0.0; // irk.hpp:415
@@ -295,7 +298,7 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 				x2 = fma(acc, acc, x2);
 				if (iter) Yr[s] += acc;
 			}
-			const double xnorm2 = seg8_sum(x2); // irk.hpp:466
+			const double xnorm2 = seg_sum<SEG>(x2); // irk.hpp:466
 			if (iter && REHUEL_SKIP_DEAD_RESIDUAL && xnorm2 < a.xtol2) { // the residual of irk.hpp:469-472 would never be looked at
 				c_fun += S;                                               // (see irk_thread.cuh); its evaluations are booked
 				nstat = kNewtonSuccess;
@@ -395,7 +398,7 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 		{ // irk.hpp:733-746
 			const double sc = fma(a.rtol, fmax(fabs(yr), fabs(yn)), a.atol);
 			const double q = row ? ev / sc : 0.0;
-			tot = seg8_sum(q * q);
+			tot = seg_sum<SEG>(q * q);
 		}
 		if (ok) {
 			err = sqrt(tot / (double)N);

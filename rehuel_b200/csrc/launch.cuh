@@ -374,7 +374,8 @@ int launch_wseg(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ke
 	}
 	if (ka.M == 0) return REHUEL_OK;
 	if (ka.io.rtol) return set_error(REHUEL_EINVAL, "per-member tolerances are not built for the warp-per-system kernels");
-	const unsigned long long want = (ka.M + 3) / 4, cap = (unsigned long long)sms * per_sm;
+	constexpr unsigned long long MPW = WsSmem<F, S>::MPW;
+	const unsigned long long want = (ka.M + MPW - 1) / MPW, cap = (unsigned long long)sms * per_sm;
 	unsigned grid = (unsigned)(want < cap ? want : cap);
 	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
 	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
@@ -394,7 +395,9 @@ int launch_block(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, K
 	if constexpr (KB <= 4 && F::N >= 2 * KB + 2) {
 		return launch_warp<F, S, NR, NC, EST>(ka, tb, stream, info);
 	} else if constexpr (F::N <= 8) {
-		// four members per warp; dense output and stored samples are only built into the one-member-per-warp kernel
+		// four members per warp (two per warp at 8 < n <= 16 was measured and buys nothing: there the matrices of ONE
+		// member already fill the warp in irk_wdense.cuh); dense output and stored samples are only built into the
+		// one-member-per-warp kernel
 		if (ka.io.n_dense || (ka.store_samples && ka.io.n_samples_cap)) return launch_wdense<F, S, NR, NC, EST>(ka, tb, stream, info);
 		return launch_wseg<F, S, NR, NC, EST>(ka, tb, stream, info);
 	} else if constexpr (F::N <= 16) {
