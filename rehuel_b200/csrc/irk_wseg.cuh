@@ -1,6 +1,8 @@
-// Segment-per-system ensemble integrator for the SMALLEST dense systems beyond the thread kernel: FOUR members
-// (4 < n <= 8) or TWO (8 < n <= 16, three-stage methods) share a warp, each in its own segment of 8 or 16 lanes;
-// persistent warps pull members from the global queue.
+// Segment-per-system ensemble integrator for the SMALLEST dense systems beyond the thread kernel (4 < n <= 8): FOUR
+// members share a warp, each in its own segment of 8 lanes; persistent warps pull members from the global queue.
+// (The segment width is a template parameter: two members per warp in 16-lane segments work as well, but at
+// 8 < n <= 16 the matrices of one member already fill the warp in irk_wdense.cuh and nothing is gained, so
+// launch.cuh only routes n <= 8 here.)
 //
 // Same algorithm, statement for statement, as the other kernels (irk_thread.cuh, irk_warp.cuh, irk_wdense.cuh,
 // irk_cta.cuh) and hence as the reference loop irk.hpp:604-860 / newton_solve_stages irk.hpp:398-493; the linear

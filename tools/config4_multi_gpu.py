@@ -14,7 +14,7 @@ out, base = {"members": M}, None
 for g in (1, 2, 4, 8):
     if g > torch.cuda.device_count():
         break
-    capi.irk_ensemble(capi.BRUSSELATOR_1D, 232, 0.0, 0.05, 1e-6, y0, P[:, :4096].copy(), o, n_gpus=g, n_hint=64)  # warm-up: contexts, pools
+    capi.irk_ensemble(capi.BRUSSELATOR_1D, 232, 0.0, 0.02, 1e-6, y0, P, o, n_gpus=g, n_hint=64)  # warm-up at full size: contexts, pools, cached slabs
     t = time.perf_counter()
     r = capi.irk_ensemble(capi.BRUSSELATOR_1D, 232, 0.0, 10.0, 1e-6, y0, P, o, n_gpus=g, n_hint=64)
     wall = (time.perf_counter() - t) * 1e3
