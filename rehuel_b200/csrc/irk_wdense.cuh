@@ -28,6 +28,9 @@
 #include "irk_warp.cuh"
 #include "tableau.hpp"
 
+#ifndef REHUEL_WD_ROLLED
+#define REHUEL_WD_ROLLED 1
+#endif
 #ifndef REHUEL_WD_MINB8
 #define REHUEL_WD_MINB8 12
 #endif
@@ -107,6 +110,106 @@ __device__ __forceinline__ void wd_factor(double (&ar)[N], double (&ai)[N], bool
 			ar[j] = fma(-lr, ur, fma(li, ui, ar[j])); // lr = li = 0 on the rows that take no part
 			ai[j] = fma(-lr, ui, fma(-li, ur, ai[j]));
 		}
+	}
+}
+
+// The same factorisation as a ROLLED loop.  Static register indexing forces wd_factor to unroll its N steps, and the
+// kernels built on it are straight-line code that every warp streams through once per attempt: ncu shows them bound
+// by instruction FETCH (`no_instruction` 2.3 - 3.7 stalls per issue at 32 - 40 % issue-slot use), not by arithmetic.
+// Here the register row is ROTATED by one slot per step, so that the pivot column always sits in slot 0 and column
+// k + j in slot j: one loop body serves every step (N times less code for the LU), at the price of 2N register moves
+// per step and plane; after N steps the row is back in place, packed exactly like wd_factor's.  Same operations on
+// the same numbers, so the factors are bit-identical.  Measured (n = 16, one member per warp): RADAU_IIA_53 40 -> 23.5 ms
+// per 16 384 members; LOBATTO_IIIC_85, where four matrices make the LU the bulk of the executed instructions and the
+// kernel spills, 77 -> 101 ms -- so the kernels roll the LU for the methods with up to three stages only.
+template <int N, int SEG>
+__device__ __forceinline__ void wd_factor_rolled(double (&ar)[N], double (&ai)[N], bool active, int &rsrc)
+{
+	const int wi = threadIdx.x % SEG;
+	rsrc = wi;
+#pragma unroll 1
+	for (int k = 0; k < N; ++k) {
+		double v = (active && wi >= k && wi < N) ? fabs(ar[0]) + fabs(ai[0]) : -1.0;
+		int bi = wi;
+#pragma unroll
+		for (int o = SEG / 2; o > 0; o >>= 1) {
+			const double ov = __shfl_xor_sync(0xffffffffu, v, o, SEG);
+			const int oi = __shfl_xor_sync(0xffffffffu, bi, o, SEG);
+			if (ov > v || (ov == v && oi < bi)) {
+				v = ov;
+				bi = oi;
+			}
+		}
+		const int p = active ? bi : k;
+		if (__any_sync(0xffffffffu, p != k)) { // every lane holds the same rotation, so whole rows can still be exchanged
+			const int src = (wi == k) ? p : (wi == p ? k : wi);
+#pragma unroll
+			for (int j = 0; j < N; ++j) {
+				ar[j] = __shfl_sync(0xffffffffu, ar[j], src, SEG);
+				ai[j] = __shfl_sync(0xffffffffu, ai[j], src, SEG);
+			}
+			rsrc = __shfl_sync(0xffffffffu, rsrc, src, SEG);
+		}
+		const double pr = __shfl_sync(0xffffffffu, ar[0], k, SEG), pi = __shfl_sync(0xffffffffu, ai[0], k, SEG);
+		const double rden = fast_rcp(fma(pr, pr, pi * pi));
+		const double rr = pr * rden, ri = -pi * rden;
+		const bool below = wi > k && wi < N;
+		const double lr = below ? fma(ar[0], rr, -ai[0] * ri) : 0.0;
+		const double li = below ? fma(ar[0], ri, ai[0] * rr) : 0.0;
+		const double kr = below ? lr : (wi == k ? rr : ar[0]), ki = below ? li : (wi == k ? ri : ai[0]); // column k as it is kept
+#pragma unroll
+		for (int j = 1; j < N; ++j) {
+			if (j < N - k) { // warp-uniform: slot j holds column k + j
+				const double ur = __shfl_sync(0xffffffffu, ar[j], k, SEG), ui = __shfl_sync(0xffffffffu, ai[j], k, SEG);
+				ar[j] = fma(-lr, ur, fma(li, ui, ar[j]));
+				ai[j] = fma(-lr, ui, fma(-li, ur, ai[j]));
+			}
+		}
+#pragma unroll
+		for (int j = 0; j + 1 < N; ++j) {
+			ar[j] = ar[j + 1];
+			ai[j] = ai[j + 1];
+		}
+		ar[N - 1] = kr;
+		ai[N - 1] = ki;
+	}
+}
+
+template <int N, int SEG>
+__device__ __forceinline__ void wd_factor_real_rolled(double (&ar)[N], bool active, int &rsrc)
+{
+	const int wi = threadIdx.x % SEG;
+	rsrc = wi;
+#pragma unroll 1
+	for (int k = 0; k < N; ++k) {
+		double v = (active && wi >= k && wi < N) ? fabs(ar[0]) : -1.0;
+		int bi = wi;
+#pragma unroll
+		for (int o = SEG / 2; o > 0; o >>= 1) {
+			const double ov = __shfl_xor_sync(0xffffffffu, v, o, SEG);
+			const int oi = __shfl_xor_sync(0xffffffffu, bi, o, SEG);
+			if (ov > v || (ov == v && oi < bi)) {
+				v = ov;
+				bi = oi;
+			}
+		}
+		const int p = active ? bi : k;
+		if (__any_sync(0xffffffffu, p != k)) {
+			const int src = (wi == k) ? p : (wi == p ? k : wi);
+#pragma unroll
+			for (int j = 0; j < N; ++j) ar[j] = __shfl_sync(0xffffffffu, ar[j], src, SEG);
+			rsrc = __shfl_sync(0xffffffffu, rsrc, src, SEG);
+		}
+		const double rr = fast_rcp(__shfl_sync(0xffffffffu, ar[0], k, SEG));
+		const bool below = wi > k && wi < N;
+		const double l = below ? ar[0] * rr : 0.0;
+		const double kr = below ? l : (wi == k ? rr : ar[0]);
+#pragma unroll
+		for (int j = 1; j < N; ++j)
+			if (j < N - k) ar[j] = fma(-l, __shfl_sync(0xffffffffu, ar[j], k, SEG), ar[j]);
+#pragma unroll
+		for (int j = 0; j + 1 < N; ++j) ar[j] = ar[j + 1];
+		ar[N - 1] = kr;
 	}
 }
 
@@ -324,7 +427,10 @@ ensemble_irk_wdense(const __grid_constant__ KernelArgs a, const __grid_constant_
 			++c_jac;
 			// -------- all factorisations: NSEG matrices side by side per pass, row partial pivoting (LAPACK's choice)
 #pragma unroll
-			for (int ps = 0; ps < PASSES; ++ps) wd_factor<N, SEG>(fr[ps], fi[ps], m_type[ps] != M_NONE, rsrc[ps]);
+			for (int ps = 0; ps < PASSES; ++ps) {
+				if (REHUEL_WD_ROLLED && S <= 3) wd_factor_rolled<N, SEG>(fr[ps], fi[ps], m_type[ps] != M_NONE, rsrc[ps]);
+				else wd_factor<N, SEG>(fr[ps], fi[ps], m_type[ps] != M_NONE, rsrc[ps]);
+			}
 
 			// -------- simplified Newton (irk.hpp:398-493)
 #pragma unroll

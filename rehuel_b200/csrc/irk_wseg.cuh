@@ -231,10 +231,17 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			}
 		}
 		if (on) ++c_jac;
-		if (NR) wd_factor_real<N, SEG>(ar, on, rs_r);
+		if (REHUEL_WD_ROLLED && S <= 3) { // rolled loops over rotating register rows (see wd_factor_rolled)
+			if (NR) wd_factor_real_rolled<N, SEG>(ar, on, rs_r);
 #pragma unroll
-		for (int c = 0; c < NC; ++c) wd_factor<N, SEG>(cr[c], ci[c], on, rs_c[c]);
-		if (EST == EST_OWN_LU) wd_factor_real<N, SEG>(er, on, rs_e);
+			for (int c = 0; c < NC; ++c) wd_factor_rolled<N, SEG>(cr[c], ci[c], on, rs_c[c]);
+			if (EST == EST_OWN_LU) wd_factor_real_rolled<N, SEG>(er, on, rs_e);
+		} else {
+			if (NR) wd_factor_real<N, SEG>(ar, on, rs_r);
+#pragma unroll
+			for (int c = 0; c < NC; ++c) wd_factor<N, SEG>(cr[c], ci[c], on, rs_c[c]);
+			if (EST == EST_OWN_LU) wd_factor_real<N, SEG>(er, on, rs_e);
+		}
 
 		// -------- simplified Newton (irk.hpp:398-493), the four members in lockstep
 		double Yr[S], Rr[S];
