@@ -100,6 +100,25 @@ def host_cores() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+_JSON_OUT = None
+
+
+def claim_stdout() -> None:
+    """stdout carries the ONE JSON line and nothing else: file descriptor 1 is pointed at stderr for the rest of
+    the process (NCCL writes its version banner to fd 1 from C, below Python's sys.stdout) and the line goes to a
+    duplicate of the original descriptor."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -124,7 +143,7 @@ def run_reference_arm(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -218,8 +237,6 @@ def run_gpu_arm(args) -> None:
     numa_note = bind_to_gpu_numa_node(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the ONE JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
 
@@ -371,7 +388,7 @@ def run_gpu_arm(args) -> None:
                       "max_attempts": tot["max_attempt"], "mass_conservation_max_abs_err_rank0": mass_err,
                       "step_ms": step_ms, "kernel_ms": kernel_ms},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -389,6 +406,7 @@ def main() -> None:
                     help="order in which members are handed to the GPU lanes (results do not depend on it)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
