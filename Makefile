@@ -14,7 +14,7 @@ NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC
              --expt-relaxed-constexpr -Xptxas -v
 SRC       := rehuel_b200/csrc
 LIB       := rehuel_b200/librehuel_b200.so
-INST      := robertson van_der_pol exponential stiff_eq brusselator lorenz harmonic dimer kinetic4 \
+INST      := robertson van_der_pol exponential stiff_eq brusselator lorenz harmonic dimer kinetic4 three_body \
              bruss1d_64 bruss1d_32 bruss1d_16 bruss1d_12 bruss1d_8 bruss1d_dense_64 bruss1d_dense_32 bruss1d_dense_16 bruss1d_dense_12 bruss1d_dense_8
 OBJS      := build/capi.o build/order.o build/selftest.o build/tableau.o $(INST:%=build/inst_%.o)
 KHDRS     := $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/irk_warp.cuh $(SRC)/irk_wdense.cuh $(SRC)/irk_wseg.cuh $(SRC)/band_twisted.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh \

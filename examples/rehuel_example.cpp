@@ -42,6 +42,7 @@ const equation kEquations[] = {
     {"harmonic", {1.0}, {0.0, 1.0}, 0},
     {"dimer", {1.0}, {1.0, 0.0}, 0},
     {"kinetic-4", {0.5, 0.3, 0.2}, {1.0, 0.0, 0.0, 0.0}, 0},
+    {"three-body", {1.0, 1.0, 1.0}, {1.0, 0.0, 3.0, 2.0, 0.0, 3.0, 0.0, 2.0, -1.0, 0.0, -1.0, 0.0}, 0}, // example_equations.cpp:341-343
     {"brusselator-1d", {0.02, 1.0, 3.0}, {}, 64},
 };
 
@@ -66,7 +67,7 @@ void print_usage()
 	             "                 [--param <value>]... [--dense <K> <dt>] [--max-samples <rows>]\n"
 	             "with\n"
 	             "\t<equation>: exponential, stiff-equation, robertson, van-der-pol, brusselator, lorenz,\n"
-	             "\t            harmonic, dimer, kinetic-4, brusselator-1d\n"
+	             "\t            harmonic, dimer, kinetic-4, three-body, brusselator-1d\n"
 	             "\t<method>:   IMPLICIT_EULER, RADAU_IIA_32/53/95/137, LOBATTO_IIIC_43/64/85 (default LOBATTO_IIIC_85)\n"
 	             "\t<M>:        number of ensemble members; member i gets parameter_j * 10^(sweep*(u_ij - 1/2))\n";
 }

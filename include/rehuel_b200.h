@@ -63,6 +63,7 @@ extern "C" {
 #define REHUEL_PROBLEM_HARMONIC       9 /* n=2, params (w);        test_equations.hpp:63-84 */
 #define REHUEL_PROBLEM_DIMER         10 /* n=2, params (rate);     test_equations.hpp:180-203 */
 #define REHUEL_PROBLEM_KINETIC_4     11 /* n=4, params (b2,b3,b4); test_equations.hpp:484-517 */
+#define REHUEL_PROBLEM_THREE_BODY    12 /* n=12, params (m1,m2,m3); test_equations.hpp:254-421, fun and jac as written there */
 
 /* Solver options.  Replaces irk::solver_options (irk.hpp:95-124) : common_solver_options
  * (options.hpp:40-85), the newton::options it points to (newton.hpp:57-78; only tol, dx_delta,
@@ -119,7 +120,7 @@ int rehuel_name_to_method(const char *name);
 const char *rehuel_method_to_name(int method);
 
 /* Problem registry ("robertson", "van-der-pol", "brusselator-1d", "brusselator-1d-dense", "exponential",
- * "stiff-equation", "brusselator", "lorenz", "harmonic", "dimer", "kinetic-4").  Unknown -> 0. */
+ * "stiff-equation", "brusselator", "lorenz", "harmonic", "dimer", "kinetic-4", "three-body").  Unknown -> 0. */
 int rehuel_name_to_problem(const char *name);
 /* n = number of equations, p = number of parameters.  n_hint selects n for size-generic
  * problems (brusselator-1d: n = 2*Ng), ignored otherwise.  Returns REHUEL_EINVAL if unknown. */

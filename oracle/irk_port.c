@@ -245,7 +245,7 @@ static void inv_transpose_times(const tableau *tb, const double *w, double *d)
 /* ------------------------------------------------------------------ problems (functor concept) */
 enum { REF_ROBERTSON = 1, REF_VDPOL = 2, REF_BRUSS1D = 3, REF_ROBER_HARDCODED = 4,
        REF_EXPONENTIAL = 5, REF_STIFF_EQ = 6, REF_BRUSS2 = 7, REF_LORENZ = 8, REF_HARMONIC = 9, REF_DIMER = 10,
-       REF_KINETIC4 = 11 };
+       REF_KINETIC4 = 11, REF_THREE_BODY = 12 };
 
 typedef struct {
 	int id, n;
@@ -314,6 +314,26 @@ static void fun(const problem *pr, double t, const double *y, double *f)
 		f[1] = y[0]*y[0] - y[0]*y[1] + b3*y[2] - b2*y[1];
 		f[2] = y[0]*y[1] - y[0]*y[2] + b4*y[3] - b3*y[2];
 		f[3] = y[0]*y[2] - b4*y[3];
+		break;
+	}
+	case REF_THREE_BODY: { /* test_equations.hpp:263-302, as written (dydt[9] uses x3mx2) */
+		const double m1 = pr->p[0], m2 = pr->p[1], m3 = pr->p[2];
+		f[0] = y[6] / m1; f[1] = y[7] / m1;
+		f[2] = y[8] / m2; f[3] = y[9] / m2;
+		f[4] = y[10] / m3; f[5] = y[11] / m3;
+		double x2mx1 = y[2] - y[0], y2my1 = y[3] - y[1];
+		double x3mx1 = y[4] - y[0], y3my1 = y[5] - y[1];
+		double x3mx2 = y[4] - y[2], y3my2 = y[5] - y[3];
+		double r12_2 = x2mx1*x2mx1 + y2my1*y2my1;
+		double r13_2 = x3mx1*x3mx1 + y3my1*y3my1;
+		double r23_2 = x3mx2*x3mx2 + y3my2*y3my2;
+		double r12_3 = r12_2*sqrt(r12_2), r13_3 = r13_2*sqrt(r13_2), r23_3 = r23_2*sqrt(r23_2);
+		f[6]  =  m1*m3*x3mx1 / r13_3 + m1*m2*x2mx1 / r12_3;
+		f[7]  =  m1*m3*y3my1 / r13_3 + m1*m2*y2my1 / r12_3;
+		f[8]  = -m1*m2*x2mx1 / r12_3 + m2*m3*x3mx2 / r23_3;
+		f[9]  = -m1*m2*y2my1 / r12_3 + m2*m3*x3mx2 / r23_3;
+		f[10] = -m2*m3*x3mx2 / r23_3 - m1*m3*x3mx1 / r13_3;
+		f[11] = -m2*m3*y3my2 / r23_3 - m1*m3*y3my1 / r13_3;
 		break;
 	}
 	case REF_BRUSS1D: { /* ours; twin of bruss1d in ref_driver.cpp */
@@ -396,6 +416,46 @@ static void jac(const problem *pr, double t, const double *y, double *J)
 		AT(J,n,3,0) = y[2]; AT(J,n,3,1) = 0; AT(J,n,3,2) = y[0]; AT(J,n,3,3) = -b4;
 		break;
 	}
+	case REF_THREE_BODY: { /* test_equations.hpp:304-421, as written: the function returns -J of this matrix */
+		const double m1 = pr->p[0], m2 = pr->p[1], m3 = pr->p[2];
+		double x2mx1 = y[2] - y[0], y2my1 = y[3] - y[1];
+		double x3mx1 = y[4] - y[0], y3my1 = y[5] - y[1];
+		double x3mx2 = y[4] - y[2], y3my2 = y[5] - y[3];
+		double x2mx1_2 = x2mx1*x2mx1, y2my1_2 = y2my1*y2my1;
+		double x3mx1_2 = x3mx1*x3mx1, y3my1_2 = y3my1*y3my1;
+		double x3mx2_2 = x3mx2*x3mx2, y3my2_2 = y3my2*y3my2;
+		double r12_2 = x2mx1_2 + y2my1_2, r13_2 = x3mx1_2 + y3my1_2, r23_2 = x3mx2_2 + y3my2_2;
+		double r12_3 = r12_2*sqrt(r12_2), r13_3 = r13_2*sqrt(r13_2), r23_3 = r23_2*sqrt(r23_2);
+		double r12_5 = r12_3*r12_2, r13_5 = r13_3*r13_2, r23_5 = r23_3*r23_2;
+		AT(J,n, 6, 6) = -m1*m3 / r13_3 + 3*m1*m3*x3mx1_2 / r13_5 - m1*m2 / r12_3 + 3*m1*m2*x2mx1_2 / r12_5;
+		AT(J,n, 8, 8) = -m2*m3 / r23_3 + 3*m2*m3*x3mx2_2 / r23_5 - m1*m2 / r12_3 + 3*m1*m2*x2mx1_2 / r12_5;
+		AT(J,n,10,10) = -m1*m3 / r13_3 + 3*m1*m3*x3mx1_2 / r13_5 - m2*m3 / r23_3 + 3*m2*m3*x3mx2_2 / r23_5;
+		AT(J,n, 7, 7) = -m1*m3 / r13_3 + 3*m1*m3*y3my1_2 / r13_5 - m1*m2 / r12_3 + 3*m1*m2*y2my1_2 / r12_5;
+		AT(J,n, 9, 9) = -m2*m3 / r23_3 + 3*m2*m3*y3my2_2 / r23_5 - m1*m2 / r13_3 + 3*m1*m2*y2my1_2 / r12_5;
+		AT(J,n,11,11) = -m1*m3 / r13_3 + 3*m1*m3*y3my1_2 / r13_5 - m2*m3 / r23_3 + 3*m2*m3*y3my2_2 / r23_5;
+		AT(J,n, 7, 6) = 3*m1*m3*x3mx1*y3my1 / r13_5 +3*m1*m2*x2mx1*y2my1 / r12_5;
+		AT(J,n, 8, 6) = m1*m2/r12_3 - 3*m1*m2*x2mx1_2 / r12_5;
+		AT(J,n, 9, 6) = -3*m1*m2*x2mx1*y2my1 / r12_5;
+		AT(J,n,10, 6) = m1*m3/r13_3 - 3*m1*m3*x3mx1_2 / r13_5;
+		AT(J,n,11, 6) = -3*m1*m3*x3mx1*y3my1 / r13_5;
+		AT(J,n, 8, 7) = -3*m1*m2*x2mx1*y2my1 / r12_5;
+		AT(J,n, 9, 7) = m1*m2/r12_3 - 3*m1*m2*y2my1_2 / r12_5;
+		AT(J,n,10, 7) = -3*m1*m3*x3mx1*y3my1 / r13_5;
+		AT(J,n,11, 7) = m1*m3/r13_2 - 3*m1*m3*y3my1_2 / r13_5;
+		AT(J,n, 9, 8) = 3*m2*m3*x3mx2*y3my2 / r23_5 + 3*m1*m2*x2mx1*y2my1 / r12_5;
+		AT(J,n,10, 8) = m2*m3 / r23_3 - 3*m2*m3*x3mx2_2 / r23_5;
+		AT(J,n,11, 8) = -3*m2*m3*x3mx2*y3my2 / r23_5;
+		AT(J,n,10, 9) = -3*m2*m3*x3mx2*y3my2 / r23_5;
+		AT(J,n,11, 9) = m2*m3/r23_3 - 3*m2*m3*y3my2_2 / r23_5;
+		AT(J,n,11,10) = 3*m2*m3*x3mx2*y3my2 / r23_5 + 3*m1*m3*x3mx1*y3my1 / r13_5;
+		for (int a = 6; a < 12; ++a)
+			for (int b = a + 1; b < 12; ++b) AT(J,n,a,b) = AT(J,n,b,a);
+		AT(J,n,0,0) = 1.0 / m1; AT(J,n,1,1) = 1.0 / m1;
+		AT(J,n,2,2) = 1.0 / m2; AT(J,n,3,3) = 1.0 / m2;
+		AT(J,n,4,4) = 1.0 / m3; AT(J,n,5,5) = 1.0 / m3;
+		for (int k = 0; k < n*n; ++k) J[k] = -J[k];
+		break;
+	}
 	case REF_BRUSS1D: {
 		const int Ng = n / 2;
 		const double alpha = pr->p[0], B = pr->p[2];
@@ -428,6 +488,7 @@ int ref_problem_dims(int id, int n_hint, int *n, int *p)
 	case REF_HARMONIC: *n = 2; *p = 1; return 0;
 	case REF_DIMER: *n = 2; *p = 1; return 0;
 	case REF_KINETIC4: *n = 4; *p = 3; return 0;
+	case REF_THREE_BODY: *n = 12; *p = 3; return 0;
 	}
 	return -1;
 }
@@ -904,4 +965,24 @@ int ref_fixed_step(int problem_id, int method, int n_hint, const double *params,
 	for (int k = 0; k < n; ++k) y_out[k] = y[k];
 	ws_free(&w);
 	return failed;
+}
+
+/* fun/jac of the restated functors, J row-major (see ref_driver.cpp ref_eval_functor). */
+int ref_eval_functor(int problem_id, int n_hint, const double *params, double t, const double *y, double *f_out,
+                     double *J_out)
+{
+	int n = 0, P = 0;
+	if (ref_problem_dims(problem_id, n_hint, &n, &P)) return -1;
+	problem pr;
+	pr.id = problem_id;
+	pr.n = n;
+	for (int k = 0; k < 4; ++k) pr.p[k] = (params && k < P) ? params[k] : 0.0;
+	double *J = (double *)malloc(sizeof(double) * (size_t)n * (size_t)n);
+	if (!J) return -2;
+	fun(&pr, t, y, f_out);
+	jac(&pr, t, y, J);
+	for (int i = 0; i < n; ++i)
+		for (int j = 0; j < n; ++j) J_out[i*n + j] = AT(J, n, i, j);
+	free(J);
+	return 0;
 }

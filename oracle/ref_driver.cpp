@@ -113,7 +113,7 @@ struct ref_options {
 
 enum { REF_ROBERTSON = 1, REF_VDPOL = 2, REF_BRUSS1D = 3, REF_ROBER_HARDCODED = 4,
        REF_EXPONENTIAL = 5, REF_STIFF_EQ = 6, REF_BRUSS2 = 7, REF_LORENZ = 8, REF_HARMONIC = 9, REF_DIMER = 10,
-       REF_KINETIC4 = 11 };
+       REF_KINETIC4 = 11, REF_THREE_BODY = 12 };
 
 int ref_problem_dims(int problem, int n_hint, int *n, int *p)
 {
@@ -129,6 +129,7 @@ int ref_problem_dims(int problem, int n_hint, int *n, int *p)
 	case REF_HARMONIC: *n = 2; *p = 1; return 0;
 	case REF_DIMER: *n = 2; *p = 1; return 0;
 	case REF_KINETIC4: *n = 4; *p = 3; return 0;
+	case REF_THREE_BODY: *n = 12; *p = 3; return 0;
 	}
 	return -1;
 }
@@ -285,6 +286,7 @@ int ref_irk_ensemble(int problem, int method, double t0, double t1, double dt0,
 			case REF_HARMONIC: { test_equations::harmonic f(par(0)); RUN(f); break; }
 			case REF_DIMER: { test_equations::dimer f(par(0)); RUN(f); break; }
 			case REF_KINETIC4: { test_equations::kinetic_4 f(par(0), par(1), par(2)); RUN(f); break; }
+			case REF_THREE_BODY: { test_equations::three_body f(par(0), par(1), par(2)); RUN(f); break; }
 			}
 #undef RUN
 		}
@@ -341,6 +343,7 @@ int ref_newton_solve_stages(int problem, int method, int variant, int n_hint, co
 		case REF_HARMONIC: { test_equations::harmonic f(params[0]); CALL(f); break; }
 		case REF_DIMER: { test_equations::dimer f(params[0]); CALL(f); break; }
 		case REF_KINETIC4: { test_equations::kinetic_4 f(params[0], params[1], params[2]); CALL(f); break; }
+		case REF_THREE_BODY: { test_equations::three_body f(params[0], params[1], params[2]); CALL(f); break; }
 		}
 #undef CALL
 	} catch (std::exception &e) {
@@ -400,6 +403,7 @@ int ref_fixed_step(int problem, int method, int n_hint, const double *params, co
 			case REF_HARMONIC: { test_equations::harmonic f(params[0]); CALL(f); break; }
 			case REF_DIMER: { test_equations::dimer f(params[0]); CALL(f); break; }
 			case REF_KINETIC4: { test_equations::kinetic_4 f(params[0], params[1], params[2]); CALL(f); break; }
+			case REF_THREE_BODY: { test_equations::three_body f(params[0], params[1], params[2]); CALL(f); break; }
 			}
 #undef CALL
 			if (status != newton::SUCCESS) ++failed;
@@ -414,6 +418,46 @@ int ref_fixed_step(int problem, int method, int n_hint, const double *params, co
 	}
 	for (int k = 0; k < n; ++k) y_out[k] = y(k);
 	return failed;
+}
+
+// fun(t,y) and jac(t,y) of a reference test functor as they stand (functor.hpp:35-73); J is returned row-major,
+// J[i*n + j] = jac(i,j).  Lets the device functors be checked against the reference's own expressions -- the only
+// meaningful check for three_body, whose jac() is not the derivative of its fun().
+int ref_eval_functor(int problem, int n_hint, const double *params, double t, const double *y_in, double *f_out,
+                     double *J_out)
+{
+	int n = 0, P = 0;
+	if (ref_problem_dims(problem, n_hint, &n, &P)) return -1;
+	vec_type y(n);
+	for (int k = 0; k < n; ++k) y(k) = y_in[k];
+	vec_type f;
+	arma::mat J;
+	try {
+#define CALL(F) do { f = F.fun(t, y); J = F.jac(t, y); } while (0)
+		switch (problem) {
+		case REF_ROBERTSON: { rober_p fn(params[0], params[1], params[2]); CALL(fn); break; }
+		case REF_VDPOL: { test_equations::vdpol fn(params[0]); CALL(fn); break; }
+		case REF_BRUSS1D: { bruss1d fn(n/2, params[0], params[1], params[2]); CALL(fn); break; }
+		case REF_ROBER_HARDCODED: { test_equations::rober fn; CALL(fn); break; }
+		case REF_EXPONENTIAL: { test_equations::exponential fn(params[0]); CALL(fn); break; }
+		case REF_STIFF_EQ: { test_equations::stiff_eq fn; CALL(fn); break; }
+		case REF_BRUSS2: { test_equations::bruss fn(params[0], params[1]); CALL(fn); break; }
+		case REF_LORENZ: { test_equations::lorenz fn(params[0], params[1], params[2]); CALL(fn); break; }
+		case REF_HARMONIC: { test_equations::harmonic fn(params[0]); CALL(fn); break; }
+		case REF_DIMER: { test_equations::dimer fn(params[0]); CALL(fn); break; }
+		case REF_KINETIC4: { test_equations::kinetic_4 fn(params[0], params[1], params[2]); CALL(fn); break; }
+		case REF_THREE_BODY: { test_equations::three_body fn(params[0], params[1], params[2]); CALL(fn); break; }
+		}
+#undef CALL
+	} catch (std::exception &e) {
+		g_err = e.what();
+		return -2;
+	}
+	for (int i = 0; i < n; ++i) {
+		f_out[i] = f(i);
+		for (int j = 0; j < n; ++j) J_out[i*n + j] = J(i, j);
+	}
+	return 0;
 }
 
 // irk::merge_rk_output (irk.cpp:750-783) on two synthetic legs: returns merged counters and

@@ -24,12 +24,12 @@ LIB_PATHS = {
 
 # problem ids shared by ref_driver.cpp and irk_port.c (NOT the product's ids)
 ROBERTSON, VDPOL, BRUSS1D, ROBER_HARDCODED, EXPONENTIAL, STIFF_EQ, BRUSS2 = 1, 2, 3, 4, 5, 6, 7
-LORENZ, HARMONIC, DIMER, KINETIC4 = 8, 9, 10, 11
+LORENZ, HARMONIC, DIMER, KINETIC4, THREE_BODY = 8, 9, 10, 11, 12
 PROBLEM_IDS = {
     "robertson": ROBERTSON, "van-der-pol": VDPOL, "brusselator-1d": BRUSS1D,
     "robertson-hardcoded": ROBER_HARDCODED, "exponential": EXPONENTIAL,
     "stiff-equation": STIFF_EQ, "brusselator": BRUSS2, "lorenz": LORENZ, "harmonic": HARMONIC, "dimer": DIMER,
-    "kinetic-4": KINETIC4,
+    "kinetic-4": KINETIC4, "three-body": THREE_BODY,
 }
 COUNTER_NAMES = ("attempt", "reject_newton", "reject_err", "newton_success", "newton_incr_diverge",
                  "newton_iter_error_too_large", "newton_maxit_exceed", "fun_evals", "jac_evals")
@@ -192,3 +192,16 @@ class RefSolver:
         if failed < 0:
             raise RuntimeError(f"ref_fixed_step rc={failed}")
         return dict(y=out, failed=failed, newton_iters=its.value)
+
+    def eval_functor(self, problem, t, y, params, n_hint=0):
+        """``fun(t, y)`` and ``jac(t, y)`` (row-major n x n) of a test functor as the reference writes them."""
+        pid = PROBLEM_IDS[problem] if isinstance(problem, str) else problem
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        params = np.ascontiguousarray(params if params is not None else [0.0], dtype=np.float64)
+        n = y.shape[0]
+        f = np.zeros(n)
+        J = np.zeros((n, n))
+        rc = self.lib.ref_eval_functor(C.c_int(pid), C.c_int(n_hint or n), _p(params), C.c_double(t), _p(y), _p(f), _p(J))
+        if rc:
+            raise RuntimeError(f"ref_eval_functor rc={rc}")
+        return f, J

@@ -25,7 +25,7 @@ IMPLICIT_EULER, RADAU_IIA_32, RADAU_IIA_53, RADAU_IIA_95, RADAU_IIA_137 = 200, 2
 LOBATTO_IIIC_43, LOBATTO_IIIC_64, LOBATTO_IIIC_85 = 230, 231, 232
 # problem ids
 ROBERTSON, VAN_DER_POL, BRUSSELATOR_1D, EXPONENTIAL, STIFF_EQ, BRUSSELATOR = 1, 2, 3, 5, 6, 7
-LORENZ, HARMONIC, DIMER, KINETIC_4 = 8, 9, 10, 11
+LORENZ, HARMONIC, DIMER, KINETIC_4, THREE_BODY = 8, 9, 10, 11, 12
 BRUSSELATOR_1D_DENSE = 4  # the same system with its Jacobian treated as dense (CTA-per-system kernel)
 # status codes (enums.hpp:103-127)
 SUCCESS, GENERAL_ERROR, ERROR_MAX_STEPS_EXCEEDED = 0, 4, 128

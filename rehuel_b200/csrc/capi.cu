@@ -98,6 +98,7 @@ static const ProblemInfo kProblems[] = {
     {REHUEL_PROBLEM_HARMONIC, "harmonic", 2, 1},
     {REHUEL_PROBLEM_DIMER, "dimer", 2, 1},
     {REHUEL_PROBLEM_KINETIC_4, "kinetic-4", 4, 3},
+    {REHUEL_PROBLEM_THREE_BODY, "three-body", 12, 3},
 };
 static const ProblemInfo *find_problem(int id)
 {
@@ -117,6 +118,7 @@ LaunchFn launcher_lorenz();
 LaunchFn launcher_harmonic();
 LaunchFn launcher_dimer();
 LaunchFn launcher_kinetic4();
+LaunchFn launcher_three_body();
 LaunchFn launcher_bruss1d_64();
 LaunchFn launcher_bruss1d_8();
 LaunchFn launcher_bruss1d_32();
@@ -137,6 +139,7 @@ EvalFn evaluator_lorenz();
 EvalFn evaluator_harmonic();
 EvalFn evaluator_dimer();
 EvalFn evaluator_kinetic4();
+EvalFn evaluator_three_body();
 EvalFn evaluator_bruss1d_64();
 EvalFn evaluator_bruss1d_8();
 EvalFn evaluator_bruss1d_32();
@@ -170,6 +173,7 @@ static LaunchFn find_launcher(int problem, int n)
 	case REHUEL_PROBLEM_HARMONIC: return launcher_harmonic();
 	case REHUEL_PROBLEM_DIMER: return launcher_dimer();
 	case REHUEL_PROBLEM_KINETIC_4: return launcher_kinetic4();
+	case REHUEL_PROBLEM_THREE_BODY: return launcher_three_body();
 	}
 	set_error(REHUEL_EINVAL, "problem %d has no GPU kernel", problem);
 	return nullptr;
@@ -187,6 +191,7 @@ static EvalFn find_evaluator(int problem, int n)
 	case REHUEL_PROBLEM_HARMONIC: return evaluator_harmonic();
 	case REHUEL_PROBLEM_DIMER: return evaluator_dimer();
 	case REHUEL_PROBLEM_KINETIC_4: return evaluator_kinetic4();
+	case REHUEL_PROBLEM_THREE_BODY: return evaluator_three_body();
 	case REHUEL_PROBLEM_BRUSSELATOR_1D: return n == 64 ? evaluator_bruss1d_64() : (n == 32 ? evaluator_bruss1d_32() : (n == 16 ? evaluator_bruss1d_16() : (n == 12 ? evaluator_bruss1d_12() : (n == 8 ? evaluator_bruss1d_8() : nullptr))));
 	case REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE:
 		return n == 64 ? evaluator_bruss1d_dense_64()

@@ -213,6 +213,85 @@ struct Kinetic4F {
 	}
 };
 
+// test_equations.hpp:254-421 (`three_body`): planar three-body problem, y = (x0,y0,x1,y1,x2,y2, p0..p5), p = (m1,m2,m3).
+// Reproduced AS WRITTEN in the reference (parity, not repair): dydt[9] uses x3mx2 where y3my2 is meant
+// (:296), and jac() returns MINUS a matrix that puts the force derivatives in the momentum-momentum block and 1/m on
+// the position diagonal (:329-420, with r13_3 for an m1*m2 term at :344 and r13_2 at :363) -- it is not the derivative
+// of fun(), the simplified Newton iteration merely converges linearly with it.  Componentwise (n = 12): dense Jacobian,
+// one warp per system with the matrices in registers (irk_wdense.cuh).
+struct ThreeBodyF {
+	static constexpr int N = 12;
+	static constexpr int P = 3;
+	static constexpr bool kAutonomous = true;
+	__device__ __forceinline__ static double fun(int i, double, const double *y, const double *p)
+	{
+		const double m1 = p[0], m2 = p[1], m3 = p[2];
+		if (i < 6) return y[6 + i] / (i < 2 ? m1 : (i < 4 ? m2 : m3));
+		const double x2mx1 = y[2] - y[0], y2my1 = y[3] - y[1];
+		const double x3mx1 = y[4] - y[0], y3my1 = y[5] - y[1];
+		const double x3mx2 = y[4] - y[2], y3my2 = y[5] - y[3];
+		const double r12_2 = x2mx1 * x2mx1 + y2my1 * y2my1;
+		const double r13_2 = x3mx1 * x3mx1 + y3my1 * y3my1;
+		const double r23_2 = x3mx2 * x3mx2 + y3my2 * y3my2;
+		const double r12_3 = r12_2 * sqrt(r12_2), r13_3 = r13_2 * sqrt(r13_2), r23_3 = r23_2 * sqrt(r23_2);
+		switch (i) {
+		case 6: return m1 * m3 * x3mx1 / r13_3 + m1 * m2 * x2mx1 / r12_3;
+		case 7: return m1 * m3 * y3my1 / r13_3 + m1 * m2 * y2my1 / r12_3;
+		case 8: return -m1 * m2 * x2mx1 / r12_3 + m2 * m3 * x3mx2 / r23_3;
+		case 9: return -m1 * m2 * y2my1 / r12_3 + m2 * m3 * x3mx2 / r23_3; // sic (:296)
+		case 10: return -m2 * m3 * x3mx2 / r23_3 - m1 * m3 * x3mx1 / r13_3;
+		default: return -m2 * m3 * y3my2 / r23_3 - m1 * m3 * y3my1 / r13_3;
+		}
+	}
+	// entry (a, b), a >= b, of the reference's symmetric 6 x 6 block J(6+a, 6+b) BEFORE the final negation
+	__device__ __forceinline__ static double block(int a, int b, const double *y, const double *p)
+	{
+		const double m1 = p[0], m2 = p[1], m3 = p[2];
+		const double x2mx1 = y[2] - y[0], y2my1 = y[3] - y[1];
+		const double x3mx1 = y[4] - y[0], y3my1 = y[5] - y[1];
+		const double x3mx2 = y[4] - y[2], y3my2 = y[5] - y[3];
+		const double x2mx1_2 = x2mx1 * x2mx1, y2my1_2 = y2my1 * y2my1;
+		const double x3mx1_2 = x3mx1 * x3mx1, y3my1_2 = y3my1 * y3my1;
+		const double x3mx2_2 = x3mx2 * x3mx2, y3my2_2 = y3my2 * y3my2;
+		const double r12_2 = x2mx1_2 + y2my1_2, r13_2 = x3mx1_2 + y3my1_2, r23_2 = x3mx2_2 + y3my2_2;
+		const double r12_3 = r12_2 * sqrt(r12_2), r13_3 = r13_2 * sqrt(r13_2), r23_3 = r23_2 * sqrt(r23_2);
+		const double r12_5 = r12_3 * r12_2, r13_5 = r13_3 * r13_2, r23_5 = r23_3 * r23_2;
+		switch (a * 6 + b) {
+		case 0 * 6 + 0: return -m1 * m3 / r13_3 + 3 * m1 * m3 * x3mx1_2 / r13_5 - m1 * m2 / r12_3 + 3 * m1 * m2 * x2mx1_2 / r12_5;
+		case 1 * 6 + 1: return -m1 * m3 / r13_3 + 3 * m1 * m3 * y3my1_2 / r13_5 - m1 * m2 / r12_3 + 3 * m1 * m2 * y2my1_2 / r12_5;
+		case 2 * 6 + 2: return -m2 * m3 / r23_3 + 3 * m2 * m3 * x3mx2_2 / r23_5 - m1 * m2 / r12_3 + 3 * m1 * m2 * x2mx1_2 / r12_5;
+		case 3 * 6 + 3: return -m2 * m3 / r23_3 + 3 * m2 * m3 * y3my2_2 / r23_5 - m1 * m2 / r13_3 + 3 * m1 * m2 * y2my1_2 / r12_5; // sic (:344)
+		case 4 * 6 + 4: return -m1 * m3 / r13_3 + 3 * m1 * m3 * x3mx1_2 / r13_5 - m2 * m3 / r23_3 + 3 * m2 * m3 * x3mx2_2 / r23_5;
+		case 5 * 6 + 5: return -m1 * m3 / r13_3 + 3 * m1 * m3 * y3my1_2 / r13_5 - m2 * m3 / r23_3 + 3 * m2 * m3 * y3my2_2 / r23_5;
+		case 1 * 6 + 0: return 3 * m1 * m3 * x3mx1 * y3my1 / r13_5 + 3 * m1 * m2 * x2mx1 * y2my1 / r12_5;
+		case 2 * 6 + 0: return m1 * m2 / r12_3 - 3 * m1 * m2 * x2mx1_2 / r12_5;
+		case 3 * 6 + 0: return -3 * m1 * m2 * x2mx1 * y2my1 / r12_5;
+		case 4 * 6 + 0: return m1 * m3 / r13_3 - 3 * m1 * m3 * x3mx1_2 / r13_5;
+		case 5 * 6 + 0: return -3 * m1 * m3 * x3mx1 * y3my1 / r13_5;
+		case 2 * 6 + 1: return -3 * m1 * m2 * x2mx1 * y2my1 / r12_5;
+		case 3 * 6 + 1: return m1 * m2 / r12_3 - 3 * m1 * m2 * y2my1_2 / r12_5;
+		case 4 * 6 + 1: return -3 * m1 * m3 * x3mx1 * y3my1 / r13_5;
+		case 5 * 6 + 1: return m1 * m3 / r13_2 - 3 * m1 * m3 * y3my1_2 / r13_5; // sic (:363)
+		case 3 * 6 + 2: return 3 * m2 * m3 * x3mx2 * y3my2 / r23_5 + 3 * m1 * m2 * x2mx1 * y2my1 / r12_5;
+		case 4 * 6 + 2: return m2 * m3 / r23_3 - 3 * m2 * m3 * x3mx2_2 / r23_5;
+		case 5 * 6 + 2: return -3 * m2 * m3 * x3mx2 * y3my2 / r23_5;
+		case 4 * 6 + 3: return -3 * m2 * m3 * x3mx2 * y3my2 / r23_5;
+		case 5 * 6 + 3: return m2 * m3 / r23_3 - 3 * m2 * m3 * y3my2_2 / r23_5;
+		default: return 3 * m2 * m3 * x3mx2 * y3my2 / r23_5 + 3 * m1 * m3 * x3mx1 * y3my1 / r13_5; // (5, 4)
+		}
+	}
+	__device__ __forceinline__ static void jac_row(int i, double, const double *y, const double *p, double *row)
+	{
+		if (i < 6) {
+			row[i] = -(1.0 / (i < 2 ? p[0] : (i < 4 ? p[1] : p[2])));
+			return;
+		}
+		const int a = i - 6;
+#pragma unroll
+		for (int b = 0; b < 6; ++b) row[6 + b] = -(a >= b ? block(a, b, y, p) : block(b, a, y, p));
+	}
+};
+
 // 1-D Brusselator, method of lines on NG interior grid points, interleaved (u_i, v_i), boundary
 // values u = 1, v = 3 (the reference only has a "TODO: Discretization of a
 // PDE", test_equations.hpp:546).  p = (alpha, A, B).  Componentwise functor for the CTA-per-system

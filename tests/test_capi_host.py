@@ -63,6 +63,7 @@ def test_method_and_problem_names(capi, port):
     assert capi.name_to_problem("brusselator-1d") == capi.BRUSSELATOR_1D
     assert [capi.name_to_problem(k) for k in ("lorenz", "harmonic", "dimer", "kinetic-4", "brusselator-1d-dense")] == [8, 9, 10, 11, 4]
     assert capi.problem_dims(capi.KINETIC_4) == (4, 3) and capi.problem_dims(capi.LORENZ) == (3, 3)
+    assert capi.name_to_problem("three-body") == capi.THREE_BODY == 12 and capi.problem_dims(capi.THREE_BODY) == (12, 3)
     assert capi.name_to_problem("nope") == 0
     assert capi.problem_dims(capi.ROBERTSON) == (3, 3)
     assert capi.problem_dims(capi.VAN_DER_POL) == (2, 1)

@@ -28,7 +28,7 @@ def capi():
 
 
 PROBLEM_ID = {"robertson": 1, "van-der-pol": 2, "brusselator-1d": 3, "exponential": 5, "stiff-equation": 6, "brusselator": 7,
-              "lorenz": 8, "harmonic": 9, "dimer": 10, "kinetic-4": 11}
+              "lorenz": 8, "harmonic": 9, "dimer": 10, "kinetic-4": 11, "three-body": 12}
 
 
 def _gpu_single(capi, c, **kw):
@@ -181,6 +181,44 @@ def test_analytic_jacobians_match_finite_differences(capi):
     # and the right-hand side itself against the host-side restatement used for the ensembles' initial data
     f, _ = capi.eval_functor(capi.ROBERTSON, 0.0, [1.0, 2e-5, 0.1], [0.04, 1e4, 3e7])
     np.testing.assert_allclose(f, [-0.04 + 1e4 * 2e-5 * 0.1, 0.04 - 1e4 * 2e-5 * 0.1 - 3e7 * 4e-10, 3e7 * 4e-10], rtol=1e-14)
+
+
+def test_device_functors_equal_the_reference_functors(capi, port):
+    """f(t, y) and J(t, y) of the DEVICE functors (rehuel_eval_functor) against the oracle's restatement of
+    test_equations.hpp, which tests/test_oracle.py holds bit-identical to the reference's: to rounding (the device
+    contracts FMAs).  This is the check that covers three_body (n = 12, warp-per-system register LU), whose jac() is
+    not the derivative of its fun() in the reference (test_equations.hpp:304-421) and is reproduced as written."""
+    rng = np.random.default_rng(12)
+    cases = [(capi.ROBERTSON, "robertson", [0.04, 1e4, 3e7], 3), (capi.VAN_DER_POL, "van-der-pol", [1e-2], 2),
+             (capi.LORENZ, "lorenz", [10.0, 28.0, 8.0 / 3.0], 3), (capi.KINETIC_4, "kinetic-4", [0.5, 0.3, 0.2], 4),
+             (capi.THREE_BODY, "three-body", [0.5, 2.0, 3.0], 12), (capi.THREE_BODY, "three-body", [1.0, 1.0, 1000.0], 12),
+             (capi.BRUSSELATOR_1D, "brusselator-1d", [0.02, 1.0, 3.0], 16)]
+    for prob, name, par, n in cases:
+        for _ in range(3):
+            y = rng.uniform(-1.5, 1.5, n)
+            f, J = capi.eval_functor(prob, 0.3, y, par, n_hint=n)
+            fr, Jr = port.eval_functor(name, 0.3, y, par)
+            np.testing.assert_allclose(f, fr, rtol=1e-13, atol=1e-13 * np.abs(fr).max(), err_msg=name)
+            np.testing.assert_allclose(np.asarray(J).reshape(n, n), Jr, rtol=1e-13, atol=1e-13 * np.abs(Jr).max(), err_msg=name)
+
+
+def test_three_body_ensemble_warp_per_system(capi, port):
+    """A mass-swept ensemble of the reference's three_body (n = 12, dense: irk_wdense.cuh) against the oracle, member by
+    member, for the three tableaux of the BASELINE configs; attempt counts next to the oracle's."""
+    M = 24
+    rng = np.random.default_rng(3)
+    P = np.ascontiguousarray(rng.uniform(0.5, 2.0, (3, M)))
+    y0 = np.array([1.0, 0.0, 3.0, 2.0, 0.0, 3.0, 0.0, 2.0, -1.0, 0.0, -1.0, 0.0])  # examples/example_equations.cpp:341-343
+    for method, t1 in ((211, 1.0), (230, 1.0), (232, 1.0)):  # (beyond t = 1 some members have dozens of Newton failures: slow on the CPU)
+        g = capi.irk_ensemble(capi.THREE_BODY, method, 0.0, t1, 1e-6, y0, P, capi.make_options(1e-6, 1e-6))
+        r = port.solve("three-body", method, 0.0, t1, 1e-6, y0, P, ref_options(rel_tol=1e-6, abs_tol=1e-6))
+        assert np.array_equal(g.status, r.status) and np.all(g.status == 0)
+        se = scaled_err(g.y, r.y, 1e-6, 1e-6)
+        same = int(np.sum(g.counters["attempt"] == r.counters["attempt"]))
+        print(f"\nthree-body {method}: worst scaled error {se.max():.3e}, identical attempt counts {same}/{M}, "
+              f"attempts {int(r.counters['attempt'].min())}..{int(r.counters['attempt'].max())}, kernel {g.kernel_ms:.2f} ms")
+        assert se.max() <= PARITY_BOUND, (method, se.max())
+        assert same >= 0.9 * M
 
 
 def test_fixed_step_convergence_orders(capi):

@@ -97,6 +97,26 @@ def test_reference_live_equals_port(reference, port):
     assert np.array_equal(a.counters["fun_evals"], b.counters["fun_evals"])
 
 
+def test_functor_evaluations_port_equals_reference(reference, port):
+    """fun(t, y) and jac(t, y) of every restated test functor, bit for bit against the reference's own
+    (test_equations.hpp) at random states -- including three_body, whose jac() is NOT the derivative of its fun()
+    (test_equations.hpp:304-421) and is reproduced as written."""
+    rng = np.random.default_rng(11)
+    cases = [("robertson", [0.04, 1e4, 3e7], 3), ("van-der-pol", [1e-2], 2), ("exponential", [-0.4], 1),
+             ("stiff-equation", None, 2), ("brusselator", [1.0, 3.5], 2), ("lorenz", [10.0, 28.0, 8.0 / 3.0], 3),
+             ("harmonic", [3.0], 2), ("dimer", [5.0], 2), ("kinetic-4", [0.5, 0.3, 0.2], 4),
+             ("three-body", [0.5, 2.0, 3.0], 12), ("three-body", [1.0, 1.0, 1000.0], 12), ("brusselator-1d", [0.02, 1.0, 3.0], 16)]
+    for prob, par, n in cases:
+        for _ in range(4):
+            y = rng.uniform(-1.5, 1.5, n)
+            fa, Ja = reference.eval_functor(prob, 0.3, y, par)
+            fb, Jb = port.eval_functor(prob, 0.3, y, par)
+            assert np.array_equal(fa, fb) and np.array_equal(Ja, Jb), prob
+    # the three-body "Jacobian" really is not one: the momentum rows of fun() depend on the positions only
+    f, J = port.eval_functor("three-body", 0.0, rng.uniform(-1.5, 1.5, 12), [1.0, 1.0, 1.0])
+    assert np.all(J[6:, :6] == 0.0) and np.any(J[6:, 6:] != 0.0) and np.all(np.diag(J)[:6] == -1.0)
+
+
 def test_reference_rober_p_equals_hardcoded_rober(reference):
     """Our parameterised Robertson functor with (0.04,1e4,3e7) is the reference's `rober` bit for bit."""
     o = make_options(rel_tol=1e-6, abs_tol=1e-6)

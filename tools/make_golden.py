@@ -22,6 +22,9 @@ from oracle.refsolver import RefSolver, make_options  # noqa: E402
 from rehuel_b200 import ensembles  # noqa: E402  (host-side parameter generators only)
 
 
+THREE_BODY_Y0 = [1.0, 0.0, 3.0, 2.0, 0.0, 3.0, 0.0, 2.0, -1.0, 0.0, -1.0, 0.0]
+
+
 def hx(a):
     return [float(v).hex() for v in np.asarray(a, dtype=np.float64).ravel()]
 
@@ -83,6 +86,12 @@ def main():
         ("kinetic-4", [0.5, 0.3, 0.2], [1.0, 0.0, 0.0, 0.0], 230, 0.0, 10.0, 1e-6, o6),
         ("kinetic-4", [0.5, 0.3, 0.2], [1.0, 0.0, 0.0, 0.0], 232, 0.0, 2.0, 1e-6, o6),
         ("kinetic-4", [0.5, 0.3, 0.2], [1.0, 0.0, 0.0, 0.0], 212, 0.0, 10.0, 1e-6, o6),
+        # three_body (n = 12, test_equations.hpp:254-421) from the example driver's initial state
+        # (examples/example_equations.cpp:341-343); its jac() is not the derivative of its fun() -- reproduced as written
+        ("three-body", [1.0, 1.0, 1.0], THREE_BODY_Y0, 211, 0.0, 5.0, 1e-6, o6),  # includes a Newton failure
+        ("three-body", [1.0, 1.0, 1.0], THREE_BODY_Y0, 230, 0.0, 2.0, 1e-6, o6),
+        ("three-body", [1.0, 1.0, 1.0], THREE_BODY_Y0, 232, 0.0, 2.0, 1e-6, o6),
+        ("three-body", [0.5, 2.0, 3.0], THREE_BODY_Y0, 211, 0.0, 2.0, 1e-6, o6),
         ("brusselator-1d", [0.02, 1.0, 3.0], list(ensembles.bruss1d_y0(4)), 211, 0.0, 1.0, 1e-6, o6),
         ("brusselator-1d", [0.02, 1.0, 3.0], list(ensembles.bruss1d_y0(4)), 232, 0.0, 1.0, 1e-6, o6),
     ]
