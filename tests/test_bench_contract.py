@@ -32,3 +32,13 @@ def test_reference_arm_other_ranks_exit_quietly():
     p = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert p.returncode == 0, p.stderr[-2000:]
     assert p.stdout.strip() == ""
+
+
+def test_gpu_arm_without_a_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present: the GPU arm would run")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT)
+    assert p.returncode != 0 and p.stdout.strip() == "" and "no CPU fallback" in p.stderr
