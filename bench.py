@@ -40,6 +40,12 @@ SPANS = {"short": (0.0, 40.0), "long": (0.0, 1e11)}
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2: SMs x FP64 lanes x 2 x max SM clock
 
 
+# how the CPU arm was built (oracle/Makefile): the reference's own Makefile:3 adds -march=native -mtune=native, which is
+# left out because the library is built in one container and run on another host
+CPU_BUILD_NOTE = ("unmodified reference sources over oracle/arma_shim, g++ -std=c++11 -O2 -ffp-contract=off, no -DNDEBUG "
+                  "(the LU sits in an assert), no -march=native (built on a different host)")
+
+
 def workload_name(span: str, M: int) -> str:
     t0, t1 = SPANS[span]
     return (f"robertson-sweep M={M}/GPU (k1,k2,k3 = nominal*10^(u-1/2), splitmix64 seed 0x5EED), RADAU_IIA_53, "
@@ -53,8 +59,11 @@ _WORKER = r"""
 import sys, json, time
 sys.path.insert(0, {root!r})
 import numpy as np
+import importlib.util, os
 from oracle.refsolver import RefSolver, make_options
-from rehuel_b200 import ensembles
+# the parameter generator is loaded by PATH: this process must not import (and thereby map) the product library
+_spec = importlib.util.spec_from_file_location("_ensembles", os.path.join({root!r}, "rehuel_b200", "ensembles.py"))
+ensembles = importlib.util.module_from_spec(_spec); _spec.loader.exec_module(ensembles)
 kind, start, stride, total, t1 = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5])
 s = RefSolver(kind)
 P = ensembles.robertson_params(total)
@@ -89,7 +98,8 @@ def cpu_reference_run(span: str, sample: int, cores: int) -> dict:
     assert n == sample and all(o["ok"] == o["n"] for o in outs)
     return dict(value=n / slowest, unit=UNIT, cores=cores, kind=kind,
                 sample=f"members 0..{sample - 1} of the same sweep, striped over {cores} processes "
-                       f"(one per core); time = slowest process ({slowest:.2f} s; wall incl. start-up {wall:.2f} s)",
+                       f"(one per core); time = slowest process ({slowest:.2f} s; wall incl. start-up {wall:.2f} s); "
+                       + CPU_BUILD_NOTE,
                 per_core=n / slowest / cores, seconds=slowest, attempts=sum(o["attempts"] for o in outs))
 
 
@@ -139,7 +149,7 @@ def run_reference_arm(args) -> None:
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.span, M_PER_GPU), "sample_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r["kind"],
-                         "sample": f"each step = members 0..{per_step - 1} of the sweep, one process per core, time = slowest process"},
+                         "sample": f"each step = members 0..{per_step - 1} of the sweep, one process per core, time = slowest process; " + CPU_BUILD_NOTE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -187,7 +197,8 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = [c for c, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+                "samples": len(sm), "samples_under_load": len(busy) if len(busy) < len(sm) else None,
+                "power_w_max": max(power)}
 
 
 def bind_to_gpu_numa_node(local_rank: int) -> str:
@@ -216,9 +227,41 @@ def bind_to_gpu_numa_node(local_rank: int) -> str:
         return f"numa: not bound ({type(e).__name__})"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ensemble_irk_thread<RobertsonF,...> at 2^20 members, t in [0,40]
-# (profiles/r1_v8_ncu_summary.txt: 248.26 MB + 290.20 MB)
+# dram__bytes_read.sum + dram__bytes_write.sum of ensemble_irk_thread<RobertsonF,...> at 2^20 members, t in [0,40]: a
+# CONSTANT from the ncu --set full capture of this command, not measured in the run (profiles/README.md names the file)
 NCU_DRAM_BYTES_PER_LAUNCH = 538.46e6
+NCU_DRAM_SOURCE = "profiles/r1_v8_ncu_summary.txt (248.26 MB read + 290.20 MB written)"
+
+
+def device_ms(fn, torch, reps=1, warm=1):
+    """Device time of fn() (CUDA events on the current stream), best of `reps` after `warm` untimed calls."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def counter_sums(ens, torch):
+    """Sums of the per-member counters of a DeviceEnsemble after a solve (python ints)."""
+    c = ens.counters.to(torch.int64).sum(dim=1).tolist()
+    from rehuel_b200 import capi
+    d = dict(zip(capi.COUNTER_ROWS, c))
+    d["members"] = ens.M
+    d["n_failed"] = int((ens.status != 0).sum())
+    d["max_attempt"] = int(ens.counter("attempt").max())
+    return d
+
+
+def model_flops(model, cs):
+    return model.total(cs["members"], cs["attempt"], cs["newton_success"], cs["reject_err"], cs["fun_evals"])
 
 
 def run_gpu_arm(args) -> None:
@@ -226,7 +269,7 @@ def run_gpu_arm(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from rehuel_b200 import capi, ensembles, sharding
+    from rehuel_b200 import capi, ensembles, flopmodel, sharding
     from rehuel_b200.device import DeviceEnsemble
 
     rank = int(os.environ.get("RANK", "0"))
@@ -244,6 +287,7 @@ def run_gpu_arm(args) -> None:
     t0, t1 = SPANS[args.span]
     handout = {"index": capi.ORDER_INDEX, "locality": capi.ORDER_LOCALITY, "locality_desc": capi.ORDER_LOCALITY_DESC}[args.handout]
     opts = capi.make_options(RTOL, ATOL, handout_order=handout)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     # rank r owns members [r*M, (r+1)*M) of the sweep (weak scaling; any rank can generate its slice)
     P_host = torch.from_numpy(ensembles.robertson_params(M, start=rank * M)).pin_memory()
     y0_host = torch.from_numpy(ensembles.ROBERTSON_Y0.copy()).pin_memory()
@@ -257,7 +301,15 @@ def run_gpu_arm(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     peak_tflops = capi.fp64_peak_tflops()
+    rob = flopmodel.thread_kernel(3, capi.RADAU_IIA_53, 11, 8)
 
     # ---------------- value: inputs resident in HBM, device-timed
     for _ in range(args.warmup):
@@ -289,35 +341,31 @@ def run_gpu_arm(args) -> None:
     total_ms_max, kernel_ms_max = tt[0].item(), tt[1].item()
 
     # ---------------- statistics from the kernel's own counters (the one collective of the path)
-    att = ens.counter("attempt").double()
-    its = ens.counter("newton_iters").double()
-    fun = ens.counter("fun_evals").double()
-    nok = ens.counter("newton_success").double()
-    alt_uses = fun - 3.0 * (nok + its) - nok  # attempts that also evaluated formula 8.20
+    cs = counter_sums(ens, torch)
+    uses_820 = cs["members"] + cs["reject_err"]
     fixed, extra820, per_newton = ensembles.flops_per_attempt_dense_model(3, 3, 11, 8)
-    flops_dense = fixed * att.sum() + per_newton * its.sum() + extra820 * alt_uses.sum()
-    # DESIGN.md section 6; the last term: final residual evaluations the kernel skips as dead work (measured share of
-    # the successful Newton solves whose step test fires first: REHUEL_COUNT_SKIPS build, 0.962 short span / 0.999 long)
-    skip_share = 0.962 if args.span == "short" else 0.999
-    flops_exec = 259.0 * att.sum() + 369.0 * its.sum() + 30.0 * alt_uses.sum() - 132.0 * skip_share * nok.sum()
-    local = sharding.pack_stats(members=M, attempt=att, steps=ens.counter("steps").double(), newton_iters=its,
-                                fun_evals=fun, jac_evals=ens.counter("jac_evals").double(),
-                                reject_err=ens.counter("reject_err").double(),
-                                reject_newton=ens.counter("reject_newton").double(),
-                                n_failed=(ens.status != 0).double(), flops_dense_model=flops_dense,
+    flops_dense = fixed * cs["attempt"] + per_newton * cs["newton_iters"] + extra820 * uses_820
+    flops_exec = model_flops(rob, cs)
+    local = sharding.pack_stats(members=M, attempt=cs["attempt"], steps=cs["steps"], newton_iters=cs["newton_iters"],
+                                fun_evals=cs["fun_evals"], jac_evals=cs["jac_evals"], reject_err=cs["reject_err"],
+                                reject_newton=cs["reject_newton"], n_failed=cs["n_failed"], flops_dense_model=flops_dense,
                                 flops_executed_model=flops_exec)
+    local["max_attempt"] = float(cs["max_attempt"])
     tot = sharding.allreduce_stats(local, device=dev)
     mass_err = float((ens.y.sum(0) - 1.0).abs().max())
 
-    # ---------------- e2e: the public C-ABI call with host buffers
+    # ---------------- e2e: the public C-ABI call with host buffers; the caller asks for the states and the status
+    # (options.result_mask = 0): the ensemble sums of the counters come back with every call
+    e2e_opts = capi.make_options(RTOL, ATOL, handout_order=handout, result_mask=0)
+
     def e2e_call():
         res = capi.Result()
         capi.check(capi.lib.rehuel_irk_ensemble(
             capi.ROBERTSON, capi.RADAU_IIA_53, t0, t1, DT0, M, 3,
             capi.C.cast(y0_host.data_ptr(), capi._PD), 1, capi.C.cast(P_host.data_ptr(), capi._PD),
-            capi.C.byref(opts), 0, 1, capi.C.byref(res)))
-        d2h = (3 + 1 + 1) * 8 * M + 4 * M + 4 * M * capi.NCOUNTERS
-        checksum = res.sum.attempt
+            capi.C.byref(e2e_opts), 0, 1, capi.C.byref(res)))
+        d2h = 3 * 8 * M + 4 * M + 13 * 8 * 8   # y rows, status, the statistics words of the 8 chunks
+        checksum = (res.sum.attempt, res.sum.n_failed, res.y[M - 1])
         capi.lib.rehuel_result_free(capi.C.byref(res))
         return d2h, checksum
 
@@ -329,11 +377,41 @@ def run_gpu_arm(args) -> None:
         d2h_bytes, chk = e2e_call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - e0
-    et = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-    e2e_value = world * M * args.steps / et.item()
-    clocks = sampler.stop() if sampler else None  # sampled over the device-timed AND the e2e region
+    e2e_s_max = max_over_ranks(e2e_s)
+    e2e_value = world * M * args.steps / e2e_s_max
+    assert chk[0] == cs["attempt"] and chk[1] == 0, "the C-ABI call and the device-resident solve disagree"
+
+    # ---------------- the long span (t in [0,1e11], the reference's own Robertson set-up: test_adaptive_step/main.cpp:119-134)
+    # as a second timed block: ~0.1 s per launch, so the clock record has samples under load
+    long_line = None
+    if args.span == "short" and not args.quick:
+        lt0, lt1 = SPANS["long"]
+        ens.solve(lt0, lt1, DT0, opts)
+        barrier()
+        lev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(2)) for _ in range(args.long_steps)]
+        for a, b in lev:
+            ens.reorder()
+            a.record()
+            ens.launch(lt0, lt1, DT0, opts)
+            b.record()
+        barrier()
+        lms = max_over_ranks(sum(a.elapsed_time(b) for a, b in lev) / len(lev))
+        lcs = counter_sums(ens, torch)
+        lflops = model_flops(rob, lcs)
+        long_line = {"bound": "fp64", "achieved": lflops / (lms * 1e-3) / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
+                     "frac": lflops / (lms * 1e-3) / 1e12 / peak_tflops, "kernel_ms_per_launch": lms, "launches": len(lev),
+                     "systems_per_s_per_gpu": M / (lms * 1e-3), "attempts_per_member": lcs["attempt"] / M,
+                     "max_attempts": lcs["max_attempt"], "rejected_err_share": lcs["reject_err"] / lcs["attempt"],
+                     "workload": workload_name("long", M), "model": "executed flops, as in roofline (rank 0's members)"}
+    clocks = sampler.stop() if sampler else None  # sampled over the device-timed, the e2e and the long-span region
+
+    # ---------------- the other BASELINE configs, one device-timed launch each (N = 1 only; outside the headline timing)
+    configs = None
+    if world == 1 and not args.quick:
+        configs = other_configs(capi, ensembles, flopmodel, DeviceEnsemble, torch, dev, peak_tflops)
+
+    # ---------------- strong scaling: fixed totals, whatever N is
+    strong = None if args.quick else strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world, barrier, max_over_ranks)
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
@@ -356,30 +434,41 @@ def run_gpu_arm(args) -> None:
                        "parallelism": f"member-sharded x{world} (no data-path collective)",
                        "l2": "flushed between timed steps (256 MiB fill, outside the per-step event pair)",
                        "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
-                       "handout_order": args.handout + (" (Morton order of the rate constants, recomputed on the device inside every timed step"
+                       "handout_order": args.handout + (" (Morton order of the rate constants, recomputed on the device inside every timed step "
+                                                       "by two of our kernels and one cub::DeviceRadixSort -- library code on the path, ~0.1 ms"
                                                        + ("; walked from the large-k1 end, whose members need up to 39 attempts against 23, so the "
                                                           "queue drains on cheap members" if args.handout == "locality_desc" else "") + ")" if handout else ""),
                        "wall_s_timed_region_rank0": wall, "host_binding_rank0": numa_note},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P_host.numel() * 8 + 24),
-                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * et.item() / args.steps,
-                    "api": "rehuel_irk_ensemble (C ABI, pinned host buffers, results copied back)"},
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                    "bytes_per_member": {"h2d": 24, "d2h": 28},
+                    "api": "rehuel_irk_ensemble (C ABI, pinned host buffers; options.result_mask = 0: the states y[3][M] and "
+                           "status[M] of every member plus the ensemble sums of all counters are copied back; t_final, "
+                           "err_last and the nine per-member counter arrays are not asked for)"},
             "gpu_launches": int(ll.item()),
             "clocks": clocks,
             "roofline": {
-                "bound": "fp64", "achieved": ach_dense, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": ach_dense / peak_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                "traffic_note": "DRAM bytes read + written per launch of this kernel, ncu --set full capture of this command "
-                                "(profiles/r1_v8_ncu_summary.txt): 5x the 109 MB of algorithmic I/O because members are handed "
-                                "out in parameter order, so every 8-byte result lands in its own 32-byte sector; 2% of HBM peak",
+                "bound": "fp64", "achieved": ach_exec, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": ach_exec / peak_tflops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                "traffic_note": "CONSTANT, not measured in this run: DRAM bytes read + written per launch of this kernel from the "
+                                "ncu --set full capture of this command, " + NCU_DRAM_SOURCE + "; algorithmic I/O is 109 MB",
                 "kernel_ms_per_launch": kernel_ms_max / args.steps,
-                "model": "SURVEY.md 8(d) dense-algorithm flops: 873*attempts + 321*newton_iters + 41*uses_of_8.20, from the kernel's per-member counters",
+                "model": "flops of the eigen-decoupled algorithm actually executed, from the kernel's own counter sums "
+                         f"(rehuel_b200/flopmodel.py): {rob.fixed:g}*attempts + {rob.per_iteration:g}*newton_iterations + "
+                         f"{rob.extra_820:g}*uses_of_8.20 - {rob.residual:g}*newton_solves (every solve is taken to skip its dead "
+                         "final residual: a lower bound); FMA = 2, other FP64 ops = 1",
                 "peak_source": "measured in this run: register-resident DFMA chains (rehuel_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
-                "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": ach_dense / FP64_NOMINAL_TFLOPS,
-                "achieved_executed": ach_exec, "frac_executed": ach_exec / peak_tflops,
-                "model_executed": "flops of the eigen-decoupled algorithm actually run: 259*attempts + 369*newton_iters + 30*uses_of_8.20 - 132*skipped_final_residuals (DESIGN.md section 6)",
+                "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": ach_exec / FP64_NOMINAL_TFLOPS,
                 "kernel": "ensemble_irk_thread<RobertsonF,3,1,1,EST_REUSE>", "regs": info["regs"],
                 "spill_bytes": info["local_bytes"], "ctas_per_sm": info["ctas_per_sm"], "block": info["block"],
             },
+            "roofline_dense_model": {
+                "achieved": ach_dense, "frac": ach_dense / peak_tflops, "unit": "TFLOP/s",
+                "model": "SURVEY.md 8(d) flops of the REFERENCE's dense (s n) x (s n) algorithm, which the kernel does not execute: "
+                         "873*attempts + 321*newton_iters + 41*uses_of_8.20 -- a work-equivalent rate, not a hardware fraction"},
+            "roofline_long": long_line,
+            "configs": configs,
+            "strong": strong,
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "stats": {"attempts_per_member": tot["attempt"] / tot["members"], "accepted_per_member": tot["steps"] / tot["members"],
                       "rejected_err": tot["reject_err"], "rejected_newton": tot["reject_newton"],
@@ -393,6 +482,157 @@ def run_gpu_arm(args) -> None:
         dist.destroy_process_group()
 
 
+def other_configs(capi, ensembles, flopmodel, DeviceEnsemble, torch, dev, peak_tflops) -> dict:
+    """BASELINE configs 3, 4, 5 and the dense CTA-per-system kernel: one warm-up and one device-timed launch each, with the
+    executed-flop model of the kernel that runs them (rehuel_b200/flopmodel.py) against the FP64 peak of this run."""
+    import numpy as np
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    o = capi.make_options(RTOL, ATOL)
+    out = {}
+
+    def one(name, ens, t1, model, note):
+        ms = device_ms(lambda: ens.solve(0.0, t1, DT0, o), torch)
+        cs = counter_sums(ens, torch)
+        fl = model_flops(model, cs)
+        out[name] = {"ms": ms, "members": ens.M, "systems_per_s": ens.M / (ms * 1e-3), "attempts_per_member": cs["attempt"] / ens.M,
+                     "max_attempts": cs["max_attempt"], "newton_rejections": cs["reject_newton"], "failed_members": cs["n_failed"],
+                     "roofline": {"bound": "fp64", "achieved": fl / (ms * 1e-3) / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
+                                  "frac": fl / (ms * 1e-3) / 1e12 / peak_tflops,
+                                  "model": f"executed flops (flopmodel.py): fixed {model.fixed:g}/attempt, {model.per_iteration:g}/Newton iteration"},
+                     "kernel": note}
+        return ens
+
+    # config 3: Van der Pol sweep, LOBATTO_IIIC_43, thread-per-system; stiff end handed out first
+    Mv = 1 << 20
+    ens = DeviceEnsemble(capi.VAN_DER_POL, capi.LOBATTO_IIIC_43, Mv, cu(ensembles.VDPOL_Y0.copy()), cu(ensembles.vdpol_params(Mv)),
+                         handout_order=capi.ORDER_LOCALITY)
+    one("config3_vdpol_2p20_lobatto43", ens, 2.0, flopmodel.thread_kernel(2, capi.LOBATTO_IIIC_43, 6, 7), "ensemble_irk_thread<VanDerPolF,3,1,1,EST_IDENTITY>")
+    del ens
+    # config 4: 1-D Brusselator MOL n = 64, LOBATTO_IIIC_85, warp-per-system band kernel (a sixteenth of the 65 536 members)
+    Mb = 4096
+    ens = DeviceEnsemble(capi.BRUSSELATOR_1D, capi.LOBATTO_IIIC_85, Mb, cu(ensembles.bruss1d_y0(32)), cu(ensembles.bruss1d_params(Mb)), n_hint=64)
+    one("config4_bruss1d_n64_lobatto85_4096", ens, 10.0, flopmodel.band_kernel(64, 2, capi.LOBATTO_IIIC_85, 10, 8), "ensemble_irk_warp<Brusselator1dF<32>,5,1,2,EST_OWN_LU> (band kernel)")
+    del ens
+    # the literal "CTA-per-system shared-memory block LU": the same system declared dense, short span
+    Mc = 296
+    ens = DeviceEnsemble(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, Mc, cu(ensembles.bruss1d_y0(32)), cu(ensembles.bruss1d_params(Mc)), n_hint=64)
+    one("dense_cta_bruss1d_n64_lobatto85_t0.5", ens, 0.5, flopmodel.dense_kernel(64, capi.LOBATTO_IIIC_85, 10, 64 * 8), "ensemble_irk_cta<Brusselator1dDenseF<32>,5,1,2,EST_OWN_LU,256>")
+    del ens
+    return out
+
+
+def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world, barrier, max_over_ranks) -> dict:
+    """Strong scaling: fixed totals over the N ranks.
+    config 2 at 2^20 members in all: rank r integrates the contiguous members [r M/N, (r+1) M/N).
+    config 5 at 10 485 760 members in all (even index Robertson / RADAU_IIA_53 / t in [0,40], odd index Van der Pol /
+    LOBATTO_IIIC_43 / t in [0,2], rtol = atol = 10^(-3-6v), newton tol = 0.1 rtol): cut into 128 chunks that the ranks CLAIM
+    from a cursor in shared memory (rehuel_cursor) as they finish, six chunks in flight per GPU."""
+    import numpy as np
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    o = capi.make_options(RTOL, ATOL)
+    out = {}
+    # ---- config 2, 2^20 members in all
+    Mt = 1 << 20
+    lo, hi = Mt * rank // world, Mt * (rank + 1) // world
+    ens = DeviceEnsemble(capi.ROBERTSON, capi.RADAU_IIA_53, hi - lo, cu(ensembles.ROBERTSON_Y0.copy()),
+                         cu(ensembles.robertson_params(hi - lo, start=lo)), handout_order=capi.ORDER_LOCALITY_DESC)
+    ens.solve(0.0, 40.0, DT0, o)
+    barrier()
+    ms = max_over_ranks(device_ms(lambda: ens.solve(0.0, 40.0, DT0, o), torch, reps=3, warm=0))
+    out["config2_robertson_2p20_total"] = {"ms": ms, "systems_per_s": Mt / (ms * 1e-3), "members_total": Mt}
+    del ens
+    # ---- config 5, 10 485 760 members in all, chunks claimed from the shared cursor
+    Mt, n_chunks, depth = 10485760, 128, 6
+    half = Mt // 2
+    per = half // n_chunks                      # members of each class per chunk
+    name = f"rehuel_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
+    cur = capi.Cursor(name, True) if rank == 0 else None
+    barrier()
+    if rank != 0:
+        cur = capi.Cursor(name, False)
+    tol_all = ensembles.mixed_tolerances(Mt)
+    streams = [(torch.cuda.Stream(), torch.cuda.Stream()) for _ in range(depth)]
+    slots = [None] * depth
+
+    def chunk_ens(c):
+        j0 = c * per
+        tr, tv = tol_all[0::2][j0:j0 + per], tol_all[1::2][j0:j0 + per]
+        Pr, Pv = ensembles.robertson_params(per, start=j0), ensembles.vdpol_params(per, start=j0, total=half)
+        pair = []
+        for prob, method, t1, y0h, P, tl in ((capi.ROBERTSON, capi.RADAU_IIA_53, 40.0, ensembles.ROBERTSON_Y0, Pr, tr),
+                                             (capi.VAN_DER_POL, capi.LOBATTO_IIIC_43, 2.0, ensembles.VDPOL_Y0, Pv, tv)):
+            tl_d = cu(tl)
+            keys = cu(np.vstack([tl[None, :], P[:2]]))          # the tolerance is a cost dimension like any parameter
+            pair.append((DeviceEnsemble(prob, method, per, cu(y0h.copy()), cu(P), rtol=tl_d, atol=tl_d.clone(),
+                                        newton_tol=(0.1 * tl_d).contiguous(), handout_order=capi.ORDER_LOCALITY, handout_keys=keys), t1))
+        return pair
+
+    # every rank may end up with any chunk: all of them are staged on every GPU beforehand (synthetic inputs, ~0.4 GB)
+    chunks = [chunk_ens(c) for c in range(n_chunks)]
+
+    def run_all():
+        mine = []
+        main = torch.cuda.current_stream()
+        k = 0
+        while True:
+            slot = k % depth
+            if slots[slot] is not None:
+                slots[slot].synchronize()       # a slot is free again when its chunk is done: only then claim more work
+            c = cur.next(1)
+            if c >= n_chunks:
+                break
+            for (de, t1), st in zip(chunks[c], streams[slot]):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    de.solve(0.0, t1, DT0, o)
+            # the slot is done when BOTH its streams are: join them on the second stream
+            streams[slot][1].wait_stream(streams[slot][0])
+            e = torch.cuda.Event()
+            e.record(streams[slot][1])
+            slots[slot] = e
+            mine.append(c)
+            k += 1
+        for pair in streams:
+            for st in pair:
+                main.wait_stream(st)
+        return mine
+
+    def timed():
+        for i in range(depth):
+            slots[i] = None
+        barrier()
+        if rank == 0:
+            cur.reset()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mine = run_all()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), mine
+
+    timed()                                      # warm-up (also the first touch of every chunk's buffers)
+    ms, mine = timed()
+    ms = max_over_ranks(ms)
+    failed = sum(int((de.status != 0).sum()) for c in mine for de, _ in chunks[c])
+    att = sum(int(de.counter("attempt").sum()) for c in mine for de, _ in chunks[c])
+    t = torch.tensor([float(failed), float(att), float(len(mine)), float(-len(mine))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t[:3])
+        lo_hi = torch.tensor([float(len(mine)), float(-len(mine))], dtype=torch.float64, device=dev)
+        dist.all_reduce(lo_hi, op=dist.ReduceOp.MAX)
+        most, least = int(lo_hi[0].item()), int(-lo_hi[1].item())
+    else:
+        most = least = len(mine)
+    out["config5_mixed_10485760_total"] = {"ms": ms, "systems_per_s": Mt / (ms * 1e-3), "members_total": Mt, "chunks": n_chunks,
+                                           "chunks_in_flight_per_gpu": depth, "chunks_claimed_min_max": [least, most],
+                                           "failed_members": int(t[0].item()), "attempts_per_member": t[1].item() / Mt,
+                                           "balance": "chunks claimed from a shared-memory cursor (rehuel_cursor) as GPUs finish"}
+    barrier()
+    cur.close()
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -402,6 +642,8 @@ def main() -> None:
     ap.add_argument("--span", choices=tuple(SPANS), default="short")
     ap.add_argument("--members", type=int, default=M_PER_GPU, help="members per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline + e2e only (no long span, other configs, strong block)")
+    ap.add_argument("--long-steps", type=int, default=4, help="timed launches of the long-span block")
     ap.add_argument("--handout", choices=("index", "locality", "locality_desc"), default="locality_desc",
                     help="order in which members are handed to the GPU lanes (results do not depend on it)")
     args = ap.parse_args()

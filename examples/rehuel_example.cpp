@@ -47,7 +47,7 @@ const equation kEquations[] = {
 };
 
 struct user_options {
-	std::string eq = "exponential", method = "LOBATTO_IIIC_85", output_fname;
+	std::string eq = "exponential", method = "LOBATTO_IIIC_85", output_fname, stream_fname;
 	double t0 = 0.0, t1 = 10.0, dt = 1e-2, rel_tol = 1e-5, abs_tol = 1e-4; // example_equations.cpp:40-43
 	int out_interval = 0, time_internals = 0, gpus = 1;
 	std::size_t ensemble = 1, member = 0, max_samples = 1u << 16, dense = 0;
@@ -62,7 +62,7 @@ void print_usage()
 	             "                 --time-span <t0> <t1> --dt <dt>\n"
 	             "                 --rel-tol <rtol> --abs-tol <atol>\n"
 	             "                 --out-interval <interval> --time-internals <0/1>\n"
-	             "                 --output-file <fname>\n"
+	             "                 --output-file <fname> [--write-to-file <fname>]\n"
 	             "                 [--ensemble <M>] [--sweep <decades>] [--member <i>] [--gpus <N>]\n"
 	             "                 [--param <value>]... [--dense <K> <dt>] [--max-samples <rows>]\n"
 	             "with\n"
@@ -77,7 +77,7 @@ int parse_opts(int argc, char **argv, user_options &u)
 {
 	const std::map<std::string, int> arity = {
 	    {"--equation", 1}, {"--method", 1}, {"--time-span", 2}, {"--dt", 1}, {"--rel-tol", 1}, {"--abs-tol", 1},
-	    {"--out-interval", 1}, {"--time-internals", 1}, {"--output-file", 1}, {"--ensemble", 1}, {"--sweep", 1},
+	    {"--out-interval", 1}, {"--time-internals", 1}, {"--output-file", 1}, {"--write-to-file", 1}, {"--ensemble", 1}, {"--sweep", 1},
 	    {"--member", 1}, {"--gpus", 1}, {"--param", 1}, {"--dense", 2}, {"--max-samples", 1}};
 	for (int i = 1; i < argc;) {
 		const std::string arg = argv[i];
@@ -109,6 +109,7 @@ int parse_opts(int argc, char **argv, user_options &u)
 				return -2;
 			}
 		} else if (arg == "--output-file") u.output_fname = v;
+		else if (arg == "--write-to-file") u.stream_fname = v; // output_options::WRITE_TO_FILE inside the integrator (irk.hpp:837-843)
 		else if (arg == "--ensemble") u.ensemble = (std::size_t)std::atoll(v);
 		else if (arg == "--sweep") u.sweep = std::atof(v);
 		else if (arg == "--member") u.member = (std::size_t)std::atoll(v);
@@ -192,6 +193,7 @@ int main(int argc, char **argv)
 	s_opts.abs_tol = u.abs_tol;
 	s_opts.out_interval = u.out_interval;
 	s_opts.time_internals = u.time_internals != 0;
+	s_opts.trace_member = u.member;
 	n_opts.tol = 0.1 * std::min(s_opts.rel_tol, s_opts.abs_tol);
 	output_options output_opts;
 	output_opts.max_samples = u.dense ? 0 : u.max_samples;
@@ -200,6 +202,7 @@ int main(int argc, char **argv)
 		output_opts.dense_t0 = u.t0;
 		output_opts.dense_dt = u.dense_dt;
 	}
+	if (!u.stream_fname.empty()) output_opts.set_output_file(u.stream_fname);
 	std::ofstream file;
 	if (!u.output_fname.empty()) {
 		std::cerr << "Writing to file\n";
@@ -215,6 +218,8 @@ int main(int argc, char **argv)
 			return 2;
 		}
 		const std::size_t i = u.member;
+		if (u.out_interval > 0) std::cout << sol.log(); // output_opts.log_out is std::cout in the reference (options.hpp:106)
+		if (u.time_internals) std::cerr << sol.timing_breakdown(irk::method_to_name(method)); // irk.hpp:866
 		if (u.dense) {
 			for (std::size_t g = 0; g < sol.n_dense(); ++g) {
 				os << u.t0 + (double)g * u.dense_dt;

@@ -74,12 +74,17 @@ typedef struct rehuel_options {
 	double max_dt;                  /* options.hpp:52   0 = no cap */
 	long long max_steps;            /* options.hpp:53   <0 = unlimited; compared against ACCEPTED steps (irk.hpp:612) */
 	int adaptive_step_size;         /* irk.hpp:103      default 1 */
-	int out_interval;               /* options.hpp:55   >0: keep a per-attempt trace "step t dt err iters" (irk.hpp:805-810) */
+	int out_interval;               /* options.hpp:55   >0: the host-buffer entry points keep the reference's per-attempt log
+	                                   "step t dt err iters" (irk.hpp:575-577, 805-810) of member `trace_member`: one row per
+	                                   attempt that reaches the error estimate and whose accepted-step count is a multiple of
+	                                   out_interval (rehuel_result.trace; text form: rehuel_result_format_log) */
 	double newton_tol;              /* newton.hpp:58    tol      -> Rtol, default 1e-4 */
 	double newton_dx_delta;         /* newton.hpp:58    dx_delta -> xtol, default 1e-4 */
 	int newton_maxit;               /* newton.hpp:58    default 5000 */
 	int newton_refresh_jac;         /* newton.hpp:59    default 10 */
-	int output_mode;                /* options.hpp:96-103 bit 0: store samples (STORE_IN_VECTORS); default 1 */
+	int output_mode;                /* options.hpp:96-103 bit 0: store samples (STORE_IN_VECTORS); bit 1: WRITE_TO_FILE, the
+	                                   samples of member `trace_member` are also written to `output_file` as "t y0 y1 ...\n"
+	                                   lines (irk.hpp:837-843); default 1 */
 	unsigned long long output_interval; /* options.hpp:104 every k-th ACCEPTED step is a sample; default 1 */
 	int keep_state;                 /* NEW: != 0 makes the host-buffer entry points return the controller state at exit
 	                                   (rehuel_result.state) so that rehuel_irk_ensemble_continue can carry on where
@@ -95,15 +100,37 @@ typedef struct rehuel_options {
 	                                   the host-buffer entry points hand members to the GPU lanes.  REHUEL_ORDER_INDEX,
 	                                   REHUEL_ORDER_LOCALITY (default) or REHUEL_ORDER_LOCALITY_DESC.  Results do not
 	                                   depend on it. */
-	int shard_mode;                 /* NEW: how rehuel_irk_ensemble(..., n_gpus > 1) deals members to the GPUs:
-	                                   REHUEL_SHARD_CONTIGUOUS (default): GPU g owns members [M g/G, M (g+1)/G);
-	                                   REHUEL_SHARD_INTERLEAVED: chunks of >= 16 Ki members go to the GPUs in turn, for
-	                                   ensembles whose cost grows along the index (a stiffness sweep).  Results do not
-	                                   depend on it. */
+	int shard_mode;                 /* NEW: how rehuel_irk_ensemble(..., n_gpus > 1) deals members to the GPUs.  One
+	                                   issuing host thread per device in every mode.
+	                                   REHUEL_SHARD_DYNAMIC (default): [0, M) is cut into small chunks (>= 16 Ki members, up to
+	                                   64 per GPU) that the devices claim from a shared atomic cursor as they finish, so a GPU
+	                                   that gets cheap members takes more of them;
+	                                   REHUEL_SHARD_CONTIGUOUS: GPU g owns members [M g/G, M (g+1)/G), 8 chunks each;
+	                                   REHUEL_SHARD_INTERLEAVED: chunks of >= 128 Ki members go to the GPUs in turn.
+	                                   Results do not depend on it (a member's result does not depend on where it runs). */
+	unsigned long long trace_member; /* NEW: the member out_interval and WRITE_TO_FILE report on (the reference integrates one
+	                                   system per call, so it has no such choice).  Default 0. */
+	const char *output_file;        /* output_options::output_stream (options.hpp:107,119-123) as a path; NULL = none.  Opened for
+	                                   writing by the call when output_mode bit 1 is set. */
+	unsigned result_mask;           /* NEW: which per-member arrays of rehuel_result the host-buffer entry points copy back
+	                                   (REHUEL_OUT_* bits).  y, status and the ensemble sums always come back; an array that
+	                                   is not asked for is NULL in the result.  On success t_final == t1 for every member and
+	                                   the counters are summed on the device (rehuel_result.sum), so a caller that only
+	                                   wants the states moves 8n + 4 bytes per member instead of 8n + 56.
+	                                   Default REHUEL_OUT_ALL (every field of rk_output, irk.hpp:140-163). */
+	int time_internals;             /* irk.hpp:106, 328-360: != 0 fills rehuel_result.phase_ms (device time of the host-to-device
+	                                   copies, the hand-out ordering, the integration kernels and the device-to-host copies,
+	                                   CUDA events; the reference times its six host phases with a wall clock).  Default 0. */
 } rehuel_options;
+
+#define REHUEL_OUT_T_FINAL   1u   /* rehuel_result.t_final */
+#define REHUEL_OUT_ERR_LAST  2u   /* rehuel_result.err_last */
+#define REHUEL_OUT_COUNTERS  4u   /* the nine per-member counter arrays */
+#define REHUEL_OUT_ALL       7u
 
 #define REHUEL_SHARD_CONTIGUOUS  0
 #define REHUEL_SHARD_INTERLEAVED 1
+#define REHUEL_SHARD_DYNAMIC     2
 
 #define REHUEL_ORDER_INDEX          0 /* member i is the i-th to be handed out */
 #define REHUEL_ORDER_LOCALITY       1 /* space-filling-curve order of the parameter vectors: members with nearby
@@ -150,7 +177,8 @@ typedef struct rehuel_result {
 	int n;
 	double *t_final;        /* [M]    time reached (== t1 on success) */
 	double *y;              /* [n][M] state at t_final */
-	double *err_last;       /* [M]    scaled error norm of the last accepted step (rk_output::err.back()) */
+	double *err_last;       /* [M]    scaled error norm of the last attempt that reached the error estimate (for a member
+	                           that ran to t1 that is its last accepted step, rk_output::err.back()) */
 	int *status;            /* [M]    REHUEL_SUCCESS or a status bit */
 	unsigned *attempt, *reject_newton, *reject_err, *newton_success, *newton_maxit_exceed,
 	    *fun_evals, *jac_evals, *newton_iters, *steps; /* [M] each */
@@ -167,15 +195,33 @@ typedef struct rehuel_result {
 	double kernel_ms;       /* device time of the integration kernel(s), max over GPUs */
 	double accept_frac;     /* sum(steps)/sum(attempt)  (irk.hpp:864) */
 	rehuel_stats sum;
+	size_t trace_len;       /* rows of `trace` (options.out_interval > 0), else 0 */
+	double *trace;          /* [trace_len][5]: step, t, dt, err, newton iterations of member options.trace_member, one row
+	                           per logged attempt in the order the reference prints them (irk.hpp:805-810) */
+	double phase_ms[4];     /* options.time_internals: REHUEL_PHASE_* device times in ms, summed over chunks and devices */
 	void *impl;             /* private */
 } rehuel_result;
+
+#define REHUEL_PHASE_H2D     0
+#define REHUEL_PHASE_ORDER   1
+#define REHUEL_PHASE_KERNEL  2
+#define REHUEL_PHASE_D2H     3
+
+/* The reference's log text for rehuel_result.trace: the header line "    Rehuel: step  t  dt   err   iters" (irk.hpp:576)
+ * and one "    Rehuel: <step> <t> <dt> <err> <iters>" line per row (irk.hpp:807-809) at `precision` significant digits
+ * (the reference streams at the stream's precision; 6 = the iostream default).  Writes at most cap-1 characters + NUL;
+ * returns the length the full text needs (like snprintf). */
+size_t rehuel_result_format_log(const rehuel_result *res, int precision, char *buf, size_t cap);
+/* print_timing_breakdown (irk.hpp:328-360) for rehuel_result.phase_ms, same layout ("    Rehuel: <method> done solving,
+ * timings (ms | %):" + one line per phase); snprintf-like. */
+size_t rehuel_result_format_timings(const rehuel_result *res, const char *method_name, char *buf, size_t cap);
 
 /* Batched irk::odeint (irk.hpp:884-898): every member is its own adaptive integration.
  *   y0      [n][M], or [n] when y0_broadcast != 0
  *   params  [p][M]
  *   n_hint  see rehuel_problem_dims
  *   n_samples_cap  rows of sample storage per member (0: final state only)
- *   n_gpus  devices 0..n_gpus-1 of this process each take a contiguous share of the members
+ *   n_gpus  devices 0..n_gpus-1 of this process share the members (options.shard_mode)
  * Blocking.  Returns REHUEL_OK or a negative library error; numerical failures are reported per
  * member in out->status[]. */
 int rehuel_irk_ensemble(int problem, int method, double t0, double t1, double dt0, size_t M,
@@ -286,6 +332,20 @@ int rehuel_irk_ensemble_continue(int problem, int method, double t1, int n_hint,
  * into `a` (counters added -- fun_evals/jac_evals are NOT, exactly like the reference --, status
  * OR-ed, accept_frac weighted by the number of stored samples).  `b` is left untouched. */
 int rehuel_result_merge(rehuel_result *a, const rehuel_result *b);
+
+/* Work cursor shared by the processes of one node ("over-decompose into chunks pulled from a host-side
+ * atomic"): a 64-bit counter in a named POSIX shared-memory object.  One process per GPU (the torchrun layout) cuts the
+ * ensemble into chunks and every rank claims the next chunk index with rehuel_cursor_next until the indices run out, so
+ * a rank whose members are cheap takes more of them; inside ONE process rehuel_irk_ensemble(..., n_gpus > 1) does the
+ * same with REHUEL_SHARD_DYNAMIC.  `name` without slashes; create != 0 creates (or re-creates) the object and zeroes
+ * the counter, create == 0 opens an existing one.  NULL on error (rehuel_last_error()). */
+typedef struct rehuel_cursor rehuel_cursor;
+rehuel_cursor *rehuel_cursor_open(const char *name, int create);
+/* Atomically adds `count` and returns the value before the add (the first index claimed). */
+unsigned long long rehuel_cursor_next(rehuel_cursor *c, unsigned long long count);
+void rehuel_cursor_reset(rehuel_cursor *c);
+/* Unmaps; unlink != 0 also removes the name (the creating rank does that). */
+void rehuel_cursor_close(rehuel_cursor *c, int unlink);
 
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
 unsigned long long rehuel_kernel_launches(void);

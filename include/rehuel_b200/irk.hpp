@@ -61,6 +61,14 @@ struct output_options {
 	std::size_t output_mode = STORE_IN_VECTORS;
 	std::size_t output_interval = 1;
 	std::size_t max_samples = 0; // NEW: rows of sample storage per member (0 = final state only)
+	// options.hpp:107,119-123: the reference holds an ostream*; across the C ABI the stream is a path
+	std::string output_file;
+	bool write_to_file() const { return output_mode & 2; }
+	void set_output_file(const std::string &path)
+	{
+		output_file = path;
+		output_mode |= 2;
+	}
 	// NEW: dense output on the uniform grid dense_t0 + k*dense_dt, k < dense_samples (project_b, irk.cpp:731-747)
 	std::size_t dense_samples = 0;
 	double dense_t0 = 0.0, dense_dt = 0.0;
@@ -81,11 +89,13 @@ enum rk_methods {
 struct solver_options : common_solver_options {
 	solver_options() : adaptive_step_size(true), use_newton_iters_adaptive_step(true), verbose_newton(false),
 	                   extrapolate_stage(false), keep_state(false), handout_order(REHUEL_ORDER_LOCALITY),
-	                   shard_mode(REHUEL_SHARD_CONTIGUOUS) {}
+	                   shard_mode(REHUEL_SHARD_DYNAMIC), trace_member(0), result_mask(REHUEL_OUT_ALL) {}
 	bool adaptive_step_size, use_newton_iters_adaptive_step, verbose_newton, extrapolate_stage;
 	bool keep_state; // NEW: keep the controller state so that irk::odeint_continue can carry on (restore_state, irk.cpp:786)
 	int handout_order; // NEW: REHUEL_ORDER_* (scheduling of the batched overload only; results do not depend on it)
 	int shard_mode;    // NEW: REHUEL_SHARD_* (how n_gpus > 1 deals members to the devices)
+	unsigned long long trace_member; // NEW: the member out_interval / WRITE_TO_FILE report on
+	unsigned result_mask;            // NEW: REHUEL_OUT_* -- which per-member arrays come back (default: all of rk_output)
 };
 inline solver_options default_solver_options() { return solver_options(); }
 
@@ -97,6 +107,7 @@ inline rehuel_options to_c_options(const solver_options &so, const output_option
 {
 	if (!so.newton_opts) throw std::invalid_argument("Newton solver options not set!"); // irk.hpp:548
 	rehuel_options o;
+	rehuel_default_options(&o);
 	o.rel_tol = so.rel_tol;
 	o.abs_tol = so.abs_tol;
 	o.max_dt = so.max_dt;
@@ -115,6 +126,10 @@ inline rehuel_options to_c_options(const solver_options &so, const output_option
 	o.dense_dt = oo.dense_dt;
 	o.handout_order = so.handout_order;
 	o.shard_mode = so.shard_mode;
+	o.trace_member = so.trace_member;
+	o.output_file = oo.write_to_file() ? oo.output_file.c_str() : nullptr; // borrowed: `oo` outlives the call
+	o.result_mask = so.result_mask;
+	o.time_internals = so.time_internals ? 1 : 0;
 	return o;
 }
 
@@ -145,7 +160,23 @@ public:
 		for (std::size_t i = 0; i < r_.M; ++i) s |= r_.status[i];
 		return s;
 	}
-	double t_final(std::size_t i) const { return r_.t_final[i]; }
+	double t_final(std::size_t i) const { return r_.t_final[i]; } // needs REHUEL_OUT_T_FINAL (the default)
+	// the reference's per-attempt log (irk.hpp:575-577, 805-810) of solver_opts.trace_member, as text
+	std::string log(int precision = 6) const
+	{
+		std::string text(rehuel_result_format_log(&r_, precision, nullptr, 0) + 1, '\0');
+		rehuel_result_format_log(&r_, precision, &text[0], text.size());
+		text.pop_back();
+		return text;
+	}
+	// print_timing_breakdown (irk.hpp:328-360) for solver_opts.time_internals
+	std::string timing_breakdown(const char *method_name) const
+	{
+		std::string text(rehuel_result_format_timings(&r_, method_name, nullptr, 0) + 1, '\0');
+		rehuel_result_format_timings(&r_, method_name, &text[0], text.size());
+		text.pop_back();
+		return text;
+	}
 	double y(std::size_t i, int k) const { return r_.y[(std::size_t)k * r_.M + i]; }
 	std::vector<double> y(std::size_t i) const
 	{

@@ -41,11 +41,15 @@ class Options(C.Structure):
         ("output_mode", C.c_int), ("output_interval", C.c_ulonglong),
         ("keep_state", C.c_int), ("dense_samples", C.c_ulonglong), ("dense_t0", C.c_double), ("dense_dt", C.c_double),
         ("handout_order", C.c_int), ("shard_mode", C.c_int),
+        ("trace_member", C.c_ulonglong), ("output_file", C.c_char_p), ("result_mask", C.c_uint),
+        ("time_internals", C.c_int),
     ]
 
 
 ORDER_INDEX, ORDER_LOCALITY, ORDER_LOCALITY_DESC = 0, 1, 2
-SHARD_CONTIGUOUS, SHARD_INTERLEAVED = 0, 1
+SHARD_CONTIGUOUS, SHARD_INTERLEAVED, SHARD_DYNAMIC = 0, 1, 2
+OUT_T_FINAL, OUT_ERR_LAST, OUT_COUNTERS, OUT_ALL = 1, 2, 4, 7  # rehuel_options.result_mask
+PHASES = ("h2d", "order", "kernel", "d2h")                      # rehuel_result.phase_ms
 NSTATE = 8  # rows of the controller state (REHUEL_STATE_*)
 
 
@@ -72,7 +76,7 @@ class Result(C.Structure):
         ("t_samples", _PD), ("y_samples", _PD), ("err_samples", _PD),
         ("state", _PD), ("n_dense", C.c_size_t), ("y_dense", _PD),
         ("elapsed_ms", C.c_double), ("kernel_ms", C.c_double), ("accept_frac", C.c_double),
-        ("sum", Stats), ("impl", C.c_void_p),
+        ("sum", Stats), ("trace_len", C.c_size_t), ("trace", _PD), ("phase_ms", C.c_double * 4), ("impl", C.c_void_p),
     ]
 
 
@@ -125,6 +129,16 @@ def _load() -> C.CDLL:
         C.POINTER(Result)]
     lib.rehuel_result_free.argtypes = [C.POINTER(Result)]
     lib.rehuel_result_merge.argtypes = [C.POINTER(Result), C.POINTER(Result)]
+    lib.rehuel_cursor_open.restype = C.c_void_p
+    lib.rehuel_cursor_open.argtypes = [C.c_char_p, C.c_int]
+    lib.rehuel_cursor_next.restype = C.c_ulonglong
+    lib.rehuel_cursor_next.argtypes = [C.c_void_p, C.c_ulonglong]
+    lib.rehuel_cursor_reset.argtypes = [C.c_void_p]
+    lib.rehuel_cursor_close.argtypes = [C.c_void_p, C.c_int]
+    lib.rehuel_result_format_log.restype = C.c_size_t
+    lib.rehuel_result_format_log.argtypes = [C.POINTER(Result), C.c_int, C.c_char_p, C.c_size_t]
+    lib.rehuel_result_format_timings.restype = C.c_size_t
+    lib.rehuel_result_format_timings.argtypes = [C.POINTER(Result), C.c_char_p, C.c_char_p, C.c_size_t]
     return lib
 
 
@@ -137,8 +151,30 @@ EXPORTS = (
     "rehuel_irk_single", "rehuel_irk_ensemble_device", "rehuel_result_merge", "rehuel_kernel_launches",
     "rehuel_kernel_info", "rehuel_last_error", "rehuel_version", "rehuel_fp64_peak", "rehuel_release_cached_memory",
     "rehuel_locality_order_workspace", "rehuel_locality_order", "rehuel_irk_ensemble_continue", "rehuel_selftest_band",
-    "rehuel_eval_functor", "rehuel_debug_force_pivot",
+    "rehuel_eval_functor", "rehuel_debug_force_pivot", "rehuel_result_format_log", "rehuel_result_format_timings",
+    "rehuel_cursor_open", "rehuel_cursor_next", "rehuel_cursor_reset", "rehuel_cursor_close",
 )
+
+
+class Cursor:
+    """rehuel_cursor: a work cursor shared by the ranks of one node (named POSIX shared memory)."""
+
+    def __init__(self, name: str, create: bool):
+        self.h = lib.rehuel_cursor_open(name.encode(), int(create))
+        self.owner = create
+        if not self.h:
+            raise RehuelError(-1, last_error())
+
+    def next(self, count: int = 1) -> int:
+        return int(lib.rehuel_cursor_next(self.h, count))
+
+    def reset(self) -> None:
+        lib.rehuel_cursor_reset(self.h)
+
+    def close(self) -> None:
+        if self.h:
+            lib.rehuel_cursor_close(self.h, int(self.owner))
+            self.h = None
 
 
 def last_error() -> str:
@@ -159,7 +195,8 @@ def default_options() -> Options:
 def make_options(rel_tol=1e-4, abs_tol=None, max_dt=0.0, max_steps=-1, adaptive=True, out_interval=0,
                  newton_tol=None, newton_dx_delta=1e-4, newton_maxit=5000, newton_refresh_jac=10,
                  output_mode=1, output_interval=1, handout_order=ORDER_LOCALITY, keep_state=False,
-                 dense_samples=0, dense_t0=0.0, dense_dt=0.0, shard_mode=0) -> Options:
+                 dense_samples=0, dense_t0=0.0, dense_dt=0.0, shard_mode=SHARD_DYNAMIC, trace_member=0, output_file=None,
+                 result_mask=OUT_ALL, time_internals=False) -> Options:
     """Reference defaults, with newton_tol = 0.1*min(rtol, atol) unless given -- what the example
     driver and the 4-argument odeint do (examples/example_equations.cpp:220, irk.hpp:921)."""
     if abs_tol is None:
@@ -168,7 +205,8 @@ def make_options(rel_tol=1e-4, abs_tol=None, max_dt=0.0, max_steps=-1, adaptive=
         newton_tol = 0.1 * min(rel_tol, abs_tol)
     return Options(rel_tol, abs_tol, max_dt, max_steps, int(adaptive), out_interval, newton_tol,
                    newton_dx_delta, newton_maxit, newton_refresh_jac, output_mode, output_interval, int(keep_state),
-                   dense_samples, dense_t0, dense_dt, handout_order, shard_mode)
+                   dense_samples, dense_t0, dense_dt, handout_order, shard_mode, trace_member,
+                   output_file.encode() if isinstance(output_file, str) else output_file, result_mask, int(time_internals))
 
 
 def name_to_method(name: str) -> int:
@@ -269,6 +307,9 @@ class EnsembleOutput:
     sum: dict
     state: np.ndarray | None = None    # [NSTATE, M] controller state at exit (options.keep_state)
     y_dense: np.ndarray | None = None  # [n_dense, n, M] dense-output samples (options.dense_samples)
+    trace: np.ndarray | None = None    # [trace_len, 5] step, t, dt, err, iters of options.trace_member (options.out_interval)
+    log: str = ""                      # the same as the reference prints it (irk.hpp:575-577, 805-810), 17 digits
+    phase_ms: dict | None = None       # options.time_internals: device ms per phase
 
 
 def _as_np(ptr, shape, dtype):
@@ -304,9 +345,9 @@ def to_output(res: Result) -> EnsembleOutput:
     """Copy a raw ``rehuel_result`` into numpy arrays (the C result stays owned by the caller)."""
     n, M, cap = res.n, res.M, res.n_samples_cap
     return EnsembleOutput(
-        y=_as_np(res.y, (n, M), np.float64), t_final=_as_np(res.t_final, (M,), np.float64),
-        err_last=_as_np(res.err_last, (M,), np.float64), status=_as_np(res.status, (M,), np.int32),
-        counters={k: _as_np(getattr(res, k), (M,), np.uint32) for k in COUNTER_ROWS},
+        y=_as_np(res.y, (n, M), np.float64), t_final=_as_np(res.t_final, (M,), np.float64) if res.t_final else None,
+        err_last=_as_np(res.err_last, (M,), np.float64) if res.err_last else None, status=_as_np(res.status, (M,), np.int32),
+        counters={k: _as_np(getattr(res, k), (M,), np.uint32) for k in COUNTER_ROWS} if res.attempt else None,
         n_samples=_as_np(res.n_samples, (M,), np.uint32),
         t_samples=_as_np(res.t_samples, (cap, M), np.float64) if cap else None,
         y_samples=_as_np(res.y_samples, (cap, n, M), np.float64) if cap else None,
@@ -314,7 +355,25 @@ def to_output(res: Result) -> EnsembleOutput:
         elapsed_ms=res.elapsed_ms, kernel_ms=res.kernel_ms, accept_frac=res.accept_frac,
         sum={k: int(getattr(res.sum, k)) for k, _ in Stats._fields_},
         state=_as_np(res.state, (NSTATE, M), np.float64) if res.state else None,
-        y_dense=_as_np(res.y_dense, (res.n_dense, n, M), np.float64) if res.n_dense else None)
+        y_dense=_as_np(res.y_dense, (res.n_dense, n, M), np.float64) if res.n_dense else None,
+        trace=_as_np(res.trace, (res.trace_len, 5), np.float64) if res.trace else None,
+        log=format_log(res, 17) if res.trace else "",
+        phase_ms=dict(zip(PHASES, list(res.phase_ms))))
+
+
+def format_log(res: Result, precision: int = 6) -> str:
+    """rehuel_result_format_log: the per-attempt log in the reference's words."""
+    need = lib.rehuel_result_format_log(C.byref(res), precision, None, 0)
+    buf = C.create_string_buffer(need + 1)
+    lib.rehuel_result_format_log(C.byref(res), precision, buf, need + 1)
+    return buf.value.decode()
+
+
+def format_timings(res: Result, method_name: str) -> str:
+    need = lib.rehuel_result_format_timings(C.byref(res), method_name.encode(), None, 0)
+    buf = C.create_string_buffer(need + 1)
+    lib.rehuel_result_format_timings(C.byref(res), method_name.encode(), buf, need + 1)
+    return buf.value.decode()
 
 
 def irk_ensemble_continue(problem: int, method: int, t1: float, params, opts: Options, prev: Result,

@@ -47,6 +47,7 @@ struct KernelArgs {
 	// warp of the grid; force_pivot != 0 sends every attempt through that fallback (rehuel_debug_force_pivot)
 	double *pivot_scratch;
 	int force_pivot;
+	int trace_interval; // io.trace: log the attempts whose accepted-step count is a multiple of this (irk.hpp:805-806)
 };
 
 constexpr double kMachinePrecision = 1e-17; // enums.hpp:129
@@ -60,12 +61,13 @@ constexpr int kFastIters = REHUEL_FAST_ITERS; // Newton iterations a lane may ta
 #endif
 constexpr int kParkLanes = REHUEL_PARK_LANES; // parked lanes per warp that trigger a slow trip
 
-// Reciprocal for LU pivots and 1/dt: MUFU.RCP64H seed (~20 bits) + two Newton steps (quadratic:
-// 20 -> 40 -> 80 bits, i.e. correctly rounded up to ~1 ulp), 5 instructions and no slow path
-// instead of the ~14-instruction IEEE division.  Only used where the result feeds the LINEAR
-// SOLVES (their rounding is not part of the parity contract: the decoupled solve already differs
-// from the reference's dense LU in the last bits); the step-size controller and the error norm
-// keep IEEE divisions.  0, Inf and NaN pivots still produce Inf/NaN and fail the Newton iteration.
+// Reciprocal: MUFU.RCP64H seed (~20 bits) + two Newton steps (quadratic: 20 -> 40 -> 80 bits, i.e.
+// correctly rounded up to ~1 ulp), 5 instructions and no slow path instead of the ~14-instruction
+// IEEE division.  Used for the LU pivots and 1/dt (the rounding of the LINEAR SOLVES is not part of the
+// parity contract: the decoupled solve already differs from the reference's dense LU in the last bits)
+// and, for the same reason -- everything downstream of the solve carries that last-bit difference --,
+// for the scaled error norm and the step-size proposal (propose_dt).  0, Inf and NaN arguments still
+// produce Inf/NaN, so a singular pivot fails the Newton iteration as it does in the reference.
 __device__ __forceinline__ double fast_rcp(double x)
 {
 	double r;
@@ -75,6 +77,27 @@ __device__ __forceinline__ double fast_rcp(double x)
 	e = fma(-x, r, 1.0);
 	r = fma(r, e, r);
 	return r;
+}
+
+// One row of the per-attempt log of member io.trace_member, irk.hpp:805-810 ("step t dt err iters"; the reference prints
+// it for the attempts that reach the error estimate, accepted or not, when step % out_interval == 0).  Attempts whose
+// Newton iteration failed are logged too, with err = -1 (the reference has that message commented out, irk.hpp:649-656).
+// Called by the one thread that speaks for the member.
+__device__ __forceinline__ void trace_row(const KernelArgs &a, unsigned long long mem, long long step, double t, double dt,
+                                          double err, int iters)
+{
+	const rehuel_device_io &io = a.io;
+	if (io.trace && mem == io.trace_member && (a.trace_interval <= 1 || step % a.trace_interval == 0)) {
+		const unsigned r = atomicAdd(io.trace_len, 1u);
+		if (r < io.trace_cap) {
+			double *row = io.trace + 5 * (size_t)r;
+			row[0] = (double)step;
+			row[1] = t;
+			row[2] = dt;
+			row[3] = err;
+			row[4] = (double)iters;
+		}
+	}
 }
 
 // ------------------------------------------------------------------ small dense LU, registers
@@ -350,8 +373,8 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	const rehuel_device_io &io = a.io;
 	// ensemble sums (io.stats): a finishing member adds its counters to the CTA's shared-memory totals, the CTA adds
 	// them to global memory once at the end -- no separate reduction pass over the counter arrays
-	__shared__ unsigned s_stats[REHUEL_NSTATS];
-	if (threadIdx.x < REHUEL_NSTATS) s_stats[threadIdx.x] = 0u;
+	__shared__ unsigned long long s_stats[REHUEL_NSTATS];
+	if (threadIdx.x < REHUEL_NSTATS) s_stats[threadIdx.x] = 0ull;
 	__syncthreads();
 
 	// ---- lane-persistent member state
@@ -667,9 +690,10 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					if (Rnorm2 < (TOLV ? m_Rtol2 : a.Rtol2)) { nstat = kNewtonSuccess; break; } // irk.hpp:473-476
 					if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; } // irk.hpp:477-480
 					if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac; // irk.hpp:485-487 (no-op refactor)
-					if (!(Rnorm2 <= 1.79769313486231570e308)) {
-						// NaN/Inf residual can never pass either test again (Y stays non-finite):
-						// the reference spins to maxit; account the remaining evaluations and stop.
+					if (!(Rnorm2 <= 1.79769313486231570e308) && !(xnorm2 <= 1.79769313486231570e308)) {
+						// A non-finite update makes Y non-finite, and Y + dY can never become finite again: neither
+						// test can pass any more, the reference spins to maxit.  Account the remaining evaluations
+						// and stop.  (|R|^2 alone may overflow with R and Y finite -- then the iteration goes on.)
 						const int rest = maxit - 1 - it;
 						if (rest > 0) {
 							c_fun += (unsigned)rest * S;
@@ -695,6 +719,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					parked = true;
 				} else if (nstat != kNewtonSuccess) { // irk.hpp:634-665
 					parked = false;
+					trace_row(a, mem, step, t, dt, -1.0, it);
 					if (!a.adaptive) {
 						status = REHUEL_GENERAL_ERROR;
 						finished = true;
@@ -705,13 +730,6 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							last_relax = step;
 						}
 						++c_rej_newton;
-					}
-					if (io.trace && mem == io.trace_member) {
-						unsigned r = atomicAdd(io.trace_len, 1u);
-						if (r < io.trace_cap) {
-							double *row = io.trace + 5 * (size_t)r;
-							row[0] = (double)step; row[1] = t; row[2] = dt; row[3] = -1.0; row[4] = (double)it;
-						}
 					}
 				} else {
 					parked = false;
@@ -791,13 +809,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					// -------- step-size proposal, irk.hpp:770-801 (shifts the error history, irk.hpp:756-758)
 					const double new_dt = propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
 
-					if (io.trace && mem == io.trace_member) { // irk.hpp:805-810
-						unsigned r = atomicAdd(io.trace_len, 1u);
-						if (r < io.trace_cap) {
-							double *row = io.trace + 5 * (size_t)r;
-							row[0] = (double)step; row[1] = t; row[2] = dt; row[3] = err; row[4] = (double)it;
-						}
-					}
+					trace_row(a, mem, step, t, dt, err, it); // irk.hpp:805-810
 					if (!rejected) { // irk.hpp:813-846
 						if (DENSE) { // grid times inside (t, t + dt] from this step's collocation polynomial
 							const double t_new = t + dt;
@@ -870,24 +882,21 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				io.counters[REHUEL_CNT_STEPS * M + mem] = steps_here;
 			}
 			if (io.stats) {
-				// the lanes that finish a member in this trip add up first (one REDUX each), their leader adds the
-				// sums to the CTA's 32-bit shared-memory totals (native atomics); the totals move on to the
-				// 64-bit global words before they can overflow, and at the end of the kernel
+				// the lanes that finish a member in this trip add up first (REDUX), their leader adds the sums to the
+				// CTA's 64-bit shared-memory totals, which go to the global words at the end of the kernel
 				const unsigned fm = __activemask();
-				unsigned v[REHUEL_NCOUNTERS] = {c_attempt, c_rej_newton, c_rej_err, c_newton_ok, c_rej_newton, c_fun, c_jac, c_iters, steps_here};
+				const unsigned v[REHUEL_NCOUNTERS] = {c_attempt, c_rej_newton, c_rej_err, c_newton_ok, c_rej_newton, c_fun, c_jac, c_iters, steps_here};
+				unsigned long long w[REHUEL_NCOUNTERS];
 #pragma unroll
-				for (int c = 0; c < REHUEL_NCOUNTERS; ++c) v[c] = __reduce_add_sync(fm, v[c]);
+				for (int c = 0; c < REHUEL_NCOUNTERS; ++c) // 16-bit halves: a sum over 32 lanes cannot wrap
+					w[c] = (unsigned long long)__reduce_add_sync(fm, v[c] & 0xffffu) + ((unsigned long long)__reduce_add_sync(fm, v[c] >> 16) << 16);
 				const unsigned nfail = __reduce_add_sync(fm, status != 0 ? 1u : 0u);
 				const unsigned amax = __reduce_max_sync(fm, c_attempt);
 				if ((int)lane == __ffs(fm) - 1) {
 #pragma unroll
-					for (int c = 0; c < REHUEL_NCOUNTERS; ++c) atomicAdd(&s_stats[c], v[c]);
-					atomicAdd(&s_stats[REHUEL_NCOUNTERS], nfail);
-					atomicMax(&s_stats[REHUEL_NCOUNTERS + 1], amax);
-					if (s_stats[REHUEL_CNT_FUN_EVALS] > 0x40000000u) { // the fastest-growing total: hand everything on
-#pragma unroll
-						for (int c = 0; c <= REHUEL_NCOUNTERS; ++c) atomicAdd(io.stats + c, (unsigned long long)atomicExch(&s_stats[c], 0u));
-					}
+					for (int c = 0; c < REHUEL_NCOUNTERS; ++c) atomicAdd(&s_stats[c], w[c]);
+					atomicAdd(&s_stats[REHUEL_NCOUNTERS], (unsigned long long)nfail);
+					atomicMax(&s_stats[REHUEL_NCOUNTERS + 1], (unsigned long long)amax);
 				}
 			}
 			if (io.n_samples) io.n_samples[mem] = n_stored;
@@ -907,8 +916,8 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	}
 	__syncthreads(); // every warp of the CTA has left the loop
 	if (io.stats && threadIdx.x < REHUEL_NSTATS && s_stats[threadIdx.x]) {
-		if (threadIdx.x == REHUEL_NCOUNTERS + 1) atomicMax(io.stats + threadIdx.x, (unsigned long long)s_stats[threadIdx.x]);
-		else atomicAdd(io.stats + threadIdx.x, (unsigned long long)s_stats[threadIdx.x]);
+		if (threadIdx.x == REHUEL_NCOUNTERS + 1) atomicMax(io.stats + threadIdx.x, s_stats[threadIdx.x]);
+		else atomicAdd(io.stats + threadIdx.x, s_stats[threadIdx.x]);
 	}
 }
 

@@ -417,6 +417,9 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 		int maxit = a.maxit0;
 		long long step = 0, last_relax = 0;
 		int status = REHUEL_SUCCESS;
+		// per-member tolerances (io.rtol/atol/newton_tol, mixed-tolerance ensembles) or the uniform ones of the options
+		const double m_rtol = io.rtol ? io.rtol[mem] : a.rtol, m_atol = io.rtol ? io.atol[mem] : a.atol;
+		const double m_Rtol2 = io.rtol ? io.newton_tol[mem] * io.newton_tol[mem] : a.Rtol2;
 		unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0, c_iters = 0,
 		         n_stored = 0;
 		if (io.state_in) { // continue a stopped integration: the loop variables as they were at exit
@@ -634,10 +637,10 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 					break;
 				}
 				Rnorm2 = residual();
-				if (Rnorm2 < a.Rtol2) { nstat = kNewtonSuccess; break; }
+				if (Rnorm2 < m_Rtol2) { nstat = kNewtonSuccess; break; }
 				if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; }
 				if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac;
-				if (!(Rnorm2 <= 1.79769313486231570e308)) { // NaN/Inf: see irk_thread.cuh
+				if (!(Rnorm2 <= 1.79769313486231570e308) && !(xnorm2 <= 1.79769313486231570e308)) { // non-finite iterate: see irk_thread.cuh
 					const int rest = maxit - 1 - it;
 					if (rest > 0) {
 						c_fun += (unsigned)rest * S;
@@ -649,6 +652,7 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			}
 
 			if (nstat != kNewtonSuccess) { // irk.hpp:634-665
+				if (lane == 0) trace_row(a, mem, step, t, dt, -1.0, it);
 				if (!a.adaptive) {
 					status = REHUEL_GENERAL_ERROR;
 					break;
@@ -736,7 +740,7 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 #pragma unroll
 			for (int j = 0; j < NPL; ++j) { // irk.hpp:733-746
 				const int i = lane + 32 * j;
-				const double sc = fma(a.rtol, fmax(fabs(yr[j]), fabs(yn[j])), a.atol);
+				const double sc = fma(m_rtol, fmax(fabs(yr[j]), fabs(yn[j])), m_atol);
 				const double q = (FULL || i < N) ? ev[j] / sc : 0.0;
 				tot = fma(q, q, tot);
 			}
@@ -750,6 +754,7 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			}
 			// -------- step-size proposal (irk.hpp:770-801; shifts the error history, irk.hpp:756-758)
 			const double new_dt = propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
+			if (lane == 0) trace_row(a, mem, step, t, dt, err, it); // irk.hpp:805-810
 			bool stuck = false;
 			if (!rejected) { // irk.hpp:813-846
 				if (DENSE) { // grid times inside (t, t + dt] from this step's collocation polynomial

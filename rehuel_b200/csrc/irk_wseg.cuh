@@ -137,6 +137,7 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 	int maxit = a.maxit0;
 	long long step = 0, last_relax = 0, step0 = 0;
 	int status = REHUEL_SUCCESS;
+	double m_rtol = a.rtol, m_atol = a.atol, m_Rtol2 = a.Rtol2; // per-member tolerances when io.rtol is given
 	unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0, c_iters = 0, n_stored = 0;
 	// ---- this lane's rows of its member's factors
 	double ar[N], cr[NCA][N], ci[NCA][N], er[N];
@@ -173,6 +174,11 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 					step = 0;
 					last_relax = 0;
 					status = REHUEL_SUCCESS;
+					if (io.rtol) {
+						m_rtol = io.rtol[mem];
+						m_atol = io.atol[mem];
+						m_Rtol2 = io.newton_tol[mem] * io.newton_tol[mem];
+					}
 					c_attempt = c_rej_newton = c_rej_err = c_newton_ok = c_fun = c_jac = c_iters = 0;
 					if (io.state_in) { // continue a stopped integration: the loop variables as they were at exit
 						const double *si = io.state_in + mem;
@@ -321,12 +327,12 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 				}
 			}
 			if (iter) {
-				if (Rnorm2 < a.Rtol2 || xnorm2 < a.xtol2) {
+				if (Rnorm2 < m_Rtol2 || xnorm2 < a.xtol2) {
 					nstat = kNewtonSuccess;
 					iter = false;
 				} else {
 					if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac;
-					if (!(Rnorm2 <= 1.79769313486231570e308)) { // NaN/Inf: see irk_thread.cuh
+					if (!(Rnorm2 <= 1.79769313486231570e308) && !(xnorm2 <= 1.79769313486231570e308)) { // non-finite iterate: see irk_thread.cuh
 						const int rest = maxit - 1 - it;
 						if (rest > 0) {
 							c_fun += (unsigned)rest * S;
@@ -344,6 +350,7 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 
 		const bool ok = on && nstat == kNewtonSuccess;
 		if (on && !ok) { // irk.hpp:634-665
+			if (wi == 0) trace_row(a, mem, step, t, dt, -1.0, it);
 			if (!a.adaptive) {
 				status = REHUEL_GENERAL_ERROR;
 				fin = true;
@@ -405,7 +412,7 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 		}
 		double tot = 0.0;
 		{ // irk.hpp:733-746
-			const double sc = fma(a.rtol, fmax(fabs(yr), fabs(yn)), a.atol);
+			const double sc = fma(m_rtol, fmax(fabs(yr), fabs(yn)), m_atol);
 			const double q = row ? ev / sc : 0.0;
 			tot = seg_sum<SEG>(q * q);
 		}
@@ -419,6 +426,7 @@ ensemble_irk_wseg(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			}
 			// step-size proposal (irk.hpp:770-801; shifts the error history, irk.hpp:756-758)
 			const double new_dt = propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
+			if (wi == 0) trace_row(a, mem, step, t, dt, err, it); // irk.hpp:805-810
 			bool stuck = false;
 			if (!rejected) { // irk.hpp:813-846
 				yr = yn;

@@ -59,6 +59,14 @@ int locality_order(const double *params, int p, size_t M, int descending, unsign
 			                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
 	} while (0)
 
+// work-queue cursor and trace length start at zero for every launch
+inline cudaError_t reset_cursors(const KernelArgs &ka, cudaStream_t stream)
+{
+	cudaError_t e = cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream);
+	if (e == cudaSuccess && ka.io.trace_len) e = cudaMemsetAsync(ka.io.trace_len, 0, sizeof(unsigned), stream);
+	return e;
+}
+
 #ifndef REHUEL_CTA_SMALL_THREADS
 #define REHUEL_CTA_SMALL_THREADS 128
 #endif
@@ -78,11 +86,7 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 	constexpr int BLOCK = REHUEL_BLOCK, MIN_BLOCKS = (S * F::N <= 9) ? REHUEL_MINB : 2;
 	void (*kern)(const KernelArgs, const DevTableau<S, NC>) = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS, false>;
 	if (ka.io.rtol) { // per-member tolerances: separate instantiation so the uniform kernels stay lean
-		if constexpr (S == 3) {
-			kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS, true>;
-		} else {
-			return set_error(REHUEL_EINVAL, "per-member tolerances are built for the 3-stage methods only");
-		}
+		kern = ensemble_irk_thread<F, S, NR, NC, EST, BLOCK, MIN_BLOCKS, true>;
 	}
 	if (ka.io.n_dense) { // dense output: separate instantiation (the stage values stay live to the end of the attempt)
 		if (ka.io.rtol) return set_error(REHUEL_EINVAL, "dense output and per-member tolerances cannot be combined");
@@ -130,8 +134,7 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 	unsigned long long cap = (unsigned long long)sms * per_sm;
 	unsigned grid = (unsigned)(want < cap ? want : cap);
 	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
-	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
-	if (ka.io.trace_len) REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.trace_len, 0, sizeof(unsigned), stream));
+	REHUEL_CUDA_TRY(reset_cursors(ka, stream));
 	kern<<<grid, BLOCK, 0, stream>>>(ka, dtb);
 	REHUEL_CUDA_TRY(cudaGetLastError());
 	count_launch();
@@ -180,9 +183,12 @@ template <class F, bool COMPONENTWISE>
 int eval_functor(double t, const double *y, const double *p, double *f, double *J)
 {
 	constexpr int N = F::N, PA = F::P > 0 ? F::P : 1;
-	double *d = nullptr;
-	REHUEL_CUDA_TRY(cudaMalloc(&d, sizeof(double) * (N + PA + N + N * N)));
-	double *dy = d, *dp = d + N, *df = dp + PA, *dJ = df + N;
+	struct Scratch { // freed on every exit path
+		double *d = nullptr;
+		~Scratch() { cudaFree(d); }
+	} sc;
+	REHUEL_CUDA_TRY(cudaMalloc(&sc.d, sizeof(double) * (N + PA + N + N * N)));
+	double *dy = sc.d, *dp = sc.d + N, *df = dp + PA, *dJ = df + N;
 	REHUEL_CUDA_TRY(cudaMemcpy(dy, y, sizeof(double) * N, cudaMemcpyHostToDevice));
 	if (F::P > 0) REHUEL_CUDA_TRY(cudaMemcpy(dp, p, sizeof(double) * F::P, cudaMemcpyHostToDevice));
 	if constexpr (COMPONENTWISE) eval_functor_rows_kernel<F><<<1, 64>>>(t, dy, dp, df, dJ);
@@ -191,7 +197,6 @@ int eval_functor(double t, const double *y, const double *p, double *f, double *
 	count_launch();
 	REHUEL_CUDA_TRY(cudaMemcpy(f, df, sizeof(double) * N, cudaMemcpyDeviceToHost));
 	REHUEL_CUDA_TRY(cudaMemcpy(J, dJ, sizeof(double) * N * N, cudaMemcpyDeviceToHost));
-	cudaFree(d);
 	return REHUEL_OK;
 }
 
@@ -245,11 +250,10 @@ int launch_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ker
 		return REHUEL_OK;
 	}
 	if (ka.M == 0) return REHUEL_OK;
-	if (ka.io.rtol) return set_error(REHUEL_EINVAL, "per-member tolerances are not built for the CTA-per-system kernels");
 	unsigned long long cap = (unsigned long long)sms * per_sm;
 	unsigned grid = (unsigned)(ka.M < cap ? ka.M : cap);
 	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
-	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	REHUEL_CUDA_TRY(reset_cursors(ka, stream));
 	kern<<<grid, THREADS, smem, stream>>>(ka, dtb);
 	REHUEL_CUDA_TRY(cudaGetLastError());
 	count_launch();
@@ -288,11 +292,10 @@ int launch_warp(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ke
 		return REHUEL_OK;
 	}
 	if (ka.M == 0) return REHUEL_OK;
-	if (ka.io.rtol) return set_error(REHUEL_EINVAL, "per-member tolerances are not built for the warp-per-system kernels");
 	unsigned long long cap = (unsigned long long)sms * per_sm;
 	unsigned grid = (unsigned)(ka.M < cap ? ka.M : cap);
 	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
-	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	REHUEL_CUDA_TRY(reset_cursors(ka, stream));
 	// one slab per warp for the pivoted band fallback (irk_warp.cuh); stream-ordered, so concurrent launches on other
 	// streams get their own and the block goes back to the (retained) pool as soon as this kernel is done
 	KernelArgs k = ka;
@@ -301,8 +304,9 @@ int launch_warp(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ke
 	REHUEL_CUDA_TRY(cudaMallocAsync((void **)&k.pivot_scratch, WarpSmem<F, S, NC, EST>::slab_doubles * sizeof(double) * grid, stream));
 	k.force_pivot = debug_force_pivot();
 	kern<<<grid, 32, smem, stream>>>(k, dtb);
-	REHUEL_CUDA_TRY(cudaGetLastError());
+	const cudaError_t launched = cudaGetLastError(); // the slab goes back to the pool whether or not the launch worked
 	REHUEL_CUDA_TRY(cudaFreeAsync(k.pivot_scratch, stream));
+	REHUEL_CUDA_TRY(launched);
 	count_launch();
 	return REHUEL_OK;
 }
@@ -338,11 +342,10 @@ int launch_wdense(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 		return REHUEL_OK;
 	}
 	if (ka.M == 0) return REHUEL_OK;
-	if (ka.io.rtol) return set_error(REHUEL_EINVAL, "per-member tolerances are not built for the warp-per-system kernels");
 	unsigned long long cap = (unsigned long long)sms * per_sm;
 	unsigned grid = (unsigned)(ka.M < cap ? ka.M : cap);
 	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
-	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	REHUEL_CUDA_TRY(reset_cursors(ka, stream));
 	kern<<<grid, 32, smem, stream>>>(ka, dtb);
 	REHUEL_CUDA_TRY(cudaGetLastError());
 	count_launch();
@@ -373,12 +376,11 @@ int launch_wseg(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ke
 		return REHUEL_OK;
 	}
 	if (ka.M == 0) return REHUEL_OK;
-	if (ka.io.rtol) return set_error(REHUEL_EINVAL, "per-member tolerances are not built for the warp-per-system kernels");
 	constexpr unsigned long long MPW = WsSmem<F, S>::MPW;
 	const unsigned long long want = (ka.M + MPW - 1) / MPW, cap = (unsigned long long)sms * per_sm;
 	unsigned grid = (unsigned)(want < cap ? want : cap);
 	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
-	REHUEL_CUDA_TRY(cudaMemsetAsync(ka.io.queue, 0, sizeof(unsigned long long), stream));
+	REHUEL_CUDA_TRY(reset_cursors(ka, stream));
 	kern<<<grid, 32, smem, stream>>>(ka, dtb);
 	REHUEL_CUDA_TRY(cudaGetLastError());
 	count_launch();
@@ -416,6 +418,7 @@ int dispatch_method_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t st
 	case REHUEL_RADAU_IIA_32: return launch_block<F, 2, 0, 1, EST_OWN_LU>(ka, tb, stream, info);
 	case REHUEL_RADAU_IIA_53: return launch_block<F, 3, 1, 1, EST_REUSE>(ka, tb, stream, info);
 	case REHUEL_RADAU_IIA_95: return launch_block<F, 5, 1, 2, EST_REUSE>(ka, tb, stream, info);
+	case REHUEL_RADAU_IIA_137: return launch_block<F, 7, 1, 3, EST_REUSE>(ka, tb, stream, info);
 	case REHUEL_LOBATTO_IIIC_43: return launch_block<F, 3, 1, 1, EST_IDENTITY>(ka, tb, stream, info);
 	case REHUEL_LOBATTO_IIIC_64: return launch_block<F, 4, 0, 2, EST_IDENTITY>(ka, tb, stream, info);
 	case REHUEL_LOBATTO_IIIC_85: return launch_block<F, 5, 1, 2, EST_OWN_LU>(ka, tb, stream, info);

@@ -95,7 +95,7 @@ class DeviceEnsemble:
         stream = torch.cuda.current_stream(self.y.device).cuda_stream
         with torch.cuda.device(self.y.device):
             capi.check(capi.lib.rehuel_locality_order(
-                self.params.data_ptr(), self.p, self.M, int(self.handout_order == capi.ORDER_LOCALITY_DESC),
+                self.keys.data_ptr(), int(self.keys.shape[0]), self.M, int(self.handout_order == capi.ORDER_LOCALITY_DESC),
                 self.order.data_ptr(), self.order_ws.data_ptr(), self.order_ws.numel(), C.c_void_p(stream)))
 
     def launch(self, t0: float, t1: float, dt0: float, opts: capi.Options) -> None:

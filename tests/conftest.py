@@ -25,6 +25,28 @@ def golden():
     return d["cases"]
 
 
+@pytest.fixture(scope="session")
+def golden_configs():
+    """Members of BASELINE configs 4 and 5 and per-attempt logs, integrated once by the unmodified reference
+    (tools/make_golden_configs.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "config_cases.json")) as fh:
+        d = json.load(fh)
+    return d["cases"]
+
+
+def parse_reference_log(text):
+    """Rows (step, t, dt, err, iters) of the reference's per-attempt log, irk.hpp:575-577, 805-810."""
+    rows = []
+    seen_header = False
+    for line in text.splitlines():
+        f = line.split()
+        if f[:2] == ["Rehuel:", "step"]:
+            seen_header = True
+        elif seen_header and len(f) == 6 and f[0] == "Rehuel:":
+            rows.append([float(x) for x in f[1:]])
+    return np.array(rows)
+
+
 def cases_of(golden, kind):
     return [c for c in golden if c["kind"] == kind]
 

@@ -354,13 +354,15 @@ def test_full_size_properties_1M(capi, port):
     assert se.max() <= PARITY_BOUND
 
 
-def test_full_size_configs_3_and_4(capi, port):
+def test_full_size_configs_3_and_4(capi, port, golden_configs):
     """BASELINE configs 3 and 4 at FULL size.  Config 3: 2^20 Van der Pol members (mu_ref = 1 .. 1e-6, LOBATTO_IIIC_43,
     thread-per-system; the stiff end runs into Newton failures) -- counter identities on every member, a strided
     sample against the oracle.  Config 4: 65 536 members of the 64-equation Brusselator (LOBATTO_IIIC_85, t in [0,10],
-    ~2150 attempts per member, warp-per-system) -- the CPU oracle needs ~90 s per member there, so: counter identities
-    on every member, a sample re-run alone must be bit-identical (results do not depend on placement), and a few members
-    against the CTA-per-system kernel, whose dense LUs share no linear-algebra code with the twisted band solves."""
+    ~2150 attempts per member, warp-per-system) -- counter identities on every member, a sample re-run alone must be
+    bit-identical (results do not depend on placement), the 16 members spread over the sweep that the UNMODIFIED
+    REFERENCE integrated once (~50 s each; tests/golden/config_cases.json, tools/make_golden_configs.py) must match it
+    within the parity bound with the attempt counts next to each other, and a few members must match the CTA-per-system
+    kernel, whose dense LUs share no linear-algebra code with the twisted band solves."""
     from rehuel_b200 import ensembles
     o, ro = capi.make_options(1e-6, 1e-6), ref_options(1e-6, 1e-6)
     # ---- config 3
@@ -395,6 +397,26 @@ def test_full_size_configs_3_and_4(capi, port):
     assert np.array_equal(solo.y, g.y[:, idx])
     for k in c:
         assert np.array_equal(solo.counters[k], c[k][idx]), k
+    # ---- config 4 against the unmodified reference: 16 members spread over the sweep, inside the full run
+    gold = [c for c in golden_configs if c["kind"] == "config4"]
+    assert len(gold) == 16
+    gi = np.array([c["index"] for c in gold])
+    assert np.array_equal(P[:, gi], np.array([unhex(c["params"]) for c in gold]).T)      # same members
+    yref = np.array([unhex(c["y"]) for c in gold]).T
+    se_ref = scaled_err(g.y[:, gi], yref, 1e-6, 1e-6)
+    att_ref = np.array([c["counters"]["attempt"] for c in gold])
+    rej_ref = np.array([c["counters"]["reject_err"] for c in gold])
+    fun_ref = np.array([c["counters"]["fun_evals"] for c in gold])
+    print("config 4 vs the unmodified reference (member: scaled err | attempts gpu/ref | rejected gpu/ref | fun gpu/ref):")
+    for k, i in enumerate(gi):
+        print(f"  {i:6d}: {se_ref[k]:.3e} | {c_att(c, i)}/{att_ref[k]} | {int(c['reject_err'][i])}/{rej_ref[k]} | {int(c['fun_evals'][i])}/{fun_ref[k]}")
+    assert se_ref.max() <= PARITY_BOUND
+    assert all(g.status[i] == gc["status"] == 0 for i, gc in zip(gi, gold))
+    assert np.all(np.array([gc["counters"]["reject_newton"] for gc in gold]) == c["reject_newton"][gi])
+    # a few accept/reject decisions sit within rounding of err = 1 over ~2300 attempts: counts agree to 1 %
+    assert np.abs(c["attempt"][gi].astype(np.int64) - att_ref).max() <= 0.01 * att_ref.max()
+    assert np.abs(c["fun_evals"][gi].astype(np.int64) - fun_ref).max() <= 0.015 * fun_ref.max()
+    print(f"  identical attempt counts: {int(np.sum(c['attempt'][gi] == att_ref))}/16")
     few = idx[::24]
     d = capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, capi.LOBATTO_IIIC_85, 0.0, 10.0, 1e-6, y0, P[:, few].copy(), o, n_hint=64)
     se = scaled_err(g.y[:, few], d.y, 1e-6, 1e-6)
@@ -403,6 +425,10 @@ def test_full_size_configs_3_and_4(capi, port):
           f"attempts {c['attempt'][few].tolist()} / {d.counters['attempt'].tolist()}")
     assert se.max() <= PARITY_BOUND
     assert np.abs(c["attempt"][few].astype(np.int64) - d.counters["attempt"].astype(np.int64)).max() <= 0.02 * c["attempt"][few].max()
+
+
+def c_att(c, i):
+    return int(c["attempt"][i])
 
 
 def test_merge_two_legs(capi):
@@ -997,7 +1023,7 @@ def test_c_abi_multi_gpu_sharding_is_bit_identical(capi):
     o = capi.make_options(1e-6, 1e-6)
     one = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, o, n_gpus=1)
     for g in sorted({2, G}):
-        for mode in (capi.SHARD_CONTIGUOUS, capi.SHARD_INTERLEAVED):
+        for mode in (capi.SHARD_CONTIGUOUS, capi.SHARD_INTERLEAVED, capi.SHARD_DYNAMIC):
             om = capi.make_options(1e-6, 1e-6, shard_mode=mode)
             many = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, om, n_gpus=g)
             assert np.array_equal(one.y, many.y) and np.array_equal(one.status, many.status)
@@ -1008,12 +1034,208 @@ def test_c_abi_multi_gpu_sharding_is_bit_identical(capi):
     Mv = 1 << 18
     Pv = ensembles.vdpol_params(Mv)
     times = {}
-    for mode in (capi.SHARD_CONTIGUOUS, capi.SHARD_INTERLEAVED):
+    for mode in (capi.SHARD_CONTIGUOUS, capi.SHARD_INTERLEAVED, capi.SHARD_DYNAMIC):
         om = capi.make_options(1e-6, 1e-6, shard_mode=mode)
         r = [capi.irk_ensemble(capi.VAN_DER_POL, 230, 0.0, 2.0, 1e-6, ensembles.VDPOL_Y0, Pv, om, n_gpus=2) for _ in range(2)][-1]
         times[mode] = r.kernel_ms
         assert r.sum["n_failed"] == 0
-    print(f"\nVan der Pol 2^18 on 2 GPUs: kernel {times[0]:.1f} ms contiguous, {times[1]:.1f} ms interleaved")
+    print(f"\nVan der Pol 2^18 on 2 GPUs: kernel {times[0]:.1f} ms contiguous, {times[1]:.1f} ms interleaved, {times[2]:.1f} ms dynamic")
     # (both are close to the ~24 ms a lane needs for two of the stiffest members)
     # both are bound by the same stiffest members, so this only guards against a gross imbalance
     assert times[capi.SHARD_INTERLEAVED] <= 1.25 * times[capi.SHARD_CONTIGUOUS]
+
+
+def test_config5_members_at_the_extreme_tolerances_vs_the_reference(capi, golden_configs):
+    """16 members of BASELINE config 5 (10 485 760 mixed Robertson / Van der Pol members, rtol = atol = 10^(-3-6v)) at the
+    two ends of the tolerance sweep, two per octant of the index range, each integrated by the unmodified reference
+    with ITS tolerances (tests/golden/config_cases.json).  Here: the same members as two per-member-tolerance ensembles."""
+    import torch
+    from rehuel_b200.device import DeviceEnsemble
+    gold = [c for c in golden_configs if c["kind"] == "config5"]
+    assert len(gold) == 16
+    worst = 0.0
+    for prob, pid, y0 in (("robertson", capi.ROBERTSON, [1.0, 0.0, 0.0]), ("van-der-pol", capi.VAN_DER_POL, [2.0, 0.0])):
+        cs = [c for c in gold if c["problem"] == prob]
+        assert len(cs) == 8
+        tol = np.array([float.fromhex(c["tol"]) for c in cs])
+        assert tol.min() < 1.1e-9 and tol.max() > 0.9e-3
+        P = np.ascontiguousarray(np.array([unhex(c["params"]) for c in cs]).T)
+        tl = torch.from_numpy(tol).cuda()
+        de = DeviceEnsemble(pid, cs[0]["method"], len(cs), torch.tensor(y0, dtype=torch.float64).cuda(), torch.from_numpy(P).cuda(),
+                            rtol=tl, atol=tl.clone(), newton_tol=(0.1 * tl).contiguous())
+        de.solve(0.0, cs[0]["t1"], 1e-6, capi.make_options(1e-6, 1e-6))
+        torch.cuda.synchronize()
+        y = de.y.cpu().numpy()
+        att = de.counter("attempt").cpu().numpy()
+        rejn = de.counter("reject_newton").cpu().numpy()
+        assert int((de.status != 0).sum()) == 0
+        print(f"\n{prob}: index tol | scaled err | attempts gpu/ref | newton rejections gpu/ref")
+        for k, c in enumerate(cs):
+            se = float(scaled_err(y[:, k:k + 1], unhex(c["y"])[:, None], tol[k], tol[k])[0])
+            worst = max(worst, se)
+            print(f"  {c['index']:9d} {tol[k]:.2e} | {se:.3e} | {att[k]}/{c['counters']['attempt']} | {rejn[k]}/{c['counters']['reject_newton']}")
+            assert se <= PARITY_BOUND, (prob, c["index"], se)
+            assert abs(int(att[k]) - c["counters"]["attempt"]) <= max(2, 0.01 * c["counters"]["attempt"])
+            assert int(rejn[k]) == c["counters"]["reject_newton"]
+    print(f"config 5 extremes: worst scaled error {worst:.3e}")
+
+
+def test_per_attempt_log_matches_the_reference_log(capi, golden_configs):
+    """options.out_interval > 0: the reference writes "    Rehuel: <step> <t> <dt> <err> <iters>" for the attempts that
+    reach the error estimate and whose step count is a multiple of out_interval (irk.hpp:575-577, 805-810).  The same
+    rows come back in rehuel_result.trace for options.trace_member; rehuel_result_format_log prints them in the
+    reference's words.  Golden: the log of the unmodified reference (tests/golden/config_cases.json)."""
+    from conftest import parse_reference_log
+    from rehuel_b200 import ensembles
+    pid = {"robertson": capi.ROBERTSON, "van-der-pol": capi.VAN_DER_POL}
+    for c in [c for c in golden_configs if c["kind"] == "trace"]:
+        ref = parse_reference_log(c["log"])
+        # the traced member sits in the middle of an ensemble of other members
+        M, who = 5000, 4321
+        P = np.repeat(np.array(c["params"], dtype=np.float64)[:, None], M, axis=1)
+        P[:, :who] *= 1.01
+        o = capi.make_options(1e-6, 1e-6, out_interval=c["out_interval"], trace_member=who)
+        g = capi.irk_ensemble(pid[c["problem"]], c["method"], 0.0, c["t1"], 1e-6, np.array(c["y0"]), P, o)
+        rows = g.trace[g.trace[:, 3] >= 0.0]          # Newton failures are logged with err = -1; the reference is silent there
+        assert len(rows) == len(ref), (c["problem"], len(rows), len(ref))
+        assert np.array_equal(rows[:, 0], ref[:, 0])                      # accepted-step count at each logged attempt
+        assert np.array_equal(rows[:, 4], ref[:, 4])                      # Newton iterations
+        np.testing.assert_allclose(rows[:, 1], ref[:, 1], rtol=1e-9)      # t
+        np.testing.assert_allclose(rows[:, 2], ref[:, 2], rtol=2e-7)      # dt (the proposal goes through one root + fast reciprocals)
+        # err spans 1e-17 .. 1; estimates near the 1e-17 floor are rounding noise
+        big = ref[:, 3] > 1e-10
+        np.testing.assert_allclose(rows[big, 3], ref[big, 3], rtol=2e-5)
+        assert np.array_equal(rows[:, 3] > 1.0, ref[:, 3] > 1.0)          # the same attempts are rejected
+        assert int(g.counters["attempt"][who]) == c["counters"]["attempt"]
+        # text form, in the reference's words and at the precision its driver streamed with
+        text = g.log.splitlines()
+        assert text[0] == "    Rehuel: step  t  dt   err   iters"
+        ref_lines = [ln for ln in c["log"].splitlines() if ln.split()[:1] == ["Rehuel:"] and len(ln.split()) == 6 and ln.split()[1] != "step"]
+        assert len(text) - 1 == len(ref_lines)
+        for a, b in list(zip(text[1:], ref_lines))[:3]:
+            fa, fb = a.split(), b.split()
+            assert fa[0] == fb[0] and fa[1] == fb[1] and fa[5] == fb[5] and a.startswith("    Rehuel: ")
+    # no out_interval: no trace
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, ensembles.robertson_params(8), capi.make_options(1e-6, 1e-6))
+    assert g.trace is None and g.log == ""
+    # the warp-per-system kernels log as well (n = 8 Brusselator: four members per warp, one member per warp, band)
+    y0 = ensembles.bruss1d_y0(4)
+    Pb = ensembles.bruss1d_params(64)
+    for prob in (capi.BRUSSELATOR_1D, capi.BRUSSELATOR_1D_DENSE):
+        o = capi.make_options(1e-6, 1e-6, out_interval=1, trace_member=37)
+        g = capi.irk_ensemble(prob, 211, 0.0, 1.0, 1e-6, y0, Pb, o, n_hint=8)
+        rows = g.trace
+        assert len(rows) == int(g.counters["attempt"][37]) and int((rows[:, 3] > 1.0).sum()) == int(g.counters["reject_err"][37])
+        assert rows[0, 1] == 0.0 and abs(rows[-1, 1] + rows[-1, 2] - 1.0) < 1e-12 and int(rows[:, 4].sum()) == int(g.counters["newton_iters"][37])
+
+
+def test_result_mask_write_to_file_and_time_internals(capi, tmp_path):
+    """options.result_mask: y, status and the ensemble sums always come back, every other per-member array only when
+    asked for (the C-ABI path then moves 8n + 4 bytes per member instead of 8n + 56).  WRITE_TO_FILE (irk.hpp:837-843)
+    and time_internals (irk.hpp:328-360) through the boundary."""
+    from rehuel_b200 import ensembles
+    M = 300_000
+    P = ensembles.robertson_params(M)
+    full = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, capi.make_options(1e-6, 1e-6))
+    for mask in (0, capi.OUT_T_FINAL, capi.OUT_ERR_LAST, capi.OUT_COUNTERS, capi.OUT_T_FINAL | capi.OUT_COUNTERS):
+        g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, capi.make_options(1e-6, 1e-6, result_mask=mask))
+        assert np.array_equal(g.y, full.y) and np.array_equal(g.status, full.status) and g.sum == full.sum
+        assert (g.t_final is not None) == bool(mask & capi.OUT_T_FINAL) and (g.err_last is not None) == bool(mask & capi.OUT_ERR_LAST)
+        assert (g.counters is not None) == bool(mask & capi.OUT_COUNTERS)
+        if g.t_final is not None:
+            assert np.array_equal(g.t_final, full.t_final)
+        if g.err_last is not None:
+            assert np.array_equal(g.err_last, full.err_last)
+        if g.counters is not None:
+            assert all(np.array_equal(g.counters[k], full.counters[k]) for k in full.counters)
+    # WRITE_TO_FILE: the stored steps of trace_member as "t y0 y1 y2" lines, 6 significant digits
+    path = tmp_path / "traj.txt"
+    o = capi.make_options(1e-6, 1e-6, output_mode=3, output_file=str(path), trace_member=7)
+    g = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, :64].copy(), o, n_samples_cap=128)
+    rows = np.loadtxt(path)
+    ns = int(g.n_samples[7])
+    assert rows.shape == (ns - 1, 4)                                 # the initial state is stored but not written
+    np.testing.assert_allclose(rows[:, 0], g.t_samples[1:ns, 7], rtol=1e-5)
+    np.testing.assert_allclose(rows[:, 1:], g.y_samples[1:ns, :, 7], rtol=1e-5, atol=1e-12)
+    with pytest.raises(capi.RehuelError):
+        capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P[:, :64].copy(),
+                          capi.make_options(1e-6, 1e-6, output_mode=3), n_samples_cap=128)          # no path
+    # time_internals: device time per phase, and the reference's breakdown layout
+    res = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, capi.make_options(1e-6, 1e-6, time_internals=True), raw=True)
+    ph = list(res.phase_ms)
+    text = capi.format_timings(res, "RADAU_IIA_53")
+    capi.result_free(res)
+    print("\n" + text)
+    assert all(v > 0.0 for v in ph) and ph[2] == max(ph)
+    assert text.startswith("    Rehuel: RADAU_IIA_53 done solving, timings (ms | %):") and "Integration kernels:" in text
+    assert list(full.phase_ms.values()) == [0.0] * 4
+
+
+def test_handout_keys_change_the_order_not_the_results(capi):
+    """DeviceEnsemble(handout_keys=...): the hand-out order is computed from the caller's keys (e.g. tolerance AND
+    parameters for a mixed-tolerance ensemble), not from the parameters; results stay bit-identical."""
+    import torch
+    from rehuel_b200 import ensembles
+    from rehuel_b200.device import DeviceEnsemble
+    M = 1 << 15
+    P = torch.from_numpy(ensembles.robertson_params(M)).cuda()
+    y0 = torch.from_numpy(ensembles.ROBERTSON_Y0.copy()).cuda()
+    tol = ensembles.mixed_tolerances(M)
+    tl = torch.from_numpy(tol).cuda()
+    o = capi.make_options(1e-6, 1e-6)
+    out = {}
+    for name, keys in (("params", None), ("tol+params", torch.vstack([tl[None, :], P[:2]]).contiguous()), ("tol", tl[None, :].contiguous())):
+        de = DeviceEnsemble(capi.ROBERTSON, 211, M, y0, P, rtol=tl, atol=tl.clone(), newton_tol=(0.1 * tl).contiguous(),
+                            handout_order=capi.ORDER_LOCALITY, handout_keys=keys)
+        de.solve(0.0, 40.0, 1e-6, o)
+        torch.cuda.synchronize()
+        out[name] = (de.order.cpu().numpy().copy(), de.y.cpu().numpy().copy(), de.counters.cpu().numpy().copy())
+        assert np.array_equal(np.sort(out[name][0]), np.arange(M))
+    assert not np.array_equal(out["params"][0], out["tol+params"][0]) and not np.array_equal(out["tol"][0], out["tol+params"][0])
+    # ordered by tolerance alone, the tolerances along the hand-out order are monotone
+    assert np.all(np.diff(tol[out["tol"][0]]) >= 0)
+    for name in ("tol+params", "tol"):
+        assert np.array_equal(out[name][1], out["params"][1]) and np.array_equal(out[name][2], out["params"][2])
+
+
+def test_per_member_tolerances_and_radau137_on_the_larger_kernels(capi, port):
+    """Per-member tolerances on every kernel family (5-stage thread kernels, warp-per-system band / register-LU,
+    CTA-per-system) and RADAU_IIA_137 on the n > 4 kernels, each against the oracle member by member."""
+    import torch
+    from rehuel_b200 import ensembles
+    from rehuel_b200.device import DeviceEnsemble
+    M = 24
+    tol = 10.0 ** (-3.0 - 5.0 * ensembles.splitmix64_uniform(0, M, 0x77))
+    tl = torch.from_numpy(tol).cuda()
+    cases = [("robertson", capi.ROBERTSON, 232, 40.0, ensembles.ROBERTSON_Y0, ensembles.robertson_params(M), 0),
+             ("robertson", capi.ROBERTSON, 212, 40.0, ensembles.ROBERTSON_Y0, ensembles.robertson_params(M), 0),
+             ("brusselator-1d", capi.BRUSSELATOR_1D, 211, 1.0, ensembles.bruss1d_y0(4), ensembles.bruss1d_params(M), 8),
+             ("brusselator-1d", capi.BRUSSELATOR_1D_DENSE, 211, 1.0, ensembles.bruss1d_y0(4), ensembles.bruss1d_params(M), 8),
+             ("brusselator-1d", capi.BRUSSELATOR_1D_DENSE, 232, 0.5, ensembles.bruss1d_y0(8), ensembles.bruss1d_params(M), 16),
+             ("brusselator-1d", capi.BRUSSELATOR_1D_DENSE, 211, 0.25, ensembles.bruss1d_y0(16), ensembles.bruss1d_params(M), 32)]
+    for name, pid, method, t1, y0, P, n_hint in cases:
+        de = DeviceEnsemble(pid, method, M, torch.from_numpy(np.ascontiguousarray(y0)).cuda(), torch.from_numpy(P).cuda(), n_hint=n_hint,
+                            rtol=tl, atol=tl.clone(), newton_tol=(0.1 * tl).contiguous())
+        de.solve(0.0, t1, 1e-6, capi.make_options(1e-6, 1e-6))
+        torch.cuda.synchronize()
+        y, att = de.y.cpu().numpy(), de.counter("attempt").cpu().numpy()
+        assert int((de.status != 0).sum()) == 0
+        same = 0
+        for i in range(M):
+            r = port.solve(name, method, 0.0, t1, 1e-6, y0, P[:, i:i + 1].copy(), ref_options(tol[i], tol[i], newton_tol=0.1 * tol[i]), M=1)
+            se = float(scaled_err(y[:, i:i + 1], r.y, tol[i], tol[i])[0])
+            assert se <= PARITY_BOUND, (name, method, n_hint, i, se)
+            same += int(att[i] == r.counters["attempt"][0])
+        print(f"\nper-member tolerances, {name} n={n_hint or len(y0)} method {method}: identical attempt counts {same}/{M}")
+        assert same >= (0.9 if method != 212 else 0.5) * M
+    # RADAU_IIA_137 (7 stages: one real + three complex blocks) on the band, register-LU and CTA kernels
+    P = ensembles.bruss1d_params(8)
+    for pid, n in ((capi.BRUSSELATOR_1D, 8), (capi.BRUSSELATOR_1D_DENSE, 8), (capi.BRUSSELATOR_1D_DENSE, 16), (capi.BRUSSELATOR_1D, 64)):
+        y0 = ensembles.bruss1d_y0(n // 2)
+        t1 = 0.25 if n == 64 else 1.0
+        g = capi.irk_ensemble(pid, 213, 0.0, t1, 1e-6, y0, P, capi.make_options(1e-6, 1e-6), n_hint=n)
+        r = port.solve("brusselator-1d", 213, 0.0, t1, 1e-6, y0, P, ref_options(1e-6, 1e-6))
+        se = scaled_err(g.y, r.y, 1e-6, 1e-6)
+        print(f"RADAU_IIA_137 n={n} problem {pid}: max scaled err {se.max():.3e}; attempts gpu/ref {g.counters['attempt'].tolist()}/{r.counters['attempt'].tolist()}")
+        assert np.all(g.status == 0) and se.max() <= PARITY_BOUND
+        assert np.all(np.abs(g.counters["attempt"].astype(np.int64) - r.counters["attempt"].astype(np.int64)) <= np.maximum(3, 0.2 * r.counters["attempt"]))

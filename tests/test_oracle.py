@@ -170,3 +170,46 @@ def test_high_order_step_counts_are_noise(port):
             counts[method].append(int(r.counters["attempt"][0]))
     assert len(set(counts[211])) == 1, counts
     assert max(counts[212]) - min(counts[212]) > 0.1 * max(counts[212]), counts
+
+
+def test_port_matches_reference_on_config_members(port, golden_configs):
+    """tests/golden/config_cases.json (the unmodified reference on members of BASELINE configs 4 and 5): the C port
+    reproduces every config-5 member and the cheapest config-4 member (n = 64, LOBATTO_IIIC_85, t in [0,10]: the
+    reference's dense 320 x 320 LU, ~15 s through the port) bit for bit."""
+    import importlib.util, os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("_ens", os.path.join(ROOT, "rehuel_b200", "ensembles.py"))
+    ens = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ens)
+    c5 = cases_of(golden_configs, "config5")
+    assert len(c5) == 16
+    for c in c5:
+        tol = float.fromhex(c["tol"])
+        P = unhex(c["params"])[:, None]
+        r = port.solve(c["problem"], c["method"], 0.0, c["t1"], 1e-6, np.array(c["y0"]), P,
+                       make_options(tol, tol, newton_tol=0.1 * tol), M=1)
+        assert np.array_equal(r.y[:, 0], unhex(c["y"])), c["index"]
+        assert {k: int(v[0]) for k, v in r.counters.items()} == c["counters"], c["index"]
+    c4 = cases_of(golden_configs, "config4")
+    assert len(c4) == 16
+    c = min(c4, key=lambda c: c["counters"]["attempt"])
+    P = unhex(c["params"])[:, None]
+    assert np.array_equal(P, ens.bruss1d_params(1, start=c["index"]))
+    r = port.solve("brusselator-1d", 232, 0.0, 10.0, 1e-6, ens.bruss1d_y0(32), P, make_options(1e-6, 1e-6), M=1)
+    assert np.array_equal(r.y[:, 0], unhex(c["y"])) and int(r.status[0]) == c["status"] == 0
+    assert {k: int(v[0]) for k, v in r.counters.items()} == c["counters"]
+
+
+def test_reference_log_golden_is_consistent(golden_configs):
+    """The per-attempt logs in the fixture: one line per attempt that reached the error estimate (Newton failures print
+    nothing, irk.hpp:649-656) whose step count is a multiple of out_interval."""
+    from conftest import parse_reference_log
+    tr = cases_of(golden_configs, "trace")
+    assert len(tr) == 3
+    for c in tr:
+        rows = parse_reference_log(c["log"])
+        k = c["counters"]
+        if c["out_interval"] == 1:
+            assert len(rows) == k["attempt"] - k["reject_newton"]
+            assert int((rows[:, 3] > 1.0).sum()) == k["reject_err"]
+        assert np.all(rows[:, 0] % c["out_interval"] == 0) and rows[0, 1] == 0.0
