@@ -349,8 +349,7 @@ def run_gpu_arm(args) -> None:
     local = sharding.pack_stats(members=M, attempt=cs["attempt"], steps=cs["steps"], newton_iters=cs["newton_iters"],
                                 fun_evals=cs["fun_evals"], jac_evals=cs["jac_evals"], reject_err=cs["reject_err"],
                                 reject_newton=cs["reject_newton"], n_failed=cs["n_failed"], flops_dense_model=flops_dense,
-                                flops_executed_model=flops_exec)
-    local["max_attempt"] = float(cs["max_attempt"])
+                                flops_executed_model=flops_exec, max_attempt=cs["max_attempt"])
     tot = sharding.allreduce_stats(local, device=dev)
     mass_err = float((ens.y.sum(0) - 1.0).abs().max())
 

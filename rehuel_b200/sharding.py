@@ -27,7 +27,8 @@ def pack_stats(**kw) -> dict:
         v = kw.get(k, 0)
         out[k] = float(v.sum()) if hasattr(v, "sum") else float(v)
     att = kw.get("attempt", None)
-    out["max_attempt"] = float(att.max()) if att is not None and len(att) else 0.0
+    out["max_attempt"] = float(kw["max_attempt"]) if "max_attempt" in kw else (
+        float(att.max()) if att is not None and hasattr(att, "max") and len(att) else 0.0)
     return out
 
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Dev aid: build a library variant with extra -D flags:  tools/build_variant.sh NAME [-DREHUEL_MINB=5 ...]
-# -> build/var/NAME.so; time it on the GPU with tools/time_variants.py build/var/NAME.so
+# -> build/var/NAME.so; time it on the GPU with tools/gpu_dev.py variants build/var/NAME.so
 # (only the Robertson and Van der Pol instantiations are rebuilt with the flags; the rest is linked as built)
 set -e
 cd "$(dirname "$0")/.."
