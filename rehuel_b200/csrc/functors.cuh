@@ -15,6 +15,7 @@ struct RobertsonF {
 	static constexpr int P = 3;
 	static constexpr bool kAutonomous = true;
 	static constexpr int kFunFlops = 11, kJacFlops = 8; // SURVEY.md 8(d) accounting
+	static constexpr unsigned kJacZeroMask = (1u << (2 * 3 + 0)) | (1u << (2 * 3 + 2)); // J(2,0) = J(2,2) = 0
 	__device__ __forceinline__ static void fun(double, const double (&y)[N], const double (&p)[P], double (&f)[N])
 	{
 		f[0] = -p[0] * y[0] + p[1] * y[1] * y[2];

@@ -131,10 +131,13 @@ __device__ __forceinline__ constexpr int piv_shift(int slot, int k) { return (sl
 // PIVOT = false: returns true if partial pivoting would have exchanged rows (the factors are then
 //                not the ones LAPACK would produce and the caller falls back);
 // PIVOT = true:  records the interchanges in `pivs`, returns true if there was any.
-template <bool PIVOT, int N>
+// ZCOL0: bit i set = entry (i, 0), i > 0, is structurally zero (the functor's kJacZeroMask): its multiplier is zero and
+// the row update of the first elimination step is skipped.  Only meaningful without interchanges (PIVOT = false).
+template <bool PIVOT, unsigned ZCOL0 = 0u, int N>
 __device__ __forceinline__ bool lu_factor(LuReal<N> &m, unsigned &pivs, int slot)
 {
 	static_assert(N <= 4, "interchanges are packed as 2-bit offsets");
+	static_assert(!PIVOT || ZCOL0 == 0u, "structural zeros move when rows are interchanged");
 	bool flag = false;
 #pragma unroll
 	for (int k = 0; k < N; ++k) {
@@ -143,6 +146,7 @@ __device__ __forceinline__ bool lu_factor(LuReal<N> &m, unsigned &pivs, int slot
 			double best = fabs(m.a[k][k]);
 #pragma unroll
 			for (int i = k + 1; i < N; ++i) {
+				if (k == 0 && (ZCOL0 >> i & 1u)) continue;
 				const double v = fabs(m.a[i][k]);
 				if (v > best) {
 					best = v;
@@ -168,6 +172,10 @@ __device__ __forceinline__ bool lu_factor(LuReal<N> &m, unsigned &pivs, int slot
 		m.a[k][k] = rp;
 #pragma unroll
 		for (int i = k + 1; i < N; ++i) {
+			if (k == 0 && (ZCOL0 >> i & 1u)) {
+				m.a[i][k] = 0.0;
+				continue;
+			}
 			m.a[i][k] *= rp;
 #pragma unroll
 			for (int j = k + 1; j < N; ++j) m.a[i][j] = fma(-m.a[i][k], m.a[k][j], m.a[i][j]);
@@ -194,13 +202,16 @@ __device__ __forceinline__ void apply_row_swaps(unsigned pivs, int slot, double 
 }
 
 // x <- U^-1 L^-1 x (the interchanges, if any, have been applied to x already)
-template <int N>
+template <unsigned ZCOL0 = 0u, int N>
 __device__ __forceinline__ void lu_solve(const LuReal<N> &m, double (&x)[N])
 {
 #pragma unroll
 	for (int i = 1; i < N; ++i)
 #pragma unroll
-		for (int k = 0; k < i; ++k) x[i] = fma(-m.a[i][k], x[k], x[i]);
+		for (int k = 0; k < i; ++k) {
+			if (k == 0 && (ZCOL0 >> i & 1u)) continue; // multiplier structurally zero
+			x[i] = fma(-m.a[i][k], x[k], x[i]);
+		}
 #pragma unroll
 	for (int i = N - 1; i >= 0; --i) {
 #pragma unroll
@@ -209,19 +220,27 @@ __device__ __forceinline__ void lu_solve(const LuReal<N> &m, double (&x)[N])
 	}
 }
 
-template <bool PIVOT, int N>
+// The complex Newton matrices are (mr + i mi) I - J: when they arrive here their imaginary part is mi on the diagonal
+// and ZERO elsewhere.  DIAGIM = true tells the first elimination step so (multipliers and updates of that step then take
+// half the arithmetic: the compiler cannot drop a multiplication by a literal 0.0 itself, NaN/-0 semantics); only without
+// interchanges, which would move the diagonal.  After that step row 0 of U still has a real off-diagonal part, which
+// lu_solve<..., true> uses.
+template <bool PIVOT, unsigned ZCOL0 = 0u, bool DIAGIM = false, int N>
 __device__ __forceinline__ bool lu_factor(LuCplx<N> &m, unsigned &pivs, int slot)
 {
 	static_assert(N <= 4, "interchanges are packed as 2-bit offsets");
+	static_assert(!PIVOT || (ZCOL0 == 0u && !DIAGIM), "structural zeros move when rows are interchanged");
 	bool flag = false;
 #pragma unroll
 	for (int k = 0; k < N; ++k) {
+		const bool first = DIAGIM && k == 0;
 		if (k + 1 < N) {
 			int p = k;
 			double best = fabs(m.re[k][k]) + fabs(m.im[k][k]); // izamax's |re|+|im|
 #pragma unroll
 			for (int i = k + 1; i < N; ++i) {
-				const double v = fabs(m.re[i][k]) + fabs(m.im[i][k]);
+				if (k == 0 && (ZCOL0 >> i & 1u)) continue;
+				const double v = first ? fabs(m.re[i][k]) : fabs(m.re[i][k]) + fabs(m.im[i][k]);
 				if (v > best) {
 					best = v;
 					p = i;
@@ -254,27 +273,45 @@ __device__ __forceinline__ bool lu_factor(LuCplx<N> &m, unsigned &pivs, int slot
 		m.im[k][k] = ri;
 #pragma unroll
 		for (int i = k + 1; i < N; ++i) {
-			const double lr = fma(m.re[i][k], rr, -m.im[i][k] * ri);
-			const double li = fma(m.re[i][k], ri, m.im[i][k] * rr);
+			if (k == 0 && (ZCOL0 >> i & 1u)) {
+				m.re[i][k] = 0.0;
+				m.im[i][k] = 0.0;
+				continue;
+			}
+			double lr, li;
+			if (first) { // im[i][0] == 0
+				lr = m.re[i][k] * rr;
+				li = m.re[i][k] * ri;
+			} else {
+				lr = fma(m.re[i][k], rr, -m.im[i][k] * ri);
+				li = fma(m.re[i][k], ri, m.im[i][k] * rr);
+			}
 			m.re[i][k] = lr;
 			m.im[i][k] = li;
 #pragma unroll
 			for (int j = k + 1; j < N; ++j) {
-				m.re[i][j] = fma(-lr, m.re[k][j], fma(li, m.im[k][j], m.re[i][j]));
-				m.im[i][j] = fma(-lr, m.im[k][j], fma(-li, m.re[k][j], m.im[i][j]));
+				if (first) { // im[0][j] == 0; im[i][j] is mi on the diagonal, 0 elsewhere
+					m.re[i][j] = fma(-lr, m.re[k][j], m.re[i][j]);
+					m.im[i][j] = (i == j) ? fma(-li, m.re[k][j], m.im[i][j]) : -li * m.re[k][j];
+				} else {
+					m.re[i][j] = fma(-lr, m.re[k][j], fma(li, m.im[k][j], m.re[i][j]));
+					m.im[i][j] = fma(-lr, m.im[k][j], fma(-li, m.re[k][j], m.im[i][j]));
+				}
 			}
 		}
 	}
 	return flag;
 }
 
-template <int N>
+// ROW0RE: row 0 of U has no imaginary off-diagonal part (the matrix came through lu_factor<false, ..., true>)
+template <unsigned ZCOL0 = 0u, bool ROW0RE = false, int N>
 __device__ __forceinline__ void lu_solve(const LuCplx<N> &m, double (&xr)[N], double (&xi)[N])
 {
 #pragma unroll
 	for (int i = 1; i < N; ++i)
 #pragma unroll
 		for (int k = 0; k < i; ++k) {
+			if (k == 0 && (ZCOL0 >> i & 1u)) continue; // multiplier structurally zero
 			xr[i] = fma(-m.re[i][k], xr[k], fma(m.im[i][k], xi[k], xr[i]));
 			xi[i] = fma(-m.re[i][k], xi[k], fma(-m.im[i][k], xr[k], xi[i]));
 		}
@@ -282,8 +319,13 @@ __device__ __forceinline__ void lu_solve(const LuCplx<N> &m, double (&xr)[N], do
 	for (int i = N - 1; i >= 0; --i) {
 #pragma unroll
 		for (int k = i + 1; k < N; ++k) {
-			xr[i] = fma(-m.re[i][k], xr[k], fma(m.im[i][k], xi[k], xr[i]));
-			xi[i] = fma(-m.re[i][k], xi[k], fma(-m.im[i][k], xr[k], xi[i]));
+			if (ROW0RE && i == 0) {
+				xr[i] = fma(-m.re[i][k], xr[k], xr[i]);
+				xi[i] = fma(-m.re[i][k], xi[k], xi[i]);
+			} else {
+				xr[i] = fma(-m.re[i][k], xr[k], fma(m.im[i][k], xi[k], xr[i]));
+				xi[i] = fma(-m.re[i][k], xi[k], fma(-m.im[i][k], xr[k], xi[i]));
+			}
 		}
 		const double tr = xr[i], ti = xi[i];
 		xr[i] = fma(tr, m.re[i][i], -ti * m.im[i][i]);
@@ -291,11 +333,42 @@ __device__ __forceinline__ void lu_solve(const LuCplx<N> &m, double (&xr)[N], do
 	}
 }
 
+// Optional functor trait: `static constexpr unsigned kJacZeroMask`: bit i*N + j set promises that J(i, j) is identically
+// zero.  The kernel uses the entries of column 0 (multipliers that are zero in the first elimination step of mu I - J).
+template <class F, typename = void>
+struct jac_zero_col0 { static constexpr unsigned value = 0u; };
+template <class F>
+struct jac_zero_col0<F, decltype((void)F::kJacZeroMask)> {
+	static constexpr unsigned make()
+	{
+		unsigned m = 0u;
+		for (int i = 1; i < F::N; ++i)
+			if (F::kJacZeroMask >> (i * F::N) & 1u) m |= 1u << i;
+		return m;
+	}
+	static constexpr unsigned value = make();
+};
+
 // Optional functor trait: `static constexpr bool kAutonomous = true` promises f(t, y) does not depend
 // on t.  Every attempt starts its Newton iteration from Y = 0 (irk.hpp:415), where all S stage
 // evaluations of the first residual are the same f(t + c_i dt, y) = f(y): the kernel then evaluates
 // it once (the evaluation counters still book the S calls the reference makes) and reuses it for
 // the gamma*dt*f(t, y) term of the error estimate (irk.hpp:702).
+#ifndef REHUEL_STRUCT_ZEROS
+#define REHUEL_STRUCT_ZEROS 1 // use the structural zeros of mu I - J in the unpivoted factorisations and solves
+#endif
+#ifndef REHUEL_TREE_NORMS
+#define REHUEL_TREE_NORMS 1 // |R|^2 and |dY|^2 as S partial sums (dependency chains of n + S instead of n S FMAs)
+#endif
+#ifndef REHUEL_CANONICAL_TABLEAU
+#define REHUEL_CANONICAL_TABLEAU 1 // use d = e_s and the unit last row of T (Tableau::canonical, tableau.hpp) instead of multiplying by 1 and 0
+#endif
+#ifndef REHUEL_PEEL_FIRST
+#define REHUEL_PEEL_FIRST 1 // first Newton iteration as its own instance: Y = dY instead of Y = 0; Y += dY
+#endif
+#ifndef REHUEL_ROOT_CONTROLLER
+#define REHUEL_ROOT_CONTROLLER 1 // step-size proposal from err^2 with one k-th root (propose_dt_sq) instead of three square roots
+#endif
 #ifndef REHUEL_SKIP_DEAD_RESIDUAL
 #define REHUEL_SKIP_DEAD_RESIDUAL 1
 #endif
@@ -340,6 +413,69 @@ __device__ __forceinline__ double propose_dt(double dt, double err, double &q_pr
 	return new_dt;
 }
 
+// The same proposal from the SQUARED error norm x = err^2 (the thread-per-system kernels): with k = 2 (1 + min_order),
+//   s27 = (1/err)^e = x^(-1/k)    and    q = err^e = x^(1/k) = x * (x^(-1/k))^(k-1),
+// so the three chained square roots of err = sqrt(x), q = sqrt(sqrt(err)) (and the reciprocal of q) become ONE k-th
+// root: x is scaled by an exact power of two into [2^(-k/2), 2^(k/2)], a float-precision seed
+// exp2(-log2(x)/k) (MUFU.LG2/EX2, ~2^-21) is refined by two Newton steps on r^-k = x (error ~5 e^2 per step:
+// 2^-21 -> 1e-12 -> rounding level), and the power of two is put back by exponent arithmetic.  About 17 FP64
+// instructions in two short dependency chains instead of ~40 in one long one; the result differs from the
+// sqrt/reciprocal form by an ulp or two, like everything else in this function.  x must be positive and finite
+// (the caller floors it at 1e-34 and sends non-finite values through propose_dt).
+template <int K>
+__device__ __forceinline__ double pow_int(double r)
+{
+	if (K == 1) return r;
+	const double h = pow_int<(K > 1 ? K / 2 : 1)>(r);
+	return (K & 1) ? h * h * r : h * h;
+}
+
+template <int K>
+__device__ __forceinline__ void inv_root(double x, double &r_out, double &q_out)
+{
+	const int hi = __double2hiint(x);
+	const int E = ((hi >> 20) & 0x7ff) - 1023; // floor(log2 x)
+	const int j = (E >= 0 ? E + K / 2 : E - K / 2) / K; // round(E / K)
+	const double xs = __hiloint2double(hi - K * j * 0x100000, __double2loint(x)); // x 2^(-K j), exact
+	double r = (double)exp2f(__log2f((float)xs) * (-1.0f / K));
+#pragma unroll
+	for (int step = 0; step < 2; ++step) {
+		const double e = fma(-xs, pow_int<K>(r), 1.0);
+		r = fma(r * e, 1.0 / K, r);
+	}
+	const double q = xs * pow_int<K - 1>(r);
+	r_out = __hiloint2double(__double2hiint(r) - j * 0x100000, __double2loint(r)); // r 2^(-j)
+	q_out = __hiloint2double(__double2hiint(q) + j * 0x100000, __double2loint(q)); // q 2^(+j)
+}
+
+__device__ __forceinline__ double propose_dt_sq(double dt, double errsq, double &q_prev, double dts0, double dts1, int maxit,
+                                                int iters, int min_order, double expo, double max_dt)
+{
+	double s27, q;
+	if (!(errsq <= 1e300)) { // Inf or NaN: keep the reference's arithmetic (the step is lost anyway)
+		q = ctrl_pow(sqrt(errsq), min_order, expo);
+		s27 = fast_rcp(q);
+	} else if (min_order == 3) {
+		inv_root<8>(errsq, s27, q);
+	} else if (min_order == 2) {
+		inv_root<6>(errsq, s27, q);
+	} else if (min_order == 5) {
+		inv_root<12>(errsq, s27, q);
+	} else if (min_order == 4) {
+		inv_root<10>(errsq, s27, q);
+	} else {
+		q = ctrl_pow(sqrt(errsq), min_order, expo);
+		s27 = fast_rcp(q);
+	}
+	const double s28 = s27 * (dts0 * fast_rcp(dts1)) * (q_prev * s27);
+	q_prev = q; // irk.hpp:756-758: the history shifts on every attempt that reaches the estimator
+	const double fac = (0.9 * (maxit + 1.0)) * fast_rcp((double)(maxit + iters));
+	const double msc = (s28 < s27) ? s28 : s27;
+	double new_dt = fac * dt * (msc < 8.0 ? msc : 8.0);
+	if (max_dt > 0.0) new_dt = new_dt < max_dt ? new_dt : max_dt;
+	return new_dt;
+}
+
 // Dense-output weights of one grid time inside an accepted step:
 // w_i(theta) = sum_k Wd[i][k] theta^(S-k) by Horner, so that y(t + theta dt) = y + sum_i w_i Y_i.
 template <int S, int NC>
@@ -368,6 +504,8 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	constexpr int N = F::N;
 	constexpr int PA = F::P > 0 ? F::P : 1;
 	constexpr int kAuto = is_autonomous<F>::value ? REHUEL_AUTONOMOUS_OPT : 0;
+	constexpr unsigned ZC = REHUEL_STRUCT_ZEROS ? jac_zero_col0<F>::value : 0u; // rows i with J(i, 0) == 0
+	constexpr bool DIAGIM = REHUEL_STRUCT_ZEROS != 0;
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned long long M = a.M;
 	const rehuel_device_io &io = a.io;
@@ -537,7 +675,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						for (int i = 0; i < N; ++i)
 #pragma unroll
 							for (int j = 0; j < N; ++j) lur.a[i][j] = (i == j ? mur : 0.0) - J[i][j];
-						flag |= lu_factor<PIV>(lur, pivs, 0);
+						flag |= lu_factor<PIV, PIV ? 0u : ZC>(lur, pivs, 0);
 					}
 #pragma unroll
 					for (int c = 0; c < NC; ++c) {
@@ -549,7 +687,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 								luc[c].re[i][j] = (i == j ? mr : 0.0) - J[i][j];
 								luc[c].im[i][j] = (i == j ? mi : 0.0);
 							}
-						flag |= lu_factor<PIV>(luc[c], pivs, 1 + c);
+						flag |= lu_factor<PIV, PIV ? 0u : ZC, !PIV && DIAGIM>(luc[c], pivs, 1 + c);
 					}
 					if (EST == EST_OWN_LU) {
 						const double mue = tb.rgamma * rdt;
@@ -557,7 +695,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						for (int i = 0; i < N; ++i)
 #pragma unroll
 							for (int j = 0; j < N; ++j) lue.a[i][j] = (i == j ? mue : 0.0) - J[i][j];
-						flag |= lu_factor<PIV>(lue, pivs, 4);
+						flag |= lu_factor<PIV, PIV ? 0u : ZC>(lue, pivs, 4);
 					}
 					return flag;
 				};
@@ -579,37 +717,44 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						F::fun(fma(tb.c[i], dt, t), yi, p, Fv[i]);
 					}
 					c_fun += S;
-					double r2 = 0.0;
+					double r2[S]; // one partial sum per stage: short dependency chains
 #pragma unroll
-					for (int i = 0; i < S; ++i)
+					for (int i = 0; i < S; ++i) {
+						r2[i] = 0.0;
 #pragma unroll
 						for (int k = 0; k < N; ++k) {
 							double acc = 0.0;
 #pragma unroll
 							for (int j = 0; j < S; ++j) acc = fma(tb.A[i][j], Fv[j][k], acc);
 							R[i][k] = fma(-dt, acc, Y[i][k]);
-							r2 = fma(R[i][k], R[i][k], r2);
+							r2[REHUEL_TREE_NORMS ? i : 0] = fma(R[i][k], R[i][k], r2[REHUEL_TREE_NORMS ? i : 0]);
 						}
-					return r2;
+					}
+					double tot = r2[0];
+#pragma unroll
+					for (int i = 1; i < S; ++i)
+						if (REHUEL_TREE_NORMS) tot += r2[i];
+					return tot;
 				};
 
+				if (!(REHUEL_PEEL_FIRST && kAuto)) { // irk.hpp:415 (otherwise the first iteration writes Y = dY)
 #pragma unroll
-				for (int i = 0; i < S; ++i)
+					for (int i = 0; i < S; ++i)
 #pragma unroll
-					for (int k = 0; k < N; ++k) Y[i][k] = 0.0; // irk.hpp:415
+						for (int k = 0; k < N; ++k) Y[i][k] = 0.0;
+				}
 				double f0[N]; // f(t, y) (autonomous functors)
 				double Rnorm2;
 				if (kAuto) { // Y = 0: R_i = -dt * sum_j A_ij f(y)
 					F::fun(t, y, p, f0);
 					c_fun += S;
-					Rnorm2 = 0.0;
+					Rnorm2 = 0.0; // (the reference does not test the residual before the first update either, irk.hpp:443-458)
+					if (!REHUEL_PEEL_FIRST) {
 #pragma unroll
-					for (int i = 0; i < S; ++i) {
-						const double ai = -dt * tb.Asum[i];
+						for (int i = 0; i < S; ++i) {
+							const double ai = -dt * tb.Asum[i];
 #pragma unroll
-						for (int k = 0; k < N; ++k) {
-							R[i][k] = ai * f0[k];
-							Rnorm2 = fma(R[i][k], R[i][k], Rnorm2);
+							for (int k = 0; k < N; ++k) R[i][k] = ai * f0[k];
 						}
 					}
 				} else {
@@ -617,27 +762,37 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				}
 				int nstat = kNewtonMaxit;
 				int it = 1;
+				int refresh_in = a.refresh_jac; // iterations until the next (no-op) Jacobian refresh, irk.hpp:485-487
 				const int cap = (slow_trip || maxit <= kFastIters) ? maxit : kFastIters + 1;
-				// The iteration loop exists twice: the common instance knows at compile time that no row was
-				// interchanged; the rare one permutes the right-hand sides.  (One loop with a run-time test
-				// costs ~25 register moves per iteration around the skipped block.)
-				auto newton_loop = [&](auto swaps_tag) {
-				constexpr bool SWAPS = decltype(swaps_tag)::value;
-				for (; it < cap; ++it) { // irk.hpp:458 (cap == maxit unless this is a fast trip)
+				// One iteration; returns true when the loop is over (converged, or the iterate is beyond recovery).
+				// FIRST: Y is still zero, so Y = dY (the zero fill and the additions are never executed).
+				auto iteration = [&](auto swaps_tag, auto first_tag) -> bool {
+					constexpr bool SWAPS = decltype(swaps_tag)::value;
+					constexpr bool FIRST = decltype(first_tag)::value;
 #if defined(REHUEL_COUNT_SKIPS) && REHUEL_COUNT_SKIPS == 2
 					if (slow_trip) ++c_skips; // dev builds (mode 2): Newton iterations actually EXECUTED in slow trips
 #endif
 					// dY = -(I - dt A(x)J)^-1 R through the decoupled blocks
 					double Z[S][N];
+					if (FIRST) {
+						// Y = 0 and f autonomous: R_i = -dt Asum_i f(y) has rank one, so does Z = (Ti (x) I) R
 #pragma unroll
-					for (int i = 0; i < S; ++i)
+						for (int i = 0; i < S; ++i) {
+							const double gi = -dt * tb.TiAsum[i];
 #pragma unroll
-						for (int k = 0; k < N; ++k) {
-							double acc = 0.0;
-#pragma unroll
-							for (int j = 0; j < S; ++j) acc = fma(tb.Ti[i][j], R[j][k], acc);
-							Z[i][k] = acc;
+							for (int k = 0; k < N; ++k) Z[i][k] = gi * f0[k];
 						}
+					} else {
+#pragma unroll
+						for (int i = 0; i < S; ++i)
+#pragma unroll
+							for (int k = 0; k < N; ++k) {
+								double acc = 0.0;
+#pragma unroll
+								for (int j = 0; j < S; ++j) acc = fma(tb.Ti[i][j], R[j][k], acc);
+								Z[i][k] = acc;
+							}
+					}
 					if (SWAPS) { // the right-hand sides follow the recorded row interchanges
 						if (NR) apply_row_swaps(pivs, 0, Z[0]);
 #pragma unroll
@@ -647,14 +802,14 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						}
 					}
 					if (NR) {
-						lu_solve(lur, Z[0]);
+						lu_solve<SWAPS ? 0u : ZC>(lur, Z[0]);
 #pragma unroll
 						for (int k = 0; k < N; ++k) Z[0][k] *= -mur;
 					}
 #pragma unroll
 					for (int c = 0; c < NC; ++c) {
 						const double mr = tb.alpha[c] * rdt, mi = tb.beta[c] * rdt;
-						lu_solve(luc[c], Z[NR + 2 * c], Z[NR + 2 * c + 1]);
+						lu_solve<SWAPS ? 0u : ZC, !SWAPS && DIAGIM>(luc[c], Z[NR + 2 * c], Z[NR + 2 * c + 1]);
 #pragma unroll
 						for (int k = 0; k < N; ++k) { // w = -(mr + i mi) * w
 							const double wr = Z[NR + 2 * c][k], wi = Z[NR + 2 * c + 1][k];
@@ -662,17 +817,31 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							Z[NR + 2 * c + 1][k] = fma(-mr, wi, -mi * wr);
 						}
 					}
-					double xnorm2 = 0.0;
+					double x2[S]; // |dY|^2 as one partial sum per stage
 #pragma unroll
-					for (int i = 0; i < S; ++i)
+					for (int i = 0; i < S; ++i) {
+						x2[i] = 0.0;
 #pragma unroll
 						for (int k = 0; k < N; ++k) {
 							double acc = 0.0;
+							if (REHUEL_CANONICAL_TABLEAU && i == S - 1) {
+								// last row of T: 1 for the real block, (1, 0) for every complex pair (Tableau::canonical)
+								acc = Z[0][k];
 #pragma unroll
-							for (int j = 0; j < S; ++j) acc = fma(tb.T[i][j], Z[j][k], acc);
-							xnorm2 = fma(acc, acc, xnorm2); // irk.hpp:466
-							Y[i][k] += acc;                 // irk.hpp:468 (step == 1)
+								for (int j = NR ? 1 : 2; j < S; j += 2) acc += Z[j][k];
+							} else {
+#pragma unroll
+								for (int j = 0; j < S; ++j) acc = fma(tb.T[i][j], Z[j][k], acc);
+							}
+							x2[REHUEL_TREE_NORMS ? i : 0] = fma(acc, acc, x2[REHUEL_TREE_NORMS ? i : 0]); // irk.hpp:466
+							if (FIRST) Y[i][k] = acc;       // Y was 0 (irk.hpp:415)
+							else Y[i][k] += acc;            // irk.hpp:468 (step == 1)
 						}
+					}
+					double xnorm2 = x2[0];
+#pragma unroll
+					for (int i = 1; i < S; ++i)
+						if (REHUEL_TREE_NORMS) xnorm2 += x2[i];
 					// The reference evaluates R(Y) (irk.hpp:469-472) and then stops on |R|^2 < tol^2 (473-476) OR
 					// |dY|^2 < dx_delta^2 (477-480), both with the same status and iteration count, and never
 					// looks at that residual again.  When the step test already holds -- with the default
@@ -684,12 +853,15 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 #endif
 						c_fun += S;
 						nstat = kNewtonSuccess;
-						break;
+						return true;
 					}
 					Rnorm2 = residual();                    // irk.hpp:469-472
-					if (Rnorm2 < (TOLV ? m_Rtol2 : a.Rtol2)) { nstat = kNewtonSuccess; break; } // irk.hpp:473-476
-					if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; } // irk.hpp:477-480
-					if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac; // irk.hpp:485-487 (no-op refactor)
+					if (Rnorm2 < (TOLV ? m_Rtol2 : a.Rtol2)) { nstat = kNewtonSuccess; return true; } // irk.hpp:473-476
+					if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; return true; } // irk.hpp:477-480
+					if (--refresh_in == 0) { // it % refresh_jac == 0, irk.hpp:485-487 (a no-op refactorisation: only counted)
+						++c_jac;
+						refresh_in = a.refresh_jac;
+					}
 					if (!(Rnorm2 <= 1.79769313486231570e308) && !(xnorm2 <= 1.79769313486231570e308)) {
 						// A non-finite update makes Y non-finite, and Y + dY can never become finite again: neither
 						// test can pass any more, the reference spins to maxit.  Account the remaining evaluations
@@ -700,9 +872,21 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							if (a.refresh_jac > 0) c_jac += (unsigned)((maxit - 1) / a.refresh_jac - it / a.refresh_jac);
 						}
 						it = maxit;
-						break;
+						return true;
 					}
-				}
+					return false;
+				};
+				// The iteration loop exists twice: the common instance knows at compile time that no row was
+				// interchanged; the rare one permutes the right-hand sides.  (One loop with a run-time test
+				// costs ~25 register moves per iteration around the skipped block.)
+				auto newton_loop = [&](auto swaps_tag) { // irk.hpp:458 (cap == maxit unless this is a fast trip)
+					if (REHUEL_PEEL_FIRST && kAuto) {
+						if (!(it < cap)) return;
+						if (iteration(swaps_tag, std::true_type())) return;
+						++it;
+					}
+					for (; it < cap; ++it)
+						if (iteration(swaps_tag, std::false_type())) return;
 				};
 				if (piv_any) newton_loop(std::true_type());
 				else newton_loop(std::false_type());
@@ -743,10 +927,10 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						double s1 = 0.0, s2 = 0.0;
 #pragma unroll
 						for (int i = 0; i < S; ++i) {
-							s1 = fma(Y[i][k], tb.d[i], s1);
+							if (!REHUEL_CANONICAL_TABLEAU) s1 = fma(Y[i][k], tb.d[i], s1);
 							s2 = fma(Y[i][k], tb.d2[i], s2);
 						}
-						dy[k] = s1;
+						dy[k] = REHUEL_CANONICAL_TABLEAU ? Y[S - 1][k] : s1; // d = A^-T b = e_s: stiffly accurate (Tableau::canonical)
 						dalt[k] = s2;
 					}
 					if (EST != EST_IDENTITY) { // irk.hpp:702 (multiplied by gam == 0 when EST_IDENTITY)
@@ -769,9 +953,11 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					auto apply_Einv_dt = [&](double (&v)[N]) {
 						if (EST != EST_IDENTITY && piv_any) apply_row_swaps(pivs, EST == EST_REUSE ? 0 : 4, v);
 						if (EST == EST_REUSE) {
-							lu_solve(lur, v);
+							if (ZC != 0u && !piv_any) lu_solve<ZC>(lur, v);
+							else lu_solve(lur, v);
 						} else if (EST == EST_OWN_LU) {
-							lu_solve(lue, v);
+							if (ZC != 0u && !piv_any) lu_solve<ZC>(lue, v);
+							else lu_solve(lue, v);
 						}
 						const double sc = (EST == EST_IDENTITY) ? dt : tb.rgamma;
 #pragma unroll
@@ -799,17 +985,26 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						const double q = e[k] * fast_rcp(sc);
 						tot = fma(q, q, tot);
 					}
-					err = sqrt(tot * (1.0 / (double)N));
-					if (err < kMachinePrecision) err = kMachinePrecision;
+					// `err` holds the SQUARE of the error norm with REHUEL_ROOT_CONTROLLER (the root is only taken where the
+					// norm itself goes out: trace, samples, err_last); err > 1 <=> err^2 > 1, the floor 1e-17 becomes 1e-34
+					if (REHUEL_ROOT_CONTROLLER) {
+						err = tot * (1.0 / (double)N);
+						if (err < kMachinePrecision * kMachinePrecision) err = kMachinePrecision * kMachinePrecision;
+					} else {
+						err = sqrt(tot * (1.0 / (double)N));
+						if (err < kMachinePrecision) err = kMachinePrecision;
+					}
 					const bool rejected = a.adaptive && (err > 1.0); // irk.hpp:761
 					if (rejected) {
 						alt = true;
 						++c_rej_err;
 					}
 					// -------- step-size proposal, irk.hpp:770-801 (shifts the error history, irk.hpp:756-758)
-					const double new_dt = propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
+					const double new_dt = REHUEL_ROOT_CONTROLLER
+					                          ? propose_dt_sq(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt)
+					                          : propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
 
-					trace_row(a, mem, step, t, dt, err, it); // irk.hpp:805-810
+					if (io.trace) trace_row(a, mem, step, t, dt, REHUEL_ROOT_CONTROLLER ? sqrt(err) : err, it); // irk.hpp:805-810
 					if (!rejected) { // irk.hpp:813-846
 						if (DENSE) { // grid times inside (t, t + dt] from this step's collocation polynomial
 							const double t_new = t + dt;
@@ -841,7 +1036,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							if (n_stored < io.n_samples_cap) {
 								const size_t row = n_stored;
 								io.t_samples[row * M + mem] = t;
-								if (io.err_samples) io.err_samples[row * M + mem] = err;
+								if (io.err_samples) io.err_samples[row * M + mem] = REHUEL_ROOT_CONTROLLER ? sqrt(err) : err;
 #pragma unroll
 								for (int k = 0; k < N; ++k) io.y_samples[(row * N + k) * M + mem] = y[k];
 							}
@@ -861,7 +1056,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 #pragma unroll
 			for (int k = 0; k < N; ++k) io.y[k * M + mem] = y[k];
 			io.t_final[mem] = t;
-			if (io.err_last) io.err_last[mem] = err;
+			if (io.err_last) io.err_last[mem] = REHUEL_ROOT_CONTROLLER ? sqrt(err) : err;
 			io.status[mem] = status;
 			// accepted steps of THIS call (a continued member's `step` also counts the earlier legs)
 			const unsigned steps_here = (unsigned)(step - (io.state_in ? (long long)io.state_in[REHUEL_STATE_STEP * M + mem] : 0ll));

@@ -279,6 +279,13 @@ bool get_coefficients(int method, Tableau &tb)
 				for (int i = 0; i < tb.s; ++i) tb.w_interp[i][k] = w[i];
 			}
 		}
+		// the structure the thread-per-system kernels rely on (tableau.hpp: Tableau::canonical)
+		tb.canonical = true;
+		for (int i = 0; i < tb.s; ++i) tb.canonical = tb.canonical && tb.d[i] == (i == tb.s - 1 ? 1.0 : 0.0);
+		for (int j = 0; j < tb.s; ++j) {
+			const bool unit = j < tb.n_real || ((j - tb.n_real) % 2 == 0);
+			tb.canonical = tb.canonical && tb.T[tb.s - 1][j] == (unit ? 1.0 : 0.0);
+		}
 		return true;
 	}
 	return false;

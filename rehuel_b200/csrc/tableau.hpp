@@ -38,6 +38,12 @@ struct Tableau {
 	// dense output in terms of the stage increments Y_i the kernels hold:  y(t + theta dt) = y + sum_i w_i(theta) Y_i,
 	// w(theta) = A^-T b(theta)  =>  w_i(theta) = sum_k w_interp[i][k] theta^(s-k)   (w(1) = d)
 	double w_interp[MAX_S][MAX_S] = {};
+	// The thread-per-system kernels skip multiplications by 1 and 0 that every built tableau has (checked by
+	// get_coefficients, which refuses a tableau without them):
+	//   d = A^-T b = e_s exactly (all methods here are stiffly accurate: b is the last row of A), and
+	//   the last row of T is 1 for the real block and (1, 0) for every complex pair (tools/gen_tableaux.py scales
+	//   the eigenvectors that way).
+	bool canonical = false;
 };
 
 // Returns false if the method id is unknown / unsupported by the GPU path.
@@ -55,6 +61,7 @@ template <int S, int NC>
 struct DevTableau {
 	double A[S][S];
 	double Asum[S];   // row sums of A: the stage residual at Y = 0 for an autonomous f (irk_thread.cuh)
+	double TiAsum[S]; // Ti * Asum: the same residual in the transformed variables
 	double c[S];
 	double d[S], d2[S];
 	double T[S][S], Ti[S][S];
@@ -84,6 +91,8 @@ inline DevTableau<S, NC> make_dev_tableau(const Tableau &tb)
 		dt.d[i] = tb.d[i];
 		dt.d2[i] = tb.d2[i];
 	}
+	for (int i = 0; i < S; ++i)
+		for (int j = 0; j < S; ++j) dt.TiAsum[i] += tb.Ti[i][j] * dt.Asum[j];
 	dt.gamma = tb.gamma;
 	dt.rgamma = tb.gamma != 0.0 ? 1.0 / tb.gamma : 0.0;
 	dt.gamma_hat = tb.gamma_hat;

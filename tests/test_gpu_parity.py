@@ -65,6 +65,11 @@ def test_golden_single_systems(capi, golden):
         # 1e-16 relative; the GPU path lands inside that band (225..254 across builds), results equal to 4e-5 of tol.
         slack = 0.20 if c["method"] in (212, 213) else 0.02
         assert abs(int(g.counters["attempt"][0]) - ref["attempt"]) <= max(3, slack * ref["attempt"]), rows[-1]
+        if c["method"] in (212, 213) and int(g.counters["reject_newton"][0]) != ref["reject_newton"]:
+            # a different walk can meet a different number of failing Newton solves, each of which books maxit * s
+            # function calls (5000 * 7, and 10000 * 7 once the budget has been raised): the totals are not comparable
+            assert abs(int(g.counters["reject_newton"][0]) - ref["reject_newton"]) <= 3, rows[-1]
+            continue
         assert abs(int(g.counters["fun_evals"][0]) - ref["fun_evals"]) <= max(30, (slack + 0.03) * ref["fun_evals"]), rows[-1]
     print("\nname | scaled_err | attempts gpu/ref | rejE gpu/ref | rejN gpu/ref | fun gpu/ref | jac gpu/ref")
     for r in rows:
