@@ -60,6 +60,13 @@ constexpr int kFastIters = REHUEL_FAST_ITERS; // Newton iterations a lane may ta
 #define REHUEL_PARK_LANES 16
 #endif
 constexpr int kParkLanes = REHUEL_PARK_LANES; // parked lanes per warp that trigger a slow trip
+#ifndef REHUEL_BATCH_LANES
+#define REHUEL_BATCH_LANES 4
+#endif
+// Lanes of a warp that must be waiting (member finished, or no member) before the warp stops to write results and hand
+// out new members: that code is executed by the whole warp however few lanes need it, so with ~1 member finishing per
+// trip it pays to let a lane sit out a trip or two and serve several at once.  Served at once when nothing else runs.
+constexpr int kBatchLanes = REHUEL_BATCH_LANES;
 
 // Reciprocal: MUFU.RCP64H seed (~20 bits) + two Newton steps (quadratic: 20 -> 40 -> 80 bits, i.e.
 // correctly rounded up to ~1 ulp), 5 instructions and no slow path instead of the ~14-instruction
@@ -517,6 +524,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 
 	// ---- lane-persistent member state
 	bool have = false, exhausted = false;
+	bool done = false;   // the member is finished, its results are still in this lane's registers (see kBatchLanes)
 	bool parked = false; // this lane's attempt ran past kFastIters Newton iterations: redo it in a slow trip
 	bool prefer_piv = false; // the warp's last factorisations needed row interchanges: skip the speculative plain attempt
 	unsigned long long mem = 0;
@@ -537,72 +545,134 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	double m_rtol = a.rtol, m_atol = a.atol, m_Rtol2 = a.Rtol2;
 
 	for (;;) {
-		// ---------------- refill idle lanes from the global queue (warp-aggregated)
-		const unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
-		if (need) {
-			const int leader = __ffs(need) - 1;
-			unsigned long long base = 0;
-			if ((int)lane == leader) base = atomicAdd(io.queue, (unsigned long long)__popc(need));
-			base = __shfl_sync(0xffffffffu, base, leader);
-			if (!have && !exhausted) {
-				mem = base + __popc(need & ((1u << lane) - 1u));
-				if (mem < M) {
-					if (io.order) mem = io.order[mem]; // caller-chosen hand-out order (e.g. costly members first)
+		// ---------------- service stop: write the results of finished members, refill idle lanes from the global queue
+		// (warp-aggregated).  Warp-uniform decision, see kBatchLanes.
+		const unsigned wants = __ballot_sync(0xffffffffu, (have && done) || (!have && !exhausted));
+		const unsigned busy = __ballot_sync(0xffffffffu, have && !done);
+		if (wants != 0u && (__popc(wants) >= kBatchLanes || busy == 0u)) {
+			if (have && done) {
 #pragma unroll
-					for (int k = 0; k < N; ++k) y[k] = io.y0_broadcast ? io.y0[k] : io.y0[k * M + mem];
+				for (int k = 0; k < N; ++k) io.y[k * M + mem] = y[k];
+				io.t_final[mem] = t;
+				if (io.err_last) io.err_last[mem] = REHUEL_ROOT_CONTROLLER ? sqrt(err) : err;
+				io.status[mem] = status;
+				// accepted steps of THIS call (a continued member's `step` also counts the earlier legs)
+				const unsigned steps_here = (unsigned)(step - (io.state_in ? (long long)io.state_in[REHUEL_STATE_STEP * M + mem] : 0ll));
+				if (io.counters) {
+					io.counters[REHUEL_CNT_ATTEMPT * M + mem] = c_attempt;
+					io.counters[REHUEL_CNT_REJECT_NEWTON * M + mem] = c_rej_newton;
+					io.counters[REHUEL_CNT_REJECT_ERR * M + mem] = c_rej_err;
+					io.counters[REHUEL_CNT_NEWTON_SUCCESS * M + mem] = c_newton_ok;
+#ifdef REHUEL_COUNT_SKIPS
+					io.counters[REHUEL_CNT_NEWTON_MAXIT_EXCEED * M + mem] = c_skips;
+					c_skips = 0;
+#else
+					io.counters[REHUEL_CNT_NEWTON_MAXIT_EXCEED * M + mem] = c_rej_newton;
+#endif
+					io.counters[REHUEL_CNT_FUN_EVALS * M + mem] = c_fun;
+					io.counters[REHUEL_CNT_JAC_EVALS * M + mem] = c_jac;
+					io.counters[REHUEL_CNT_NEWTON_ITERS * M + mem] = c_iters;
+					io.counters[REHUEL_CNT_STEPS * M + mem] = steps_here;
+				}
+				if (io.stats) {
+					// the lanes that finish a member in this trip add up first (REDUX), their leader adds the sums to the
+					// CTA's 64-bit shared-memory totals, which go to the global words at the end of the kernel
+					const unsigned fm = __activemask();
+					const unsigned v[REHUEL_NCOUNTERS] = {c_attempt, c_rej_newton, c_rej_err, c_newton_ok, c_rej_newton, c_fun, c_jac, c_iters, steps_here};
+					unsigned long long w[REHUEL_NCOUNTERS];
 #pragma unroll
-					for (int k = 0; k < F::P; ++k) p[k] = io.params[k * M + mem];
-					if (F::P == 0) p[0] = 0.0;
-					if (TOLV) {
-						m_rtol = io.rtol[mem];
-						m_atol = io.atol[mem];
-						const double nt = io.newton_tol[mem];
-						m_Rtol2 = nt * nt;
+					for (int c = 0; c < REHUEL_NCOUNTERS; ++c) // 16-bit halves: a sum over 32 lanes cannot wrap
+						w[c] = (unsigned long long)__reduce_add_sync(fm, v[c] & 0xffffu) + ((unsigned long long)__reduce_add_sync(fm, v[c] >> 16) << 16);
+					const unsigned nfail = __reduce_add_sync(fm, status != 0 ? 1u : 0u);
+					const unsigned amax = __reduce_max_sync(fm, c_attempt);
+					if ((int)lane == __ffs(fm) - 1) {
+#pragma unroll
+						for (int c = 0; c < REHUEL_NCOUNTERS; ++c) atomicAdd(&s_stats[c], w[c]);
+						atomicAdd(&s_stats[REHUEL_NCOUNTERS], (unsigned long long)nfail);
+						atomicMax(&s_stats[REHUEL_NCOUNTERS + 1], (unsigned long long)amax);
 					}
-					t = io.t_start ? io.t_start[mem] : a.t0;
-					dt = a.dt0;
-					if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
-					dts0 = dts1 = dt;                 // irk.hpp:572
-					q_prev = tb.q_init;               // irk.hpp:573: errs = 0.9
-					err = 0.0;
-					alt = true;                       // irk.hpp:587
-					maxit = a.maxit0;
-					step = 0;
-					last_relax = 0;
-					if (io.state_in) { // continue a stopped integration: the loop variables as they were at exit
-						const double *si = io.state_in + mem;
-						dt = si[REHUEL_STATE_DT * M];
-						dts0 = si[REHUEL_STATE_DTS0 * M];
-						dts1 = si[REHUEL_STATE_DTS1 * M];
-						q_prev = si[REHUEL_STATE_ERRQ * M];
-						alt = si[REHUEL_STATE_ALT * M] != 0.0;
-						maxit = (int)si[REHUEL_STATE_MAXIT * M];
-						step = (long long)si[REHUEL_STATE_STEP * M];
-						last_relax = (long long)si[REHUEL_STATE_LAST_RELAX * M];
-					}
-					if (DENSE) { // grid times before the start are not this call's; one AT the start is the initial state
-						kd = 0;
-						while (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) < t) ++kd;
-						if (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) == t) {
+				}
+				if (io.n_samples) io.n_samples[mem] = n_stored;
+				if (io.state_out) {
+					double *so = io.state_out + mem;
+					so[REHUEL_STATE_DT * M] = dt;
+					so[REHUEL_STATE_DTS0 * M] = dts0;
+					so[REHUEL_STATE_DTS1 * M] = dts1;
+					so[REHUEL_STATE_ERRQ * M] = q_prev;
+					so[REHUEL_STATE_ALT * M] = alt ? 1.0 : 0.0;
+					so[REHUEL_STATE_MAXIT * M] = (double)maxit;
+					so[REHUEL_STATE_STEP * M] = (double)step;
+					so[REHUEL_STATE_LAST_RELAX * M] = (double)last_relax;
+				}
+				have = false;
+				done = false;
+			}
+			const unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
+			if (need) {
+				const int leader = __ffs(need) - 1;
+				unsigned long long base = 0;
+				if ((int)lane == leader) base = atomicAdd(io.queue, (unsigned long long)__popc(need));
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if (!have && !exhausted) {
+					mem = base + __popc(need & ((1u << lane) - 1u));
+					if (mem < M) {
+						if (io.order) mem = io.order[mem]; // caller-chosen hand-out order (e.g. costly members first)
 #pragma unroll
-							for (int k = 0; k < N; ++k) io.y_dense[((size_t)kd * N + k) * M + mem] = y[k];
-							++kd;
+						for (int k = 0; k < N; ++k) y[k] = io.y0_broadcast ? io.y0[k] : io.y0[k * M + mem];
+#pragma unroll
+						for (int k = 0; k < F::P; ++k) p[k] = io.params[k * M + mem];
+						if (F::P == 0) p[0] = 0.0;
+						if (TOLV) {
+							m_rtol = io.rtol[mem];
+							m_atol = io.atol[mem];
+							const double nt = io.newton_tol[mem];
+							m_Rtol2 = nt * nt;
 						}
-					}
-					status = REHUEL_SUCCESS;
-					c_attempt = c_rej_newton = c_rej_err = c_newton_ok = c_fun = c_jac = c_iters = 0;
-					n_stored = 0;
-					parked = false;
-					have = true;
-					if (a.store_samples && io.n_samples_cap) { // sample 0 = (t0, y0), irk.hpp:581-585
-						io.t_samples[mem] = t;
-						if (io.err_samples) io.err_samples[mem] = 0.0;
+						t = io.t_start ? io.t_start[mem] : a.t0;
+						dt = a.dt0;
+						if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:514-520
+						dts0 = dts1 = dt;                 // irk.hpp:572
+						q_prev = tb.q_init;               // irk.hpp:573: errs = 0.9
+						err = 0.0;
+						alt = true;                       // irk.hpp:587
+						maxit = a.maxit0;
+						step = 0;
+						last_relax = 0;
+						if (io.state_in) { // continue a stopped integration: the loop variables as they were at exit
+							const double *si = io.state_in + mem;
+							dt = si[REHUEL_STATE_DT * M];
+							dts0 = si[REHUEL_STATE_DTS0 * M];
+							dts1 = si[REHUEL_STATE_DTS1 * M];
+							q_prev = si[REHUEL_STATE_ERRQ * M];
+							alt = si[REHUEL_STATE_ALT * M] != 0.0;
+							maxit = (int)si[REHUEL_STATE_MAXIT * M];
+							step = (long long)si[REHUEL_STATE_STEP * M];
+							last_relax = (long long)si[REHUEL_STATE_LAST_RELAX * M];
+						}
+						if (DENSE) { // grid times before the start are not this call's; one AT the start is the initial state
+							kd = 0;
+							while (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) < t) ++kd;
+							if (kd < io.n_dense && fma((double)kd, io.dense_dt, io.dense_t0) == t) {
 #pragma unroll
-						for (int k = 0; k < N; ++k) io.y_samples[k * M + mem] = y[k];
+								for (int k = 0; k < N; ++k) io.y_dense[((size_t)kd * N + k) * M + mem] = y[k];
+								++kd;
+							}
+						}
+						status = REHUEL_SUCCESS;
+						c_attempt = c_rej_newton = c_rej_err = c_newton_ok = c_fun = c_jac = c_iters = 0;
+						n_stored = 0;
+						parked = false;
+						have = true;
+						if (a.store_samples && io.n_samples_cap) { // sample 0 = (t0, y0), irk.hpp:581-585
+							io.t_samples[mem] = t;
+							if (io.err_samples) io.err_samples[mem] = 0.0;
+#pragma unroll
+							for (int k = 0; k < N; ++k) io.y_samples[k * M + mem] = y[k];
+						}
+						n_stored = a.store_samples ? 1u : 0u;
+					} else {
+						exhausted = true;
 					}
-					n_stored = a.store_samples ? 1u : 0u;
-				} else {
-					exhausted = true;
 				}
 			}
 		}
@@ -617,15 +687,15 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 		// lanes redo their attempt with the full iteration budget, side by side.  The redo starts
 		// from Y = 0 with the same (t, y, dt) as the reference does, so results and counters are
 		// unchanged; only the schedule differs.
-		const unsigned pmask = __ballot_sync(0xffffffffu, have && parked);
-		const unsigned cmask = __ballot_sync(0xffffffffu, have && !parked);
+		const unsigned pmask = __ballot_sync(0xffffffffu, have && !done && parked);
+		const unsigned cmask = __ballot_sync(0xffffffffu, have && !done && !parked);
 		const bool slow_trip = pmask != 0u && (__popc(pmask) >= kParkLanes || cmask == 0u);
 
 		// ---------------- classify this trip: finish the member, or run one attempt
 		bool finished = false, run = false;
 		if (slow_trip) {
-			run = have && parked; // attempt already counted and clamped when it was first tried
-		} else if (have && !parked) {
+			run = have && !done && parked; // attempt already counted and clamped when it was first tried
+		} else if (have && !done && !parked) {
 			if (!(t < a.t1)) { // irk.hpp:604 (also covers t0 >= t1: zero attempts)
 				finished = true;
 			} else {
@@ -1052,62 +1122,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 			}
 		}
 
-		if (finished) {
-#pragma unroll
-			for (int k = 0; k < N; ++k) io.y[k * M + mem] = y[k];
-			io.t_final[mem] = t;
-			if (io.err_last) io.err_last[mem] = REHUEL_ROOT_CONTROLLER ? sqrt(err) : err;
-			io.status[mem] = status;
-			// accepted steps of THIS call (a continued member's `step` also counts the earlier legs)
-			const unsigned steps_here = (unsigned)(step - (io.state_in ? (long long)io.state_in[REHUEL_STATE_STEP * M + mem] : 0ll));
-			if (io.counters) {
-				io.counters[REHUEL_CNT_ATTEMPT * M + mem] = c_attempt;
-				io.counters[REHUEL_CNT_REJECT_NEWTON * M + mem] = c_rej_newton;
-				io.counters[REHUEL_CNT_REJECT_ERR * M + mem] = c_rej_err;
-				io.counters[REHUEL_CNT_NEWTON_SUCCESS * M + mem] = c_newton_ok;
-#ifdef REHUEL_COUNT_SKIPS
-				io.counters[REHUEL_CNT_NEWTON_MAXIT_EXCEED * M + mem] = c_skips;
-				c_skips = 0;
-#else
-				io.counters[REHUEL_CNT_NEWTON_MAXIT_EXCEED * M + mem] = c_rej_newton;
-#endif
-				io.counters[REHUEL_CNT_FUN_EVALS * M + mem] = c_fun;
-				io.counters[REHUEL_CNT_JAC_EVALS * M + mem] = c_jac;
-				io.counters[REHUEL_CNT_NEWTON_ITERS * M + mem] = c_iters;
-				io.counters[REHUEL_CNT_STEPS * M + mem] = steps_here;
-			}
-			if (io.stats) {
-				// the lanes that finish a member in this trip add up first (REDUX), their leader adds the sums to the
-				// CTA's 64-bit shared-memory totals, which go to the global words at the end of the kernel
-				const unsigned fm = __activemask();
-				const unsigned v[REHUEL_NCOUNTERS] = {c_attempt, c_rej_newton, c_rej_err, c_newton_ok, c_rej_newton, c_fun, c_jac, c_iters, steps_here};
-				unsigned long long w[REHUEL_NCOUNTERS];
-#pragma unroll
-				for (int c = 0; c < REHUEL_NCOUNTERS; ++c) // 16-bit halves: a sum over 32 lanes cannot wrap
-					w[c] = (unsigned long long)__reduce_add_sync(fm, v[c] & 0xffffu) + ((unsigned long long)__reduce_add_sync(fm, v[c] >> 16) << 16);
-				const unsigned nfail = __reduce_add_sync(fm, status != 0 ? 1u : 0u);
-				const unsigned amax = __reduce_max_sync(fm, c_attempt);
-				if ((int)lane == __ffs(fm) - 1) {
-#pragma unroll
-					for (int c = 0; c < REHUEL_NCOUNTERS; ++c) atomicAdd(&s_stats[c], w[c]);
-					atomicAdd(&s_stats[REHUEL_NCOUNTERS], (unsigned long long)nfail);
-					atomicMax(&s_stats[REHUEL_NCOUNTERS + 1], (unsigned long long)amax);
-				}
-			}
-			if (io.n_samples) io.n_samples[mem] = n_stored;
-			if (io.state_out) {
-				double *so = io.state_out + mem;
-				so[REHUEL_STATE_DT * M] = dt;
-				so[REHUEL_STATE_DTS0 * M] = dts0;
-				so[REHUEL_STATE_DTS1 * M] = dts1;
-				so[REHUEL_STATE_ERRQ * M] = q_prev;
-				so[REHUEL_STATE_ALT * M] = alt ? 1.0 : 0.0;
-				so[REHUEL_STATE_MAXIT * M] = (double)maxit;
-				so[REHUEL_STATE_STEP * M] = (double)step;
-				so[REHUEL_STATE_LAST_RELAX * M] = (double)last_relax;
-			}
-			have = false;
-		}
+		if (finished) done = true; // results are written when the warp next stops for service (top of the loop)
 	}
 	__syncthreads(); // every warp of the CTA has left the loop
 	if (io.stats && threadIdx.x < REHUEL_NSTATS && s_stats[threadIdx.x]) {
