@@ -309,7 +309,7 @@ def run_gpu_arm(args) -> None:
         return t.item()
 
     peak_tflops = capi.fp64_peak_tflops()
-    rob = flopmodel.thread_kernel(3, capi.RADAU_IIA_53, 11, 8)
+    rob = flopmodel.thread_kernel(3, capi.RADAU_IIA_53, 11, 8, zero_col0_rows=(2,))
 
     # ---------------- value: inputs resident in HBM, device-timed
     for _ in range(args.warmup):
@@ -346,6 +346,7 @@ def run_gpu_arm(args) -> None:
     fixed, extra820, per_newton = ensembles.flops_per_attempt_dense_model(3, 3, 11, 8)
     flops_dense = fixed * cs["attempt"] + per_newton * cs["newton_iters"] + extra820 * uses_820
     flops_exec = model_flops(rob, cs)
+    flops_r1_local = 259.0 * cs["attempt"] + 369.0 * cs["newton_iters"] + 30.0 * uses_820 - 132.0 * 0.962 * cs["newton_success"]
     local = sharding.pack_stats(members=M, attempt=cs["attempt"], steps=cs["steps"], newton_iters=cs["newton_iters"],
                                 fun_evals=cs["fun_evals"], jac_evals=cs["jac_evals"], reject_err=cs["reject_err"],
                                 reject_newton=cs["reject_newton"], n_failed=cs["n_failed"], flops_dense_model=flops_dense,
@@ -424,6 +425,7 @@ def run_gpu_arm(args) -> None:
         kern_s = kernel_ms_max / args.steps * 1e-3
         ach_dense = tot["flops_dense_model"] / world / kern_s / 1e12   # per GPU, per launch
         ach_exec = tot["flops_executed_model"] / world / kern_s / 1e12
+        flops_r1 = flops_r1_local * world  # rank 0's members stand for all (the sweeps are statistically alike)
         info = capi.kernel_info(capi.ROBERTSON, capi.RADAU_IIA_53)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -461,6 +463,12 @@ def run_gpu_arm(args) -> None:
                 "kernel": "ensemble_irk_thread<RobertsonF,3,1,1,EST_REUSE>", "regs": info["regs"],
                 "spill_bytes": info["local_bytes"], "ctas_per_sm": info["ctas_per_sm"], "block": info["block"],
             },
+            "roofline_round1_model": {
+                "achieved": flops_r1 / world / kern_s / 1e12, "frac": flops_r1 / world / kern_s / 1e12 / peak_tflops, "unit": "TFLOP/s",
+                "model": "the executed-flop count of the ROUND-1 kernel on the same counters (259*attempts + 369*newton_iterations + "
+                         "30*uses_of_8.20 - 132*0.962*newton_solves): what this work cost before the multiplications by structural "
+                         "zeros and ones, the dy product, the first iteration's full transform and two of the three square roots "
+                         "were removed -- a work-equivalent rate for comparison with BENCH_r01, not a hardware fraction"},
             "roofline_dense_model": {
                 "achieved": ach_dense, "frac": ach_dense / peak_tflops, "unit": "TFLOP/s",
                 "model": "SURVEY.md 8(d) flops of the REFERENCE's dense (s n) x (s n) algorithm, which the kernel does not execute: "
@@ -525,7 +533,8 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
     config 2 at 2^20 members in all: rank r integrates the contiguous members [r M/N, (r+1) M/N).
     config 5 at 10 485 760 members in all (even index Robertson / RADAU_IIA_53 / t in [0,40], odd index Van der Pol /
     LOBATTO_IIIC_43 / t in [0,2], rtol = atol = 10^(-3-6v), newton tol = 0.1 rtol): cut into 128 chunks that the ranks CLAIM
-    from a cursor in shared memory (rehuel_cursor) as they finish, six chunks in flight per GPU."""
+    from a cursor in shared memory (rehuel_cursor) as they finish, six chunks in flight per GPU, the stiff end of the
+    sweep first (longest processing time first)."""
     import numpy as np
     cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     o = capi.make_options(RTOL, ATOL)
@@ -580,6 +589,7 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
             c = cur.next(1)
             if c >= n_chunks:
                 break
+            c = n_chunks - 1 - c                # the Van der Pol members get stiffer along the index: costly chunks first
             for (de, t1), st in zip(chunks[c], streams[slot]):
                 st.wait_stream(main)
                 with torch.cuda.stream(st):

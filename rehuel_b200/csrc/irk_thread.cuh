@@ -387,6 +387,14 @@ struct is_autonomous { static constexpr bool value = false; };
 template <class F>
 struct is_autonomous<F, decltype((void)F::kAutonomous)> { static constexpr bool value = F::kAutonomous; };
 
+// max(|a|, |b|) (irk.hpp:741: std::max(std::abs(y), std::abs(y_n))) on the integer pipe: non-negative doubles order like
+// their bit patterns.  (fmax is a DSETP + selects + moves; a NaN operand gives NaN here, the member is lost either way.)
+__device__ __forceinline__ double max_abs(double a, double b)
+{
+	const long long ia = __double_as_longlong(a) & 0x7fffffffffffffffll, ib = __double_as_longlong(b) & 0x7fffffffffffffffll;
+	return __longlong_as_double(ia > ib ? ia : ib);
+}
+
 // ------------------------------------------------------------------ controller power
 // err^(1/(1+min_order)) (irk.hpp:774-782).  The exponent is a tableau constant; the common
 // values get exact-root forms (each correctly rounded step, <= 1 ulp from pow()).
@@ -441,10 +449,14 @@ template <int K>
 __device__ __forceinline__ void inv_root(double x, double &r_out, double &q_out)
 {
 	const int hi = __double2hiint(x);
-	const int E = ((hi >> 20) & 0x7ff) - 1023; // floor(log2 x)
-	const int j = (E >= 0 ? E + K / 2 : E - K / 2) / K; // round(E / K)
-	const double xs = __hiloint2double(hi - K * j * 0x100000, __double2loint(x)); // x 2^(-K j), exact
-	double r = (double)exp2f(__log2f((float)xs) * (-1.0f / K));
+	// j = round(E / K), E = floor(log2 x) = biased exponent - 1023: unsigned arithmetic (the +1024 K keeps it positive)
+	const unsigned eb = ((unsigned)hi >> 20) & 0x7ffu;
+	const int j = (int)((eb + (unsigned)(1024 * K - 1023 + K / 2)) / (unsigned)K) - 1024;
+	const double xs = __hiloint2double(hi - K * j * 0x100000, __double2loint(x)); // x 2^(-K j), exact, in [2^(-K/2), 2^(K/2+1))
+	float lg, sd;
+	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)xs)); // no denormals here: the guarded log2f/exp2f are not needed
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(lg * (-1.0f / K)));
+	double r = (double)sd;
 #pragma unroll
 	for (int step = 0; step < 2; ++step) {
 		const double e = fma(-xs, pow_int<K>(r), 1.0);
@@ -455,23 +467,40 @@ __device__ __forceinline__ void inv_root(double x, double &r_out, double &q_out)
 	q_out = __hiloint2double(__double2hiint(q) + j * 0x100000, __double2loint(q)); // q 2^(+j)
 }
 
+// min(order, order2) of the tableau a kernel instantiation is built for (launch.cuh: one tableau per (S, NR, NC, EST));
+// 0: not known at compile time (use the run-time value).  irk.cpp:215-689.
+template <int S, int NR, int NC, int EST>
+struct static_min_order {
+	static constexpr int value = (S == 2 && NC == 1) ? 2                           // RADAU_IIA_32 (3, 2)
+	                             : (S == 3 && EST == EST_REUSE) ? 3                // RADAU_IIA_53 (5, 3)
+	                             : (S == 3 && EST == EST_IDENTITY) ? 2             // LOBATTO_IIIC_43 (4, 2)
+	                             : (S == 4) ? 4                                    // LOBATTO_IIIC_64 (6, 4)
+	                             : (S == 5) ? 5                                    // RADAU_IIA_95 (9, 5), LOBATTO_IIIC_85 (8, 5)
+	                             : (S == 7) ? 7                                    // RADAU_IIA_137 (13, 7)
+	                                        : 0;
+};
+
+template <int MO> // MO: compile-time min(order, order2), or 0: use `min_order`
 __device__ __forceinline__ double propose_dt_sq(double dt, double errsq, double &q_prev, double dts0, double dts1, int maxit,
                                                 int iters, int min_order, double expo, double max_dt)
 {
 	double s27, q;
+	const int mo = MO ? MO : min_order;
 	if (!(errsq <= 1e300)) { // Inf or NaN: keep the reference's arithmetic (the step is lost anyway)
-		q = ctrl_pow(sqrt(errsq), min_order, expo);
+		q = ctrl_pow(sqrt(errsq), mo, expo);
 		s27 = fast_rcp(q);
-	} else if (min_order == 3) {
+	} else if (mo == 3) {
 		inv_root<8>(errsq, s27, q);
-	} else if (min_order == 2) {
+	} else if (mo == 2) {
 		inv_root<6>(errsq, s27, q);
-	} else if (min_order == 5) {
+	} else if (mo == 5) {
 		inv_root<12>(errsq, s27, q);
-	} else if (min_order == 4) {
+	} else if (mo == 4) {
 		inv_root<10>(errsq, s27, q);
+	} else if (mo == 7) {
+		inv_root<16>(errsq, s27, q);
 	} else {
-		q = ctrl_pow(sqrt(errsq), min_order, expo);
+		q = ctrl_pow(sqrt(errsq), mo, expo);
 		s27 = fast_rcp(q);
 	}
 	const double s28 = s27 * (dts0 * fast_rcp(dts1)) * (q_prev * s27);
@@ -1051,7 +1080,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					double tot = 0.0;
 #pragma unroll
 					for (int k = 0; k < N; ++k) {
-						const double sc = fma(TOLV ? m_rtol : a.rtol, fmax(fabs(y[k]), fabs(yn[k])), TOLV ? m_atol : a.atol);
+						const double sc = fma(TOLV ? m_rtol : a.rtol, max_abs(y[k], yn[k]), TOLV ? m_atol : a.atol);
 						const double q = e[k] * fast_rcp(sc);
 						tot = fma(q, q, tot);
 					}
@@ -1071,7 +1100,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					}
 					// -------- step-size proposal, irk.hpp:770-801 (shifts the error history, irk.hpp:756-758)
 					const double new_dt = REHUEL_ROOT_CONTROLLER
-					                          ? propose_dt_sq(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt)
+					                          ? propose_dt_sq<static_min_order<S, NR, NC, EST>::value>(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt)
 					                          : propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
 
 					if (io.trace) trace_row(a, mem, step, t, dt, REHUEL_ROOT_CONTROLLER ? sqrt(err) : err, it); // irk.hpp:805-810

@@ -96,7 +96,9 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 			return set_error(REHUEL_EINVAL, "Chosen method does not have dense output!"); // irk.cpp:733
 		}
 	}
-	if (tb.s != S || tb.n_real != NR || tb.n_cplx != NC || tb.est_mode != EST || (REHUEL_CANONICAL_TABLEAU && !tb.canonical))
+	constexpr int MO = static_min_order<S, NR, NC, EST>::value;
+	if (tb.s != S || tb.n_real != NR || tb.n_cplx != NC || tb.est_mode != EST || (REHUEL_CANONICAL_TABLEAU && !tb.canonical) ||
+	    (MO != 0 && tb.has_b2 && MO != (tb.order < tb.order2 ? tb.order : tb.order2)))
 		return set_error(REHUEL_EINVAL, "internal: tableau %s does not have the structure its kernel was built for", tb.name);
 	int dev = 0, sms = 0, per_sm = 0;
 	REHUEL_CUDA_TRY(cudaGetDevice(&dev));

@@ -79,22 +79,60 @@ def _tail(n, S, est_solve, est, f_fun, autonomous):
     return f
 
 
-def thread_kernel(n, method, f_fun, f_jac, autonomous=True) -> AttemptFlops:
-    """ensemble_irk_thread (n <= 4): dense n x n LUs of the decoupled blocks in registers.
-    Robertson / RADAU_IIA_53: fixed 259, per iteration 369, 8.20 +30, residual 132."""
+def _lu_real_zc(n, zc_rows):
+    """lu_factor<false, ZCOL0>(LuReal): rows whose entry in column 0 is structurally zero skip the first step."""
+    f = _lu_dense(n, False)
+    return f - len(zc_rows) * (1 + 2 * (n - 1))
+
+
+def _lu_cplx_diagim(n, zc_rows):
+    """lu_factor<false, ZCOL0, true>(LuCplx): in the first elimination step the imaginary part is mi on the diagonal and
+    zero elsewhere: multipliers are two real multiplications, updates one FMA + one FMA (diagonal) or one
+    multiplication (off-diagonal); rows with a structurally zero entry in column 0 skip the step."""
+    rows = n - 1 - len(zc_rows)
+    first = 6 + rows * (2 + (n - 1) * 2 + 2 + (n - 2) * 1)  # pivot; per row: multiplier, re updates (FMA), im updates
+    rest = 0.0
+    for k in range(1, n):
+        r = n - k - 1
+        rest += 6 + 6 * r + 8 * r * r
+    return first + rest
+
+
+def thread_kernel(n, method, f_fun, f_jac, autonomous=True, zero_col0_rows=()) -> AttemptFlops:
+    """ensemble_irk_thread (n <= 4) as built (irk_thread.cuh): dense n x n LUs of the decoupled blocks in registers,
+    unpivoted path.  Counted from the source with its default switches: structural zeros (REHUEL_STRUCT_ZEROS: diagonal
+    imaginary part in the first elimination step, real row 0 of U in the complex solves, the functor's kJacZeroMask --
+    `zero_col0_rows`: Robertson (2,)), canonical tableau (d = e_s: no dy product; unit last row of T: additions),
+    peeled first iteration (rank-one right-hand side, Y = dY), step-size proposal with one k-th root (counted as 2:
+    one root, one reciprocal-free power, by the rule that div/sqrt/pow count 1)."""
     S, NR, NC, est = STRUCTURE[method]
-    lu = NR * (_lu_dense(n, False) + n + 1) + NC * (_lu_dense(n, True) + n + 2) + 1  # + diagonal shifts, mu's, 1/dt
+    zc = tuple(zero_col0_rows)
+    lu = 1  # 1/dt
+    lu += NR * (_lu_real_zc(n, zc) + n + 1)          # + diagonal shifts, mu_r
+    lu += NC * (_lu_cplx_diagim(n, zc) + n + 2)      # + diagonal shifts, mu_c (two products)
     if est == EST_OWN_LU:
-        lu += _lu_dense(n, False) + n + 1
-    est_solve = 0 if est == EST_IDENTITY else _solve_dense(n, False)
-    first = (f_fun + S * (1 + 3 * n)) if autonomous else _residual(n, S, f_fun, S)
-    tail = _tail(n, S, est_solve, est, f_fun, autonomous)
+        lu += _lu_real_zc(n, zc) + n + 1
+    solve_r = _solve_dense(n, False) - 2 * len(zc)                     # forward term (i, 0) skipped
+    solve_c = _solve_dense(n, True) - 4 * (n - 1) - 8 * len(zc)        # real row 0 of U; forward term (i, 0) skipped
+    est_solve = 0 if est == EST_IDENTITY else solve_r
+    # tail: dalt (S n FMA); gam; yn; gam*f + dalt (FMA) - dy; E^-1 and scaling; norm (abs, abs, max, FMA, rcp, mul, FMA per
+    # component; mean); controller: root 2, ratio 5, fac 4, new_dt 2
+    tail = 2 * S * n + 1 + n
+    if est != EST_IDENTITY:
+        tail += 2 * n + (0 if autonomous else f_fun)
+    tail += n + est_solve + n + 9 * n + 1 + 13
+    resid = _residual(n, S, f_fun, S) + (S - 1)                         # + the partial sums of |R|^2
+    units = NR + NC                                                     # unit entries in the last row of T
+    transforms_T = 2 * S * n * (S - 1) + (units - 1) * n                # T (x) I with the canonical last row
+    solves = NR * (solve_r + n) + NC * (solve_c + 6 * n)                # + the -mu scalings
+    per_it = 2 * S * S * n + solves + transforms_T + 2 * S * n + (S - 1) + S * n + resid
+    if autonomous:   # first iteration peeled: Z = (-dt TiAsum_i) f(y): S + S n products; Y = dY
+        first = f_fun - (2 * S * S * n - (S + S * n)) - S * n
+    else:
+        first = resid
     fixed = f_jac + lu + first + tail
-    transforms = 2 * S * S * n * 2                  # Ti (x) I and T (x) I products
-    solves = NR * (_solve_dense(n, False) + n) + NC * (_solve_dense(n, True) + 6 * n)  # + the -mu scalings
-    per_it = transforms + solves + 2 * S * n + S * n + _residual(n, S, f_fun, S)       # |dY|^2, Y += dY
-    extra = (n + (f_fun if est != EST_IDENTITY else 0) + (2 * n if est != EST_IDENTITY else 0) + n + est_solve + n)
-    return AttemptFlops(S, fixed, tail, per_it, extra, _residual(n, S, f_fun, S))
+    extra = n + (f_fun + 2 * n if est != EST_IDENTITY else 0) + n + est_solve + n
+    return AttemptFlops(S, fixed, tail, per_it, extra, resid)
 
 
 def _lu_band(n, kb, cplx):

@@ -65,3 +65,23 @@ def test_sharding_world_size_2_gloo():
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "SHARD-OK" in outs[0]
+
+
+def test_executed_flop_model_of_the_thread_kernel():
+    """rehuel_b200/flopmodel.py: the counts DESIGN.md section 6 quotes, and the counter identity behind `total`."""
+    from rehuel_b200 import flopmodel as fm
+    rob = fm.thread_kernel(3, 211, 11, 8, zero_col0_rows=(2,))
+    assert (rob.S, rob.fixed, rob.tail, rob.per_iteration, rob.extra_820, rob.residual) == (3, 118, 88, 340, 39, 134)
+    vdp = fm.thread_kernel(2, 230, 6, 7)
+    assert vdp.per_iteration == 212 and vdp.extra_820 == 6          # LOBATTO_IIIC_43: E = I, no estimator solve
+    # one member, 3 attempts, one of them rejected, 2 + 1 + 2 Newton iterations, every final residual booked:
+    # fun_evals = S * (attempts + iterations) + newton_success + uses of 8.20 (first attempt + the one after the rejection)
+    att, its, nok, rej = 3, 5, 3, 1
+    fun = 3 * (att + its) + nok + (1 + rej)
+    total = rob.total(1, att, nok, rej, fun)
+    assert total == rob.fixed * 3 + rob.per_iteration * 5 + rob.extra_820 * 2 - rob.residual * 3
+    # a failed Newton solve has no tail
+    assert rob.total(1, att + 1, nok, rej, fun + 3 * (1 + 4)) == total + (rob.fixed - rob.tail) + 4 * rob.per_iteration
+    band = fm.band_kernel(64, 2, 232, 10, 8)
+    dense = fm.dense_kernel(64, 232, 10, 64 * 8)
+    assert dense.fixed > 50 * band.fixed                            # three dense 64 x 64 LUs against band LUs
