@@ -197,7 +197,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = [c for c, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "samples_under_load": len(busy) if len(busy) < len(sm) else None,
+                "samples": len(sm), "samples_under_load": len(busy),
                 "power_w_max": max(power)}
 
 
