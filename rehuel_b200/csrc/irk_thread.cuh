@@ -552,19 +552,27 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	__syncthreads();
 
 	// ---- lane-persistent member state
-	bool have = false, exhausted = false;
-	bool done = false;   // the member is finished, its results are still in this lane's registers (see kBatchLanes)
-	bool parked = false; // this lane's attempt ran past kFastIters Newton iterations: redo it in a slow trip
-	bool prefer_piv = false; // the warp's last factorisations needed row interchanges: skip the speculative plain attempt
+	// lane state flags in one word (as separate bools they were spilled byte by byte)
+	struct LaneFlags {
+		unsigned have : 1;       // the lane holds a member
+		unsigned done : 1;       // the member is finished, its results are still in this lane's registers (see kBatchLanes)
+		unsigned exhausted : 1;  // the queue had nothing left for this lane
+		unsigned parked : 1;     // this lane's attempt ran past kFastIters Newton iterations: redo it in a slow trip
+		unsigned prefer_piv : 1; // the warp's last factorisations needed row interchanges: skip the speculative plain attempt
+		unsigned alt : 1;        // alternative_error_formula, irk.hpp:587, 763, 845
+	} fl{};
+	fl.alt = 1;
 	unsigned long long mem = 0;
 	double y[N], p[PA];
 	double t = 0.0, dt = 0.0;
 	double dts0 = 0.0, dts1 = 0.0, q_prev = tb.q_init, err = 0.0; // q_prev = errs[1]^expo, see propose_dt
-	bool alt = true;
 	int maxit = a.maxit0;
-	long long step = 0, last_relax = 0;
-	int status = REHUEL_SUCCESS;
-	unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_newton_ok = 0, c_fun = 0, c_jac = 0,
+	// accepted steps of THIS call and since the Newton budget was last raised (irk.hpp:644-648); a continued member's
+	// earlier legs stay in io.state_in and are only added where the total is needed (max_steps, log, samples, state_out)
+	unsigned steps = 0, since_relax = 0;
+	int status = REHUEL_SUCCESS; // kAborted marks an attempt that was counted but neither accepted nor rejected
+	constexpr int kAborted = 1 << 30;
+	unsigned c_attempt = 0, c_rej_newton = 0, c_rej_err = 0, c_fun = 0, c_jac = 0,
 	         c_iters = 0, n_stored = 0;
 	unsigned kd = 0; // dense output: index of the next grid time (DENSE kernels only)
 #ifdef REHUEL_COUNT_SKIPS
@@ -573,20 +581,24 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 	// per-member tolerances (TOLV kernels only; otherwise the uniform values of the options)
 	double m_rtol = a.rtol, m_atol = a.atol, m_Rtol2 = a.Rtol2;
 
+	auto total_step = [&]() -> long long { // irk_guts' `step`: accepted steps including earlier legs
+		return (long long)steps + (io.state_in ? (long long)io.state_in[REHUEL_STATE_STEP * M + mem] : 0ll);
+	};
 	for (;;) {
 		// ---------------- service stop: write the results of finished members, refill idle lanes from the global queue
 		// (warp-aggregated).  Warp-uniform decision, see kBatchLanes.
-		const unsigned wants = __ballot_sync(0xffffffffu, (have && done) || (!have && !exhausted));
-		const unsigned busy = __ballot_sync(0xffffffffu, have && !done);
+		const unsigned wants = __ballot_sync(0xffffffffu, (fl.have && fl.done) || (!fl.have && !fl.exhausted));
+		const unsigned busy = __ballot_sync(0xffffffffu, fl.have && !fl.done);
 		if (wants != 0u && (__popc(wants) >= kBatchLanes || busy == 0u)) {
-			if (have && done) {
+			if (fl.have && fl.done) {
 #pragma unroll
 				for (int k = 0; k < N; ++k) io.y[k * M + mem] = y[k];
 				io.t_final[mem] = t;
 				if (io.err_last) io.err_last[mem] = REHUEL_ROOT_CONTROLLER ? sqrt(err) : err;
-				io.status[mem] = status;
-				// accepted steps of THIS call (a continued member's `step` also counts the earlier legs)
-				const unsigned steps_here = (unsigned)(step - (io.state_in ? (long long)io.state_in[REHUEL_STATE_STEP * M + mem] : 0ll));
+				io.status[mem] = status & ~kAborted;
+				const unsigned steps_here = steps;
+				// every attempt ends accepted, rejected or -- once, ending the member -- aborted
+				const unsigned c_newton_ok = c_attempt - c_rej_newton - ((status & kAborted) ? 1u : 0u);
 				if (io.counters) {
 					io.counters[REHUEL_CNT_ATTEMPT * M + mem] = c_attempt;
 					io.counters[REHUEL_CNT_REJECT_NEWTON * M + mem] = c_rej_newton;
@@ -612,7 +624,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 #pragma unroll
 					for (int c = 0; c < REHUEL_NCOUNTERS; ++c) // 16-bit halves: a sum over 32 lanes cannot wrap
 						w[c] = (unsigned long long)__reduce_add_sync(fm, v[c] & 0xffffu) + ((unsigned long long)__reduce_add_sync(fm, v[c] >> 16) << 16);
-					const unsigned nfail = __reduce_add_sync(fm, status != 0 ? 1u : 0u);
+					const unsigned nfail = __reduce_add_sync(fm, (status & ~kAborted) != 0 ? 1u : 0u);
 					const unsigned amax = __reduce_max_sync(fm, c_attempt);
 					if ((int)lane == __ffs(fm) - 1) {
 #pragma unroll
@@ -628,21 +640,21 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					so[REHUEL_STATE_DTS0 * M] = dts0;
 					so[REHUEL_STATE_DTS1 * M] = dts1;
 					so[REHUEL_STATE_ERRQ * M] = q_prev;
-					so[REHUEL_STATE_ALT * M] = alt ? 1.0 : 0.0;
+					so[REHUEL_STATE_ALT * M] = fl.alt ? 1.0 : 0.0;
 					so[REHUEL_STATE_MAXIT * M] = (double)maxit;
-					so[REHUEL_STATE_STEP * M] = (double)step;
-					so[REHUEL_STATE_LAST_RELAX * M] = (double)last_relax;
+					so[REHUEL_STATE_STEP * M] = (double)total_step();
+					so[REHUEL_STATE_LAST_RELAX * M] = (double)(total_step() - (long long)since_relax);
 				}
-				have = false;
-				done = false;
+				fl.have = false;
+				fl.done = false;
 			}
-			const unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
+			const unsigned need = __ballot_sync(0xffffffffu, !fl.have && !fl.exhausted);
 			if (need) {
 				const int leader = __ffs(need) - 1;
 				unsigned long long base = 0;
 				if ((int)lane == leader) base = atomicAdd(io.queue, (unsigned long long)__popc(need));
 				base = __shfl_sync(0xffffffffu, base, leader);
-				if (!have && !exhausted) {
+				if (!fl.have && !fl.exhausted) {
 					mem = base + __popc(need & ((1u << lane) - 1u));
 					if (mem < M) {
 						if (io.order) mem = io.order[mem]; // caller-chosen hand-out order (e.g. costly members first)
@@ -663,20 +675,20 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						dts0 = dts1 = dt;                 // irk.hpp:572
 						q_prev = tb.q_init;               // irk.hpp:573: errs = 0.9
 						err = 0.0;
-						alt = true;                       // irk.hpp:587
+						fl.alt = true;                       // irk.hpp:587
 						maxit = a.maxit0;
-						step = 0;
-						last_relax = 0;
+						steps = 0;
+						since_relax = 0;
 						if (io.state_in) { // continue a stopped integration: the loop variables as they were at exit
 							const double *si = io.state_in + mem;
 							dt = si[REHUEL_STATE_DT * M];
 							dts0 = si[REHUEL_STATE_DTS0 * M];
 							dts1 = si[REHUEL_STATE_DTS1 * M];
 							q_prev = si[REHUEL_STATE_ERRQ * M];
-							alt = si[REHUEL_STATE_ALT * M] != 0.0;
+							fl.alt = si[REHUEL_STATE_ALT * M] != 0.0;
 							maxit = (int)si[REHUEL_STATE_MAXIT * M];
-							step = (long long)si[REHUEL_STATE_STEP * M];
-							last_relax = (long long)si[REHUEL_STATE_LAST_RELAX * M];
+							const double gap = si[REHUEL_STATE_STEP * M] - si[REHUEL_STATE_LAST_RELAX * M];
+							since_relax = gap < 4e9 ? (unsigned)gap : 4000000000u;
 						}
 						if (DENSE) { // grid times before the start are not this call's; one AT the start is the initial state
 							kd = 0;
@@ -688,10 +700,10 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							}
 						}
 						status = REHUEL_SUCCESS;
-						c_attempt = c_rej_newton = c_rej_err = c_newton_ok = c_fun = c_jac = c_iters = 0;
+						c_attempt = c_rej_newton = c_rej_err = c_fun = c_jac = c_iters = 0;
 						n_stored = 0;
-						parked = false;
-						have = true;
+						fl.parked = false;
+						fl.have = true;
 						if (a.store_samples && io.n_samples_cap) { // sample 0 = (t0, y0), irk.hpp:581-585
 							io.t_samples[mem] = t;
 							if (io.err_samples) io.err_samples[mem] = 0.0;
@@ -700,12 +712,12 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						}
 						n_stored = a.store_samples ? 1u : 0u;
 					} else {
-						exhausted = true;
+						fl.exhausted = true;
 					}
 				}
 			}
 		}
-		if (__all_sync(0xffffffffu, !have)) break;
+		if (__all_sync(0xffffffffu, !fl.have)) break;
 
 		// ---------------- slow-lane handling.  A failing simplified Newton iteration spins to maxit
 		// (4999 iterations by default; the reference has no divergence test, irk.hpp:458-488) while
@@ -716,29 +728,29 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 		// lanes redo their attempt with the full iteration budget, side by side.  The redo starts
 		// from Y = 0 with the same (t, y, dt) as the reference does, so results and counters are
 		// unchanged; only the schedule differs.
-		const unsigned pmask = __ballot_sync(0xffffffffu, have && !done && parked);
-		const unsigned cmask = __ballot_sync(0xffffffffu, have && !done && !parked);
+		const unsigned pmask = __ballot_sync(0xffffffffu, fl.have && !fl.done && fl.parked);
+		const unsigned cmask = __ballot_sync(0xffffffffu, fl.have && !fl.done && !fl.parked);
 		const bool slow_trip = pmask != 0u && (__popc(pmask) >= kParkLanes || cmask == 0u);
 
 		// ---------------- classify this trip: finish the member, or run one attempt
 		bool finished = false, run = false;
 		if (slow_trip) {
-			run = have && !done && parked; // attempt already counted and clamped when it was first tried
-		} else if (have && !done && !parked) {
+			run = fl.have && !fl.done && fl.parked; // attempt already counted and clamped when it was first tried
+		} else if (fl.have && !fl.done && !fl.parked) {
 			if (!(t < a.t1)) { // irk.hpp:604 (also covers t0 >= t1: zero attempts)
 				finished = true;
 			} else {
 				if (t + dt > a.t1) dt = a.t1 - t; // irk.hpp:607-609
 				++c_attempt;
-				if (a.max_steps >= 0 && step > a.max_steps) { // irk.hpp:612-616
-					status = REHUEL_ERROR_MAX_STEPS_EXCEEDED;
+				if (a.max_steps >= 0 && total_step() > a.max_steps) { // irk.hpp:612-616
+					status = REHUEL_ERROR_MAX_STEPS_EXCEEDED | kAborted;
 					finished = true;
 				} else if (!(dt >= 2.2250738585072014e-308)) {
 					// DELIBERATE DEVIATION: a subnormal dt (endless Newton back-offs: 0.7*denorm_min
 					// rounds back to denorm_min, so dt never even reaches 0) or a NaN dt (a NaN error
 					// estimate is "accepted" by irk.hpp:761) makes the reference loop forever; a GPU
 					// lane must terminate.  Flag the member instead.
-					status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
+					status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL | kAborted;
 					finished = true;
 				} else {
 					run = true;
@@ -801,9 +813,9 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				++c_jac;
 				// warp-uniform decisions (every lane of amask is here): plain elimination unless the
 				// warp's previous factorisations interchanged rows; pivoted redo if any lane needs it
-				bool piv_any = (REHUEL_PIVOT_MODE == 1) || __any_sync(amask, prefer_piv);
+				bool piv_any = (REHUEL_PIVOT_MODE == 1) || __any_sync(amask, fl.prefer_piv);
 				if (!piv_any) piv_any = __any_sync(amask, factor_all(std::false_type()));
-				if (piv_any) prefer_piv = __any_sync(amask, factor_all(std::true_type()));
+				if (piv_any) fl.prefer_piv = __any_sync(amask, factor_all(std::true_type()));
 
 				// residual R = Y - dt*(A (x) I) F(y + Y), irk.hpp:366-386
 				auto residual = [&]() -> double {
@@ -999,24 +1011,23 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					// one Jacobian, and one no-op refresh per refresh_jac iterations)
 					c_fun -= (unsigned)(S * cap);
 					c_jac -= 1u + (a.refresh_jac > 0 ? (unsigned)((cap - 1) / a.refresh_jac) : 0u);
-					parked = true;
+					fl.parked = true;
 				} else if (nstat != kNewtonSuccess) { // irk.hpp:634-665
-					parked = false;
-					trace_row(a, mem, step, t, dt, -1.0, it);
+					fl.parked = false;
+					if (io.trace) trace_row(a, mem, total_step(), t, dt, -1.0, it);
 					if (!a.adaptive) {
-						status = REHUEL_GENERAL_ERROR;
+						status = REHUEL_GENERAL_ERROR | kAborted;
 						finished = true;
 					} else {
 						dt *= 0.7;
-						if (step - last_relax > 15) {
+						if (since_relax > 15u) { // step - last_maxit_relax_step > 15
 							maxit += a.maxit0;
-							last_relax = step;
+							since_relax = 0u;
 						}
 						++c_rej_newton;
 					}
 				} else {
-					parked = false;
-					++c_newton_ok;
+					fl.parked = false;
 					c_iters += (unsigned)it;
 					// -------- new solution + embedded error, irk.hpp:691-731
 					const double gam = tb.gamma * dt;
@@ -1063,7 +1074,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						for (int k = 0; k < N; ++k) v[k] *= sc;
 					};
 					apply_Einv_dt(e); // 8.19, irk.hpp:718
-					if (alt) {        // 8.20, irk.hpp:722-731
+					if (fl.alt) {        // 8.20, irk.hpp:722-731
 						double y2[N], f2[N];
 #pragma unroll
 						for (int k = 0; k < N; ++k) y2[k] = y[k] + e[k];
@@ -1095,7 +1106,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					}
 					const bool rejected = a.adaptive && (err > 1.0); // irk.hpp:761
 					if (rejected) {
-						alt = true;
+						fl.alt = true;
 						++c_rej_err;
 					}
 					// -------- step-size proposal, irk.hpp:770-801 (shifts the error history, irk.hpp:756-758)
@@ -1103,7 +1114,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 					                          ? propose_dt_sq<static_min_order<S, NR, NC, EST>::value>(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt)
 					                          : propose_dt(dt, err, q_prev, dts0, dts1, maxit, it, tb.min_order, tb.expo, a.max_dt);
 
-					if (io.trace) trace_row(a, mem, step, t, dt, REHUEL_ROOT_CONTROLLER ? sqrt(err) : err, it); // irk.hpp:805-810
+					if (io.trace) trace_row(a, mem, total_step(), t, dt, REHUEL_ROOT_CONTROLLER ? sqrt(err) : err, it); // irk.hpp:805-810
 					if (!rejected) { // irk.hpp:813-846
 						if (DENSE) { // grid times inside (t, t + dt] from this step's collocation polynomial
 							const double t_new = t + dt;
@@ -1126,12 +1137,13 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						for (int k = 0; k < N; ++k) y[k] = yn[k];
 						const double t_old = t;
 						t += dt;
-						++step;
+						++steps;
+						if (since_relax < 0xffffffffu) ++since_relax;
 						if (t == t_old) { // dt below ulp(t): the reference would accept steps forever
 							status = REHUEL_GENERAL_ERROR | REHUEL_DT_TOO_SMALL;
 							finished = true;
 						}
-						if (a.store_samples && (a.output_interval == 1ull || (unsigned long long)step % a.output_interval == 0ull)) {
+						if (a.store_samples && (a.output_interval == 1ull || (unsigned long long)total_step() % a.output_interval == 0ull)) {
 							if (n_stored < io.n_samples_cap) {
 								const size_t row = n_stored;
 								io.t_samples[row * M + mem] = t;
@@ -1141,7 +1153,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 							}
 							++n_stored;
 						}
-						alt = false;
+						fl.alt = false;
 						if (!(t < a.t1)) finished = true;
 					}
 					if (a.adaptive) dt = new_dt; // irk.hpp:850-852
@@ -1151,7 +1163,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 			}
 		}
 
-		if (finished) done = true; // results are written when the warp next stops for service (top of the loop)
+		if (finished) fl.done = true; // results are written when the warp next stops for service (top of the loop)
 	}
 	__syncthreads(); // every warp of the CTA has left the loop
 	if (io.stats && threadIdx.x < REHUEL_NSTATS && s_stats[threadIdx.x]) {
