@@ -25,12 +25,17 @@
 	} while (0)
 
 // ---------------------------------------------------------------- 1. issue model
-template <int MODE> // 0: DFMA only; 1: + one integer op per DFMA; 2: + one FFMA per DFMA
+template <int MODE> // 0: DFMA only; 1: + 2-3 ALU integer ops per DFMA; 2: + one FFMA; 3: + one IMAD; 4: + one LOP3; 5: + one shared-memory load
 __global__ void __launch_bounds__(256) issue_kernel(double *sink, int iters, double a, double b, unsigned m, float fa)
 {
 	double x[8];
 	unsigned u[8];
 	float f[8];
+	__shared__ unsigned smem[1024];
+	if (MODE == 5) {
+		for (int e = threadIdx.x; e < 1024; e += blockDim.x) smem[e] = e * m;
+		__syncthreads();
+	}
 #pragma unroll
 	for (int i = 0; i < 8; ++i) {
 		x[i] = threadIdx.x * 1e-9 + i;
@@ -45,6 +50,9 @@ __global__ void __launch_bounds__(256) issue_kernel(double *sink, int iters, dou
 				x[i] = fma(x[i], a, b);
 				if (MODE == 1) u[i] = (u[i] ^ m) + (u[i] >> 3); // LOP3 + shift/add: 2-3 integer instructions
 				if (MODE == 2) f[i] = fmaf(f[i], fa, 1.0f);
+				if (MODE == 3) u[i] = u[i] * m + 12345u;            // IMAD (FMA pipe)
+				if (MODE == 4) u[i] = u[i] ^ (m + (unsigned)r);     // one LOP3 (ALU pipe)
+				if (MODE == 5) u[i] += smem[(threadIdx.x + i * 32 + r) & 1023]; // LDS + IADD
 			}
 		}
 	}
@@ -180,9 +188,13 @@ int main(int argc, char **argv)
 		float t0 = best_ms([&] { issue_kernel<0><<<grid, block>>>(sink, iters, 1.0000001, 1e-9, 0x9e3779b9u, 1.0001f); });
 		float t1 = best_ms([&] { issue_kernel<1><<<grid, block>>>(sink, iters, 1.0000001, 1e-9, 0x9e3779b9u, 1.0001f); });
 		float t2 = best_ms([&] { issue_kernel<2><<<grid, block>>>(sink, iters, 1.0000001, 1e-9, 0x9e3779b9u, 1.0001f); });
+		float t3 = best_ms([&] { issue_kernel<3><<<grid, block>>>(sink, iters, 1.0000001, 1e-9, 0x9e3779b9u, 1.0001f); });
+		float t4 = best_ms([&] { issue_kernel<4><<<grid, block>>>(sink, iters, 1.0000001, 1e-9, 0x9e3779b9u, 1.0001f); });
+		float t5 = best_ms([&] { issue_kernel<5><<<grid, block>>>(sink, iters, 1.0000001, 1e-9, 0x9e3779b9u, 1.0001f); });
 		std::printf("{\"experiment\": \"issue_model\", \"dfma_only_ms\": %.4f, \"dfma_plus_int_ms\": %.4f, \"dfma_plus_ffma_ms\": %.4f, "
-		            "\"dfma_only_tflops\": %.2f, \"int_over_dfma\": %.3f, \"ffma_over_dfma\": %.3f}\n",
-		            t0, t1, t2, 2 * fmas / (t0 * 1e-3) / 1e12, t1 / t0, t2 / t0);
+		            "\"dfma_only_tflops\": %.2f, \"int_over_dfma\": %.3f, \"ffma_over_dfma\": %.3f, \"imad_over_dfma\": %.3f, "
+		            "\"lop3_over_dfma\": %.3f, \"lds_iadd_over_dfma\": %.3f}\n",
+		            t0, t1, t2, 2 * fmas / (t0 * 1e-3) / 1e12, t1 / t0, t2 / t0, t3 / t0, t4 / t0, t5 / t0);
 		float td = best_ms([&] { dmma_kernel<<<grid, block>>>(sink, iters, 1.0000001, 1e-9); });
 		const double dflops = 2.0 * 256.0 * 64.0 * iters * (block / 32.0) * grid; // 8 x 8 x 4 FMAs per warp-instruction
 		std::printf("{\"experiment\": \"dmma_rate\", \"dmma_ms\": %.4f, \"dmma_tflops\": %.2f, \"dfma_tflops\": %.2f, \"dmma_over_dfma\": %.3f}\n", td,
