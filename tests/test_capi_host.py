@@ -212,3 +212,71 @@ def test_twisted_band_factorisation_on_the_host(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     print(out.stdout)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK")
+
+
+def test_new_option_defaults_and_argument_errors(capi):
+    """Round-2 additions to rehuel_options: defaults, and the combinations that are refused before any GPU work."""
+    from rehuel_b200 import ensembles
+    o = capi.default_options()
+    assert (o.trace_member, o.output_file, o.result_mask, o.time_internals, o.shard_mode) == (0, None, capi.OUT_ALL, 0, capi.SHARD_DYNAMIC)
+    P = ensembles.robertson_params(4)
+    for kw, needle in ((dict(out_interval=1, trace_member=4), "trace_member"),               # not a member
+                       (dict(output_mode=3), "output_file"),                                # WRITE_TO_FILE without a path
+                       (dict(output_mode=3, output_file="/tmp/x.txt"), "n_samples_cap"),    # ... without sample storage
+                       (dict(shard_mode=5), "shard_mode")):
+        with pytest.raises(capi.RehuelError) as ei:
+            capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 1.0, 1e-6, ensembles.ROBERTSON_Y0, P, capi.make_options(1e-6, 1e-6, **kw))
+        assert ei.value.code == -1 and needle in str(ei.value), (needle, str(ei.value))
+
+
+def test_log_and_timing_text_of_a_result(capi):
+    """rehuel_result_format_log / _format_timings are host-side: the reference's words around the numbers of a
+    result (irk.hpp:576, 807-809; 346-359)."""
+    res = capi.Result()
+    rows = np.array([[0, 0.0, 1e-6, 1e-17, 1], [1, 1e-6, 7.2e-6, -1.0, 4999], [1, 1e-6, 5.04e-6, 0.25, 2]])  # the middle one: a failed Newton solve
+    res.trace = rows.ctypes.data_as(C.POINTER(C.c_double))
+    res.trace_len = 3
+    text = capi.format_log(res, 6).splitlines()
+    assert text == ["    Rehuel: step  t  dt   err   iters", "    Rehuel: 0 0 1e-06 1e-17 1", "    Rehuel: 1 1e-06 5.04e-06 0.25 2"]
+    assert capi.format_log(res, 17).splitlines()[2] == "    Rehuel: 1 9.9999999999999995e-07 5.04e-06 0.25 2"
+    assert capi.lib.rehuel_result_format_log(C.byref(res), 6, None, 0) == len("\n".join(text)) + 1   # snprintf-like length
+    res.phase_ms[0], res.phase_ms[1], res.phase_ms[2], res.phase_ms[3] = 1.0, 0.5, 8.0, 0.5
+    t = capi.format_timings(res, "RADAU_IIA_53").splitlines()
+    assert t[0] == "    Rehuel: RADAU_IIA_53 done solving, timings (ms | %):" and len(t) == 6
+    assert t[1].split("|")[0].split()[-1] == "10" and t[4].strip().startswith("Integration kernels:") and t[4].strip().endswith("80")
+
+
+def test_shared_work_cursor_across_processes(capi):
+    """rehuel_cursor: four processes claim indices from one counter in POSIX shared memory; every index is handed out
+    exactly once (the cross-process form of REHUEL_SHARD_DYNAMIC)."""
+    import multiprocessing as mp
+    name = f"rehuel_test_{os.getpid()}"
+    cur = capi.Cursor(name, True)
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+
+    def worker():
+        c = capi.Cursor(name, False)
+        got = []
+        while True:
+            i = c.next(2)          # two indices per claim
+            if i >= 1000:
+                break
+            got += [i, i + 1]
+        c.close()
+        q.put(got)
+
+    procs = [ctx.Process(target=worker) for _ in range(4)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=60) for _ in procs]
+    for p in procs:
+        p.join()
+    assert sorted(sum(res, [])) == list(range(1000))
+    cur.reset()
+    assert cur.next(1) == 0
+    cur.close()
+    with pytest.raises(capi.RehuelError):
+        capi.Cursor(name, False)   # unlinked by its creator
+    with pytest.raises(capi.RehuelError):
+        capi.Cursor("a/b", True)
