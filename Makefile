@@ -20,7 +20,8 @@ OBJS      := build/capi.o build/order.o build/selftest.o build/tableau.o $(INST:
 KHDRS     := $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/irk_warp.cuh $(SRC)/irk_wdense.cuh $(SRC)/irk_wseg.cuh $(SRC)/band_twisted.cuh $(SRC)/launch.cuh $(SRC)/functors.cuh \
              $(SRC)/tableau.hpp include/rehuel_b200.h
 
-.PHONY: all oracle clean sass examples tableaux
+.PHONY: all oracle clean sass examples tableaux microbench
+microbench: build/microbench
 all: $(LIB)
 
 build:
@@ -61,6 +62,10 @@ build/rehuel_example: examples/rehuel_example.cpp include/rehuel_b200/irk.hpp in
 build/user_functor: examples/user_functor.cu include/rehuel_b200/irk.cuh include/rehuel_b200/irk.hpp $(KHDRS) $(LIB)
 	$(NVCC) -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) --expt-relaxed-constexpr -Iinclude $< -o $@ \
 	    -Lrehuel_b200 -lrehuel_b200 -cudart shared -Xlinker -rpath,'$$ORIGIN/../rehuel_b200'
+
+# stand-alone micro-benchmarks behind DESIGN.md 5.1 (issue model) and 5.5 (DMMA vs FMA pipe)
+build/microbench: tools/microbench.cu | build
+	$(NVCC) -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) $< -o $@
 
 oracle:
 	$(MAKE) -C oracle all

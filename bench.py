@@ -532,8 +532,8 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
     """Strong scaling: fixed totals over the N ranks.
     config 2 at 2^20 members in all: rank r integrates the contiguous members [r M/N, (r+1) M/N).
     config 5 at 10 485 760 members in all (even index Robertson / RADAU_IIA_53 / t in [0,40], odd index Van der Pol /
-    LOBATTO_IIIC_43 / t in [0,2], rtol = atol = 10^(-3-6v), newton tol = 0.1 rtol): cut into 128 chunks that the ranks CLAIM
-    from a cursor in shared memory (rehuel_cursor) as they finish, six chunks in flight per GPU, the stiff end of the
+    LOBATTO_IIIC_43 / t in [0,2], rtol = atol = 10^(-3-6v), newton tol = 0.1 rtol): cut into 256 chunks that the ranks CLAIM
+    from a cursor in shared memory (rehuel_cursor) as they finish, eight chunks in flight per GPU, the stiff end of the
     sweep first (longest processing time first)."""
     import numpy as np
     cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -550,7 +550,7 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
     out["config2_robertson_2p20_total"] = {"ms": ms, "systems_per_s": Mt / (ms * 1e-3), "members_total": Mt}
     del ens
     # ---- config 5, 10 485 760 members in all, chunks claimed from the shared cursor
-    Mt, n_chunks, depth = 10485760, 128, 6
+    Mt, n_chunks, depth = 10485760, 256, 8
     half = Mt // 2
     per = half // n_chunks                      # members of each class per chunk
     name = f"rehuel_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
@@ -560,7 +560,6 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
         cur = capi.Cursor(name, False)
     tol_all = ensembles.mixed_tolerances(Mt)
     streams = [(torch.cuda.Stream(), torch.cuda.Stream()) for _ in range(depth)]
-    slots = [None] * depth
 
     def chunk_ens(c):
         j0 = c * per
@@ -581,15 +580,19 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
     def run_all():
         mine = []
         main = torch.cuda.current_stream()
-        k = 0
+        free, busy = list(range(depth)), {}
         while True:
-            slot = k % depth
-            if slots[slot] is not None:
-                slots[slot].synchronize()       # a slot is free again when its chunk is done: only then claim more work
-            c = cur.next(1)
+            for sl in [sl for sl, e in busy.items() if e.query()]:   # a slot is free again when its chunk is done
+                del busy[sl]
+                free.append(sl)
+            if not free:
+                time.sleep(0)
+                continue
+            c = cur.next(1)                     # only a rank with a free slot claims more work
             if c >= n_chunks:
                 break
             c = n_chunks - 1 - c                # the Van der Pol members get stiffer along the index: costly chunks first
+            slot = free.pop()
             for (de, t1), st in zip(chunks[c], streams[slot]):
                 st.wait_stream(main)
                 with torch.cuda.stream(st):
@@ -598,17 +601,14 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
             streams[slot][1].wait_stream(streams[slot][0])
             e = torch.cuda.Event()
             e.record(streams[slot][1])
-            slots[slot] = e
+            busy[slot] = e
             mine.append(c)
-            k += 1
         for pair in streams:
             for st in pair:
                 main.wait_stream(st)
         return mine
 
     def timed():
-        for i in range(depth):
-            slots[i] = None
         barrier()
         if rank == 0:
             cur.reset()
