@@ -21,8 +21,8 @@ KHDRS     := $(SRC)/irk_thread.cuh $(SRC)/irk_cta.cuh $(SRC)/irk_warp.cuh $(SRC)
              $(SRC)/tableau.hpp include/rehuel_b200.h
 
 .PHONY: all oracle clean sass examples tableaux microbench
-microbench: build/microbench
 all: $(LIB)
+microbench: build/microbench
 
 build:
 	mkdir -p build

