@@ -531,6 +531,7 @@ def other_configs(capi, ensembles, flopmodel, DeviceEnsemble, torch, dev, peak_t
 def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world, barrier, max_over_ranks) -> dict:
     """Strong scaling: fixed totals over the N ranks.
     config 2 at 2^20 members in all: rank r integrates the contiguous members [r M/N, (r+1) M/N).
+    config 3 at 2^20 Van der Pol members in all, dealt i mod N.
     config 5 at 10 485 760 members in all (even index Robertson / RADAU_IIA_53 / t in [0,40], odd index Van der Pol /
     LOBATTO_IIIC_43 / t in [0,2], rtol = atol = 10^(-3-6v), newton tol = 0.1 rtol): cut into 256 chunks that the ranks CLAIM
     from a cursor in shared memory (rehuel_cursor) as they finish, eight chunks in flight per GPU, the stiff end of the
@@ -548,6 +549,18 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
     barrier()
     ms = max_over_ranks(device_ms(lambda: ens.solve(0.0, 40.0, DT0, o), torch, reps=3, warm=0))
     out["config2_robertson_2p20_total"] = {"ms": ms, "systems_per_s": Mt / (ms * 1e-3), "members_total": Mt}
+    del ens
+    # ---- config 3, 2^20 Van der Pol members in all (mu_ref = 10^(-6 i/(M-1)), LOBATTO_IIIC_43), member i on rank i mod N
+    # (cost grows along the index), stiff end handed out first
+    Mv = 1 << 20
+    Pv = ensembles.vdpol_params(Mv)[:, rank::world]
+    ens = DeviceEnsemble(capi.VAN_DER_POL, capi.LOBATTO_IIIC_43, Pv.shape[1], cu(ensembles.VDPOL_Y0.copy()), cu(Pv), handout_order=capi.ORDER_LOCALITY)
+    ens.solve(0.0, 2.0, DT0, o)
+    barrier()
+    ms = max_over_ranks(device_ms(lambda: ens.solve(0.0, 2.0, DT0, o), torch, reps=2, warm=0))
+    out["config3_vdpol_2p20_total"] = {"ms": ms, "systems_per_s": Mv / (ms * 1e-3), "members_total": Mv,
+                                       "max_attempts_rank0": int(ens.counter("attempt").max()),
+                                       "newton_rejections_rank0": int(ens.counter("reject_newton").sum())}
     del ens
     # ---- config 5, 10 485 760 members in all, chunks claimed from the shared cursor
     Mt, n_chunks, depth = 10485760, 256, 8
