@@ -49,13 +49,11 @@ struct Tw {
 __host__ __device__ __forceinline__ double tw_rcp(double x)
 {
 #ifdef __CUDA_ARCH__
-	double r; // MUFU.RCP64H seed + two Newton steps, see fast_rcp (irk_thread.cuh)
+	double r; // MUFU.RCP64H seed + one cubic step, see fast_rcp (irk_thread.cuh)
 	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-	double e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	return r;
+	const double e = fma(-x, r, 1.0); // |e| <= 2^-20: the seed carries the upper 20 mantissa bits
+	const double t = fma(e, e, e);    // r (1 + e + e^2): the neglected e^3 is below 2^-60
+	return fma(r, t, r);
 #else
 	return 1.0 / x;
 #endif

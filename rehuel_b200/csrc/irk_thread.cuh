@@ -77,9 +77,9 @@ constexpr int kParkLanes = REHUEL_PARK_LANES; // parked lanes per warp that trig
 constexpr int kBatchLanes = REHUEL_BATCH_LANES;
 constexpr int kWaitShift = REHUEL_WAIT_SHIFT;
 
-// Reciprocal: MUFU.RCP64H seed (~20 bits) + two Newton steps (quadratic: 20 -> 40 -> 80 bits, i.e.
-// correctly rounded up to ~1 ulp), 5 instructions and no slow path instead of the ~14-instruction
-// IEEE division.  Used for the LU pivots and 1/dt (the rounding of the LINEAR SOLVES is not part of the
+// Reciprocal: MUFU.RCP64H seed (rcp.approx.f64: the upper 20 mantissa bits) + ONE cubically convergent step
+// r (1 + e + e^2), e = 1 - x r (2^-20 -> 2^-60, i.e. correctly rounded up to ~1 ulp): 4 instructions and no slow
+// path instead of the ~14-instruction IEEE division (two Newton steps would be 5).  Used for the LU pivots and 1/dt (the rounding of the LINEAR SOLVES is not part of the
 // parity contract: the decoupled solve already differs from the reference's dense LU in the last bits)
 // and, for the same reason -- everything downstream of the solve carries that last-bit difference --,
 // for the scaled error norm and the step-size proposal (propose_dt).  0, Inf and NaN arguments still
@@ -88,11 +88,9 @@ __device__ __forceinline__ double fast_rcp(double x)
 {
 	double r;
 	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-	double e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	return r;
+	const double e = fma(-x, r, 1.0); // |e| <= 2^-20: the seed carries the upper 20 mantissa bits
+	const double t = fma(e, e, e);    // r (1 + e + e^2): the neglected e^3 is below 2^-60
+	return fma(r, t, r);
 }
 
 // One row of the per-attempt log of member io.trace_member, irk.hpp:805-810 ("step t dt err iters"; the reference prints
