@@ -439,9 +439,9 @@ __device__ __forceinline__ double propose_dt(double dt, double err, double &q_pr
 //   s27 = (1/err)^e = x^(-1/k)    and    q = err^e = x^(1/k) = x * (x^(-1/k))^(k-1),
 // so the three chained square roots of err = sqrt(x), q = sqrt(sqrt(err)) (and the reciprocal of q) become ONE k-th
 // root: x is scaled by an exact power of two into [2^(-k/2), 2^(k/2)], a float-precision seed
-// exp2(-log2(x)/k) (MUFU.LG2/EX2, ~2^-21) is refined by two Newton steps on r^-k = x (error ~5 e^2 per step:
-// 2^-21 -> 1e-12 -> rounding level), and the power of two is put back by exponent arithmetic.  About 17 FP64
-// instructions in two short dependency chains instead of ~40 in one long one; the result differs from the
+// exp2(-log2(x)/k) (MUFU.LG2/EX2, ~2^-22) is refined by one cubically convergent step on r^-k = x, and the power
+// of two is put back by exponent arithmetic.  About 12 FP64 instructions in two short dependency chains instead
+// of ~40 in one long one; the result differs from the
 // sqrt/reciprocal form by an ulp or two, like everything else in this function.  x must be positive and finite
 // (the caller floors it at 1e-34 and sends non-finite values through propose_dt).
 template <int K>
@@ -464,10 +464,11 @@ __device__ __forceinline__ void inv_root(double x, double &r_out, double &q_out)
 	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)xs)); // no denormals here: the guarded log2f/exp2f are not needed
 	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(lg * (-1.0f / K)));
 	double r = (double)sd;
-#pragma unroll
-	for (int step = 0; step < 2; ++step) {
+	{ // ONE cubically convergent step:  r (1 - e)^(-1/K) = r (1 + e/K + (K+1) e^2 / (2 K^2) + O(e^3)),  e = 1 - x r^K.
+	  // The seed is good to ~2^-22, so |e| <= K 2^-22 and the neglected term (K+1)(2K+1)/(6 K^3) e^3 is below 2^-58.
 		const double e = fma(-xs, pow_int<K>(r), 1.0);
-		r = fma(r * e, 1.0 / K, r);
+		const double t = fma(e, (K + 1.0) / (2.0 * K * K), 1.0 / K) * e;
+		r = fma(r, t, r);
 	}
 	const double q = xs * pow_int<K - 1>(r);
 	r_out = __hiloint2double(__double2hiint(r) - j * 0x100000, __double2loint(r)); // r 2^(-j)
