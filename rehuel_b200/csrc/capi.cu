@@ -799,10 +799,32 @@ int ensemble_host_from(LaunchFn launch, int n, int p, int method, double t0, dou
 	} else if (mode == REHUEL_SHARD_INTERLEAVED) {
 		add_chunks(0, M, chunks_for(M / (size_t)n_gpus, 8) * (size_t)n_gpus, false, dev0, n_gpus); // chunk k -> GPU k mod G
 	} else {
+		// The thread-per-system kernels take their members in gangs of 32 per warp (irk_thread.cuh: kBatchLanes), so a
+		// chunk costs whole gang rounds: cut a device's share in multiples of the persistent grid's lanes.
+		size_t lanes = 0;
+		if (n <= 4 && !n_samples_cap && env_chunks == 0 && n_wts == 0) {
+			KernelInfo ki{};
+			int sms = 0;
+			if (launch(hc.ka, hc.tb, nullptr, &ki) == REHUEL_OK && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev0) == cudaSuccess)
+				lanes = (size_t)sms * (size_t)ki.ctas_per_sm * (size_t)ki.block;
+			if (lanes % 1024 != 0) lanes = 0; // chunk boundaries stay 4 KiB-aligned
+		}
 		for (int g = 0; g < n_gpus; ++g) {
 			const size_t lo = M * (size_t)g / (size_t)n_gpus, hi = M * (size_t)(g + 1) / (size_t)n_gpus;
 			const bool weighted = n_wts >= 1 && !n_samples_cap && n_gpus == 1;
-			add_chunks(lo, hi, weighted ? n_wts : chunks_for(hi - lo, 8), weighted, dev0 + g, 1);
+			if (lanes && hi - lo >= 3 * lanes) {
+				size_t per = ((hi - lo) / 8 + lanes / 2) / lanes; // rounds per chunk: about an eighth of the share
+				per = (per < 1 ? 1 : per) * lanes;
+				for (size_t at = lo; at < hi; at += per) {
+					shards.emplace_back();
+					DeviceShard &sh = shards.back();
+					sh.dev = dev0 + g;
+					sh.off = at;
+					sh.m = (hi - at < per) ? hi - at : per;
+				}
+			} else {
+				add_chunks(lo, hi, weighted ? n_wts : chunks_for(hi - lo, 8), weighted, dev0 + g, 1);
+			}
 		}
 	}
 	const size_t n_shards = shards.size();

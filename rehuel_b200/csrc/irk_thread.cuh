@@ -47,6 +47,7 @@ struct KernelArgs {
 	// warp of the grid; force_pivot != 0 sends every attempt through that fallback (rehuel_debug_force_pivot)
 	double *pivot_scratch;
 	int force_pivot;
+	int batch_lanes; // thread-per-system kernels (filled in by launch_thread): waiting lanes that trigger a service stop, see kBatchLanes
 	int trace_interval; // io.trace: log the attempts whose accepted-step count is a multiple of this (irk.hpp:805-806)
 };
 
@@ -73,8 +74,13 @@ constexpr int kParkLanes = REHUEL_PARK_LANES; // parked lanes per warp that trig
 // own member's attempts, whichever comes first, so that a warp whose members differ widely in length (an unsorted
 // long-span ensemble) does not idle behind its slowest member; then every waiting lane is served at once.  Served at
 // once, too, when nothing else runs.  Measured on the 2^20-member sweep: 1.71 -> 1.49 ms (Morton hand-out), 1.92 ->
-// 1.64 ms (index order) against serving four lanes at a time.
+// 1.64 ms (index order) against serving four lanes at a time.  A gang costs a warp as many trips as its longest
+// member, so a launch with only a few members per lane is quantised in whole gangs (1.7 members per lane take two
+// gang times): launch_thread falls back to serving four lanes at a time (kSmallBatchLanes) below kGangMinPerLane
+// members per lane, and the host layer cuts its chunks in multiples of the grid's lanes.
 constexpr int kBatchLanes = REHUEL_BATCH_LANES;
+constexpr int kSmallBatchLanes = 4;
+constexpr int kGangMinPerLane = 4;
 constexpr int kWaitShift = REHUEL_WAIT_SHIFT;
 
 // Reciprocal: MUFU.RCP64H seed (rcp.approx.f64: the upper 20 mantissa bits) + ONE cubically convergent step
@@ -604,7 +610,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 			impatient = fl.waited >= patience;
 			if (fl.waited < 0xffffu) fl.waited = fl.waited + 1u;
 		}
-		if (wants != 0u && (__popc(wants) >= kBatchLanes || busy == 0u || __any_sync(0xffffffffu, impatient))) {
+		if (wants != 0u && (__popc(wants) >= a.batch_lanes || busy == 0u || __any_sync(0xffffffffu, impatient))) {
 			if (fl.have && fl.done) {
 #pragma unroll
 				for (int k = 0; k < N; ++k) io.y[k * M + mem] = y[k];

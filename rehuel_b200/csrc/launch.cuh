@@ -137,7 +137,13 @@ int launch_thread(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, 
 	unsigned grid = (unsigned)(want < cap ? want : cap);
 	DevTableau<S, NC> dtb = make_dev_tableau<S, NC>(tb);
 	REHUEL_CUDA_TRY(reset_cursors(ka, stream));
-	kern<<<grid, BLOCK, 0, stream>>>(ka, dtb);
+	KernelArgs k = ka;
+	if (k.batch_lanes <= 0) { // gangs of 32, unless the launch is so small that whole gangs quantise it (irk_thread.cuh: kBatchLanes)
+		const unsigned long long lanes = cap * BLOCK;
+		const bool whole_gangs = ka.M % lanes == 0; // the host layer's chunks: every lane gets the same number of members
+		k.batch_lanes = (whole_gangs || ka.M >= (unsigned long long)kGangMinPerLane * lanes) ? kBatchLanes : kSmallBatchLanes;
+	}
+	kern<<<grid, BLOCK, 0, stream>>>(k, dtb);
 	REHUEL_CUDA_TRY(cudaGetLastError());
 	count_launch();
 	return REHUEL_OK;
