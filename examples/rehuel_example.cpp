@@ -50,7 +50,7 @@ struct user_options {
 	std::string eq = "exponential", method = "LOBATTO_IIIC_85", output_fname, stream_fname;
 	double t0 = 0.0, t1 = 10.0, dt = 1e-2, rel_tol = 1e-5, abs_tol = 1e-4; // example_equations.cpp:40-43
 	int out_interval = 0, time_internals = 0, gpus = 1;
-	std::size_t ensemble = 1, member = 0, max_samples = 1u << 16, dense = 0;
+	std::size_t ensemble = 1, member = 0, max_samples = 0, dense = 0; // max_samples 0: chosen from the ensemble size
 	double sweep = 0.0, dense_dt = 0.0;
 	std::vector<double> params;
 };
@@ -196,7 +196,11 @@ int main(int argc, char **argv)
 	s_opts.trace_member = u.member;
 	n_opts.tol = 0.1 * std::min(s_opts.rel_tol, s_opts.abs_tol);
 	output_options output_opts;
-	output_opts.max_samples = u.dense ? 0 : u.max_samples;
+	// rows of sample storage per member: the whole trajectory of a single system; for an ensemble as many rows as 2^24
+	// stored states allow (the storage is page-locked host memory: 65 536 rows x 5000 members would be 13 GB)
+	std::size_t rows = u.max_samples;
+	if (rows == 0) rows = std::min<std::size_t>(std::size_t(1) << 16, std::max<std::size_t>(64, (std::size_t(1) << 24) / M));
+	output_opts.max_samples = u.dense ? 0 : rows;
 	if (u.dense) {
 		output_opts.dense_samples = u.dense;
 		output_opts.dense_t0 = u.t0;
