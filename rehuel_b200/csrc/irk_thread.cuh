@@ -64,6 +64,12 @@ constexpr int kParkLanes = REHUEL_PARK_LANES; // parked lanes per warp that trig
 #ifndef REHUEL_BATCH_LANES
 #define REHUEL_BATCH_LANES 32
 #endif
+#ifndef REHUEL_COHORT
+#define REHUEL_COHORT 1
+#endif
+#ifndef REHUEL_IDLE_SHIFT
+#define REHUEL_IDLE_SHIFT 3
+#endif
 #ifndef REHUEL_WAIT_SHIFT
 #define REHUEL_WAIT_SHIFT 3
 #endif
@@ -74,7 +80,12 @@ constexpr int kParkLanes = REHUEL_PARK_LANES; // parked lanes per warp that trig
 // own member's attempts, whichever comes first, so that a warp whose members differ widely in length (an unsorted
 // long-span ensemble) does not idle behind its slowest member; then every waiting lane is served at once.  Served at
 // once, too, when nothing else runs.  Measured on the 2^20-member sweep: 1.71 -> 1.49 ms (Morton hand-out), 1.92 ->
-// 1.64 ms (index order) against serving four lanes at a time.  A gang costs a warp as many trips as its longest
+// 1.64 ms (index order) against serving four lanes at a time.
+// COHORTS (REHUEL_COHORT): a served lane is not given a new member while other lanes of the warp still integrate --
+// the warp's 32 members start together and so stay at the same stage -- unless it has been idle for an eighth
+// (2^-REHUEL_IDLE_SHIFT) of the attempts its last member took.  Long span (t1 = 1e11, 2^18 members, Morton hand-out)
+// 21.3 -> 19.9 ms, short span unchanged; in index order (neighbours unrelated) 24.2 -> 25.0 ms, which is what the idle
+// bound is for (without it 27.0 ms).  A gang costs a warp as many trips as its longest
 // member, so a launch with only a few members per lane is quantised in whole gangs (1.7 members per lane take two
 // gang times): launch_thread falls back to serving four lanes at a time (kSmallBatchLanes) below kGangMinPerLane
 // members per lane, and the host layer cuts its chunks in multiples of the grid's lanes.
@@ -574,7 +585,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 		unsigned parked : 1;     // this lane's attempt ran past kFastIters Newton iterations: redo it in a slow trip
 		unsigned prefer_piv : 1; // the warp's last factorisations needed row interchanges: skip the speculative plain attempt
 		unsigned alt : 1;        // alternative_error_formula, irk.hpp:587, 763, 845
-		unsigned waited : 16;    // trips this lane has sat out with a finished member (see kBatchLanes)
+		unsigned waited : 16;    // trips this lane has sat out with a finished member, or idle (see kBatchLanes)
 	} fl{};
 	fl.alt = 1;
 	unsigned long long mem = 0;
@@ -604,13 +615,18 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 		// (warp-aggregated).  Warp-uniform decision, see kBatchLanes.
 		const unsigned wants = __ballot_sync(0xffffffffu, (fl.have && fl.done) || (!fl.have && !fl.exhausted));
 		const unsigned busy = __ballot_sync(0xffffffffu, fl.have && !fl.done);
-		bool impatient = false;
+		bool impatient = false, idle_long = false;
 		if (fl.have && fl.done) {
 			const unsigned patience = (c_attempt >> kWaitShift) > 2u ? (c_attempt >> kWaitShift) : 2u;
 			impatient = fl.waited >= patience;
 			if (fl.waited < 0xffffu) fl.waited = fl.waited + 1u;
+		} else if (REHUEL_COHORT && !fl.have && !fl.exhausted) { // c_attempt: the member this lane had before
+			const unsigned patience = (c_attempt >> REHUEL_IDLE_SHIFT) > 2u ? (c_attempt >> REHUEL_IDLE_SHIFT) : 2u;
+			idle_long = fl.waited >= patience;
+			if (fl.waited < 0xffffu) fl.waited = fl.waited + 1u;
 		}
-		if (wants != 0u && (__popc(wants) >= a.batch_lanes || busy == 0u || __any_sync(0xffffffffu, impatient))) {
+		const bool refill = !REHUEL_COHORT || a.batch_lanes < 32 || busy == 0u || __any_sync(0xffffffffu, idle_long);
+		if (wants != 0u && (__popc(wants) >= a.batch_lanes || busy == 0u || __any_sync(0xffffffffu, impatient) || (REHUEL_COHORT && refill))) {
 			if (fl.have && fl.done) {
 #pragma unroll
 				for (int k = 0; k < N; ++k) io.y[k * M + mem] = y[k];
@@ -670,7 +686,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				fl.done = false;
 				fl.waited = 0u;
 			}
-			const unsigned need = __ballot_sync(0xffffffffu, !fl.have && !fl.exhausted);
+			const unsigned need = __ballot_sync(0xffffffffu, !fl.have && !fl.exhausted && refill);
 			if (need) {
 				const int leader = __ffs(need) - 1;
 				unsigned long long base = 0;
@@ -726,6 +742,7 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 						n_stored = 0;
 						fl.parked = false;
 						fl.have = true;
+						if (REHUEL_COHORT) fl.waited = 0u;
 						if (a.store_samples && io.n_samples_cap) { // sample 0 = (t0, y0), irk.hpp:581-585
 							io.t_samples[mem] = t;
 							if (io.err_samples) io.err_samples[mem] = 0.0;
@@ -1025,6 +1042,9 @@ ensemble_irk_thread(const __grid_constant__ KernelArgs a, const __grid_constant_
 				else newton_loop(std::false_type());
 
 				__syncwarp(amask);
+#if defined(REHUEL_COUNT_SKIPS) && REHUEL_COUNT_SKIPS == 3
+				c_skips += __reduce_max_sync(amask, (unsigned)it); // dev builds (mode 3): iterations the WARP ran in this lane's attempts
+#endif
 
 				if (nstat != kNewtonSuccess && it < maxit) {
 					// fast-trip budget exhausted: forget this try (counters back to the attempt's

@@ -51,9 +51,13 @@ def cmd_variants_child():
         de = _ensemble(capi.ROBERTSON, 211, M, t1, handout=int(os.environ.get("TV_HANDOUT", "2")))
         ms = _timed(torch, lambda: de.solve(0.0, t1, 1e-6, o), warm=2)
         out.append(f"{span} {ms:.3f} ms (att {float(de.counter('attempt').double().mean()):.2f})")
-    de = _ensemble(capi.VAN_DER_POL, 230, 1 << 18, 2.0)
+        if os.environ.get("TV_DIV"):  # libraries built with -DREHUEL_COUNT_SKIPS=3: iterations the warp ran / iterations the lane needed
+            out.append(f"warp-its/lane-its {float(de.counter('newton_maxit_exceed').double().sum() / de.counter('newton_iters').double().sum()):.3f}"
+                       f" its/att {float(de.counter('newton_iters').double().sum() / de.counter('newton_success').double().sum()):.3f}")
+    vm = int(os.environ.get("TV_VDP_M", str(1 << 18)))
+    de = _ensemble(capi.VAN_DER_POL, 230, vm, 2.0)
     ms = _timed(torch, lambda: de.solve(0.0, 2.0, 1e-6, o), reps=2)
-    out.append(f"vdpol-256k {ms:.2f} ms (rejN {int(de.counter('reject_newton').sum())}, fun {float(de.counter('fun_evals').double().sum()):.4g})")
+    out.append(f"vdpol-{vm >> 10}k {ms:.2f} ms (rejN {int(de.counter('reject_newton').sum())}, fun {float(de.counter('fun_evals').double().sum()):.4g})")
     print(os.path.basename(os.environ.get("REHUEL_B200_LIB", "default")), capi.kernel_info(capi.ROBERTSON, 211), " | ".join(out), flush=True)
 
 
