@@ -36,5 +36,12 @@ int main()
 	            "%llu Jacobi matrix evaluations.\nmember 0: %zu samples, t_end = %g, y = %g %g %g\n",
 	            M, sol.elapsed_time(), 100 * sol.accept_frac(), sol.count().fun_evals, sol.count().jac_evals,
 	            sol.n_samples(0), sol.t_final(0), sol.y(0, 0), sol.y(0, 1), sol.y(0, 2));
+	// The "sane default" form, irk.hpp:915-926: nothing but the problem and the span (tests/golden/odeint_defaults.json
+	// holds what the reference's own 4-argument odeint returns for this system).
+	const double nominal[3] = {0.04, 1e4, 3e7};
+	irk::ensemble_output dflt = irk::odeint(REHUEL_PROBLEM_ROBERTSON, 0.0, 40.0, y0, true, nominal, 1);
+	if (dflt.status()) return 3;
+	std::printf("defaults: y = %a %a %a attempts %llu fun_evals %llu\n", dflt.y(0, 0), dflt.y(0, 1), dflt.y(0, 2),
+	            dflt.count().attempt, dflt.count().fun_evals);
 	return 0;
 }

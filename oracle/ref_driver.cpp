@@ -305,6 +305,43 @@ int ref_irk_ensemble(int problem, int method, double t0, double t1, double dt0,
 	return 0;
 }
 
+// The reference's 4-argument "sane default" irk::odeint(func, t0, t1, y0) (irk.hpp:915-926) for ONE system: whatever
+// defaults it picks (method, first step, tolerances, Newton options) are the reference's, none are passed in.
+int ref_odeint_defaults(int problem, int n_hint, double t0, double t1, const double *y0, const double *params,
+                        double *y, double *t_final, double *err_last, int *status, unsigned long long *counters)
+{
+	int n = 0, P = 0;
+	if (ref_problem_dims(problem, n_hint, &n, &P)) return -1;
+	cout_silencer quiet;
+	vec_type Y0(n);
+	for (int k = 0; k < n; ++k) Y0(k) = y0[k];
+	irk::rk_output sol;
+	try {
+		switch (problem) {
+		case REF_ROBERTSON: { rober_p f(params[0], params[1], params[2]); sol = irk::odeint(f, t0, t1, Y0); break; }
+		case REF_VDPOL: { test_equations::vdpol f(params[0]); sol = irk::odeint(f, t0, t1, Y0); break; }
+		case REF_ROBER_HARDCODED: { test_equations::rober f; sol = irk::odeint(f, t0, t1, Y0); break; }
+		case REF_EXPONENTIAL: { test_equations::exponential f(params[0]); sol = irk::odeint(f, t0, t1, Y0); break; }
+		case REF_BRUSS2: { test_equations::bruss f(params[0], params[1]); sol = irk::odeint(f, t0, t1, Y0); break; }
+		default: return -1;
+		}
+	} catch (std::exception &e) {
+		g_err = e.what();
+		return -2;
+	}
+	const std::size_t ns = sol.t_vals.size();
+	if (!ns) return -3;
+	*status = sol.status;
+	*t_final = sol.t_vals[ns-1];
+	*err_last = sol.err[ns-1];
+	for (int k = 0; k < n; ++k) y[k] = sol.y_vals[ns-1](k);
+	const unsigned long long c[9] = {sol.count.attempt, sol.count.reject_newton, sol.count.reject_err, sol.count.newton_success,
+	                                 sol.count.newton_incr_diverge, sol.count.newton_iter_error_too_large,
+	                                 sol.count.newton_maxit_exceed, sol.count.fun_evals, sol.count.jac_evals};
+	for (int k = 0; k < 9; ++k) counters[k] = c[k];
+	return 0;
+}
+
 // One call of irk::newton_solve_stages (irk.hpp:398-493) + the solution update of
 // irk.hpp:695-705, i.e. exactly what the reference's own known-answer test does
 // (test/irk.cpp:250-296).  variant 0: default template arguments <F,true,false> (damped,

@@ -157,6 +157,21 @@ class RefSolver:
             res.log = log_buf.value.decode(errors="replace")
         return res
 
+    # ------------------------------------------------------------------ the 4-argument odeint (reference library only)
+    def odeint_defaults(self, problem, t0, t1, y0, params, n_hint=0):
+        """irk::odeint(func, t0, t1, y0), irk.hpp:915-926: the reference picks every default itself.  One system."""
+        assert self.kind == "reference", "only the unmodified reference knows its own defaults"
+        pid = PROBLEM_IDS[problem] if isinstance(problem, str) else problem
+        y0 = np.ascontiguousarray(y0, dtype=np.float64)
+        params = np.ascontiguousarray(params if len(params) else [0.0], dtype=np.float64)
+        y = np.full(y0.shape[0], np.nan); tf = np.zeros(1); el = np.zeros(1)
+        st = np.full(1, -1, dtype=np.int32); cnt = np.zeros(9, dtype=np.uint64)
+        rc = self.lib.ref_odeint_defaults(C.c_int(pid), C.c_int(n_hint), C.c_double(t0), C.c_double(t1), _p(y0), _p(params),
+                                          _p(y), _p(tf), _p(el), _p(st, C.c_int), _p(cnt, C.c_ulonglong))
+        if rc != 0:
+            raise RuntimeError(f"ref_odeint_defaults rc={rc}: {self.lib.ref_last_error().decode()}")
+        return EnsembleResult(y[:, None], tf, el, st, {k: cnt[i:i + 1] for i, k in enumerate(COUNTER_NAMES)}, np.full(1, np.nan), 0.0)
+
     # ------------------------------------------------------------------ one Newton solve (KAT)
     def newton_solve_stages(self, problem, method, variant, params, y, t, dt, maxit, refresh_jac, xtol, Rtol,
                             n_hint=0):

@@ -34,6 +34,13 @@ def golden_configs():
     return d["cases"]
 
 
+@pytest.fixture(scope="session")
+def golden_defaults():
+    """What the reference's 4-argument irk::odeint(func, t0, t1, y0) returns (tools/make_golden_defaults.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "odeint_defaults.json")) as fh:
+        return json.load(fh)["cases"]
+
+
 def parse_reference_log(text):
     """Rows (step, t, dt, err, iters) of the reference's per-attempt log, irk.hpp:575-577, 805-810."""
     rows = []

@@ -1253,3 +1253,38 @@ def test_per_member_tolerances_and_radau137_on_the_larger_kernels(capi, port):
         print(f"RADAU_IIA_137 n={n} problem {pid}: max scaled err {se.max():.3e}; attempts gpu/ref {g.counters['attempt'].tolist()}/{r.counters['attempt'].tolist()}")
         assert np.all(g.status == 0) and se.max() <= PARITY_BOUND
         assert np.all(np.abs(g.counters["attempt"].astype(np.int64) - r.counters["attempt"].astype(np.int64)) <= np.maximum(3, 0.2 * r.counters["attempt"]))
+
+
+@pytest.mark.gpu
+def test_four_argument_odeint_defaults(capi, golden_defaults):
+    """The "sane default" odeint (irk.hpp:915-926) against what the reference's own 4-argument call returns
+    (tests/golden/odeint_defaults.json): through the C ABI with the defaults spelled out, and through the C++ mirror's
+    default form (examples/cpp_api.cpp), which is given nothing but the problem and the span."""
+    import os
+    import re
+    import subprocess
+    from conftest import ROOT
+    o = capi.make_options(rel_tol=1e-4, abs_tol=1e-3, newton_tol=1e-5, newton_refresh_jac=25)
+    for c in golden_defaults:
+        g = capi.irk_ensemble(capi.name_to_problem(c["problem"]), 211, c["t0"], c["t1"], 1e-6, np.array(c["y0"]),
+                              np.array(c["params"])[:, None], o)
+        se = scaled_err(g.y, unhex(c["y"])[:, None], 1e-4, 1e-3)
+        print(f"\n{c['name']}: scaled err {se.max():.3e}; attempts gpu/ref {int(g.counters['attempt'][0])}/{c['counters']['attempt']}, "
+              f"fun_evals {int(g.counters['fun_evals'][0])}/{c['counters']['fun_evals']}")
+        assert g.status[0] == 0 and g.t_final[0] == c["t1"] and se.max() <= PARITY_BOUND
+        if c["counters"]["reject_newton"] == 0:
+            assert int(g.counters["attempt"][0]) == c["counters"]["attempt"]
+            assert int(g.counters["reject_err"][0]) == c["counters"]["reject_err"]
+            assert int(g.counters["fun_evals"][0]) == c["counters"]["fun_evals"]
+        else:  # failing Newton solves (thousands of iterations each) magnify last-bit differences: same path, not same count
+            assert abs(int(g.counters["attempt"][0]) - c["counters"]["attempt"]) <= 0.05 * c["counters"]["attempt"]
+    path = os.path.join(ROOT, "build", "cpp_api")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", ROOT, "examples"])
+    r = subprocess.run([path], capture_output=True, text=True, timeout=120)
+    m = re.search(r"defaults: y = (\S+) (\S+) (\S+) attempts (\d+) fun_evals (\d+)", r.stdout)
+    assert r.returncode == 0 and m, (r.stdout, r.stderr)
+    c = golden_defaults[0]
+    y = np.array([float.fromhex(m.group(i)) for i in (1, 2, 3)])
+    assert scaled_err(y[:, None], unhex(c["y"])[:, None], 1e-4, 1e-3).max() <= PARITY_BOUND
+    assert int(m.group(4)) == c["counters"]["attempt"] and int(m.group(5)) == c["counters"]["fun_evals"]

@@ -213,3 +213,26 @@ def test_reference_log_golden_is_consistent(golden_configs):
             assert len(rows) == k["attempt"] - k["reject_newton"]
             assert int((rows[:, 3] > 1.0).sum()) == k["reject_err"]
         assert np.all(rows[:, 0] % c["out_interval"] == 0) and rows[0, 1] == 0.0
+
+
+def test_four_argument_odeint_defaults_are_pinned(port, golden_defaults):
+    """irk.hpp:915-926: RADAU_IIA_53, dt = 1e-6, rel_tol = 1e-4, abs_tol = 1e-3 (options.hpp), refresh_jac = 25,
+    Newton tol = 0.1*min(abs_tol, rel_tol).  The fixture comes from the reference's own 4-argument call, which is not
+    told any of these: stating them to the port must reproduce it bit for bit."""
+    from oracle import refsolver
+    o = refsolver.make_options(rel_tol=1e-4, abs_tol=1e-3, newton_tol=1e-5, newton_refresh_jac=25)
+    for c in golden_defaults:
+        r = port.solve(c["problem"], 211, c["t0"], c["t1"], 1e-6, np.array(c["y0"]), np.array(c["params"])[:, None], o)
+        assert int(r.status[0]) == c["status"] == 0
+        assert np.array_equal(r.y[:, 0], unhex(c["y"])), c["name"]
+        assert r.t_final[0] == unhex(c["t_final"])[0] and r.err_last[0] == unhex(c["err_last"])[0]
+        assert {k: int(v[0]) for k, v in r.counters.items()} == c["counters"], c["name"]
+
+
+def test_four_argument_odeint_of_the_reference_library(reference, golden_defaults):
+    """The fixture regenerates from the unmodified reference (skipped where oracle/_ref was built before this entry point existed)."""
+    if not hasattr(reference.lib, "ref_odeint_defaults"):
+        pytest.skip("oracle/_ref predates ref_odeint_defaults")
+    for c in golden_defaults[:3]:
+        r = reference.odeint_defaults(c["problem"], c["t0"], c["t1"], c["y0"], c["params"])
+        assert np.array_equal(r.y[:, 0], unhex(c["y"])) and {k: int(v[0]) for k, v in r.counters.items()} == c["counters"]
