@@ -24,6 +24,9 @@
 //   __device__ static void   jac_row(int i, double t, const double *y, const double *p, double *row); // row i, pre-zeroed
 #pragma once
 
+#ifdef REHUEL_CTA_PHASE_CLOCKS
+#include <cstdio>
+#endif
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -77,6 +80,22 @@ struct CtaSmem {
 	static constexpr int n_int = N * (2 + NC) + 1 + 8;
 	static constexpr size_t bytes = (size_t)o_int * 8 + (size_t)n_int * 4;
 };
+
+// Dev builds (-DREHUEL_CTA_PHASE_CLOCKS): thread 0 of block 0 adds up clock64() between marks that follow block barriers
+// and prints the totals at the end of the kernel: 0 setup+Jacobian+matrices, 1 panel, 2 exchanges+L11 solve, 3 trailing
+// update, 4 residuals, 5 transforms+norms, 6 Newton solves, 7 estimate, 8 rest of the attempt.
+#ifdef REHUEL_CTA_PHASE_CLOCKS
+struct PhaseClock {
+	long long t, acc[9];
+	bool on;
+	__device__ void start() { if (on) t = clock64(); }
+	__device__ void mark(int i) { if (on) { const long long now = clock64(); acc[i] += now - t; t = now; } }
+};
+#define REHUEL_PHASE_MARK(pc, i) (pc).mark(i)
+#else
+struct PhaseClock {};
+#define REHUEL_PHASE_MARK(pc, i) ((void)0)
+#endif
 
 // Sum over the block, identical on every thread (fixed order: butterfly inside a warp, then the
 // warp partials in ascending order).  Two block barriers.
@@ -230,11 +249,421 @@ __device__ __forceinline__ void lu_factor_set(double *Ar, double *Ac, double *Ae
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// PANEL-BLOCKED LU for dense matrices (N a multiple of kPanel): the same eliminations in the same order as
+// lu_factor_set -- every entry sees the identical sequence of FMAs, so the factors are bit-identical -- but
+//   A. a panel of kPanel columns is factorised by ONE warp per matrix in registers (two rows per lane, pivot search by
+//      three REDUX, row exchanges and the pivot-row broadcast by shuffles): no block barrier inside the panel;
+//   B. the panel's row exchanges and the unit-lower triangular solve are applied to the columns right of it, one thread
+//      per column and matrix;
+//   C. the trailing block takes the rank-kPanel update A22 -= L21 U12 in register tiles (4 x 4 real, 2 x 4 complex):
+//      per FMA 0.5 (real) / 0.4 (complex) shared-memory accesses instead of 2.3 for a rank-1 update.
+// Three block barriers per panel (24 per set of factorisations for N = 64) instead of two per column (128).
+// Row exchanges follow LAPACK inside a panel (whole panel rows are exchanged, so the multipliers of the earlier panel
+// columns move with their rows) and leave the columns LEFT of the panel alone: the forward solve applies the kPanel
+// exchanges of a panel before its kPanel elimination steps (PANEL flag of the solves).
+#ifndef REHUEL_CTA_PANEL
+#define REHUEL_CTA_PANEL 1
+#endif
+constexpr int kPanel = 8;
+
+// warp-wide argmax of a non-negative double (one candidate per lane, `row` its row index; best < 0: no candidate):
+// the smallest row among the maxima, N if there is none (NaN column)
+template <int N>
+__device__ __forceinline__ int warp_pivot_row(double best, int row)
+{
+	const int hi = __double2hiint(best); // non-negative doubles order like their bit patterns
+	const int mh = __reduce_max_sync(0xffffffffu, hi);
+	const unsigned lo = (hi == mh) ? (unsigned)__double2loint(best) : 0u;
+	const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+	const unsigned cand = (mh >= 0 && hi == mh && lo == ml) ? (unsigned)row : (unsigned)N;
+	return (int)__reduce_min_sync(0xffffffffu, cand);
+}
+
+// One warp factorises a panel: the loop over its kPanel columns is ROLLED -- straight-line code that one warp runs once
+// is bound by instruction fetch (the unrolled version spent half its time without an instruction) -- so the registers
+// hold a window of the panel whose column 0 is the current column: a step stores its finished column (multipliers)
+// and pivot row to shared memory and shifts the window left while it updates it.
+template <int N, int LD>
+__device__ __forceinline__ void lu_panel_real(double *A, double *rd, int *perm, int c0)
+{
+	constexpr int PW = kPanel, Q = (N + 31) / 32;
+	const int lane = threadIdx.x & 31;
+	double a[Q][PW];
+#pragma unroll
+	for (int q = 0; q < Q; ++q) {
+		const int r = lane + 32 * q;
+#pragma unroll
+		for (int j = 0; j < PW; ++j) a[q][j] = (r >= c0 && r < N) ? A[r * LD + c0 + j] : 0.0;
+	}
+#pragma unroll 1
+	for (int j = 0; j < PW; ++j) {
+		const int k = c0 + j;
+		double best = -1.0;
+		int brow = N;
+#pragma unroll
+		for (int q = 0; q < Q; ++q) {
+			const int r = lane + 32 * q;
+			const double v = fabs(a[q][0]);
+			if (r >= k && r < N && v > best) {
+				best = v;
+				brow = r;
+			}
+		}
+		int p = warp_pivot_row<N>(best, brow);
+		if (p >= N) p = k;
+		if (lane == 0) perm[k] = p;
+		const int lk = k & 31, lp = p & 31;
+		const bool qk = Q > 1 && k >= 32, qp = Q > 1 && p >= 32;
+		if (p != k) { // warp-uniform: exchange the panel rows k and p -- the window, and the finished columns in memory
+#pragma unroll
+			for (int jj = 0; jj < PW; ++jj) {
+				const double vk = __shfl_sync(0xffffffffu, qk ? a[Q - 1][jj] : a[0][jj], lk);
+				const double vp = __shfl_sync(0xffffffffu, qp ? a[Q - 1][jj] : a[0][jj], lp);
+#pragma unroll
+				for (int q = 0; q < Q; ++q) {
+					const int r = lane + 32 * q;
+					if (r == k) a[q][jj] = vp;
+					if (r == p) a[q][jj] = vk;
+				}
+			}
+			if (lane < j) {
+				const double v = A[k * LD + c0 + lane];
+				A[k * LD + c0 + lane] = A[p * LD + c0 + lane];
+				A[p * LD + c0 + lane] = v;
+			}
+		}
+		double u[PW];
+#pragma unroll
+		for (int jj = 0; jj < PW; ++jj) u[jj] = __shfl_sync(0xffffffffu, qk ? a[Q - 1][jj] : a[0][jj], lk);
+		const double rp = fast_rcp(u[0]);
+		if (lane == 0) rd[k] = rp;
+		// the pivot row is final: lane jj stores U(k, k + jj)
+		{
+			double mine = u[0];
+#pragma unroll
+			for (int jj = 1; jj < PW; ++jj)
+				if (lane == jj) mine = u[jj];
+			if (lane < PW - j) A[k * LD + k + lane] = mine;
+		}
+#pragma unroll
+		for (int q = 0; q < Q; ++q) {
+			const int r = lane + 32 * q;
+			if (r > k && r < N) {
+				const double l = a[q][0] * rp;
+				A[r * LD + k] = l;
+#pragma unroll
+				for (int jj = 1; jj < PW; ++jj) a[q][jj - 1] = fma(-l, u[jj], a[q][jj]);
+				a[q][PW - 1] = 0.0;
+			}
+		}
+		__syncwarp(); // the stored columns are exchanged by other lanes in later steps
+	}
+}
+
+template <int N, int LD>
+__device__ __forceinline__ void lu_panel_cplx(double *Are, double *rdre, double *rdim, int *perm, int c0)
+{
+	constexpr int PW = kPanel, Q = (N + 31) / 32;
+	const int lane = threadIdx.x & 31;
+	double *Aim = Are + N * LD;
+	double ar[Q][PW], ai[Q][PW];
+#pragma unroll
+	for (int q = 0; q < Q; ++q) {
+		const int r = lane + 32 * q;
+#pragma unroll
+		for (int j = 0; j < PW; ++j) {
+			const bool in = r >= c0 && r < N;
+			ar[q][j] = in ? Are[r * LD + c0 + j] : 0.0;
+			ai[q][j] = in ? Aim[r * LD + c0 + j] : 0.0;
+		}
+	}
+#pragma unroll 1
+	for (int j = 0; j < PW; ++j) {
+		const int k = c0 + j;
+		double best = -1.0;
+		int brow = N;
+#pragma unroll
+		for (int q = 0; q < Q; ++q) {
+			const int r = lane + 32 * q;
+			const double v = fabs(ar[q][0]) + fabs(ai[q][0]); // izamax
+			if (r >= k && r < N && v > best) {
+				best = v;
+				brow = r;
+			}
+		}
+		int p = warp_pivot_row<N>(best, brow);
+		if (p >= N) p = k;
+		if (lane == 0) perm[k] = p;
+		const int lk = k & 31, lp = p & 31;
+		const bool qk = Q > 1 && k >= 32, qp = Q > 1 && p >= 32;
+		if (p != k) {
+#pragma unroll
+			for (int jj = 0; jj < PW; ++jj) {
+				const double vkr = __shfl_sync(0xffffffffu, qk ? ar[Q - 1][jj] : ar[0][jj], lk);
+				const double vki = __shfl_sync(0xffffffffu, qk ? ai[Q - 1][jj] : ai[0][jj], lk);
+				const double vpr = __shfl_sync(0xffffffffu, qp ? ar[Q - 1][jj] : ar[0][jj], lp);
+				const double vpi = __shfl_sync(0xffffffffu, qp ? ai[Q - 1][jj] : ai[0][jj], lp);
+#pragma unroll
+				for (int q = 0; q < Q; ++q) {
+					const int r = lane + 32 * q;
+					if (r == k) { ar[q][jj] = vpr; ai[q][jj] = vpi; }
+					if (r == p) { ar[q][jj] = vkr; ai[q][jj] = vki; }
+				}
+			}
+			if (lane < j) {
+				double v = Are[k * LD + c0 + lane];
+				Are[k * LD + c0 + lane] = Are[p * LD + c0 + lane];
+				Are[p * LD + c0 + lane] = v;
+				v = Aim[k * LD + c0 + lane];
+				Aim[k * LD + c0 + lane] = Aim[p * LD + c0 + lane];
+				Aim[p * LD + c0 + lane] = v;
+			}
+		}
+		double ur[PW], ui[PW];
+#pragma unroll
+		for (int jj = 0; jj < PW; ++jj) {
+			ur[jj] = __shfl_sync(0xffffffffu, qk ? ar[Q - 1][jj] : ar[0][jj], lk);
+			ui[jj] = __shfl_sync(0xffffffffu, qk ? ai[Q - 1][jj] : ai[0][jj], lk);
+		}
+		const double rden = fast_rcp(fma(ur[0], ur[0], ui[0] * ui[0]));
+		const double rr = ur[0] * rden, ri = -ui[0] * rden;
+		if (lane == 0) {
+			rdre[k] = rr;
+			rdim[k] = ri;
+		}
+		{
+			double mr = ur[0], mi = ui[0];
+#pragma unroll
+			for (int jj = 1; jj < PW; ++jj)
+				if (lane == jj) {
+					mr = ur[jj];
+					mi = ui[jj];
+				}
+			if (lane < PW - j) {
+				Are[k * LD + k + lane] = mr;
+				Aim[k * LD + k + lane] = mi;
+			}
+		}
+#pragma unroll
+		for (int q = 0; q < Q; ++q) {
+			const int r = lane + 32 * q;
+			if (r > k && r < N) {
+				const double xr = ar[q][0], xi = ai[q][0];
+				const double lr = fma(xr, rr, -xi * ri), li = fma(xr, ri, xi * rr);
+				Are[r * LD + k] = lr;
+				Aim[r * LD + k] = li;
+#pragma unroll
+				for (int jj = 1; jj < PW; ++jj) {
+					ar[q][jj - 1] = fma(-lr, ur[jj], fma(li, ui[jj], ar[q][jj]));
+					ai[q][jj - 1] = fma(-lr, ui[jj], fma(-li, ur[jj], ai[q][jj]));
+				}
+				ar[q][PW - 1] = 0.0;
+				ai[q][PW - 1] = 0.0;
+			}
+		}
+		__syncwarp();
+	}
+}
+
+template <int N, int LD, int NRm, int NCm, int NEm, int THREADS>
+__device__ __forceinline__ void lu_factor_set_panel(double *Ar, double *Ac, double *Ae, double *rdr, double *rdc, double *rde,
+                                                    int *permr, int *permc, int *perme, PhaseClock &pc)
+{
+	(void)pc;
+	constexpr int PW = kPanel, NM = NRm + NCm + NEm, NREAL = NRm + NEm;
+	static_assert(N % PW == 0 && N <= 64 && NM <= THREADS / 32, "one pilot warp per matrix, two rows per lane");
+	const int tid = threadIdx.x, warp = tid >> 5;
+	// matrix m: real Newton block, estimator (the real ones first), then the complex blocks
+	auto real_mat = [&](int m) -> double * { return (NRm && m == 0) ? Ar : Ae; };
+	auto real_perm = [&](int m) -> int * { return (NRm && m == 0) ? permr : perme; };
+	for (int c0 = 0; c0 < N; c0 += PW) {
+		// ---- A: the panel, one warp per matrix
+		if (warp < NREAL) {
+			lu_panel_real<N, LD>(real_mat(warp), (NRm && warp == 0) ? rdr : rde, real_perm(warp), c0);
+		} else if (warp < NM) {
+			const int c = warp - NREAL;
+			lu_panel_cplx<N, LD>(Ac + (size_t)c * 2 * N * LD, rdc + (c * 2) * N, rdc + (c * 2 + 1) * N, permc + c * N, c0);
+		}
+		__syncthreads();
+		REHUEL_PHASE_MARK(pc, 1);
+		const int n2 = N - c0 - PW, cb = c0 + PW;
+		if (n2 <= 0) break;
+		// ---- B: exchanges + L11^-1 on the columns right of the panel: one (matrix, column) per thread
+		for (int task = tid; task < NM * N; task += THREADS) {
+			const int m = task / N, jc = task % N;
+			if (jc < cb) continue;
+			// (every load first: issued one by one between the dependent FMAs they would set the pace)
+			if (m < NREAL) {
+				double *A = real_mat(m);
+				const int *perm = real_perm(m);
+				int pv[PW];
+#pragma unroll
+				for (int j = 0; j < PW; ++j) pv[j] = perm[c0 + j];
+				double l11[PW][PW];
+#pragma unroll
+				for (int j = 0; j < PW; ++j)
+#pragma unroll
+					for (int i = j + 1; i < PW; ++i) l11[i][j] = A[(c0 + i) * LD + c0 + j];
+#pragma unroll
+				for (int j = 0; j < PW; ++j) {
+					const int k = c0 + j, p = pv[j];
+					if (p != k) {
+						const double v = A[k * LD + jc];
+						A[k * LD + jc] = A[p * LD + jc];
+						A[p * LD + jc] = v;
+					}
+				}
+				double u[PW];
+#pragma unroll
+				for (int j = 0; j < PW; ++j) u[j] = A[(c0 + j) * LD + jc];
+#pragma unroll
+				for (int j = 0; j < PW; ++j)
+#pragma unroll
+					for (int i = j + 1; i < PW; ++i) u[i] = fma(-l11[i][j], u[j], u[i]);
+#pragma unroll
+				for (int j = 1; j < PW; ++j) A[(c0 + j) * LD + jc] = u[j];
+			} else {
+				const int c = m - NREAL;
+				double *Are = Ac + (size_t)c * 2 * N * LD, *Aim = Are + N * LD;
+				const int *perm = permc + c * N;
+				int pv[PW];
+#pragma unroll
+				for (int j = 0; j < PW; ++j) pv[j] = perm[c0 + j];
+				double l11r[PW][PW], l11i[PW][PW];
+#pragma unroll
+				for (int j = 0; j < PW; ++j)
+#pragma unroll
+					for (int i = j + 1; i < PW; ++i) {
+						l11r[i][j] = Are[(c0 + i) * LD + c0 + j];
+						l11i[i][j] = Aim[(c0 + i) * LD + c0 + j];
+					}
+#pragma unroll
+				for (int j = 0; j < PW; ++j) {
+					const int k = c0 + j, p = pv[j];
+					if (p != k) {
+						double v = Are[k * LD + jc];
+						Are[k * LD + jc] = Are[p * LD + jc];
+						Are[p * LD + jc] = v;
+						v = Aim[k * LD + jc];
+						Aim[k * LD + jc] = Aim[p * LD + jc];
+						Aim[p * LD + jc] = v;
+					}
+				}
+				double ur[PW], ui[PW];
+#pragma unroll
+				for (int j = 0; j < PW; ++j) {
+					ur[j] = Are[(c0 + j) * LD + jc];
+					ui[j] = Aim[(c0 + j) * LD + jc];
+				}
+#pragma unroll
+				for (int j = 0; j < PW; ++j)
+#pragma unroll
+					for (int i = j + 1; i < PW; ++i) {
+						const double lr = l11r[i][j], li = l11i[i][j];
+						ur[i] = fma(-lr, ur[j], fma(li, ui[j], ur[i]));
+						ui[i] = fma(-lr, ui[j], fma(-li, ur[j], ui[i]));
+					}
+#pragma unroll
+				for (int j = 1; j < PW; ++j) {
+					Are[(c0 + j) * LD + jc] = ur[j];
+					Aim[(c0 + j) * LD + jc] = ui[j];
+				}
+			}
+		}
+		__syncthreads();
+		REHUEL_PHASE_MARK(pc, 2);
+		// ---- C: A22 -= L21 U12 in register tiles; the rows (columns) of a tile are n2/4 (n2/2 for the two rows of a
+		// complex tile) apart, so that neighbouring threads read neighbouring columns
+		const int TJ = n2 / 4, TI2 = n2 / 2;
+		const int n_real = NREAL * TJ * TJ, n_all = n_real + NCm * TI2 * TJ;
+		// x / d for x < 2048, d <= 512 as a multiplication (exact: x (d - 2^20 mod d) < 2^20)
+		auto magic = [](int d) -> unsigned { return (1u << 20) / (unsigned)d + 1u; };
+		const unsigned m_tj = magic(TJ), m_tt = magic(TJ * TJ), m_t2 = magic(TI2 * TJ);
+		auto divm = [](int x, unsigned m) -> int { return (int)(((unsigned)x * m) >> 20); };
+		static_assert(N <= 64, "unit indices stay below 2048");
+		for (int unit = tid; unit < n_all; unit += THREADS) {
+			if (unit < n_real) {
+				const int m = divm(unit, m_tt), w = unit - m * TJ * TJ;
+				double *A = real_mat(m);
+				const int wi = divm(w, m_tj);
+				const int r0 = cb + wi, cc = cb + w - wi * TJ;
+				double acc[4][4];
+#pragma unroll
+				for (int x = 0; x < 4; ++x)
+#pragma unroll
+					for (int y = 0; y < 4; ++y) acc[x][y] = A[(r0 + TJ * x) * LD + cc + TJ * y];
+#pragma unroll
+				for (int kk = 0; kk < PW; ++kk) {
+					double l[4], u[4];
+#pragma unroll
+					for (int x = 0; x < 4; ++x) l[x] = A[(r0 + TJ * x) * LD + c0 + kk];
+#pragma unroll
+					for (int y = 0; y < 4; ++y) u[y] = A[(c0 + kk) * LD + cc + TJ * y];
+#pragma unroll
+					for (int x = 0; x < 4; ++x)
+#pragma unroll
+						for (int y = 0; y < 4; ++y) acc[x][y] = fma(-l[x], u[y], acc[x][y]);
+				}
+#pragma unroll
+				for (int x = 0; x < 4; ++x)
+#pragma unroll
+					for (int y = 0; y < 4; ++y) A[(r0 + TJ * x) * LD + cc + TJ * y] = acc[x][y];
+			} else {
+				const int v = unit - n_real;
+				const int c = divm(v, m_t2), w = v - c * TI2 * TJ;
+				double *Are = Ac + (size_t)c * 2 * N * LD, *Aim = Are + N * LD;
+				const int wi = divm(w, m_tj);
+				const int r0 = cb + wi, cc = cb + w - wi * TJ;
+				double accr[2][4], acci[2][4];
+#pragma unroll
+				for (int x = 0; x < 2; ++x)
+#pragma unroll
+					for (int y = 0; y < 4; ++y) {
+						accr[x][y] = Are[(r0 + TI2 * x) * LD + cc + TJ * y];
+						acci[x][y] = Aim[(r0 + TI2 * x) * LD + cc + TJ * y];
+					}
+#pragma unroll
+				for (int kk = 0; kk < PW; ++kk) {
+					double lr[2], li[2], ur[4], ui[4];
+#pragma unroll
+					for (int x = 0; x < 2; ++x) {
+						lr[x] = Are[(r0 + TI2 * x) * LD + c0 + kk];
+						li[x] = Aim[(r0 + TI2 * x) * LD + c0 + kk];
+					}
+#pragma unroll
+					for (int y = 0; y < 4; ++y) {
+						ur[y] = Are[(c0 + kk) * LD + cc + TJ * y];
+						ui[y] = Aim[(c0 + kk) * LD + cc + TJ * y];
+					}
+#pragma unroll
+					for (int x = 0; x < 2; ++x)
+#pragma unroll
+						for (int y = 0; y < 4; ++y) {
+							accr[x][y] = fma(-lr[x], ur[y], fma(li[x], ui[y], accr[x][y]));
+							acci[x][y] = fma(-lr[x], ui[y], fma(-li[x], ur[y], acci[x][y]));
+						}
+				}
+#pragma unroll
+				for (int x = 0; x < 2; ++x)
+#pragma unroll
+					for (int y = 0; y < 4; ++y) {
+						Are[(r0 + TI2 * x) * LD + cc + TJ * y] = accr[x][y];
+						Aim[(r0 + TI2 * x) * LD + cc + TJ * y] = acci[x][y];
+					}
+			}
+		}
+		__syncthreads();
+		REHUEL_PHASE_MARK(pc, 3);
+	}
+}
+
 // Warp-synchronous solve with the packed real LU: x <- U^-1 L^-1 P x.  x in shared memory.
-template <int N, int LD, int KB>
+// PANEL: factors of lu_factor_set_panel -- the kPanel row exchanges of a panel come before its elimination steps.
+template <int N, int LD, int KB, bool PANEL = false>
 __device__ __forceinline__ void lu_solve_real_warp(const double *A, const double *rd, const int *perm, double *x)
 {
-	constexpr int Q = (N + 31) / 32;
+	constexpr int Q = (N + 31) / 32, GROUP = PANEL ? kPanel : 1;
 	const int lane = threadIdx.x & 31;
 	double v[Q];
 #pragma unroll
@@ -244,37 +673,70 @@ __device__ __forceinline__ void lu_solve_real_warp(const double *A, const double
 	}
 #pragma unroll
 	for (int kq = 0; kq < Q; ++kq) // forward, unit lower (kq static: v[] stays in registers)
-		for (int kk = 0; kk < 32 && kq * 32 + kk < N; ++kk) {
-			const int k = kq * 32 + kk;
-			const int p = perm[k]; // warp-uniform
-			double xk = __shfl_sync(0xffffffffu, v[kq], kk);
-			if (p != k) { // exchange entries k and p (p > k)
-				const double xp = __shfl_sync(0xffffffffu, (Q > 1 && p >= 32) ? v[Q - 1] : v[0], p & 31);
+		for (int kb = 0; kb < 32 && kq * 32 + kb < N; kb += GROUP) {
+			int pv[GROUP]; // the group's interchanges first: a load per step would stall the warp every time
+#pragma unroll
+			for (int g = 0; g < GROUP; ++g) pv[g] = perm[kq * 32 + kb + g];
+#pragma unroll
+			for (int kk = kb; kk < kb + GROUP; ++kk) {
+				const int k = kq * 32 + kk;
+				const int p = pv[kk - kb]; // warp-uniform
+				if (p != k) { // exchange entries k and p (p > k)
+					const double xk = __shfl_sync(0xffffffffu, v[kq], kk);
+					const double xp = __shfl_sync(0xffffffffu, (Q > 1 && p >= 32) ? v[Q - 1] : v[0], p & 31);
+#pragma unroll
+					for (int q = 0; q < Q; ++q) {
+						const int i = lane + 32 * q;
+						if (i == k) v[q] = xp;
+						if (i == p) v[q] = xk;
+					}
+				}
+			}
+			// the group's columns first (independent loads), so that the chain of a step is one shuffle and one FMA
+			double l[GROUP][Q];
+#pragma unroll
+			for (int g = 0; g < GROUP; ++g)
 #pragma unroll
 				for (int q = 0; q < Q; ++q) {
-					const int i = lane + 32 * q;
-					if (i == k) v[q] = xp;
-					if (i == p) v[q] = xk;
+					const int i = lane + 32 * q, k = kq * 32 + kb + g;
+					l[g][q] = (q >= kq && i > k && i < N && i <= k + KB) ? A[i * LD + k] : 0.0;
 				}
-				xk = xp;
-			}
 #pragma unroll
-			for (int q = 0; q < Q; ++q) {
-				const int i = lane + 32 * q;
-				if (i > k && i < N && i <= k + KB) v[q] = fma(-A[i * LD + k], xk, v[q]);
+			for (int g = 0; g < GROUP; ++g) {
+				const int k = kq * 32 + kb + g;
+				const double xk = __shfl_sync(0xffffffffu, v[kq], kb + g);
+#pragma unroll
+				for (int q = kq; q < Q; ++q) {
+					const int i = lane + 32 * q;
+					if (i > k && i < N && i <= k + KB) v[q] = fma(-l[g][q], xk, v[q]);
+				}
 			}
 		}
 #pragma unroll
 	for (int kq = Q - 1; kq >= 0; --kq) // backward
-		for (int kk = 31; kk >= 0; --kk) {
-			const int k = kq * 32 + kk;
-			if (k >= N) continue;
-			const double xk = __shfl_sync(0xffffffffu, v[kq], kk) * rd[k];
+		for (int kb = 32 - GROUP; kb >= 0; kb -= GROUP) {
+			if (kq * 32 + kb >= N) continue; // N is a multiple of GROUP
+			double uu[GROUP][Q], rdk[GROUP];
 #pragma unroll
-			for (int q = 0; q < Q; ++q) {
-				const int i = lane + 32 * q;
-				if (i == k) v[q] = xk;
-				if (i < k && i + 2 * KB >= k) v[q] = fma(-A[i * LD + k], xk, v[q]);
+			for (int g = 0; g < GROUP; ++g) {
+				const int k = kq * 32 + kb + g;
+				rdk[g] = rd[k];
+#pragma unroll
+				for (int q = 0; q < Q; ++q) {
+					const int i = lane + 32 * q;
+					uu[g][q] = (q <= kq && i < k && i + 2 * KB >= k) ? A[i * LD + k] : 0.0;
+				}
+			}
+#pragma unroll
+			for (int g = GROUP - 1; g >= 0; --g) {
+				const int k = kq * 32 + kb + g;
+				const double xk = __shfl_sync(0xffffffffu, v[kq], kb + g) * rdk[g];
+#pragma unroll
+				for (int q = 0; q <= kq; ++q) {
+					const int i = lane + 32 * q;
+					if (i == k) v[q] = xk;
+					if (i < k && i + 2 * KB >= k) v[q] = fma(-uu[g][q], xk, v[q]);
+				}
 			}
 		}
 	__syncwarp();
@@ -286,11 +748,11 @@ __device__ __forceinline__ void lu_solve_real_warp(const double *A, const double
 	__syncwarp();
 }
 
-template <int N, int LD, int KB>
+template <int N, int LD, int KB, bool PANEL = false>
 __device__ __forceinline__ void lu_solve_cplx_warp(const double *Are, const double *rdre, const double *rdim,
                                                    const int *perm, double *xr, double *xi)
 {
-	constexpr int Q = (N + 31) / 32;
+	constexpr int Q = (N + 31) / 32, GROUP = PANEL ? kPanel : 1;
 	const int lane = threadIdx.x & 31;
 	const double *Aim = Are + N * LD;
 	double vr[Q], vi[Q];
@@ -302,53 +764,88 @@ __device__ __forceinline__ void lu_solve_cplx_warp(const double *Are, const doub
 	}
 #pragma unroll
 	for (int kq = 0; kq < Q; ++kq)
-		for (int kk = 0; kk < 32 && kq * 32 + kk < N; ++kk) {
-			const int k = kq * 32 + kk;
-			const int p = perm[k];
-			double kr = __shfl_sync(0xffffffffu, vr[kq], kk);
-			double ki = __shfl_sync(0xffffffffu, vi[kq], kk);
-			if (p != k) {
-				const double pr = __shfl_sync(0xffffffffu, (Q > 1 && p >= 32) ? vr[Q - 1] : vr[0], p & 31);
-				const double pi = __shfl_sync(0xffffffffu, (Q > 1 && p >= 32) ? vi[Q - 1] : vi[0], p & 31);
+		for (int kb = 0; kb < 32 && kq * 32 + kb < N; kb += GROUP) {
+			int pv[GROUP];
+#pragma unroll
+			for (int g = 0; g < GROUP; ++g) pv[g] = perm[kq * 32 + kb + g];
+#pragma unroll
+			for (int kk = kb; kk < kb + GROUP; ++kk) {
+				const int k = kq * 32 + kk;
+				const int p = pv[kk - kb];
+				if (p != k) {
+					const double kr = __shfl_sync(0xffffffffu, vr[kq], kk);
+					const double ki = __shfl_sync(0xffffffffu, vi[kq], kk);
+					const double pr = __shfl_sync(0xffffffffu, (Q > 1 && p >= 32) ? vr[Q - 1] : vr[0], p & 31);
+					const double pi = __shfl_sync(0xffffffffu, (Q > 1 && p >= 32) ? vi[Q - 1] : vi[0], p & 31);
+#pragma unroll
+					for (int q = 0; q < Q; ++q) {
+						const int i = lane + 32 * q;
+						if (i == k) { vr[q] = pr; vi[q] = pi; }
+						if (i == p) { vr[q] = kr; vi[q] = ki; }
+					}
+				}
+			}
+			double lr[GROUP][Q], li[GROUP][Q];
+#pragma unroll
+			for (int g = 0; g < GROUP; ++g)
 #pragma unroll
 				for (int q = 0; q < Q; ++q) {
-					const int i = lane + 32 * q;
-					if (i == k) { vr[q] = pr; vi[q] = pi; }
-					if (i == p) { vr[q] = kr; vi[q] = ki; }
+					const int i = lane + 32 * q, k = kq * 32 + kb + g;
+					const bool on = q >= kq && i > k && i < N && i <= k + KB;
+					lr[g][q] = on ? Are[i * LD + k] : 0.0;
+					li[g][q] = on ? Aim[i * LD + k] : 0.0;
 				}
-				kr = pr;
-				ki = pi;
-			}
 #pragma unroll
-			for (int q = 0; q < Q; ++q) {
-				const int i = lane + 32 * q;
-				if (i > k && i < N && i <= k + KB) {
-					const double lr = Are[i * LD + k], li = Aim[i * LD + k];
-					vr[q] = fma(-lr, kr, fma(li, ki, vr[q]));
-					vi[q] = fma(-lr, ki, fma(-li, kr, vi[q]));
+			for (int g = 0; g < GROUP; ++g) {
+				const int k = kq * 32 + kb + g;
+				const double kr = __shfl_sync(0xffffffffu, vr[kq], kb + g);
+				const double ki = __shfl_sync(0xffffffffu, vi[kq], kb + g);
+#pragma unroll
+				for (int q = kq; q < Q; ++q) {
+					const int i = lane + 32 * q;
+					if (i > k && i < N && i <= k + KB) {
+						vr[q] = fma(-lr[g][q], kr, fma(li[g][q], ki, vr[q]));
+						vi[q] = fma(-lr[g][q], ki, fma(-li[g][q], kr, vi[q]));
+					}
 				}
 			}
 		}
 #pragma unroll
 	for (int kq = Q - 1; kq >= 0; --kq)
-		for (int kk = 31; kk >= 0; --kk) {
-			const int k = kq * 32 + kk;
-			if (k >= N) continue;
-			const double tr = __shfl_sync(0xffffffffu, vr[kq], kk);
-			const double ti = __shfl_sync(0xffffffffu, vi[kq], kk);
-			const double kr = fma(tr, rdre[k], -ti * rdim[k]);
-			const double ki = fma(tr, rdim[k], ti * rdre[k]);
+		for (int kb = 32 - GROUP; kb >= 0; kb -= GROUP) {
+			if (kq * 32 + kb >= N) continue; // N is a multiple of GROUP
+			double ur[GROUP][Q], ui[GROUP][Q], dre[GROUP], dim[GROUP];
 #pragma unroll
-			for (int q = 0; q < Q; ++q) {
-				const int i = lane + 32 * q;
-				if (i == k) {
-					vr[q] = kr;
-					vi[q] = ki;
+			for (int g = 0; g < GROUP; ++g) {
+				const int k = kq * 32 + kb + g;
+				dre[g] = rdre[k];
+				dim[g] = rdim[k];
+#pragma unroll
+				for (int q = 0; q < Q; ++q) {
+					const int i = lane + 32 * q;
+					const bool on = q <= kq && i < k && i + 2 * KB >= k;
+					ur[g][q] = on ? Are[i * LD + k] : 0.0;
+					ui[g][q] = on ? Aim[i * LD + k] : 0.0;
 				}
-				if (i < k && i + 2 * KB >= k) {
-					const double ur = Are[i * LD + k], ui = Aim[i * LD + k];
-					vr[q] = fma(-ur, kr, fma(ui, ki, vr[q]));
-					vi[q] = fma(-ur, ki, fma(-ui, kr, vi[q]));
+			}
+#pragma unroll
+			for (int g = GROUP - 1; g >= 0; --g) {
+				const int k = kq * 32 + kb + g;
+				const double tr = __shfl_sync(0xffffffffu, vr[kq], kb + g);
+				const double ti = __shfl_sync(0xffffffffu, vi[kq], kb + g);
+				const double kr = fma(tr, dre[g], -ti * dim[g]);
+				const double ki = fma(tr, dim[g], ti * dre[g]);
+#pragma unroll
+				for (int q = 0; q <= kq; ++q) {
+					const int i = lane + 32 * q;
+					if (i == k) {
+						vr[q] = kr;
+						vi[q] = ki;
+					}
+					if (i < k && i + 2 * KB >= k) {
+						vr[q] = fma(-ur[g][q], kr, fma(ui[g][q], ki, vr[q]));
+						vi[q] = fma(-ur[g][q], ki, fma(-ui[g][q], kr, vi[q]));
+					}
 				}
 			}
 		}
@@ -371,6 +868,8 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 	static_assert(S == NR + 2 * NC && NR <= 1, "eigen-structure");
 	using L = CtaSmem<F, S, NC>;
 	constexpr int N = F::N, LD = L::LD, KB = jac_band<F>::value;
+	// dense Jacobians in whole panels take the blocked factorisation (REHUEL_CTA_PANEL=0: the column-by-column one)
+	constexpr bool PANEL = REHUEL_CTA_PANEL && N % kPanel == 0 && 2 * KB >= N;
 	static_assert(N <= 64, "the warp-synchronous solves keep at most two rows per lane");
 	extern __shared__ double sm[];
 	double *y = sm + L::o_y, *yn = sm + L::o_yn, *par = sm + L::o_p, *Y = sm + L::o_Y, *R = sm + L::o_R,
@@ -384,6 +883,12 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 	const int tid = threadIdx.x, warp = tid >> 5;
 	const unsigned long long M = a.M;
 	const rehuel_device_io &io = a.io;
+	PhaseClock pc;
+#ifdef REHUEL_CTA_PHASE_CLOCKS
+	pc.on = tid == 0 && blockIdx.x == 0;
+	for (int i = 0; i < 9; ++i) pc.acc[i] = 0;
+	pc.start();
+#endif
 
 	for (;;) {
 		// ---------------- next member
@@ -499,12 +1004,16 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 			}
 			__syncthreads();
 			// all factorisations of the attempt in the same N steps, the estimator's included
-			lu_factor_set<N, LD, NR, NC, (EST == EST_OWN_LU ? 1 : 0), THREADS, KB>(LUr, LUc, J, rdr, rdc, rde, permr, permc, perme);
+			REHUEL_PHASE_MARK(pc, 0);
+			if constexpr (PANEL) lu_factor_set_panel<N, LD, NR, NC, (EST == EST_OWN_LU ? 1 : 0), THREADS>(LUr, LUc, J, rdr, rdc, rde, permr, permc, perme, pc);
+			else lu_factor_set<N, LD, NR, NC, (EST == EST_OWN_LU ? 1 : 0), THREADS, KB>(LUr, LUc, J, rdr, rdc, rde, permr, permc, perme);
 
 			// -------- simplified Newton (irk.hpp:398-493)
 			for (int e = tid; e < S * N; e += THREADS) Y[e] = 0.0; // irk.hpp:415
 			__syncthreads();
+			REHUEL_PHASE_MARK(pc, 8);
 			double Rnorm2 = residual();
+			REHUEL_PHASE_MARK(pc, 4);
 			int nstat = kNewtonMaxit;
 			int it = 1;
 			for (; it < maxit; ++it) { // irk.hpp:458
@@ -516,14 +1025,15 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 					Z[e] = acc;
 				}
 				__syncthreads();
+				REHUEL_PHASE_MARK(pc, 5);
 				if (NR && warp == 0) {
-					lu_solve_real_warp<N, LD, KB>(LUr, rdr, permr, Z);
+					lu_solve_real_warp<N, LD, KB, PANEL>(LUr, rdr, permr, Z);
 					for (int i = tid & 31; i < N; i += 32) Z[i] *= -mur;
 				}
 				if (warp >= NR && warp < NR + NC) {
 					const int c = warp - NR;
 					double *zr = Z + (NR + 2 * c) * N, *zi = zr + N;
-					lu_solve_cplx_warp<N, LD, KB>(LUc + (size_t)c * 2 * N * LD, rdc + (c * 2) * N, rdc + (c * 2 + 1) * N,
+					lu_solve_cplx_warp<N, LD, KB, PANEL>(LUc + (size_t)c * 2 * N * LD, rdc + (c * 2) * N, rdc + (c * 2 + 1) * N,
 					                          permc + c * N, zr, zi);
 					const double mr = tb.alpha[c] * rdt, mi = tb.beta[c] * rdt;
 					for (int i = tid & 31; i < N; i += 32) { // w = -(mr + i mi) w
@@ -533,6 +1043,7 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 					}
 				}
 				__syncthreads();
+				REHUEL_PHASE_MARK(pc, 6);
 				double x2 = 0.0;
 				for (int e = tid; e < S * N; e += THREADS) { // dY = (T (x) I) W ; Y += dY
 					const int s = e / N, i = e % N;
@@ -543,12 +1054,14 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 					Y[e] += acc;
 				}
 				const double xnorm2 = block_sum<THREADS>(x2, red); // irk.hpp:466 (also orders Z reads before reuse)
+				REHUEL_PHASE_MARK(pc, 5);
 				if (REHUEL_SKIP_DEAD_RESIDUAL && xnorm2 < a.xtol2) { // the residual of irk.hpp:469-472 would never be looked at
 					c_fun += S;                                       // (see irk_thread.cuh); its evaluations are booked
 					nstat = kNewtonSuccess;
 					break;
 				}
 				Rnorm2 = residual();
+				REHUEL_PHASE_MARK(pc, 4);
 				if (Rnorm2 < m_Rtol2) { nstat = kNewtonSuccess; break; }
 				if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; }
 				if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac;
@@ -579,6 +1092,7 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 			}
 			++c_newton_ok;
 			c_iters += (unsigned)it;
+			REHUEL_PHASE_MARK(pc, 8);
 
 			// -------- new solution + embedded error (irk.hpp:691-731)
 			const double gam = tb.gamma * dt;
@@ -605,8 +1119,8 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 			auto apply_Einv_dt = [&]() {
 				if (EST != EST_IDENTITY) {
 					if (warp == 0) {
-						if (EST == EST_OWN_LU) lu_solve_real_warp<N, LD, KB>(J, rde, perme, ev);
-						else lu_solve_real_warp<N, LD, KB>(LUr, rdr, permr, ev);
+						if (EST == EST_OWN_LU) lu_solve_real_warp<N, LD, KB, PANEL>(J, rde, perme, ev);
+						else lu_solve_real_warp<N, LD, KB, PANEL>(LUr, rdr, permr, ev);
 					}
 					__syncthreads();
 				}
@@ -636,6 +1150,7 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 				tot = fma(q, q, tot);
 			}
 			tot = block_sum<THREADS>(tot, red);
+			REHUEL_PHASE_MARK(pc, 7);
 			err = sqrt(tot / (double)N);
 			if (err < kMachinePrecision) err = kMachinePrecision;
 			const bool rejected = a.adaptive && (err > 1.0); // irk.hpp:761
@@ -739,6 +1254,16 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 		}
 		__syncthreads();
 	}
+#ifdef REHUEL_CTA_PHASE_CLOCKS
+	if (pc.on) {
+		long long tot = 0;
+		for (int i = 0; i < 9; ++i) tot += pc.acc[i];
+		printf("cta phase clocks (block 0, %lld cycles): setup %.1f%% panel %.1f%% exch+L11 %.1f%% update %.1f%% residual %.1f%% "
+		       "transforms %.1f%% newton-solves %.1f%% estimate %.1f%% rest %.1f%%\n", tot, 100.0 * pc.acc[0] / tot, 100.0 * pc.acc[1] / tot,
+		       100.0 * pc.acc[2] / tot, 100.0 * pc.acc[3] / tot, 100.0 * pc.acc[4] / tot, 100.0 * pc.acc[5] / tot, 100.0 * pc.acc[6] / tot,
+		       100.0 * pc.acc[7] / tot, 100.0 * pc.acc[8] / tot);
+	}
+#endif
 }
 
 } // namespace rehuel
