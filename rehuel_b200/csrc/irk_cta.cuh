@@ -24,9 +24,6 @@
 //   __device__ static void   jac_row(int i, double t, const double *y, const double *p, double *row); // row i, pre-zeroed
 #pragma once
 
-#ifdef REHUEL_CTA_PHASE_CLOCKS
-#include <cstdio>
-#endif
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -80,22 +77,6 @@ struct CtaSmem {
 	static constexpr int n_int = N * (2 + NC) + 1 + 8;
 	static constexpr size_t bytes = (size_t)o_int * 8 + (size_t)n_int * 4;
 };
-
-// Dev builds (-DREHUEL_CTA_PHASE_CLOCKS): thread 0 of block 0 adds up clock64() between marks that follow block barriers
-// and prints the totals at the end of the kernel: 0 setup+Jacobian+matrices, 1 panel, 2 exchanges+L11 solve, 3 trailing
-// update, 4 residuals, 5 transforms+norms, 6 Newton solves, 7 estimate, 8 rest of the attempt.
-#ifdef REHUEL_CTA_PHASE_CLOCKS
-struct PhaseClock {
-	long long t, acc[9];
-	bool on;
-	__device__ void start() { if (on) t = clock64(); }
-	__device__ void mark(int i) { if (on) { const long long now = clock64(); acc[i] += now - t; t = now; } }
-};
-#define REHUEL_PHASE_MARK(pc, i) (pc).mark(i)
-#else
-struct PhaseClock {};
-#define REHUEL_PHASE_MARK(pc, i) ((void)0)
-#endif
 
 // Sum over the block, identical on every thread (fixed order: butterfly inside a warp, then the
 // warp partials in ascending order).  Two block barriers.
@@ -884,7 +865,7 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 	const unsigned long long M = a.M;
 	const rehuel_device_io &io = a.io;
 	PhaseClock pc;
-#ifdef REHUEL_CTA_PHASE_CLOCKS
+#ifdef REHUEL_PHASE_CLOCKS
 	pc.on = tid == 0 && blockIdx.x == 0;
 	for (int i = 0; i < 9; ++i) pc.acc[i] = 0;
 	pc.start();
@@ -1254,7 +1235,7 @@ ensemble_irk_cta(const __grid_constant__ KernelArgs a, const __grid_constant__ D
 		}
 		__syncthreads();
 	}
-#ifdef REHUEL_CTA_PHASE_CLOCKS
+#ifdef REHUEL_PHASE_CLOCKS
 	if (pc.on) {
 		long long tot = 0;
 		for (int i = 0; i < 9; ++i) tot += pc.acc[i];

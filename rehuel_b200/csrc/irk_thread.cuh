@@ -22,6 +22,9 @@
 // registers.  All LUs are row-partial-pivoted like LAPACK's (predicated swaps, static indexing).
 #pragma once
 
+#ifdef REHUEL_PHASE_CLOCKS
+#include <cstdio>
+#endif
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -93,6 +96,21 @@ constexpr int kBatchLanes = REHUEL_BATCH_LANES;
 constexpr int kSmallBatchLanes = 4;
 constexpr int kGangMinPerLane = 4;
 constexpr int kWaitShift = REHUEL_WAIT_SHIFT;
+
+// Dev builds (-DREHUEL_PHASE_CLOCKS) of the CTA and warp kernels: one thread of block 0 adds up clock64() between marks
+// and prints the shares at the end of the kernel (the meaning of the nine slots is the kernel's).
+#ifdef REHUEL_PHASE_CLOCKS
+struct PhaseClock {
+	long long t, acc[9];
+	bool on;
+	__device__ void start() { if (on) t = clock64(); }
+	__device__ void mark(int i) { if (on) { const long long now = clock64(); acc[i] += now - t; t = now; } }
+};
+#define REHUEL_PHASE_MARK(pc, i) (pc).mark(i)
+#else
+struct PhaseClock {};
+#define REHUEL_PHASE_MARK(pc, i) ((void)0)
+#endif
 
 // Reciprocal: MUFU.RCP64H seed (rcp.approx.f64: the upper 20 mantissa bits) + ONE cubically convergent step
 // r (1 + e + e^2), e = 1 - x r (2^-20 -> 2^-60, i.e. correctly rounded up to ~1 ulp): 4 instructions and no slow

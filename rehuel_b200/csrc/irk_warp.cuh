@@ -387,6 +387,12 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 	double *p_xr = p_cplx ? work + (NR + 2 * p_c) * N : work;
 	double *p_xi = p_cplx ? work + (NR + 2 * p_c + 1) * N : work;
 
+	PhaseClock pc;
+#ifdef REHUEL_PHASE_CLOCKS
+	pc.on = threadIdx.x == 0 && blockIdx.x == 0;
+	for (int i = 0; i < 9; ++i) pc.acc[i] = 0;
+	pc.start();
+#endif
 	for (;;) {
 		// ---------------- next member
 		unsigned long long mem = 0;
@@ -563,7 +569,9 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			++c_jac;
 			// -------- all factorisations side by side, one lane pair per matrix, one routine for all of them;
 			// if partial pivoting would have exchanged rows anywhere, redo them pivoted (one lane per matrix)
+			REHUEL_PHASE_MARK(pc, 8);
 			build_twisted();
+			REHUEL_PHASE_MARK(pc, 0);
 			bool flag = false;
 			if (t_has) flag = tw_factor_pair<N, KB>(m_has, t_pr, t_pi, t_cplx, t_np, t_qr, t_qi);
 			__syncwarp();
@@ -583,7 +591,9 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			for (int s = 0; s < S; ++s)
 #pragma unroll
 				for (int j = 0; j < NPL; ++j) Yr[s][j] = 0.0; // irk.hpp:415
+			REHUEL_PHASE_MARK(pc, 1);
 			double Rnorm2 = residual();
+			REHUEL_PHASE_MARK(pc, 2);
 			int nstat = kNewtonMaxit;
 			int it = 1;
 			for (; it < maxit; ++it) { // irk.hpp:458
@@ -598,12 +608,14 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 						if (FULL || i < N) work[s * N + i] = acc;
 					}
 				__syncwarp();
+				REHUEL_PHASE_MARK(pc, 3);
 				if (!piv_any) { // all right-hand sides side by side, one lane pair each
 					if (t_rhs) tw_solve_pair<N, KB>(m_rhs, t_pr, t_pi, t_cplx, t_np, t_qr, t_qi, t_xr, t_xi, t_xs);
 				} else {
 					if (p_rhs) band_solve<N, KB, true>(p_abr, p_abi, p_cplx, p_rdr, p_rdi, p_piv, p_xr, p_xi);
 				}
 				__syncwarp();
+				REHUEL_PHASE_MARK(pc, 4);
 				double z[NPL][S]; // W = -mu Z, componentwise
 #pragma unroll
 				for (int j = 0; j < NPL; ++j) {
@@ -631,12 +643,14 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 						Yr[s][j] += acc;
 					}
 				const double xnorm2 = warp_sum(x2); // irk.hpp:466
+				REHUEL_PHASE_MARK(pc, 3);
 				if (REHUEL_SKIP_DEAD_RESIDUAL && xnorm2 < a.xtol2) { // the residual of irk.hpp:469-472 would never be looked at
 					c_fun += S;                                       // (see irk_thread.cuh); its evaluations are booked
 					nstat = kNewtonSuccess;
 					break;
 				}
 				Rnorm2 = residual();
+				REHUEL_PHASE_MARK(pc, 2);
 				if (Rnorm2 < m_Rtol2) { nstat = kNewtonSuccess; break; }
 				if (xnorm2 < a.xtol2) { nstat = kNewtonSuccess; break; }
 				if (a.refresh_jac > 0 && it % a.refresh_jac == 0) ++c_jac;
@@ -667,6 +681,7 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 			}
 			++c_newton_ok;
 			c_iters += (unsigned)it;
+			REHUEL_PHASE_MARK(pc, 8);
 
 			// -------- new solution + embedded error (irk.hpp:691-731), componentwise in registers
 			const double gam = tb.gamma * dt;
@@ -697,6 +712,7 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 						if (FULL || i < N) work[i] = ev[j];
 					}
 					__syncwarp();
+					REHUEL_PHASE_MARK(pc, 5);
 					if (!piv_any) {
 						if (t_E) tw_solve_pair<N, KB>(m_E, t_pr, t_pr, false, t_np, t_qr, t_qi, t_er, t_er, t_xs);
 					} else if (lane == 0) {
@@ -704,6 +720,7 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 						band_solve<N, KB, true>(abr + o * PL, abr, false, rdr + o * N, rdr, piv + o * N, work, work);
 					}
 					__syncwarp();
+					REHUEL_PHASE_MARK(pc, 6);
 #pragma unroll
 					for (int j = 0; j < NPL; ++j) {
 						const int i = lane + 32 * j;
@@ -745,6 +762,7 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 				tot = fma(q, q, tot);
 			}
 			tot = warp_sum(tot);
+			REHUEL_PHASE_MARK(pc, 5);
 			err = sqrt(tot / (double)N);
 			if (err < kMachinePrecision) err = kMachinePrecision;
 			const bool rejected = a.adaptive && (err > 1.0); // irk.hpp:761
@@ -863,6 +881,16 @@ ensemble_irk_warp(const __grid_constant__ KernelArgs a, const __grid_constant__ 
 		}
 		__syncwarp();
 	}
+#ifdef REHUEL_PHASE_CLOCKS
+	if (pc.on) {
+		long long tot = 0;
+		for (int i = 0; i < 9; ++i) tot += pc.acc[i];
+		printf("warp phase clocks (warp 0, %lld cycles): build %.1f%% factor %.1f%% residual %.1f%% transforms %.1f%% newton-solves %.1f%% "
+		       "estimate(other) %.1f%% estimate-solve %.1f%% rest %.1f%%\n", tot, 100.0 * pc.acc[0] / tot, 100.0 * pc.acc[1] / tot,
+		       100.0 * pc.acc[2] / tot, 100.0 * pc.acc[3] / tot, 100.0 * pc.acc[4] / tot, 100.0 * pc.acc[5] / tot, 100.0 * pc.acc[6] / tot,
+		       100.0 * pc.acc[8] / tot);
+	}
+#endif
 }
 
 } // namespace rehuel
