@@ -229,8 +229,8 @@ def bind_to_gpu_numa_node(local_rank: int) -> str:
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ensemble_irk_thread<RobertsonF,...> at 2^20 members, t in [0,40]: a
 # CONSTANT from the ncu --set full capture of this command, not measured in the run (profiles/README.md names the file)
-NCU_DRAM_BYTES_PER_LAUNCH = 538.46e6
-NCU_DRAM_SOURCE = "profiles/r1_v8_ncu_summary.txt (248.26 MB read + 290.20 MB written)"
+NCU_DRAM_BYTES_PER_LAUNCH = 526.37e6
+NCU_DRAM_SOURCE = "profiles/r2_thread_v11_short_ncu_summary.txt (240.98 MB read + 285.39 MB written)"
 
 
 def device_ms(fn, torch, reps=1, warm=1):
