@@ -364,8 +364,10 @@ def run_gpu_arm(args) -> None:
             capi.ROBERTSON, capi.RADAU_IIA_53, t0, t1, DT0, M, 3,
             capi.C.cast(y0_host.data_ptr(), capi._PD), 1, capi.C.cast(P_host.data_ptr(), capi._PD),
             capi.C.byref(e2e_opts), 0, 1, capi.C.byref(res)))
-        d2h = 3 * 8 * M + 4 * M + 13 * 8 * 8   # y rows, status, the statistics words of the 8 chunks
         checksum = (res.sum.attempt, res.sum.n_failed, res.y[M - 1])
+        # y rows and the statistics words of the (at most 8) chunks; the status row is only fetched for chunks with failed
+        # members (it is zero otherwise, and the statistics say so: capi.cu finish_chunk) -- counted in full if any failed
+        d2h = 3 * 8 * M + 13 * 8 * 8 + (4 * M if res.sum.n_failed else 0)
         capi.lib.rehuel_result_free(capi.C.byref(res))
         return d2h, checksum
 
@@ -442,10 +444,11 @@ def run_gpu_arm(args) -> None:
                        "wall_s_timed_region_rank0": wall, "host_binding_rank0": numa_note},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P_host.numel() * 8 + 24),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * e2e_s_max / args.steps,
-                    "bytes_per_member": {"h2d": 24, "d2h": 28},
+                    "bytes_per_member": {"h2d": 24, "d2h": 24 if tot["n_failed"] == 0 else 28},
                     "api": "rehuel_irk_ensemble (C ABI, pinned host buffers; options.result_mask = 0: the states y[3][M] and "
-                           "status[M] of every member plus the ensemble sums of all counters are copied back; t_final, "
-                           "err_last and the nine per-member counter arrays are not asked for)"},
+                           "status[M] of every member plus the ensemble sums of all counters come back; the status row is "
+                           "filled on the host for chunks whose statistics report no failed member and copied only otherwise; "
+                           "t_final, err_last and the nine per-member counter arrays are not asked for)"},
             "gpu_launches": int(ll.item()),
             "clocks": clocks,
             "roofline": {

@@ -116,7 +116,8 @@ typedef struct rehuel_options {
 	                                   (REHUEL_OUT_* bits).  y, status and the ensemble sums always come back; an array that
 	                                   is not asked for is NULL in the result.  On success t_final == t1 for every member and
 	                                   the counters are summed on the device (rehuel_result.sum), so a caller that only
-	                                   wants the states moves 8n + 4 bytes per member instead of 8n + 56.
+	                                   wants the states moves 8n bytes per member instead of 8n + 56 (the status row is filled on the
+	                                   host and only fetched for chunks in which a member failed).
 	                                   Default REHUEL_OUT_ALL (every field of rk_output, irk.hpp:140-163). */
 	int time_internals;             /* irk.hpp:106, 328-360: != 0 fills rehuel_result.phase_ms (device time of the host-to-device
 	                                   copies, the hand-out ordering, the integration kernels and the device-to-host copies,

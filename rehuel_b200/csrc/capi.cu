@@ -438,6 +438,8 @@ struct DeviceShard {
 	void *slab = nullptr;
 	rehuel_device_io io{};
 	unsigned long long *d_stats = nullptr;
+	size_t si = 0;             // index of the chunk (its statistics words in HostCall::h_stats)
+	bool status_lazy = false;  // the status row was not copied back: see finish_chunk
 	bool issued = false, synced = false;
 	DeviceShard() = default;
 	DeviceShard(const DeviceShard &) = delete;
@@ -650,8 +652,13 @@ static int issue_chunk(const HostCall &hc, DeviceShard &sh, size_t si)
 	                           cudaMemcpyDeviceToHost, sh.stream));
 	if ((hc.mask & REHUEL_OUT_ERR_LAST) && !(hc.mask & REHUEL_OUT_T_FINAL))
 		CUDA_TRY(cudaMemcpyAsync(hc.hdbl + (size_t)(n + 1) * M + sh.off, sh.io.err_last, sizeof(double) * m, cudaMemcpyDeviceToHost, sh.stream));
-	CUDA_TRY(cudaMemcpy2DAsync(hc.hint + sh.off, sizeof(int) * M, dint, sizeof(int) * m, sizeof(int) * m,
-	                           (hc.mask & REHUEL_OUT_COUNTERS) ? (size_t)1 + REHUEL_NCOUNTERS : (size_t)1, cudaMemcpyDeviceToHost, sh.stream));
+	// The status row is constant on success, and the chunk's statistics say whether every member succeeded: when no
+	// counter rows travel with it, finish_chunk fills it on the host and only fetches it for a chunk with failed members.
+	sh.si = si;
+	sh.status_lazy = !(hc.mask & REHUEL_OUT_COUNTERS);
+	if (!sh.status_lazy)
+		CUDA_TRY(cudaMemcpy2DAsync(hc.hint + sh.off, sizeof(int) * M, dint, sizeof(int) * m, sizeof(int) * m, (size_t)1 + REHUEL_NCOUNTERS,
+		                           cudaMemcpyDeviceToHost, sh.stream));
 	rehuel_result *out = hc.out;
 	if (hc.keep_state)
 		CUDA_TRY(cudaMemcpy2DAsync(out->state + sh.off, sizeof(double) * M, sh.io.state_out, sizeof(double) * m, sizeof(double) * m,
@@ -681,6 +688,14 @@ static int finish_chunk(const HostCall &hc, DeviceShard &sh, double *phase)
 {
 	if (!sh.issued || sh.synced) return REHUEL_OK;
 	CUDA_TRY(cudaStreamSynchronize(sh.stream));
+	if (sh.status_lazy) {
+		if (hc.h_stats[sh.si * kStatWords + REHUEL_NCOUNTERS] == 0) { // no failed member in this chunk
+			std::memset(hc.hint + sh.off, 0, sizeof(int) * sh.m);
+		} else {
+			CUDA_TRY(cudaMemcpyAsync(hc.hint + sh.off, sh.io.status, sizeof(int) * sh.m, cudaMemcpyDeviceToHost, sh.stream));
+			CUDA_TRY(cudaStreamSynchronize(sh.stream));
+		}
+	}
 	sh.synced = true;
 	if (hc.timing && phase)
 		for (int ph = 0; ph < 4; ++ph) {

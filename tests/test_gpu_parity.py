@@ -1144,7 +1144,7 @@ def test_per_attempt_log_matches_the_reference_log(capi, golden_configs):
 
 def test_result_mask_write_to_file_and_time_internals(capi, tmp_path):
     """options.result_mask: y, status and the ensemble sums always come back, every other per-member array only when
-    asked for (the C-ABI path then moves 8n + 4 bytes per member instead of 8n + 56).  WRITE_TO_FILE (irk.hpp:837-843)
+    asked for (the C-ABI path then moves 8n bytes per member instead of 8n + 56).  WRITE_TO_FILE (irk.hpp:837-843)
     and time_internals (irk.hpp:328-360) through the boundary."""
     from rehuel_b200 import ensembles
     M = 300_000
@@ -1161,6 +1161,14 @@ def test_result_mask_write_to_file_and_time_internals(capi, tmp_path):
             assert np.array_equal(g.err_last, full.err_last)
         if g.counters is not None:
             assert all(np.array_equal(g.counters[k], full.counters[k]) for k in full.counters)
+    # the status row is fetched only for chunks with failed members (and filled on the host otherwise): a run in which
+    # some members run out of steps must return the same statuses with and without the counter rows
+    lim = capi.make_options(1e-6, 1e-6, max_steps=27)
+    few = capi.make_options(1e-6, 1e-6, max_steps=27, result_mask=0)
+    a = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, lim)
+    b = capi.irk_ensemble(capi.ROBERTSON, 211, 0.0, 40.0, 1e-6, ensembles.ROBERTSON_Y0, P, few)
+    assert 0 < np.count_nonzero(a.status) < M and np.array_equal(a.status, b.status) and np.array_equal(a.y, b.y)
+    assert a.sum["n_failed"] == np.count_nonzero(a.status) == b.sum["n_failed"]
     # WRITE_TO_FILE: the stored steps of trace_member as "t y0 y1 y2" lines, 6 significant digits
     path = tmp_path / "traj.txt"
     o = capi.make_options(1e-6, 1e-6, output_mode=3, output_file=str(path), trace_member=7)
