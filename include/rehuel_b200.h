@@ -55,7 +55,9 @@ extern "C" {
 #define REHUEL_PROBLEM_ROBERTSON      1 /* n=3, params (k1,k2,k3); test_equations.hpp:150-176 with the constants as parameters */
 #define REHUEL_PROBLEM_VAN_DER_POL    2 /* n=2, params (mu);       test_equations.hpp:91-115 */
 #define REHUEL_PROBLEM_BRUSSELATOR_1D 3 /* n=2*Ng, params (alpha,A,B); 1-D method-of-lines Brusselator */
-#define REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE 4 /* the same system with its Jacobian treated as dense (general CTA-per-system kernel) */
+#define REHUEL_PROBLEM_BRUSSELATOR_1D_DENSE 4 /* the same system with its Jacobian treated as dense (general CTA-per-system kernel;
+                                                 REHUEL_EINVAL for RADAU_IIA_137 at n = 64: its four matrices exceed a block's
+                                                 shared memory -- the banded form of the problem runs every method) */
 #define REHUEL_PROBLEM_EXPONENTIAL    5 /* n=1, params (lambda);   test_equations.hpp:37-59 */
 #define REHUEL_PROBLEM_STIFF_EQ       6 /* n=2, no params;         test_equations.hpp:207-250 */
 #define REHUEL_PROBLEM_BRUSSELATOR    7 /* n=2, params (a,b);      test_equations.hpp:120-145 */

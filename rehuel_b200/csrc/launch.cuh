@@ -244,6 +244,11 @@ int launch_cta(const KernelArgs &ka, const Tableau &tb, cudaStream_t stream, Ker
 	int dev = 0, sms = 0, per_sm = 0;
 	REHUEL_CUDA_TRY(cudaGetDevice(&dev));
 	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	int smem_max = 0;
+	REHUEL_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+	if (smem > (size_t)smem_max) // e.g. RADAU_IIA_137 at n = 64 with a dense Jacobian: one real + three complex 64 x 65 matrices
+		return set_error(REHUEL_EINVAL, "the CTA-per-system kernel would need %zu bytes of shared memory for this method and system size "
+		                                "(%d stages, n = %d); a block can have %d", smem, S, (int)F::N, smem_max);
 	REHUEL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	REHUEL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
 	if (per_sm < 1) return set_error(REHUEL_ECUDA, "CTA-per-system kernel needs %zu bytes of shared memory", smem);

@@ -1252,15 +1252,19 @@ def test_per_member_tolerances_and_radau137_on_the_larger_kernels(capi, port):
         assert same >= (0.9 if method != 212 else 0.5) * M
     # RADAU_IIA_137 (7 stages: one real + three complex blocks) on the band, register-LU and CTA kernels
     P = ensembles.bruss1d_params(8)
-    for pid, n in ((capi.BRUSSELATOR_1D, 8), (capi.BRUSSELATOR_1D_DENSE, 8), (capi.BRUSSELATOR_1D_DENSE, 16), (capi.BRUSSELATOR_1D, 64)):
+    for pid, n in ((capi.BRUSSELATOR_1D, 8), (capi.BRUSSELATOR_1D_DENSE, 8), (capi.BRUSSELATOR_1D_DENSE, 16), (capi.BRUSSELATOR_1D_DENSE, 32),
+                   (capi.BRUSSELATOR_1D, 64)):
         y0 = ensembles.bruss1d_y0(n // 2)
-        t1 = 0.25 if n == 64 else 1.0
+        t1 = 0.25 if n >= 32 else 1.0
         g = capi.irk_ensemble(pid, 213, 0.0, t1, 1e-6, y0, P, capi.make_options(1e-6, 1e-6), n_hint=n)
         r = port.solve("brusselator-1d", 213, 0.0, t1, 1e-6, y0, P, ref_options(1e-6, 1e-6))
         se = scaled_err(g.y, r.y, 1e-6, 1e-6)
         print(f"RADAU_IIA_137 n={n} problem {pid}: max scaled err {se.max():.3e}; attempts gpu/ref {g.counters['attempt'].tolist()}/{r.counters['attempt'].tolist()}")
         assert np.all(g.status == 0) and se.max() <= PARITY_BOUND
         assert np.all(np.abs(g.counters["attempt"].astype(np.int64) - r.counters["attempt"].astype(np.int64)) <= np.maximum(3, 0.2 * r.counters["attempt"]))
+    # the one combination that has no kernel says so: four dense 64 x 64 matrices do not fit a block's shared memory
+    with pytest.raises(capi.RehuelError, match="shared memory"):
+        capi.irk_ensemble(capi.BRUSSELATOR_1D_DENSE, 213, 0.0, 0.25, 1e-6, ensembles.bruss1d_y0(32), P, capi.make_options(1e-6, 1e-6), n_hint=64)
 
 
 @pytest.mark.gpu
