@@ -260,8 +260,12 @@ def counter_sums(ens, torch):
     return d
 
 
-def model_flops(model, cs):
-    return model.total(cs["members"], cs["attempt"], cs["newton_success"], cs["reject_err"], cs["fun_evals"])
+def model_flops(model, cs, booked=False):
+    """Executed flops from counter sums.  With failed Newton solves in the run only the iterations of the successful ones
+    are counted (flopmodel.AttemptFlops.total: a failed solve books more evaluations than a lane with a non-finite iterate
+    executes); booked=True prices every booked iteration instead (an upper bound, reported next to it)."""
+    it = None if (booked or cs["reject_newton"] == 0) else cs["newton_iters"]
+    return model.total(cs["members"], cs["attempt"], cs["newton_success"], cs["reject_err"], cs["fun_evals"], newton_iters=it)
 
 
 def run_gpu_arm(args) -> None:
@@ -413,7 +417,8 @@ def run_gpu_arm(args) -> None:
         configs = other_configs(capi, ensembles, flopmodel, DeviceEnsemble, torch, dev, peak_tflops)
 
     # ---------------- strong scaling: fixed totals, whatever N is
-    strong = None if args.quick else strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world, barrier, max_over_ranks)
+    strong = None if args.quick else strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world, barrier, max_over_ranks,
+                                                  flopmodel, peak_tflops)
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
@@ -510,6 +515,10 @@ def other_configs(capi, ensembles, flopmodel, DeviceEnsemble, torch, dev, peak_t
                                   "frac": fl / (ms * 1e-3) / 1e12 / peak_tflops,
                                   "model": f"executed flops (flopmodel.py): fixed {model.fixed:g}/attempt, {model.per_iteration:g}/Newton iteration"},
                      "kernel": note}
+        if cs["reject_newton"]:  # failed solves: their iterations are booked as in the reference but only partly executed
+            out[name]["roofline"]["model"] += ("; the iterations of FAILED Newton solves are left out (a lane with a non-finite iterate "
+                                               "stops early and books the rest): a lower bound")
+            out[name]["roofline"]["frac_if_every_booked_iteration_ran"] = model_flops(model, cs, booked=True) / (ms * 1e-3) / 1e12 / peak_tflops
         return ens
 
     # config 3: Van der Pol sweep, LOBATTO_IIIC_43, thread-per-system; stiff end handed out first
@@ -531,7 +540,7 @@ def other_configs(capi, ensembles, flopmodel, DeviceEnsemble, torch, dev, peak_t
     return out
 
 
-def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world, barrier, max_over_ranks) -> dict:
+def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world, barrier, max_over_ranks, flopmodel, peak_tflops) -> dict:
     """Strong scaling: fixed totals over the N ranks.
     config 2 at 2^20 members in all: rank r integrates the contiguous members [r M/N, (r+1) M/N).
     config 3 at 2^20 Van der Pol members in all, dealt i mod N.
@@ -641,9 +650,12 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
     ms = max_over_ranks(ms)
     failed = sum(int((de.status != 0).sum()) for c in mine for de, _ in chunks[c])
     att = sum(int(de.counter("attempt").sum()) for c in mine for de, _ in chunks[c])
-    t = torch.tensor([float(failed), float(att), float(len(mine)), float(-len(mine))], dtype=torch.float64, device=dev)
+    # executed flops of the chunks this rank ran: the thread kernel's models of the two member classes (flopmodel.py)
+    models = (flopmodel.thread_kernel(3, capi.RADAU_IIA_53, 11, 8, zero_col0_rows=(2,)), flopmodel.thread_kernel(2, capi.LOBATTO_IIIC_43, 6, 7))
+    flops = sum(model_flops(models[k], counter_sums(de, torch)) for c in mine for k, (de, _) in enumerate(chunks[c]))
+    t = torch.tensor([float(failed), float(att), float(len(mine)), float(flops)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t[:3])
+        dist.all_reduce(t)
         lo_hi = torch.tensor([float(len(mine)), float(-len(mine))], dtype=torch.float64, device=dev)
         dist.all_reduce(lo_hi, op=dist.ReduceOp.MAX)
         most, least = int(lo_hi[0].item()), int(-lo_hi[1].item())
@@ -652,6 +664,12 @@ def strong_block(capi, ensembles, DeviceEnsemble, torch, dist, dev, rank, world,
     out["config5_mixed_10485760_total"] = {"ms": ms, "systems_per_s": Mt / (ms * 1e-3), "members_total": Mt, "chunks": n_chunks,
                                            "chunks_in_flight_per_gpu": depth, "chunks_claimed_min_max": [least, most],
                                            "failed_members": int(t[0].item()), "attempts_per_member": t[1].item() / Mt,
+                                           "roofline": {"bound": "fp64", "achieved": t[3].item() / (ms * 1e-3) / 1e12 / world, "peak": peak_tflops,
+                                                        "unit": "TFLOP/s per GPU", "frac": t[3].item() / (ms * 1e-3) / 1e12 / world / peak_tflops,
+                                                        "model": "executed flops of ensemble_irk_thread for the Robertson (RADAU_IIA_53) and Van der Pol "
+                                                                 "(LOBATTO_IIIC_43) halves, from the counters of every chunk (iterations of failed "
+                                                                 "Newton solves left out: a lower bound); wall time of the whole pipeline (ordering, "
+                                                                 "512 launches, chunk claiming) in the denominator"},
                                            "balance": "chunks claimed from a shared-memory cursor (rehuel_cursor) as GPUs finish"}
     barrier()
     cur.close()

@@ -31,15 +31,20 @@ class AttemptFlops:
     extra_820: float      # per use of formula 8.20
     residual: float       # one residual evaluation (what a skipped final residual saves)
 
-    def total(self, members, attempt, newton_success, reject_err, fun_evals):
+    def total(self, members, attempt, newton_success, reject_err, fun_evals, newton_iters=None):
         """Lower bound on the executed flops of a run, from the SUMS of the counters the kernels return.
           uses of 8.20      = members + reject_err   (first attempt, and the first estimate after every error rejection:
                                                       irk.hpp:587, 763, 845)
           residuals booked  = (fun_evals - newton_success - uses_820) / S      (irk.hpp:443-446, 469-472, 702, 728)
           Newton iterations = residuals booked - attempt   (every attempt starts with one; failed solves included)
-        Every successful solve is assumed to skip its final residual (see the module text)."""
+        Every successful solve is assumed to skip its final residual (see the module text).
+
+        A FAILED solve books the evaluations the reference would have spent (irk.hpp:458-488 spins to maxit), but a lane
+        whose iterate has become non-finite stops early (irk_thread.cuh): booked is not executed.  For runs with Newton
+        failures pass `newton_iters` (the counter: iterations of the SUCCESSFUL solves only); failed solves then count with
+        their per-attempt part alone, which keeps the total a lower bound."""
         uses = members + reject_err
-        iters = (fun_evals - newton_success - uses) / self.S - attempt
+        iters = (fun_evals - newton_success - uses) / self.S - attempt if newton_iters is None else newton_iters
         failed = attempt - newton_success
         return (self.fixed * newton_success + (self.fixed - self.tail) * failed + self.per_iteration * iters
                 + self.extra_820 * uses - self.residual * newton_success)
