@@ -82,6 +82,9 @@ def test_executed_flop_model_of_the_thread_kernel():
     assert total == rob.fixed * 3 + rob.per_iteration * 5 + rob.extra_820 * 2 - rob.residual * 3
     # a failed Newton solve has no tail
     assert rob.total(1, att + 1, nok, rej, fun + 3 * (1 + 4)) == total + (rob.fixed - rob.tail) + 4 * rob.per_iteration
+    # ... and what it books is not what a lane with a non-finite iterate executes: with the iterations of the SUCCESSFUL
+    # solves given, the failed solve counts with its per-attempt part alone (a lower bound)
+    assert rob.total(1, att + 1, nok, rej, fun + 3 * (1 + 4999), newton_iters=its) == total + (rob.fixed - rob.tail)
     band = fm.band_kernel(64, 2, 232, 10, 8)
     dense = fm.dense_kernel(64, 232, 10, 64 * 8)
     assert dense.fixed > 50 * band.fixed                            # three dense 64 x 64 LUs against band LUs
